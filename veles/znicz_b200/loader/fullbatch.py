@@ -1,0 +1,194 @@
+"""Full-batch loaders: the whole dataset lives in memory.
+
+Fresh design for ``veles.loader.fullbatch`` (FullBatchLoader, FullBatchLoaderMSE)
+as consumed by the reference's loaders (/root/reference/loader/loader_wine.py:48-66,
+/root/reference/loader/loader_mnist.py:53-186, /root/reference/samples/CIFAR10/cifar.py:47-66).
+
+Data layout: ``original_data[total, ...]`` ordered TEST, VALID, TRAIN;
+``original_labels`` a python list / int32 array of raw labels mapped to
+0..n-1 via ``labels_mapping``.
+
+B200: with ``on_device=True`` (default when the dataset fits comfortably — 180 GB
+of HBM3e makes that the common case) the dataset is uploaded once and every
+minibatch is produced by a device gather kernel (``gather_rows``), so no host
+traffic happens in the training loop; with ``on_device=False`` minibatches are
+staged through pinned memory each step (streaming mode, the path ``bench.py``
+times end-to-end).
+"""
+from __future__ import annotations
+
+import numpy
+
+from ..core.accelerated_units import host_dtype
+from ..core.memory import Array
+from .base import (Loader, LoaderMSEMixin, LoaderWithValidationRatio, TEST, VALID,
+                   TRAIN, LoaderError)
+
+
+class FullBatchLoader(Loader, LoaderWithValidationRatio):
+    hide_from_registry = True
+
+    def __init__(self, workflow, **kwargs):
+        super().__init__(workflow, **kwargs)
+        self.original_data = Array()
+        self.original_labels = []
+        self.on_device = kwargs.get("on_device", False)
+        self.validation_ratio = kwargs.get("validation_ratio", None)
+        self._mapped_original_labels = Array()
+        self._normalized = False
+
+    def init_unpickled(self):
+        super().init_unpickled()
+        self._labels_dev_ = None
+
+    def _data_loaded(self):
+        return bool(self.original_data)
+
+    @property
+    def dtype(self):
+        return host_dtype()
+
+    def create_minibatch_data(self):
+        shape = (self.max_minibatch_size,) + tuple(self.original_data.shape[1:])
+        if not self.minibatch_data or self.minibatch_data.shape != shape:
+            self.minibatch_data.reset(numpy.zeros(shape, dtype=self.dtype))
+        if self.has_labels and (
+                not self.minibatch_labels or
+                self.minibatch_labels.shape[0] != self.max_minibatch_size):
+            self.minibatch_labels.reset(
+                numpy.zeros(self.max_minibatch_size, dtype=numpy.int32))
+
+    @property
+    def has_labels(self):
+        return len(self.original_labels) > 0
+
+    def analyze_dataset(self):
+        """Map raw labels, carve validation, normalise in place (once)."""
+        if self.has_labels and not self.labels_mapping:
+            uniq = sorted(set(self.original_labels[self.class_end_offsets[VALID]:]) or
+                          set(self.original_labels))
+            # labels that only exist outside train are appended after
+            extra = sorted(set(self.original_labels) - set(uniq))
+            self.labels_mapping = {l: i for i, l in enumerate(uniq + extra)}
+            self.reversed_labels_mapping = uniq + extra
+        if self.has_labels:
+            mapped = numpy.fromiter(
+                (self.labels_mapping[l] for l in self.original_labels),
+                dtype=numpy.int32, count=len(self.original_labels))
+            self._mapped_original_labels.reset(mapped)
+        if not self._normalized:
+            self._normalize_dataset()
+            self._normalized = True
+
+    def _normalize_dataset(self):
+        data = self.original_data.mem
+        if self.normalization_type == "none":
+            if data.dtype != self.dtype:
+                self.original_data.reset(data.astype(self.dtype))
+            return
+        if data.dtype != self.dtype:
+            data = data.astype(self.dtype)
+        norm = self.normalizer
+        train = data[self.class_end_offsets[VALID]:] if self.class_lengths[TRAIN] \
+            else data
+        if not norm.is_initialized:
+            norm.analyze(train)
+        data = norm.normalize(data)
+        self.original_data.reset(data)
+
+    def fill_minibatch(self):
+        n = self.minibatch_size
+        idx = self.minibatch_indices.mem[:n]
+        self.minibatch_data.map_invalidate()
+        md = self.minibatch_data.mem
+        numpy.take(self.original_data.mem, idx, axis=0, out=md[:n])
+        if n < md.shape[0]:
+            md[n:] = 0
+        if self.has_labels:
+            self.minibatch_labels.map_invalidate()
+            ml = self.minibatch_labels.mem
+            numpy.take(self._mapped_original_labels.mem, idx, out=ml[:n])
+            ml[n:] = -1
+
+    # -- device-resident dataset ---------------------------------------------------------
+    def _cuda_setup(self):
+        super()._cuda_setup()
+        if self.on_device:
+            self.original_data.initialize(self.device)
+            if self.has_labels:
+                self._mapped_original_labels.initialize(self.device)
+            self.h2d_bytes_per_step = self.minibatch_indices.mem.nbytes + 16
+
+    def _cuda_serve(self):
+        if not self.on_device:
+            return super()._cuda_serve()
+        import torch
+        # only the indices (+header) cross PCIe; rows are gathered in HBM
+        self.minibatch_indices.unmap()
+        ext = self.device.ext
+        ext.gather_rows(self.original_data.devmem, self.minibatch_indices.devmem,
+                        self.minibatch_data.devmem, int(self.minibatch_size))
+        self.minibatch_data.dev_written()
+        if self.has_labels:
+            ext.gather_labels(self._mapped_original_labels.devmem,
+                              self.minibatch_indices.devmem,
+                              self.minibatch_labels.devmem, int(self.minibatch_size))
+            self.minibatch_labels.dev_written()
+        hdr = self._pinned_["header"]
+        hdr[0] = self.minibatch_size
+        hdr[1] = self.minibatch_class
+        hdr[2] = self.epoch_number
+        self.header_dev_.copy_(hdr, non_blocking=True)
+
+
+class FullBatchLoaderMSE(FullBatchLoader, LoaderMSEMixin):
+    """Adds ``original_targets`` → ``minibatch_targets`` for MSE workflows."""
+    hide_from_registry = True
+
+    def __init__(self, workflow, **kwargs):
+        super().__init__(workflow, **kwargs)
+        self._init_mse(kwargs)
+        self.original_targets = Array()
+        self._targets_normalized = False
+
+    def create_minibatch_data(self):
+        super().create_minibatch_data()
+        shape = (self.max_minibatch_size,) + tuple(self.original_targets.shape[1:])
+        if not self.minibatch_targets or self.minibatch_targets.shape != shape:
+            self.minibatch_targets.reset(numpy.zeros(shape, dtype=self.dtype))
+        self.targets_shape = tuple(self.original_targets.shape[1:])
+
+    def analyze_dataset(self):
+        super().analyze_dataset()
+        if not self._targets_normalized and self.target_normalization_type != "none":
+            t = self.original_targets.mem.astype(self.dtype)
+            norm = self.target_normalizer
+            train = t[self.class_end_offsets[VALID]:] if self.class_lengths[TRAIN] else t
+            if not norm.is_initialized:
+                norm.analyze(train)
+            self.original_targets.reset(norm.normalize(t))
+            if self.class_targets:
+                ct = self.class_targets.mem.astype(self.dtype)
+                self.class_targets.reset(norm.normalize(ct))
+            self._targets_normalized = True
+
+    def fill_minibatch(self):
+        super().fill_minibatch()
+        n = self.minibatch_size
+        idx = self.minibatch_indices.mem[:n]
+        self.minibatch_targets.map_invalidate()
+        mt = self.minibatch_targets.mem
+        numpy.take(self.original_targets.mem, idx, axis=0, out=mt[:n])
+        mt[n:] = 0
+
+    def _staged_arrays(self):
+        return super()._staged_arrays() + [self.minibatch_targets]
+
+    def _cuda_setup(self):
+        self.init_vectors(self.minibatch_targets)
+        super()._cuda_setup()
+
+    def _cuda_serve(self):
+        if self.on_device:
+            raise LoaderError("on_device mode is not implemented for MSE loaders")
+        return super()._cuda_serve()
