@@ -1,0 +1,119 @@
+"""CUDA-graph capture of a chain of accelerated units.
+
+The reference drives >100 tiny kernel launches per minibatch from python
+(SURVEY §3.3). On B200 the python unit graph still decides *what* runs each
+minibatch, but a chain of units (forwards+evaluator, or all GD units) is captured
+once per gate configuration into a CUDA graph and replayed:
+
+* ``cuda_prepare()`` of every unit runs on the host before each replay (uploads of
+  runtime scalars: batch size, learning rates, RNG counters) — the kernels read
+  those from HBM, so the captured graph never needs re-capturing;
+* Array coherence is preserved: arrays that the captured kernels read are uploaded
+  first if the host dirtied them, and arrays they wrote are marked device-owned
+  after every replay.
+
+Segments degrade to eager execution (same kernels, python-launched) for the first
+``warmup`` executions and whenever capture is disabled.
+"""
+from __future__ import annotations
+
+from . import memory as _memory
+
+
+class _Recorder(object):
+    def __init__(self):
+        self.reads = []
+        self.writes = []
+
+    def read(self, arr):
+        if arr not in self.reads:
+            self.reads.append(arr)
+
+    def write(self, arr):
+        if arr not in self.writes:
+            self.writes.append(arr)
+
+
+_active_recorder = None
+
+
+def recorder():
+    return _active_recorder
+
+
+class _Captured(object):
+    __slots__ = ("graph", "reads", "writes")
+
+
+class GraphSegment(object):
+    def __init__(self, name, units, key_fn=None, warmup=2, enabled=True):
+        self.name = name
+        self.units = list(units)
+        self.key_fn = key_fn or (lambda: 0)
+        self.warmup = warmup
+        self.enabled = enabled
+        self._graphs = {}
+        self._runs = {}
+        self._done_for = None
+        self.replays = 0
+        self.eager_runs = 0
+        for u in self.units:
+            u.__dict__["segment_"] = self
+
+    def detach(self):
+        for u in self.units:
+            u.__dict__.pop("segment_", None)
+
+    # called from Unit._run_timed in place of unit.run()
+    def run_unit(self, unit):
+        if unit is self.units[0]:
+            self.execute()
+        # other members were executed as part of the segment this iteration
+
+    def _eager(self):
+        for u in self.units:
+            u._backend_run_()
+        self.eager_runs += 1
+
+    def execute(self):
+        global _active_recorder
+        import torch
+        for u in self.units:
+            u.cuda_prepare()
+        key = self.key_fn()
+        cap = self._graphs.get(key)
+        if cap is not None:
+            for a in cap.reads:
+                if a._state == _memory._MAPPED_WRITE:
+                    a.unmap()
+            cap.graph.replay()
+            for a in cap.writes:
+                a._state = _memory._UNMAPPED
+            self.replays += 1
+            return
+        n = self._runs.get(key, 0)
+        self._runs[key] = n + 1
+        if not self.enabled or n < self.warmup:
+            self._eager()
+            return
+        # capture
+        rec = _Recorder()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        _active_recorder = rec
+        try:
+            # make every input current *before* capture (H2D copies are not captured)
+            with torch.cuda.graph(g):
+                for u in self.units:
+                    u._backend_run_()
+        finally:
+            _active_recorder = None
+        cap = _Captured()
+        cap.graph = g
+        cap.reads = rec.reads
+        cap.writes = rec.writes
+        self._graphs[key] = cap
+        g.replay()   # the capture pass did not execute anything
+        for a in cap.writes:
+            a._state = _memory._UNMAPPED
+        self.replays += 1

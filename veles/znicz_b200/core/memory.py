@@ -22,6 +22,11 @@ import numpy
 _MAPPED_READ, _MAPPED_WRITE, _UNMAPPED = 0, 1, 2
 
 
+def _graphs_recorder():
+    from . import graphs
+    return graphs._active_recorder
+
+
 def roundup(num, align):
     d = num % align
     return num if d == 0 else num + (align - d)
@@ -279,10 +284,23 @@ class Array(object):
     @property
     def dev(self):
         """Device tensor, made current (the common call in ``cuda_run``)."""
-        if self._state != _UNMAPPED:
-            self.unmap()
+        if self._state == _MAPPED_WRITE:
+            self._upload()
+            self._state = _MAPPED_READ
+        rec = _graphs_recorder()
+        if rec is not None:
+            rec.read(self)
         return self._devmem_
 
     def dev_written(self):
         """Mark that a kernel wrote the device copy (host copy is now stale)."""
         self._state = _UNMAPPED
+        rec = _graphs_recorder()
+        if rec is not None:
+            rec.write(self)
+
+    @property
+    def dev_out(self):
+        """Device tensor about to be fully overwritten by a kernel."""
+        self.dev_written()
+        return self._devmem_

@@ -131,6 +131,7 @@ class SnapshotterToFile(SnapshotterBase):
 
     @staticmethod
     def import_file(file_name):
+        file_name = os.path.realpath(file_name)   # "<prefix>_current.lnk" symlinks
         if file_name.endswith(".gz"):
             opener = gzip.open
         elif file_name.endswith(".bz2"):

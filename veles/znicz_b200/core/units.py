@@ -312,7 +312,11 @@ class Unit(Logger, metaclass=UnitRegistry):
         if root.common.trace.run:
             self.debug("run")
         t0 = time.perf_counter()
-        self.run()
+        seg = self.__dict__.get("segment_")
+        if seg is not None:
+            seg.run_unit(self)
+        else:
+            self.run()
         self._run_time += time.perf_counter() - t0
         self._run_calls += 1
 

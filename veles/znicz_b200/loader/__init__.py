@@ -1,0 +1,5 @@
+"""Loaders (fresh design for ``veles.loader`` + the reference's ``loader/`` package)."""
+from .base import (Loader, LoaderMSEMixin, UserLoaderRegistry, TEST, VALID, TRAIN,  # noqa
+                   CLASS_NAME, LoaderError)
+from .fullbatch import FullBatchLoader, FullBatchLoaderMSE  # noqa
+from . import synthetic  # noqa  (registers the synthetic_* loaders)

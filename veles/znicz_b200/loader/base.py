@@ -39,18 +39,24 @@ UserLoaderRegistry = make_registry("loaders")
 UserLoaderRegistry.loaders = UserLoaderRegistry.registry
 
 
-def _get_factory(name, **kwargs):
-    try:
-        cls = UserLoaderRegistry.registry[name]
-    except KeyError:
-        raise ValueError("Unknown loader %r (known: %s)" % (
-            name, sorted(UserLoaderRegistry.registry)))
+class LoaderFactory(object):
+    """Picklable ``callable(workflow, **extra) -> Loader`` bound to a registry name."""
 
-    def factory(workflow, **extra):
-        kw = dict(kwargs)
+    def __init__(self, name, kwargs):
+        if name not in UserLoaderRegistry.registry:
+            raise ValueError("Unknown loader %r (known: %s)" % (
+                name, sorted(UserLoaderRegistry.registry)))
+        self.name = name
+        self.kwargs = dict(kwargs)
+
+    def __call__(self, workflow, **extra):
+        kw = dict(self.kwargs)
         kw.update(extra)
-        return cls(workflow, **kw)
-    return factory
+        return UserLoaderRegistry.registry[self.name](workflow, **kw)
+
+
+def _get_factory(name, **kwargs):
+    return LoaderFactory(name, kwargs)
 
 
 UserLoaderRegistry.get_factory = staticmethod(_get_factory)

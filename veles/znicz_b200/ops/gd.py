@@ -23,8 +23,10 @@ from .nn_units import (ACT_LINEAR, ACT_TANH, ACT_RELU, ACT_STRICT_RELU,
                        ACT_SIGMOID)
 
 
-class GradientDescent(nn_units.GradientDescentBase):
-    MAPPING = {"all2all"}
+class GDCommon(nn_units.GradientDescentBase):
+    """Solver plumbing + the numpy fused-step oracle shared by FC/conv/deconv GDs."""
+    hide_from_registry = True
+    MAPPING = set()
     SOLVERS = ("momentum", "adagrad", "adadelta", "fast")
     ACT = ACT_LINEAR
 
@@ -145,6 +147,15 @@ class GradientDescent(nn_units.GradientDescentBase):
             if "fast" in self.solvers and not v_trans:
                 vec.mem -= self.solver_state[("fast", s)]
 
+    def on_cuda_forward_shadow(self):
+        fu = self.forward_unit
+        return fu is not None and getattr(fu, "on_cuda", False)
+
+
+class GradientDescent(GDCommon):
+    """GD for :class:`All2All` (linear)."""
+    MAPPING = {"all2all"}
+
     def numpy_weights_update(self):
         if not self.need_gradient_weights:
             return
@@ -193,10 +204,6 @@ class GradientDescent(nn_units.GradientDescentBase):
         self.numpy_bias_update()
         if self.on_cuda_forward_shadow():
             self.forward_unit.refresh_shadows()
-
-    def on_cuda_forward_shadow(self):
-        fu = self.forward_unit
-        return fu is not None and getattr(fu, "on_cuda", False)
 
     # -- sm_100a ------------------------------------------------------------------------
     def cuda_run(self):

@@ -1,0 +1,140 @@
+"""Synchronous data parallelism: replicated weights, fused reduce+update.
+
+Replaces the reference's asynchronous master/slave parameter exchange
+(/root/reference/nn_units.py:644-694): every rank runs the same unit
+graph on its shard of the minibatch; after a GD unit produced its local gradient the
+*fused update kernel* reads the gradient tiles of all ranks straight out of their
+HBM over NVLink (peer pointers from a symmetric-memory rendezvous), sums them in
+rank order — so all replicas compute bit-identical updates — applies the SGD step
+and writes the new weights locally. No NCCL call is on that path; NCCL (or gloo on
+CPU) is used for bootstrap, metric reduction at epoch ends and as the *baseline*
+implementation (``mode="nccl"``) the fused path is measured against.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy
+
+
+class DataParallel(object):
+    def __init__(self, device, rank, world_size, mode=None):
+        self.device = device
+        self.rank = rank
+        self.world_size = world_size
+        self.mode = mode or os.environ.get("ZNICZ_DP_MODE", "fused")
+        self.symm = None
+        self._step = 0
+
+    @classmethod
+    def from_env(cls, device):
+        ws = int(os.environ.get("WORLD_SIZE", "1"))
+        if ws <= 1:
+            return None
+        import torch.distributed as dist
+        rank = int(os.environ.get("RANK", "0"))
+        if not dist.is_initialized():
+            backend = "nccl" if device is not None and device.is_cuda else "gloo"
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = device.torch_device
+            dist.init_process_group(backend=backend, rank=rank, world_size=ws, **kw)
+        return cls(device, rank, ws)
+
+    # -- wiring ---------------------------------------------------------------------------
+    def attach(self, workflow):
+        """Give every GD unit / decision of ``workflow`` this context, shard the loader
+        and broadcast rank 0's initial weights so replicas start identical."""
+        from ..ops.nn_units import GradientDescentBase, Forward
+        loader = workflow.real_loader
+        loader.dp_rank = self.rank
+        loader.dp_world = self.world_size
+        for u in workflow.units:
+            if isinstance(u, GradientDescentBase):
+                u.dp_ = self
+            if hasattr(u, "dp") and not isinstance(u, type(workflow)):
+                try:
+                    u.dp = self
+                except AttributeError:
+                    pass
+        self.broadcast_parameters(
+            [u for u in workflow.forwards if isinstance(u, Forward)])
+        if self.device is not None and self.device.is_cuda and self.mode == "fused":
+            from .symmetric import SymmetricGradients
+            gds = [g for g in workflow.gds if g is not None and g.weights]
+            self.symm = SymmetricGradients(self, gds)
+
+    def broadcast_parameters(self, forwards):
+        import torch
+        import torch.distributed as dist
+        for f in forwards:
+            for arr in (f.weights, f.bias):
+                if not arr:
+                    continue
+                if arr.devmem is not None:
+                    t = arr.dev
+                    dist.broadcast(t, src=0)
+                    arr.dev_written()
+                else:
+                    t = torch.from_numpy(arr.mem)
+                    dist.broadcast(t, src=0)
+            if getattr(f, "on_cuda", False):
+                f.refresh_shadows()
+
+    # -- reductions on the slow path (epoch ends) ----------------------------------------------
+    def reduce_metrics(self, n_err=None, confusion=None, max_err=None, mse_metrics=None):
+        import torch
+        import torch.distributed as dist
+
+        def _reduce(arr, op):
+            if arr is None or not arr:
+                return
+            arr.map_read()
+            t = torch.from_numpy(numpy.ascontiguousarray(arr.mem))
+            if self.device is not None and self.device.is_cuda:
+                t = t.to(self.device.torch_device)
+            dist.all_reduce(t, op=op)
+            arr.map_invalidate()
+            arr.mem[...] = t.cpu().numpy()
+            arr.unmap()
+        _reduce(n_err, dist.ReduceOp.SUM)
+        _reduce(confusion, dist.ReduceOp.SUM)
+        _reduce(max_err, dist.ReduceOp.MAX)
+        if mse_metrics is not None and mse_metrics:
+            mse_metrics.map_read()
+            m = mse_metrics.mem
+            vals = torch.tensor([float(m[0]), float(m[1]), -float(m[2])],
+                                dtype=torch.float64)
+            if self.device is not None and self.device.is_cuda:
+                vals = vals.to(self.device.torch_device)
+            s = vals[:1].clone()
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            mx = vals[1:].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            mse_metrics.map_invalidate()
+            m[0] = float(s[0])
+            m[1] = float(mx[0])
+            m[2] = -float(mx[1])
+            mse_metrics.unmap()
+
+    def all_reduce_scalar(self, value, op="sum"):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([float(value)], dtype=torch.float64)
+        if self.device is not None and self.device.is_cuda:
+            t = t.to(self.device.torch_device)
+        dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN,
+                               "max": dist.ReduceOp.MAX}[op])
+        return float(t[0])
+
+    def barrier(self):
+        import torch.distributed as dist
+        dist.barrier()
+
+    # -- numpy / gloo gradient path (CPU multi-process tests) ------------------------------------
+    def all_reduce_numpy(self, arr):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(arr)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return arr
