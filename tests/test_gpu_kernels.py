@@ -1,0 +1,182 @@
+"""Direct numerics tests of the sm_100a kernels against plain PyTorch fp32 references."""
+import numpy
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from veles.znicz_b200.kernels import load_extension
+    return load_extension(required=True)
+
+
+def _rel(a, b):
+    a = a.float()
+    b = b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(100, 10, 1024), (128, 128, 64), (300, 72, 200),
+                                   (1999, 5625, 1776), (64, 791, 1392), (257, 32, 800)])
+def test_gemm_nt_bias_act(ext, engine, M, N, K):
+    """out = relu(a @ b^T + bias): FC forward shape family (/root/reference/
+    tests/unit/test_all2all.py:98 perf shape 1999x1777->5625 rounded to K%8==0)."""
+    torch.manual_seed(0)
+    dev = "cuda"
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=dev)
+    ref = torch.relu(a.float() @ b.float().t() + bias)
+    for out_dt in (torch.bfloat16, torch.float32):
+        out = torch.full((M, N), float("nan"), device=dev, dtype=out_dt)
+        r = ext.gemm(a, K, False, b, K, True, out, N, False, M, N, K, bias, 3, 1.0, 0.0, 1, 0,
+                     engine)
+        assert r == 0
+        torch.cuda.synchronize()
+        assert _rel(out, ref) < (2e-2 if out_dt == torch.bfloat16 else 2e-3), (engine, out_dt)
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(100, 1024, 16), (256, 64, 64), (130, 200, 72),
+                                   (100, 1392, 792)])
+def test_gemm_nn_alpha_beta(ext, engine, M, N, K):
+    """err_in = alpha * err @ W + beta * err_in  (B stored [K][N], MN-major operand)."""
+    torch.manual_seed(1)
+    dev = "cuda"
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = (torch.randn(K, N, device=dev) / K ** 0.5).bfloat16()
+    old = torch.randn(M, N, device=dev)
+    ref = 0.5 * (a.float() @ b.float()) + 2.0 * old
+    out = old.clone()
+    r = ext.gemm(a, K, False, b, N, False, out, N, False, M, N, K, None, 0, 0.5, 2.0, 1, 0, engine)
+    assert r == 0
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("M,N,K,splits", [(64, 1024, 100, 1), (792, 1392, 104, 1),
+                                           (32, 800, 25600, 8), (128, 128, 1000, 3)])
+def test_gemm_tn_splitk(ext, engine, M, N, K, splits):
+    """gradW = err^T @ x with both operands MN-major and fp32 split-K partials."""
+    torch.manual_seed(2)
+    dev = "cuda"
+    a = torch.randn(K, M, device=dev).bfloat16()      # stored [K][M]
+    b = torch.randn(K, N, device=dev).bfloat16()      # stored [K][N]
+    ref = a.float().t() @ b.float()
+    parts = torch.full((splits, M, N), float("nan"), device=dev)
+    r = ext.gemm(a, M, True, b, N, False, parts, N, False, M, N, K, None, 0, 1.0, 0.0, splits,
+                 M * N, engine)
+    assert r == 0
+    torch.cuda.synchronize()
+    assert _rel(parts.sum(0), ref) < 2e-3
+
+
+def _conv_ref(x, w, bias, ky, kx, pad, stride):
+    # x NHWC, w [F][ky*kx*C]; pad = (L, T, R, B), stride = (sx, sy)
+    n, h, ww, c = x.shape
+    f = w.shape[0]
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pad[0], pad[2], pad[1], pad[3]))
+    wt = w.view(f, ky, kx, c).permute(0, 3, 1, 2)
+    y = torch.nn.functional.conv2d(xp, wt, bias, stride=(stride[1], stride[0]))
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+CONV_CASES = [
+    # N, H, W, C, F, ky, kx, pad(L,T,R,B), stride(x,y)
+    (4, 32, 32, 3, 32, 5, 5, (2, 2, 2, 2), (1, 1)),     # CIFAR conv1
+    (4, 16, 16, 32, 32, 5, 5, (2, 2, 2, 2), (1, 1)),    # CIFAR conv2
+    (3, 8, 8, 32, 64, 5, 5, (2, 2, 2, 2), (1, 1)),      # CIFAR conv3
+    (2, 12, 12, 64, 88, 5, 5, (0, 0, 0, 0), (1, 1)),    # MNIST conv2-like
+    (2, 15, 13, 8, 16, 3, 2, (1, 0, 2, 1), (2, 1)),     # odd geometry
+    (2, 27, 27, 16, 24, 11, 11, (0, 0, 0, 0), (4, 4)),  # AlexNet conv1-like stride 4
+]
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad(ext, engine, case):
+    n, h, w_, c, f, ky, kx, pad, stride = case
+    torch.manual_seed(3)
+    dev = "cuda"
+    oh = 1 + (h - ky + pad[1] + pad[3]) // stride[1]
+    ow = 1 + (w_ - kx + pad[0] + pad[2]) // stride[0]
+    kw = ky * kx * c
+    x = torch.randn(n, h, w_, c, device=dev).bfloat16()
+    wm = (torch.randn(f, kw, device=dev) / kw ** 0.5)
+    wq = wm.bfloat16().float()
+    bias = torch.randn(f, device=dev)
+    g = [n, h, w_, c, oh, ow, f, ky, kx, stride[1], stride[0], pad[1], pad[0]]
+    xr = x.float().requires_grad_(True)
+    wr = wq.clone().requires_grad_(True)
+    ref = _conv_ref(xr, wr, bias, ky, kx, pad, stride)
+    eo = torch.randn_like(ref).bfloat16()
+    ref.backward(eo.float())
+    # fprop
+    out = torch.full((n, oh, ow, f), float("nan"), device=dev, dtype=torch.bfloat16)
+    if engine == 1:
+        ld = (kw + 7) // 8 * 8
+        wlp = torch.zeros(f, ld, device=dev, dtype=torch.bfloat16)
+        wlp[:, :kw] = wq.bfloat16()
+        r = ext.conv_fprop(x, wlp, ld, False, bias, out, g, 0, 1)
+    else:
+        r = ext.conv_fprop(x, wq.contiguous(), kw, False, bias, out, g, 0, 0)
+    assert r == 0
+    torch.cuda.synchronize()
+    assert _rel(out, ref.detach()) < 2e-2
+    # dgrad
+    ei = torch.full((n, h, w_, c), float("nan"), device=dev, dtype=torch.bfloat16)
+    if engine == 1:
+        cp = (c + 7) // 8 * 8
+        wd = torch.zeros(ky * kx * f, cp, device=dev, dtype=torch.bfloat16)
+        wd.view(ky * kx, f, cp)[:, :, :c] = wq.view(f, ky * kx, c).permute(1, 0, 2).bfloat16()
+        r = ext.conv_dgrad(eo, wd, cp, False, ei, g, 1.0, 0.0, 1)
+    else:
+        r = ext.conv_dgrad(eo, wq.contiguous(), kw, False, ei, g, 1.0, 0.0, 0)
+    assert r == 0
+    torch.cuda.synchronize()
+    assert _rel(ei, xr.grad) < 2e-2
+    # wgrad
+    if engine == 1 and f % 8:
+        return
+    splits = int(ext.pick_splits(kw, f, n * oh * ow, 16)) if engine == 1 else 4
+    parts = torch.full((splits, f, kw), float("nan"), device=dev)
+    r = ext.conv_wgrad(eo, x, parts, splits, g, False, engine)
+    assert r == 0
+    torch.cuda.synchronize()
+    assert _rel(parts.sum(0), wr.grad) < 5e-3
+
+
+def test_fused_update_matches_reference_formula(ext):
+    """K3/K4 semantics (/root/reference/cuda/gradient_descent.store_output.cu)."""
+    torch.manual_seed(4)
+    dev = "cuda"
+    rows, cols = 37, 53
+    w = torch.randn(rows, cols, device=dev)
+    g = torch.randn(3, rows, cols, device=dev)
+    acc = torch.randn(rows, cols, device=dev)
+    vel = torch.randn(rows, cols, device=dev)
+    hyper = torch.tensor([0.1, 0.01, 0.3, 0.9, 0.5, 0.25, 0.75, 0.8, 0.002, 0, 0, 0, 0, 0, 0, 0],
+                         device=dev)
+    cs = w.sum(0)
+    w0, acc0, vel0 = w.clone(), acc.clone(), vel.clone()
+    lp = torch.zeros(rows, 56, device=dev, dtype=torch.bfloat16)
+    gout = torch.zeros(rows, cols, device=dev)
+    ext.fused_update(w, [g.data_ptr()], 3, rows * cols, gout, acc, vel, hyper, cs,
+                     1 | 2 | 4 | 8, False, rows, cols, lp, 56, None, 0, 0, 0, [], 0, 0, 0)
+    torch.cuda.synchronize()
+    gs = g.sum(0)
+    lr, wd, l1, mom, aa, ab, ga, gb, ortho = [float(v) for v in hyper[:9]]
+    gd = -lr * (gs + wd * ((1 - l1) * w0 + 0.5 * l1 * torch.sign(w0)) +
+                ortho / rows * (cs - w0))
+    a = ab * acc0 + aa * gd
+    gd = gd * gb + ga * a
+    gd = gd + vel0 * mom
+    assert _rel(gout, gs) < 1e-6
+    assert _rel(acc, a) < 1e-5
+    assert _rel(vel, gd) < 1e-5
+    assert _rel(w, w0 + gd) < 1e-5
+    assert _rel(lp[:, :cols], (w0 + gd)) < 1e-2

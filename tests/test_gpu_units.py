@@ -1,0 +1,188 @@
+"""numpy-oracle vs sm_100a path for every unit (oracle style (b) of SURVEY §4;
+/root/reference/tests/unit/test_all2all.py:138-152, test_gd.py:158-175), in fp32 and bf16,
+with the 2x-NaN out-of-bounds guard idea applied to device buffers."""
+import numpy
+import pytest
+
+from veles.znicz_b200.core.config import root
+from veles.znicz_b200.core.memory import Array
+from veles.znicz_b200.core.workflow import DummyWorkflow
+from veles.znicz_b200.core.backends import get_device
+from veles.znicz_b200.ops import (all2all, gd, conv, gd_conv, pooling, gd_pooling, activation,
+                                  normalization, dropout, cutter, multiplier, summator)
+
+pytestmark = pytest.mark.gpu
+RS = numpy.random.RandomState(5)
+
+
+def _pair(fwd_cls, gd_cls, x, fkw, gkw, device, links=("weights", "bias"), extra=()):
+    wf = DummyWorkflow()
+    f = fwd_cls(wf, **fkw)
+    f.input = Array(x.copy())
+    if device is not None and device.is_cuda:
+        from veles.znicz_b200.ops.nn_units import torch_act_dtype
+        f.input.dev_dtype = torch_act_dtype()
+    f.initialize(device=device)
+    f.run()
+    kw = dict(learning_rate=0.1, learning_rate_bias=0.1, weights_decay=0.01,
+              gradient_moment=0.9, gradient_moment_bias=0.9)
+    kw.update(gkw)
+    g = gd_cls(wf, **kw)
+    rs = numpy.random.RandomState(9)
+    g.err_output = Array(rs.uniform(-1, 1, f.output.shape).astype(numpy.float32))
+    g.err_output.dev_dtype = f.output.dev_dtype
+    g.input, g.output = f.input, f.output
+    for a in links:
+        if getattr(f, a, None) is not None:
+            setattr(g, a, getattr(f, a))
+    for a in extra:
+        setattr(g, a, getattr(f, a))
+    g.forward_unit = f
+    g.initialize(device=device)
+    g.run()
+    return f, g
+
+
+def _compare(fwd_cls, gd_cls, x, fkw=None, gkw=None, links=("weights", "bias"), extra=(),
+             compute="fp32", tol=None):
+    fkw, gkw = fkw or {}, gkw or {}
+    root.common.engine.compute_type = "fp32"
+    from veles.znicz_b200.core import prng
+    prng.get(1).seed(77)
+    fn, gn = _pair(fwd_cls, gd_cls, x, fkw, gkw, None, links, extra)
+    root.common.engine.compute_type = compute
+    prng.get(1).seed(77)
+    dev = get_device("cuda")
+    fc, gc = _pair(fwd_cls, gd_cls, x, fkw, gkw, dev, links, extra)
+    tol = tol or (2e-4 if compute == "fp32" else 4e-2)
+    res = {}
+    for name, a, b in (("output", fn.output, fc.output), ("err_input", gn.err_input, gc.err_input),
+                       ("weights", getattr(fn, "weights", None), getattr(fc, "weights", None)),
+                       ("bias", getattr(fn, "bias", None), getattr(fc, "bias", None))):
+        if a is None or not a:
+            continue
+        b.map_read()
+        scale = max(1e-6, float(numpy.abs(a.mem).max()))
+        res[name] = float(numpy.abs(a.mem - b.mem.reshape(a.mem.shape)).max()) / scale
+        assert numpy.isfinite(b.mem).all(), name
+        assert res[name] < tol, (name, res, compute)
+    root.common.engine.compute_type = "fp32"
+    return res
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+@pytest.mark.parametrize("fwd,bwd", [
+    (all2all.All2All, gd.GradientDescent), (all2all.All2AllTanh, gd.GDTanh),
+    (all2all.All2AllRELU, gd.GDRELU), (all2all.All2AllStrictRELU, gd.GDStrictRELU),
+    (all2all.All2AllSigmoid, gd.GDSigmoid)])
+def test_fc(fwd, bwd, compute):
+    x = RS.uniform(-1, 1, (100, 64)).astype(numpy.float32)
+    _compare(fwd, bwd, x, {"output_sample_shape": 48, "weights_stddev": 0.2},
+             {"factor_ortho": 0.001}, compute=compute)
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+def test_fc_odd_shapes_and_softmax(compute):
+    x = RS.uniform(-1, 1, (37, 13)).astype(numpy.float32)     # K % 8 != 0 -> SIMT path
+    _compare(all2all.All2AllTanh, gd.GDTanh, x, {"output_sample_shape": 7,
+                                                 "weights_stddev": 0.3}, compute=compute)
+    x = RS.uniform(-1, 1, (50, 1024)).astype(numpy.float32)
+    _compare(all2all.All2AllSoftmax, gd.GDSoftmax, x, {"output_sample_shape": 10,
+                                                       "weights_stddev": 0.05},
+             compute=compute)
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+@pytest.mark.parametrize("fwd,bwd", [
+    (conv.Conv, gd_conv.GradientDescentConv), (conv.ConvTanh, gd_conv.GDTanhConv),
+    (conv.ConvStrictRELU, gd_conv.GDStrictRELUConv)])
+@pytest.mark.parametrize("geom", [
+    ((6, 16, 16, 32), 32, 5, 5, (2, 2, 2, 2), (1, 1)),
+    ((5, 32, 32, 3), 32, 5, 5, (2, 2, 2, 2), (1, 1)),
+    ((3, 11, 9, 8), 24, 3, 2, (1, 0, 2, 1), (2, 1))])
+def test_conv(fwd, bwd, geom, compute):
+    shape, f, ky, kx, pad, sl = geom
+    x = RS.uniform(-1, 1, shape).astype(numpy.float32)
+    kw = {"n_kernels": f, "kx": kx, "ky": ky, "padding": pad, "sliding": sl,
+          "weights_stddev": 0.1}
+    gkw = dict(kw)
+    gkw.pop("weights_stddev")
+    gkw["factor_ortho"] = 0.001
+    _compare(fwd, bwd, x, kw, gkw, compute=compute)
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+@pytest.mark.parametrize("fwd,bwd,links", [
+    (pooling.MaxPooling, gd_pooling.GDMaxPooling, ("input_offset",)),
+    (pooling.MaxAbsPooling, gd_pooling.GDMaxAbsPooling, ("input_offset",)),
+    (pooling.AvgPooling, gd_pooling.GDAvgPooling, ())])
+@pytest.mark.parametrize("k,s", [((2, 2), (2, 2)), ((3, 3), (2, 2))])
+def test_pooling(fwd, bwd, links, k, s, compute):
+    x = RS.uniform(-1, 1, (4, 17, 16, 32)).astype(numpy.float32)
+    if compute == "bf16":   # keep argmax ties identical on both paths
+        import torch
+        x = torch.from_numpy(x).bfloat16().float().numpy()
+    kw = {"kx": k[0], "ky": k[1], "sliding": s}
+    _compare(fwd, bwd, x, kw, kw, links=(), extra=links, compute=compute)
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+def test_lrn(compute):
+    x = RS.uniform(-1, 1, (4, 8, 8, 32)).astype(numpy.float32)
+    kw = {"alpha": 0.00005, "beta": 0.75, "n": 3, "k": 1}
+    _compare(normalization.LRNormalizerForward, normalization.LRNormalizerBackward, x, kw, kw,
+             links=(), compute=compute)
+    kw = {"alpha": 0.01, "beta": 0.75, "n": 5, "k": 2}
+    _compare(normalization.LRNormalizerForward, normalization.LRNormalizerBackward, x, kw, kw,
+             links=(), compute=compute)
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["Tanh", "Sigmoid", "RELU", "StrictRELU", "Log", "TanhLog",
+                                  "SinCos", "Mul"])
+def test_activation(name, compute):
+    x = RS.uniform(-4, 4, (16, 40)).astype(numpy.float32)
+    fkw = {"factor": 0.37} if name == "Mul" else {}
+    _compare(getattr(activation, "Forward" + name), getattr(activation, "Backward" + name), x,
+             fkw, fkw, links=(), compute=compute,
+             tol=None if compute == "fp32" else 6e-2)
+
+
+def test_cutter_and_dropout():
+    x = RS.uniform(-1, 1, (3, 9, 8, 4)).astype(numpy.float32)
+    kw = {"padding": (1, 2, 3, 1)}
+    _compare(cutter.Cutter, cutter.GDCutter, x, kw, kw, links=())
+    # dropout: identical hash-based mask on both paths
+    dev = get_device("cuda")
+    outs = []
+    for d in (None, dev):
+        wf = DummyWorkflow()
+        f = dropout.DropoutForward(wf, dropout_ratio=0.4, seed=1234)
+        f.input = Array(x.copy())
+        f.minibatch_class = 2
+        f.initialize(device=d)
+        f.run()
+        f.output.map_read()
+        f.mask.map_read()
+        outs.append((f.output.mem.copy(), f.mask.mem.copy()))
+    assert numpy.array_equal(outs[0][1], outs[1][1])
+    assert numpy.abs(outs[0][0] - outs[1][0]).max() < 1e-6
+    frac = float((outs[1][1] == 0).mean())
+    assert 0.3 < frac < 0.5
+
+
+def test_stochastic_pooling_gpu_valid():
+    x = RS.uniform(-1, 1, (2, 8, 8, 16)).astype(numpy.float32)
+    dev = get_device("cuda")
+    wf = DummyWorkflow()
+    f = pooling.StochasticPooling(wf, kx=2, ky=2, sliding=(2, 2), seed=99)
+    f.input = Array(x.copy())
+    f.initialize(device=dev)
+    f.run()
+    f.output.map_read()
+    f.input_offset.map_read()
+    flat = x.reshape(-1)
+    assert numpy.allclose(flat[f.input_offset.mem.ravel()], f.output.mem.ravel())
+    # chosen elements are positive whenever the window has a positive element
+    win_max = x.reshape(2, 4, 2, 4, 2, 16).max(axis=(2, 4))
+    assert ((f.output.mem > 0) | (win_max <= 0)).all()

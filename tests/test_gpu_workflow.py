@@ -1,0 +1,55 @@
+"""End-to-end StandardWorkflow on a real B200: eager + CUDA-graph segments, fp32 + bf16."""
+import numpy
+import pytest
+
+from veles.znicz_b200.core.config import root
+from veles.znicz_b200.models import cifar, mnist
+
+pytestmark = pytest.mark.gpu
+
+
+def _fast_layers():
+    layers = cifar.caffe_layers()
+    for l in layers:
+        if "<-" in l:
+            l["<-"].update(learning_rate=0.02, learning_rate_bias=0.02, weights_decay=0.0005)
+        if l["type"] == "conv":
+            l["->"]["weights_stddev"] = 0.05
+    return layers
+
+
+@pytest.mark.parametrize("compute,graphs", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_cifar_trains_on_gpu(compute, graphs):
+    root.common.engine.compute_type = compute
+    try:
+        wf = cifar.build(
+            layers=_fast_layers(), use_graphs=graphs,
+            loader_config={"minibatch_size": 20, "n_train": 400, "n_valid": 100,
+                           "normalization_type": "internal_mean", "noise": 0.3},
+            decision_config={"max_epochs": 5, "fail_iterations": 50},
+            snapshotter_config={"prefix": "cifar_g", "interval": 1, "time_interval": 0})
+        wf.initialize(device="cuda")
+        wf.run()
+        dec = wf.decision
+        assert bool(dec.complete)
+        assert dec.best_n_err_pt[1] < 50.0, dec.best_n_err_pt
+        wf.forwards[0].weights.map_read()
+        assert numpy.isfinite(wf.forwards[0].weights.mem).all()
+        if graphs:
+            assert all(s.replays > 0 for s in wf.segments_), [
+                (s.name, s.replays, s.eager_runs) for s in wf.segments_]
+    finally:
+        root.common.engine.compute_type = "fp32"
+
+
+def test_mnist_conv_fp32_gpu():
+    wf = mnist.build(
+        loader_config={"minibatch_size": 6, "n_train": 120, "n_valid": 36,
+                       "normalization_type": "linear", "noise": 0.3},
+        decision_config={"max_epochs": 3, "fail_iterations": 10},
+        snapshotter_config={"prefix": "mnist_g", "interval": 1, "time_interval": 0,
+                            "compression": ""})
+    wf.initialize(device="cuda")
+    wf.run()
+    assert bool(wf.decision.complete)
+    assert wf.decision.best_n_err_pt[1] < 60.0, wf.decision.best_n_err_pt

@@ -1,0 +1,491 @@
+"""Glue between the unit classes and the sm_100a extension.
+
+Every function takes a unit, pulls the device tensors out of its Arrays
+(``.dev`` = read, ``.dev_out`` = about to be overwritten) and launches kernels on the
+current CUDA stream. Nothing here synchronises with the host or allocates per call
+(temporaries are cached on the unit), so every function is CUDA-graph capturable.
+
+Engine selection is by *shape legality*, not by backend: bf16 activations + TMA-legal
+leading dimensions go through the tcgen05 kernels (``gemm_umma.cu``); everything else
+(fp32 compute type, leading dims that are not multiples of 8 elements, transposed weight
+storage) runs the exact-fp32 SIMT implicit-GEMM kernels. A tcgen05 launcher that refuses
+a shape raises — there is no silent fallback to PyTorch.
+"""
+from __future__ import annotations
+
+import numpy
+import torch
+
+from ..ops.nn_units import ACT_LINEAR
+
+_MAX_SPLITS = 64
+counters = {"launches": 0}
+
+
+def _ext(unit):
+    ext = unit.ext_
+    if ext is None:
+        raise RuntimeError("%s: the sm_100a extension is not loaded" % unit)
+    return ext
+
+
+def _is_bf16(t):
+    return t.dtype == torch.bfloat16
+
+
+def _tmp(unit, name, shape, dtype, zero=False):
+    key = "tmp_%s_" % name
+    t = unit.__dict__.get(key)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        dev = unit.device.torch_device
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+        unit.__dict__[key] = t
+    return t
+
+
+def _roundup(n, a):
+    return (n + a - 1) // a * a
+
+
+def _launch(n=1):
+    counters["launches"] += n
+
+
+# ------------------------------------------------------------------------------------------
+# weights: fp32 master + bf16 shadows in the layouts the tensor-core kernels consume
+# ------------------------------------------------------------------------------------------
+def lp_enabled(unit):
+    from ..ops.nn_units import compute_dtype_name
+    return compute_dtype_name() in ("bf16", "fp8") and not unit.weights_transposed
+
+
+def _shadow_spec(unit):
+    """(rows, cols, ld, conv?, taps, C, c_pad) of the weight matrix of a forward unit."""
+    rows, cols = unit.weights.shape
+    ld = _roundup(cols, 8)
+    if hasattr(unit, "kx") and hasattr(unit, "n_kernels"):
+        c = unit._n_channels
+        return rows, cols, ld, True, unit.kx * unit.ky, c, _roundup(c, 8)
+    return rows, cols, ld, False, 0, 0, 0
+
+
+def ensure_shadows(fwd):
+    if fwd.weights_lp_ is not None:
+        return
+    rows, cols, ld, is_conv, taps, c, c_pad = _shadow_spec(fwd)
+    dev = fwd.device.torch_device
+    fwd.weights_lp_ = torch.zeros((rows, ld), dtype=torch.bfloat16, device=dev)
+    if is_conv:
+        fwd.weights_lp_t_ = torch.zeros((taps * rows, c_pad), dtype=torch.bfloat16, device=dev)
+
+
+def refresh_weight_shadows(fwd):
+    """(Re)build the bf16 copies from the fp32 master (init, rollback, snapshot load)."""
+    if not fwd.weights or not lp_enabled(fwd):
+        return
+    ensure_shadows(fwd)
+    rows, cols, ld, is_conv, taps, c, c_pad = _shadow_spec(fwd)
+    _ext(fwd).refresh_shadows(fwd.weights.dev, rows, cols, fwd.weights_lp_, ld,
+                              fwd.weights_lp_t_ if is_conv else None, taps, c, c_pad)
+    _launch()
+
+
+# ------------------------------------------------------------------------------------------
+# fully connected
+# ------------------------------------------------------------------------------------------
+def fc_forward(unit, softmax=False):
+    ext = _ext(unit)
+    x = unit.input.dev
+    batch = x.shape[0]
+    n_in = x.numel() // batch
+    n_out = unit.neurons_number
+    bias = unit.bias.dev if (unit.include_bias and unit.bias) else None
+    if softmax:
+        out = _tmp(unit, "logits", (batch, n_out), torch.float32)
+    else:
+        out = unit.output.dev_out
+    use_lp = lp_enabled(unit) and _is_bf16(x) and n_in % 8 == 0
+    act = ACT_LINEAR if softmax else unit.ACT
+    if use_lp:
+        ensure_shadows(unit)
+        w = unit.weights_lp_
+        r = ext.gemm(x, n_in, False, w, w.shape[1], True, out, n_out, False,
+                     batch, n_out, n_in, bias, act, 1.0, 0.0, 1, 0, 1)
+        if r != 0:
+            raise RuntimeError("%s: tcgen05 FC forward refused the shape (code %d)" % (unit, r))
+    else:
+        w = unit.weights.dev
+        if unit.weights_transposed:   # stored [in][out]
+            ext.gemm(x, n_in, False, w, n_out, False, out, n_out, False,
+                     batch, n_out, n_in, bias, act, 1.0, 0.0, 1, 0, 0)
+        else:
+            ext.gemm(x, n_in, False, w, n_in, True, out, n_out, False,
+                     batch, n_out, n_in, bias, act, 1.0, 0.0, 1, 0, 0)
+    _launch()
+    if softmax:
+        ext.softmax_rows(out, unit.output.dev_out, unit.max_idx.dev_out)
+        _launch()
+
+
+def _bias_partials(unit, rows, cols):
+    ext = _ext(unit)
+    slices = ext.colsum_slices(rows)
+    return slices, _grad_buffer(unit, "bias_parts", (slices, cols))
+
+
+def _grad_buffer(unit, name, shape):
+    """fp32 gradient staging buffer; lives in symmetric memory when data-parallel."""
+    dp = unit.dp_
+    if dp is not None and dp.symm is not None:
+        return dp.symm.buffer(unit, name, shape)
+    return _tmp(unit, name, shape, torch.float32)
+
+
+def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols):
+    """Fused (cross-GPU reduce +) SGD step for weights or bias of a GD unit."""
+    ext = _ext(unit)
+    if is_bias:
+        w, gout = unit.bias, unit.gradient_bias
+        acc, vel = unit.accumulated_gradient_bias, unit.gradient_bias_with_moment
+    else:
+        w, gout = unit.weights, unit.gradient_weights
+        acc, vel = unit.accumulated_gradient_weights, unit.gradient_weights_with_moment
+    flags = unit.update_flags(for_bias=is_bias)
+    colsums = None
+    if not is_bias and unit.factor_ortho:
+        colsums = unit.col_sums.dev_out
+        ext.col_sums(w.dev, colsums, rows, cols, bool(unit.weights_transposed))
+        _launch()
+    fwd = unit.forward_unit
+    lp = lp_conv = None
+    ld = taps = c = c_pad = 0
+    if not is_bias and fwd is not None and getattr(fwd, "weights_lp_", None) is not None:
+        r_, c_, ld, is_conv, taps, c, c_pad = _shadow_spec(fwd)
+        lp = fwd.weights_lp_
+        lp_conv = fwd.weights_lp_t_ if is_conv else None
+    dp = unit.dp_
+    if dp is not None and dp.symm is not None:
+        ptrs, flag_ptrs, epoch_ptr, blocks = dp.symm.peers(unit, grad_buf)
+        rank = dp.rank
+    else:
+        ptrs, flag_ptrs, epoch_ptr, blocks, rank = [grad_buf.data_ptr()], [], 0, 0, 0
+    wdev = w.dev
+    ext.fused_update(wdev, ptrs, nparts, part_stride, gout.dev_out if gout else None,
+                     acc.dev if acc else None, vel.dev if vel else None, unit.hyper_dev_,
+                     colsums, flags, is_bias, rows, cols, lp, ld, lp_conv, taps, c, c_pad,
+                     flag_ptrs, epoch_ptr, rank, blocks)
+    w.dev_written()
+    if acc:
+        acc.dev_written()
+    if vel:
+        vel.dev_written()
+    _launch()
+    if dp is not None and dp.symm is None and dp.world_size > 1:
+        raise RuntimeError("data-parallel GD without symmetric buffers is not wired")
+
+
+def fc_backward(unit):
+    ext = _ext(unit)
+    err = unit.err_output.dev
+    batch = err.shape[0]
+    n_out = err.numel() // batch
+    x = unit.input.dev
+    n_in = x.numel() // batch
+    need_w = unit.need_gradient_weights and unit.weights
+    need_b = need_w and unit.include_bias and unit.bias
+    # 1. err_output *= f'(output) fused with the bias-gradient column sums
+    if unit.ACT != ACT_LINEAR or need_b:
+        parts = None
+        if need_b:
+            slices, parts = _bias_partials(unit, batch, n_out)
+        y = unit.output.dev if unit.ACT != ACT_LINEAR else None
+        if y is not None and y.dtype != err.dtype:
+            raise RuntimeError("%s: output/err_output dtype mismatch" % unit)
+        ext.err_act_colsum(err, y, batch, n_out, unit.ACT, parts)
+        unit.err_output.dev_written()
+        _launch()
+    lp_ok = (lp_enabled(unit) and _is_bf16(err) and _is_bf16(x) and
+             unit.forward_unit is not None and
+             getattr(unit.forward_unit, "weights_lp_", None) is not None)
+    # 2. err_input = alpha * err . W + beta * err_input
+    if unit.need_err_input:
+        ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
+        if lp_ok and n_out % 8 == 0:
+            w = unit.forward_unit.weights_lp_
+            r = ext.gemm(err, n_out, False, w, w.shape[1], False, ei, n_in, False,
+                         batch, n_in, n_out, None, 0, float(unit.err_input_alpha),
+                         float(unit.err_input_beta), 1, 0, 1)
+            if r != 0:
+                raise RuntimeError("%s: tcgen05 FC dgrad refused (code %d)" % (unit, r))
+        else:
+            w = unit.weights.dev
+            if unit.weights_transposed:  # stored [in][out] => B(k=out, n=in) = w[n][k]
+                ext.gemm(err, n_out, False, w, n_out, True, ei, n_in, False, batch, n_in, n_out,
+                         None, 0, float(unit.err_input_alpha), float(unit.err_input_beta), 1, 0, 0)
+            else:
+                ext.gemm(err, n_out, False, w, n_in, False, ei, n_in, False, batch, n_in, n_out,
+                         None, 0, float(unit.err_input_alpha), float(unit.err_input_beta), 1, 0, 0)
+        unit.err_input.dev_written()
+        _launch()
+    if not need_w:
+        return
+    # 3. gradW[out][in] = err^T . x  (reduction over the batch)
+    gbuf = _grad_buffer(unit, "wgrad", (1,) + tuple(unit.weights.shape))
+    if lp_ok and n_out % 8 == 0 and n_in % 8 == 0:
+        r = ext.gemm(err, n_out, True, x, n_in, False, gbuf, n_in, False,
+                     n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 1)
+        if r != 0:
+            raise RuntimeError("%s: tcgen05 FC wgrad refused (code %d)" % (unit, r))
+    else:
+        ext.gemm(err, n_out, True, x, n_in, False, gbuf, n_out if unit.weights_transposed else n_in,
+                 bool(unit.weights_transposed), n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 0)
+    _launch()
+    rows, cols = (n_out, n_in)
+    _update(unit, False, gbuf, 1, 0, rows, cols)
+    if need_b:
+        _update(unit, True, parts, slices, n_out, 1, n_out)
+
+
+# ------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------
+def _conv_geom(u):
+    return [u._batch_size, u._sy, u._sx, u._n_channels, u._ky_app, u._kx_app, u.n_kernels,
+            u.ky, u.kx, u.sliding[1], u.sliding[0], u.padding[1], u.padding[0]]
+
+
+def conv_forward(unit):
+    ext = _ext(unit)
+    x = unit.input.dev
+    out = unit.output.dev_out
+    bias = unit.bias.dev if (unit.include_bias and unit.bias) else None
+    g = _conv_geom(unit)
+    if lp_enabled(unit) and _is_bf16(x):
+        ensure_shadows(unit)
+        w = unit.weights_lp_
+        r = ext.conv_fprop(x, w, w.shape[1], False, bias, out, g, unit.ACT, 1)
+        if r != 0:
+            raise RuntimeError("%s: tcgen05 conv fprop refused (code %d)" % (unit, r))
+    else:
+        w = unit.weights.dev
+        ld = w.shape[1]
+        ext.conv_fprop(x, w, ld, bool(unit.weights_transposed), bias, out, g, unit.ACT, 0)
+    _launch()
+
+
+def conv_backward(unit):
+    ext = _ext(unit)
+    err = unit.err_output.dev
+    x = unit.input.dev
+    g = _conv_geom(unit)
+    f = unit.n_kernels
+    pixels = err.numel() // f
+    kw = unit._kernel_size
+    need_w = unit.need_gradient_weights and unit.weights
+    need_b = need_w and unit.include_bias and unit.bias
+    if unit.ACT != ACT_LINEAR or need_b:
+        parts = None
+        if need_b:
+            slices, parts = _bias_partials(unit, pixels, f)
+        y = unit.output.dev if unit.ACT != ACT_LINEAR else None
+        ext.err_act_colsum(err, y, pixels, f, unit.ACT, parts)
+        unit.err_output.dev_written()
+        _launch()
+    fwd = unit.forward_unit
+    lp_ok = (lp_enabled(unit) and _is_bf16(err) and _is_bf16(x) and fwd is not None and
+             getattr(fwd, "weights_lp_t_", None) is not None)
+    if unit.need_err_input:
+        ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
+        if lp_ok:
+            wd = fwd.weights_lp_t_
+            r = ext.conv_dgrad(err, wd, wd.shape[1], False, ei, g, float(unit.err_input_alpha),
+                               float(unit.err_input_beta), 1)
+            if r != 0:
+                raise RuntimeError("%s: tcgen05 conv dgrad refused (code %d)" % (unit, r))
+        else:
+            w = unit.weights.dev
+            ext.conv_dgrad(err, w, w.shape[1], bool(unit.weights_transposed), ei, g,
+                           float(unit.err_input_alpha), float(unit.err_input_beta), 0)
+        unit.err_input.dev_written()
+        _launch()
+    if not need_w:
+        return
+    use_umma = lp_ok and f % 8 == 0
+    if use_umma:
+        splits = int(ext.pick_splits(kw, f, pixels, _MAX_SPLITS))
+    else:
+        tiles = ((f + 63) // 64) * ((kw + 63) // 64)
+        splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
+    gbuf = _grad_buffer(unit, "wgrad", (splits, f, kw))
+    if use_umma:
+        r = ext.conv_wgrad(err, x, gbuf, splits, g, False, 1)
+        if r != 0:
+            raise RuntimeError("%s: tcgen05 conv wgrad refused (code %d)" % (unit, r))
+    else:
+        ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0)
+    _launch()
+    _update(unit, False, gbuf, splits, f * kw, f, kw)
+    if need_b:
+        _update(unit, True, parts, slices, f, 1, f)
+
+
+# ------------------------------------------------------------------------------------------
+# pooling / depooling / LRN / activations / dropout / glue ops
+# ------------------------------------------------------------------------------------------
+_POOL_MODES = {"max": 0, "maxabs": 1, "avg": 2, "stochastic": 3, "stochastic_abs": 4,
+               "stochastic_depool": 5, "stochastic_abs_depool": 6}
+
+
+def pooling_forward(unit):
+    ext = _ext(unit)
+    mode = _POOL_MODES[unit.KERNEL]
+    ox, oy = unit.out_sxy
+    x = unit.input.dev
+    offs = unit.input_offset.dev_out if hasattr(unit, "input_offset") else None
+    rng = getattr(unit, "rng_dev_", None)
+    if mode >= 5:
+        ext.pool_forward(x, None, offs, oy, ox, unit.ky, unit.kx, unit.sliding[1],
+                         unit.sliding[0], mode, rng)
+        unit.input.dev_written()
+    else:
+        ext.pool_forward(x, unit.output.dev_out, offs, oy, ox, unit.ky, unit.kx,
+                         unit.sliding[1], unit.sliding[0], mode, rng)
+    _launch()
+
+
+def pooling_backward(unit):
+    ext = _ext(unit)
+    ox, oy = unit.out_sxy
+    is_avg = unit.KERNEL == "avg"
+    offs = None if is_avg else unit.input_offset.dev
+    err = unit.err_output.dev
+    ei = unit.err_input.dev_out
+    ext.pool_backward(err.view(ei.shape[0], oy, ox, ei.shape[3]), offs, ei, oy, ox, unit.ky,
+                      unit.kx, unit.sliding[1], unit.sliding[0], is_avg)
+    _launch()
+
+
+def depooling_forward(unit):
+    ext = _ext(unit)
+    ext.scatter_offsets(unit.input.dev, unit.output_offset.dev, unit.output.dev_out)
+    _launch()
+
+
+def lrn_forward(unit):
+    _ext(unit).lrn_forward(unit.input.dev, unit.output.dev_out, unit.n, unit.alpha,
+                           unit.beta, unit.k)
+    _launch()
+
+
+def lrn_backward(unit):
+    _ext(unit).lrn_backward(unit.err_output.dev, unit.input.dev, unit.err_input.dev_out,
+                            unit.n, unit.alpha, unit.beta, unit.k)
+    _launch()
+
+
+def activation_forward(unit):
+    _ext(unit).act_forward(unit.input.dev, unit.output.dev_out, unit.CODE,
+                           float(unit.factor if unit.factor is not None else 1.0))
+    _launch()
+
+
+def activation_backward(unit):
+    x = unit.input.dev if unit.NEEDS_INPUT else None
+    y = unit.output.dev if unit.NEEDS_OUTPUT else None
+    _ext(unit).act_backward(unit.err_output.dev, x, y, unit.err_input.dev_out, unit.CODE,
+                            float(unit.factor))
+    _launch()
+
+
+def dropout_forward(unit):
+    ext = _ext(unit)
+    x = unit.input.dev
+    if unit.active:
+        ext.dropout_forward(x, unit.output.dev_out, unit.mask.dev_out, unit.rng_dev_,
+                            min(unit.threshold, 0xFFFFFFFF), 1.0 / (1.0 - unit.dropout_ratio))
+    else:
+        ext.cast_copy(x, unit.output.dev_out)
+    _launch()
+
+
+def dropout_backward(unit):
+    _ext(unit).binary_op(unit.err_output.dev, unit.mask.dev, unit.err_input.dev_out, 0)
+    _launch()
+
+
+def cutter_forward(unit):
+    _ext(unit).crop_nhwc(unit.input.dev, unit.output.dev_out, unit.padding[1],
+                         unit.padding[0], False)
+    _launch()
+
+
+def cutter_backward(unit):
+    err = unit.err_output.dev.view(unit.output_shape)
+    _ext(unit).crop_nhwc(err, unit.err_input.dev_out, unit.padding[1], unit.padding[0], True)
+    _launch()
+
+
+def cutter1d_forward(unit):
+    out = unit.output.dev if unit.beta else unit.output.dev
+    _ext(unit).axpby_2d(unit.input.dev, unit.input_offset, out, unit.output_offset,
+                        unit.length, float(unit.alpha), float(unit.beta))
+    unit.output.dev_written()
+    _launch()
+
+
+def binary_forward(unit, op):
+    _ext(unit).binary_op(unit.x.dev, unit.y.dev, unit.output.dev_out, 0 if op == "mul" else 1)
+    _launch()
+
+
+def multiplier_backward(unit):
+    _ext(unit).mul_backward(unit.x.dev, unit.y.dev, unit.err_output.dev, unit.err_x.dev_out,
+                            unit.err_y.dev_out)
+    _launch()
+
+
+def zero_filler(unit):
+    ext = _ext(unit)
+    w = unit.weights.dev
+    ext.mask_mul(w, unit.mask.dev)
+    unit.weights.dev_written()
+    _launch()
+
+
+# ------------------------------------------------------------------------------------------
+# evaluators
+# ------------------------------------------------------------------------------------------
+def evaluate_softmax(unit):
+    ext = _ext(unit)
+    y = unit.output.dev
+    if y.dtype != torch.float32:
+        raise RuntimeError("softmax probabilities must be fp32 on the device")
+    conf = unit.confusion_matrix.dev if unit.confusion_matrix else None
+    ext.evaluate_softmax(y, unit.max_idx.dev, unit.labels.dev, unit.err_output.dev_out,
+                         unit.batch_dev_, unit.n_err.dev, conf, unit.max_err_output_sum.dev)
+    unit.n_err.dev_written()
+    unit.max_err_output_sum.dev_written()
+    if conf is not None:
+        unit.confusion_matrix.dev_written()
+    _launch()
+
+
+def evaluate_mse(unit):
+    ext = _ext(unit)
+    y = unit.output.dev
+    t = unit.target.dev
+    dm = unit.__dict__.get("denorm_mul_")
+    if dm is None:
+        co = unit.denorm_coefficients()
+        dm = False if co is None else torch.from_numpy(co[0]).to(unit.device.torch_device)
+        unit.__dict__["denorm_mul_"] = dm
+    ext.evaluate_mse(y, t.view(y.shape), unit.err_output.dev_out, unit.batch_dev_,
+                     dm if dm is not False else None, bool(unit.root), unit.metrics.dev,
+                     unit.mse.dev_out)
+    unit.metrics.dev_written()
+    _launch()
+    if unit.labels and unit.class_targets:
+        ext.mse_find_closest(y, unit.class_targets.dev.float().contiguous(), unit.labels.dev,
+                             unit.batch_dev_, unit.n_err.dev)
+        unit.n_err.dev_written()
+        _launch()

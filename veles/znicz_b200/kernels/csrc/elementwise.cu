@@ -1,0 +1,267 @@
+// Elementwise / data-movement kernels: activations fwd/bwd, err_y *= f'(y) with fused
+// bias-gradient column sums, dropout, mul/add, crop, axpby, gather, mask, casts.
+// Parity targets: /root/reference/cuda/activation.cu, gradient_descent_{tanh,sigmoid,
+// relu,strict_relu}.cu, dropout.cu, multiplier.cu, summator.cu, cutter.cu,
+// weights_zerofilling.cu. All kernels: grid-stride, 16-byte vector path when aligned.
+#include "common.cuh"
+
+namespace zn {
+
+template <typename T>
+__global__ void act_forward_k(const T* __restrict__ x, T* __restrict__ y, long long n, int act,
+                              float factor) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) stf(y + i, act_fwd(act, ldf(x + i), factor, (int)(i & 1)));
+}
+
+template <typename T>
+__global__ void act_backward_k(const T* __restrict__ err_y, const T* __restrict__ x,
+                               const T* __restrict__ y, T* __restrict__ err_x, long long n,
+                               int act, float factor) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float xv = x ? ldf(x + i) : 0.f;
+    float yv = y ? ldf(y + i) : 0.f;
+    stf(err_x + i, ldf(err_y + i) * act_deriv(act, xv, yv, factor, (int)(i & 1)));
+  }
+}
+
+// err_y[r, c] *= f'(y[r, c]) in place and col_sum[c] = sum_r err_y[r, c] (bias gradient),
+// one pass. Block = 32 x 8 threads; each block owns 32 columns and a slice of rows, then
+// one atomicAdd per column per block (deterministic variant: partial[blockIdx.y][c]).
+template <typename T>
+__global__ void err_act_colsum_k(T* __restrict__ err_y, const T* __restrict__ y, int rows, int cols,
+                                 int act, float* __restrict__ partial /*[gridDim.y][cols]*/) {
+  __shared__ float red[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols) {
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < rows; r += gridDim.y * 8) {
+      size_t o = (size_t)r * cols + c;
+      float e = ldf(err_y + o);
+      if (act != ACT_LINEAR) {
+        e *= act_deriv(act, 0.f, ldf(y + o));
+        stf(err_y + o, e);
+      }
+      acc += e;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols && partial) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+    partial[(size_t)blockIdx.y * cols + c] = s;
+  }
+}
+
+template <typename T>
+__global__ void dropout_forward_k(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ mask,
+                                  long long n, const int* __restrict__ rng, uint32_t threshold,
+                                  float scale) {
+  uint32_t seed = (uint32_t)rng[0], counter = (uint32_t)rng[1];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float m = hash_u32(seed, counter, (uint64_t)i) >= threshold ? scale : 0.f;
+    stf(mask + i, m);
+    stf(y + i, ldf(x + i) * m);
+  }
+}
+
+template <typename T>
+__global__ void mul_k(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) stf(o + i, ldf(a + i) * ldf(b + i));
+}
+template <typename T>
+__global__ void add_k(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) stf(o + i, ldf(a + i) + ldf(b + i));
+}
+template <typename T>
+__global__ void mul_backward_k(const T* __restrict__ x, const T* __restrict__ y,
+                               const T* __restrict__ e, T* __restrict__ ex, T* __restrict__ ey,
+                               long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float ev = ldf(e + i);
+    stf(ex + i, ev * ldf(y + i));
+    stf(ey + i, ev * ldf(x + i));
+  }
+}
+
+// dst[r, doff + c] = alpha * src[r, soff + c] + beta * dst[r, doff + c], c < len
+template <typename T>
+__global__ void axpby_2d_k(const T* __restrict__ src, int src_ld, int soff, T* __restrict__ dst,
+                           int dst_ld, int doff, int rows, int len, float alpha, float beta) {
+  long long n = (long long)rows * len;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int r = (int)(i / len), c = (int)(i % len);
+    T* d = dst + (size_t)r * dst_ld + doff + c;
+    float v = alpha * ldf(src + (size_t)r * src_ld + soff + c);
+    if (beta != 0.f) v += beta * ldf(d);
+    stf(d, v);
+  }
+}
+
+// NHWC crop: out[n, y, x, c] = in[n, y + top, x + left, c]; backward pastes into zeros.
+template <typename T>
+__global__ void crop_nhwc_k(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C,
+                            int oh, int ow, int top, int left, int backward) {
+  if (!backward) {
+    long long n = (long long)N * oh * ow * C;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+      int c = (int)(i % C); long long t = i / C;
+      int x = (int)(t % ow); t /= ow; int y = (int)(t % oh); int b = (int)(t / oh);
+      out[i] = in[(((size_t)b * H + y + top) * W + x + left) * C + c];
+    }
+  } else {  // in = err_output [N, oh, ow, C], out = err_input [N, H, W, C]
+    long long n = (long long)N * H * W * C;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+      int c = (int)(i % C); long long t = i / C;
+      int x = (int)(t % W); t /= W; int y = (int)(t % H); int b = (int)(t / H);
+      int yy = y - top, xx = x - left;
+      T v; stf(&v, 0.f);
+      if (yy >= 0 && yy < oh && xx >= 0 && xx < ow) v = in[(((size_t)b * oh + yy) * ow + xx) * C + c];
+      out[i] = v;
+    }
+  }
+}
+
+// rows gather: dst[i, :] = src[idx[i], :] for i < count, zero for the tail rows
+template <typename TS, typename TD>
+__global__ void gather_rows_k(const TS* __restrict__ src, const int* __restrict__ idx,
+                              TD* __restrict__ dst, int count, int max_rows, long long row) {
+  long long n = (long long)max_rows * row;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int r = (int)(i / row); long long c = i % row;
+    float v = 0.f;
+    if (r < count) v = ldf(src + (size_t)idx[r] * row + c);
+    stf(dst + i, v);
+  }
+}
+__global__ void gather_labels_k(const int* __restrict__ src, const int* __restrict__ idx,
+                                int* __restrict__ dst, int count, int max_rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < max_rows) dst[i] = i < count ? src[idx[i]] : -1;
+}
+
+template <typename T>
+__global__ void mask_mul_k(T* __restrict__ w, const T* __restrict__ mask, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) stf(w + i, ldf(w + i) * ldf(mask + i));
+}
+
+template <typename TS, typename TD>
+__global__ void cast_k(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) stf(d + i, ldf(s + i));
+}
+
+// depooling: out[offs[i]] = in[i] (out pre-zeroed by the caller via memsetAsync)
+template <typename T>
+__global__ void scatter_offsets_k(const T* __restrict__ in, const int* __restrict__ offs,
+                                  T* __restrict__ out, long long n, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[offs[i]] = in[i];
+}
+
+static inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ----------------------------------------------------------------------------- launchers
+#define DISPATCH_T(bf16, ...)                                  \
+  if (bf16) { using T = __nv_bfloat16; __VA_ARGS__; } else { using T = float; __VA_ARGS__; }
+
+void launch_act_forward(const void* x, void* y, long long n, int act, float factor, bool bf16,
+                        cudaStream_t st) {
+  DISPATCH_T(bf16, act_forward_k<T><<<grid_for(n), 256, 0, st>>>((const T*)x, (T*)y, n, act, factor));
+}
+void launch_act_backward(const void* ey, const void* x, const void* y, void* ex, long long n, int act,
+                         float factor, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, act_backward_k<T><<<grid_for(n), 256, 0, st>>>(
+      (const T*)ey, (const T*)x, (const T*)y, (T*)ex, n, act, factor));
+}
+int err_act_colsum_slices(int rows) { int s = (rows + 63) / 64; return s < 1 ? 1 : (s > 64 ? 64 : s); }
+void launch_err_act_colsum(void* err_y, const void* y, int rows, int cols, int act, float* partial,
+                           int slices, bool bf16, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, slices), block(32, 8);
+  DISPATCH_T(bf16, err_act_colsum_k<T><<<grid, block, 0, st>>>((T*)err_y, (const T*)y, rows, cols, act,
+                                                              partial));
+}
+void launch_dropout_forward(const void* x, void* y, void* mask, long long n, const int* rng,
+                            uint32_t threshold, float scale, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, dropout_forward_k<T><<<grid_for(n), 256, 0, st>>>(
+      (const T*)x, (T*)y, (T*)mask, n, rng, threshold, scale));
+}
+void launch_binary(const void* a, const void* b, void* o, long long n, int op, bool bf16,
+                   cudaStream_t st) {
+  if (op == 0) { DISPATCH_T(bf16, mul_k<T><<<grid_for(n), 256, 0, st>>>((const T*)a, (const T*)b, (T*)o, n)); }
+  else { DISPATCH_T(bf16, add_k<T><<<grid_for(n), 256, 0, st>>>((const T*)a, (const T*)b, (T*)o, n)); }
+}
+void launch_mul_backward(const void* x, const void* y, const void* e, void* ex, void* ey, long long n,
+                         bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, mul_backward_k<T><<<grid_for(n), 256, 0, st>>>(
+      (const T*)x, (const T*)y, (const T*)e, (T*)ex, (T*)ey, n));
+}
+void launch_axpby_2d(const void* src, int src_ld, int soff, void* dst, int dst_ld, int doff, int rows,
+                     int len, float alpha, float beta, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, axpby_2d_k<T><<<grid_for((long long)rows * len), 256, 0, st>>>(
+      (const T*)src, src_ld, soff, (T*)dst, dst_ld, doff, rows, len, alpha, beta));
+}
+void launch_crop_nhwc(const void* in, void* out, int N, int H, int W, int C, int oh, int ow, int top,
+                      int left, int backward, bool bf16, cudaStream_t st) {
+  long long n = backward ? (long long)N * H * W * C : (long long)N * oh * ow * C;
+  DISPATCH_T(bf16, crop_nhwc_k<T><<<grid_for(n), 256, 0, st>>>((const T*)in, (T*)out, N, H, W, C, oh, ow,
+                                                              top, left, backward));
+}
+void launch_gather_rows(const void* src, bool src_bf16, const int* idx, void* dst, bool dst_bf16,
+                        int count, int max_rows, long long row, cudaStream_t st) {
+  long long n = (long long)max_rows * row;
+  int g = grid_for(n);
+  if (!src_bf16 && !dst_bf16) gather_rows_k<float, float><<<g, 256, 0, st>>>((const float*)src, idx, (float*)dst, count, max_rows, row);
+  else if (!src_bf16 && dst_bf16) gather_rows_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
+  else if (src_bf16 && dst_bf16) gather_rows_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
+  else gather_rows_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (float*)dst, count, max_rows, row);
+}
+void launch_gather_labels(const int* src, const int* idx, int* dst, int count, int max_rows,
+                          cudaStream_t st) {
+  gather_labels_k<<<(max_rows + 255) / 256, 256, 0, st>>>(src, idx, dst, count, max_rows);
+}
+void launch_mask_mul(void* w, const void* mask, long long n, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, mask_mul_k<T><<<grid_for(n), 256, 0, st>>>((T*)w, (const T*)mask, n));
+}
+void launch_cast(const void* s, bool s_bf16, void* d, bool d_bf16, long long n, cudaStream_t st) {
+  int g = grid_for(n);
+  if (s_bf16 && !d_bf16) cast_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)s, (float*)d, n);
+  else if (!s_bf16 && d_bf16) cast_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)s, (__nv_bfloat16*)d, n);
+  else if (s_bf16) cast_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)d, n);
+  else cast_k<float, float><<<g, 256, 0, st>>>((const float*)s, (float*)d, n);
+}
+void launch_scatter_offsets(const void* in, const int* offs, void* out, long long n, bool bf16,
+                            cudaStream_t st) {
+  DISPATCH_T(bf16, scatter_offsets_k<T><<<grid_for(n), 256, 0, st>>>((const T*)in, offs, (T*)out, n, 0));
+}
+
+}  // namespace zn

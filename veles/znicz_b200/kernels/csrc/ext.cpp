@@ -1,0 +1,388 @@
+// Python bindings of the znicz_b200 sm_100a kernels (the only file that sees torch headers).
+#include <torch/extension.h>
+#include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <vector>
+
+namespace zn {
+struct ConvGeom { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
+void launch_act_forward(const void*, void*, long long, int, float, bool, cudaStream_t);
+void launch_act_backward(const void*, const void*, const void*, void*, long long, int, float, bool, cudaStream_t);
+int err_act_colsum_slices(int rows);
+void launch_err_act_colsum(void*, const void*, int, int, int, float*, int, bool, cudaStream_t);
+void launch_dropout_forward(const void*, void*, void*, long long, const int*, uint32_t, float, bool, cudaStream_t);
+void launch_binary(const void*, const void*, void*, long long, int, bool, cudaStream_t);
+void launch_mul_backward(const void*, const void*, const void*, void*, void*, long long, bool, cudaStream_t);
+void launch_axpby_2d(const void*, int, int, void*, int, int, int, int, float, float, bool, cudaStream_t);
+void launch_crop_nhwc(const void*, void*, int, int, int, int, int, int, int, int, int, bool, cudaStream_t);
+void launch_gather_rows(const void*, bool, const int*, void*, bool, int, int, long long, cudaStream_t);
+void launch_gather_labels(const int*, const int*, int*, int, int, cudaStream_t);
+void launch_mask_mul(void*, const void*, long long, bool, cudaStream_t);
+void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
+void launch_scatter_offsets(const void*, const int*, void*, long long, bool, cudaStream_t);
+void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int, const int*, bool, cudaStream_t);
+void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, cudaStream_t);
+void launch_lrn_forward(const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
+void launch_lrn_backward(const void*, const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
+void launch_softmax_rows(const void*, bool, float*, int*, int, int, cudaStream_t);
+void launch_evaluate_softmax(const float*, const int*, const int*, void*, bool, const float*, int, int, int*, int*, float*, cudaStream_t);
+void launch_evaluate_mse(const void*, const void*, bool, void*, bool, const float*, int, int, const float*, int, float*, float*, cudaStream_t);
+void launch_mse_find_closest(const void*, bool, const float*, const int*, const float*, int, int, int, int*, cudaStream_t);
+int fused_update_blocks(long long size);
+void launch_fused_update(float*, const float* const*, int, int, long long, float*, float*, float*, const float*, const float*, int, int, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, uint32_t* const*, uint32_t*, int, int, cudaStream_t);
+void launch_col_sums(const float*, float*, int, int, int, cudaStream_t);
+void launch_refresh_shadows(const float*, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, cudaStream_t);
+void launch_gemm_simt(const void*, bool, long long, int, const void*, bool, long long, int, void*, bool, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
+struct ConvGeomS { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
+int umma_pick_splits(int, int, int, int);
+int launch_gemm_umma(const void*, long long, int, const void*, long long, int, void*, int, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
+int launch_conv_fprop_umma(const void*, const void*, long long, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int launch_conv_dgrad_umma(const void*, const void*, long long, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int launch_conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+}  // namespace zn
+
+// The SIMT conv launchers take a struct by value; redeclare with the real layout.
+namespace zn {
+struct ConvGeom2 { int N, H, W, C; int OH, OW, F; int KY, KX, SY, SX; int PT, PL; };
+void launch_conv_fprop_simt_raw(const void*, bool, const float*, long long, int, const float*, void*, bool, const int*, int, cudaStream_t);
+void launch_conv_dgrad_simt_raw(const void*, bool, const float*, long long, int, void*, bool, const int*, float, float, cudaStream_t);
+void launch_conv_wgrad_simt_raw(const void*, bool, const void*, bool, float*, int, const int*, int, cudaStream_t);
+}
+
+using torch::Tensor;
+static inline cudaStream_t cur() { return c10::cuda::getCurrentCUDAStream().stream(); }
+static inline bool is_bf16(const Tensor& t) { return t.scalar_type() == torch::kBFloat16; }
+static inline void chk(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+  TORCH_CHECK(t.scalar_type() == torch::kFloat32 || t.scalar_type() == torch::kBFloat16 ||
+                  t.scalar_type() == torch::kInt32,
+              name, ": unsupported dtype");
+}
+static inline void same_dt(const Tensor& a, const Tensor& b) {
+  TORCH_CHECK(a.scalar_type() == b.scalar_type(), "dtype mismatch");
+}
+static inline const float* fptr_or_null(const c10::optional<Tensor>& t) {
+  if (!t.has_value() || !t->defined() || t->numel() == 0) return nullptr;
+  TORCH_CHECK(t->scalar_type() == torch::kFloat32 && t->is_cuda());
+  return t->data_ptr<float>();
+}
+static void kcheck() {
+  cudaError_t e = cudaGetLastError();
+  TORCH_CHECK(e == cudaSuccess, "znicz_b200 kernel launch failed: ", cudaGetErrorString(e));
+}
+
+void act_forward(Tensor x, Tensor y, int64_t act, double factor) {
+  chk(x, "x"); chk(y, "y"); same_dt(x, y);
+  zn::launch_act_forward(x.data_ptr(), y.data_ptr(), x.numel(), (int)act, (float)factor, is_bf16(x), cur());
+  kcheck();
+}
+void act_backward(Tensor err_y, c10::optional<Tensor> x, c10::optional<Tensor> y, Tensor err_x,
+                  int64_t act, double factor) {
+  chk(err_y, "err_y"); chk(err_x, "err_x"); same_dt(err_y, err_x);
+  const void* xp = (x.has_value() && x->defined()) ? x->data_ptr() : nullptr;
+  const void* yp = (y.has_value() && y->defined()) ? y->data_ptr() : nullptr;
+  if (xp) same_dt(*x, err_y);
+  if (yp) same_dt(*y, err_y);
+  zn::launch_act_backward(err_y.data_ptr(), xp, yp, err_x.data_ptr(), err_y.numel(), (int)act,
+                          (float)factor, is_bf16(err_y), cur());
+  kcheck();
+}
+int64_t colsum_slices(int64_t rows) { return zn::err_act_colsum_slices((int)rows); }
+// err_y *= f'(y) in place; partial[slices, cols] receives per-slice column sums
+void err_act_colsum(Tensor err_y, c10::optional<Tensor> y, int64_t rows, int64_t cols, int64_t act,
+                    c10::optional<Tensor> partial) {
+  chk(err_y, "err_y");
+  const void* yp = nullptr;
+  if (y.has_value() && y->defined()) { same_dt(*y, err_y); yp = y->data_ptr(); }
+  float* pp = nullptr; int slices = zn::err_act_colsum_slices((int)rows);
+  if (partial.has_value() && partial->defined()) {
+    TORCH_CHECK(partial->scalar_type() == torch::kFloat32 && partial->numel() >= slices * cols);
+    pp = partial->data_ptr<float>();
+  }
+  TORCH_CHECK(act == 0 || yp, "activation derivative needs y");
+  zn::launch_err_act_colsum(err_y.data_ptr(), yp, (int)rows, (int)cols, (int)act, pp, slices,
+                            is_bf16(err_y), cur());
+  kcheck();
+}
+void dropout_forward(Tensor x, Tensor y, Tensor mask, Tensor rng, int64_t threshold, double scale) {
+  chk(x, "x"); same_dt(x, y); same_dt(x, mask);
+  zn::launch_dropout_forward(x.data_ptr(), y.data_ptr(), mask.data_ptr(), x.numel(), rng.data_ptr<int>(),
+                             (uint32_t)threshold, (float)scale, is_bf16(x), cur());
+  kcheck();
+}
+void binary_op(Tensor a, Tensor b, Tensor o, int64_t op) {
+  chk(a, "a"); same_dt(a, b); same_dt(a, o);
+  zn::launch_binary(a.data_ptr(), b.data_ptr(), o.data_ptr(), a.numel(), (int)op, is_bf16(a), cur());
+  kcheck();
+}
+void mul_backward(Tensor x, Tensor y, Tensor e, Tensor ex, Tensor ey) {
+  chk(x, "x"); same_dt(x, y); same_dt(x, e); same_dt(x, ex); same_dt(x, ey);
+  zn::launch_mul_backward(x.data_ptr(), y.data_ptr(), e.data_ptr(), ex.data_ptr(), ey.data_ptr(),
+                          x.numel(), is_bf16(x), cur());
+  kcheck();
+}
+void axpby_2d(Tensor src, int64_t soff, Tensor dst, int64_t doff, int64_t len, double alpha, double beta) {
+  chk(src, "src"); same_dt(src, dst);
+  int rows = (int)src.size(0);
+  zn::launch_axpby_2d(src.data_ptr(), (int)(src.numel() / rows), (int)soff, dst.data_ptr(),
+                      (int)(dst.numel() / rows), (int)doff, rows, (int)len, (float)alpha, (float)beta,
+                      is_bf16(src), cur());
+  kcheck();
+}
+void crop_nhwc(Tensor in, Tensor out, int64_t top, int64_t left, bool backward) {
+  chk(in, "in"); same_dt(in, out);
+  const Tensor& big = backward ? out : in;
+  const Tensor& small = backward ? in : out;
+  zn::launch_crop_nhwc(in.data_ptr(), out.data_ptr(), (int)big.size(0), (int)big.size(1), (int)big.size(2),
+                       (int)big.size(3), (int)small.size(1), (int)small.size(2), (int)top, (int)left,
+                       backward ? 1 : 0, is_bf16(in), cur());
+  kcheck();
+}
+void gather_rows(Tensor src, Tensor idx, Tensor dst, int64_t count) {
+  chk(src, "src"); chk(dst, "dst");
+  long long row = src.numel() / src.size(0);
+  zn::launch_gather_rows(src.data_ptr(), is_bf16(src), idx.data_ptr<int>(), dst.data_ptr(), is_bf16(dst),
+                         (int)count, (int)dst.size(0), row, cur());
+  kcheck();
+}
+void gather_labels(Tensor src, Tensor idx, Tensor dst, int64_t count) {
+  zn::launch_gather_labels(src.data_ptr<int>(), idx.data_ptr<int>(), dst.data_ptr<int>(), (int)count,
+                           (int)dst.size(0), cur());
+  kcheck();
+}
+void mask_mul(Tensor w, Tensor mask) {
+  chk(w, "w"); same_dt(w, mask);
+  zn::launch_mask_mul(w.data_ptr(), mask.data_ptr(), w.numel(), is_bf16(w), cur());
+  kcheck();
+}
+void cast_copy(Tensor s, Tensor d) {
+  chk(s, "s"); chk(d, "d");
+  TORCH_CHECK(s.numel() == d.numel());
+  zn::launch_cast(s.data_ptr(), is_bf16(s), d.data_ptr(), is_bf16(d), s.numel(), cur());
+  kcheck();
+}
+void scatter_offsets(Tensor in, Tensor offs, Tensor out) {
+  chk(in, "in"); same_dt(in, out);
+  cudaMemsetAsync(out.data_ptr(), 0, out.numel() * out.element_size(), cur());
+  zn::launch_scatter_offsets(in.data_ptr(), offs.data_ptr<int>(), out.data_ptr(), in.numel(), is_bf16(in), cur());
+  kcheck();
+}
+void pool_forward(Tensor in, c10::optional<Tensor> out, c10::optional<Tensor> offs, int64_t OH, int64_t OW,
+                  int64_t KY, int64_t KX, int64_t SY, int64_t SX, int64_t mode, c10::optional<Tensor> rng) {
+  chk(in, "in");
+  void* op = (out.has_value() && out->defined()) ? out->data_ptr() : nullptr;
+  int* fp = (offs.has_value() && offs->defined()) ? offs->data_ptr<int>() : nullptr;
+  const int* rp = (rng.has_value() && rng->defined()) ? rng->data_ptr<int>() : nullptr;
+  TORCH_CHECK(mode == 2 || fp, "offsets required");
+  TORCH_CHECK(mode < 3 || rp, "rng required for stochastic pooling");
+  zn::launch_pool_forward(in.data_ptr(), op, fp, (int)in.size(0), (int)in.size(1), (int)in.size(2),
+                          (int)in.size(3), (int)OH, (int)OW, (int)KY, (int)KX, (int)SY, (int)SX, (int)mode,
+                          rp, is_bf16(in), cur());
+  kcheck();
+}
+void pool_backward(Tensor err_out, c10::optional<Tensor> offs, Tensor err_in, int64_t OH, int64_t OW,
+                   int64_t KY, int64_t KX, int64_t SY, int64_t SX, bool is_avg) {
+  chk(err_out, "err_out"); same_dt(err_out, err_in);
+  const int* fp = (offs.has_value() && offs->defined()) ? offs->data_ptr<int>() : nullptr;
+  TORCH_CHECK(is_avg || fp, "offsets required");
+  zn::launch_pool_backward(err_out.data_ptr(), fp, err_in.data_ptr(), (int)err_in.size(0), (int)err_in.size(1),
+                           (int)err_in.size(2), (int)err_in.size(3), (int)OH, (int)OW, (int)KY, (int)KX,
+                           (int)SY, (int)SX, is_avg ? 1 : 0, is_bf16(err_out), cur());
+  kcheck();
+}
+void lrn_forward(Tensor x, Tensor y, int64_t n, double alpha, double beta, double k) {
+  chk(x, "x"); same_dt(x, y);
+  int C = (int)x.size(-1);
+  zn::launch_lrn_forward(x.data_ptr(), y.data_ptr(), x.numel() / C, C, (int)n, (float)alpha, (float)beta,
+                         (float)k, is_bf16(x), cur());
+  kcheck();
+}
+void lrn_backward(Tensor ey, Tensor x, Tensor eh, int64_t n, double alpha, double beta, double k) {
+  chk(x, "x"); same_dt(x, ey); same_dt(x, eh);
+  int C = (int)x.size(-1);
+  zn::launch_lrn_backward(ey.data_ptr(), x.data_ptr(), eh.data_ptr(), x.numel() / C, C, (int)n,
+                          (float)alpha, (float)beta, (float)k, is_bf16(x), cur());
+  kcheck();
+}
+void softmax_rows(Tensor in, Tensor out, Tensor max_idx) {
+  chk(in, "in");
+  TORCH_CHECK(out.scalar_type() == torch::kFloat32);
+  int rows = (int)in.size(0); int cols = (int)(in.numel() / rows);
+  zn::launch_softmax_rows(in.data_ptr(), is_bf16(in), out.data_ptr<float>(), max_idx.data_ptr<int>(), rows,
+                          cols, cur());
+  kcheck();
+}
+void evaluate_softmax(Tensor y, Tensor max_idx, Tensor labels, Tensor err, Tensor bp, Tensor n_err,
+                      c10::optional<Tensor> confusion, Tensor max_err_sum) {
+  TORCH_CHECK(y.scalar_type() == torch::kFloat32);
+  int rows = (int)y.size(0); int cols = (int)(y.numel() / rows);
+  int* cp = (confusion.has_value() && confusion->defined() && confusion->numel()) ? confusion->data_ptr<int>() : nullptr;
+  zn::launch_evaluate_softmax(y.data_ptr<float>(), max_idx.data_ptr<int>(), labels.data_ptr<int>(),
+                              err.data_ptr(), is_bf16(err), bp.data_ptr<float>(), rows, cols,
+                              n_err.data_ptr<int>(), cp, max_err_sum.data_ptr<float>(), cur());
+  kcheck();
+}
+void evaluate_mse(Tensor y, Tensor target, Tensor err, Tensor bp, c10::optional<Tensor> denorm_mul,
+                  bool root, Tensor metrics, Tensor mse) {
+  chk(y, "y"); same_dt(y, target);
+  int rows = (int)y.size(0); int cols = (int)(y.numel() / rows);
+  zn::launch_evaluate_mse(y.data_ptr(), target.data_ptr(), is_bf16(y), err.data_ptr(), is_bf16(err),
+                          bp.data_ptr<float>(), rows, cols, fptr_or_null(denorm_mul), root ? 1 : 0,
+                          metrics.data_ptr<float>(), mse.data_ptr<float>(), cur());
+  kcheck();
+}
+void mse_find_closest(Tensor y, Tensor class_targets, Tensor labels, Tensor bp, Tensor n_err) {
+  chk(y, "y");
+  int rows = (int)y.size(0); int cols = (int)(y.numel() / rows);
+  zn::launch_mse_find_closest(y.data_ptr(), is_bf16(y), class_targets.data_ptr<float>(),
+                              labels.data_ptr<int>(), bp.data_ptr<float>(), rows, cols,
+                              (int)class_targets.size(0), n_err.data_ptr<int>(), cur());
+  kcheck();
+}
+
+static __nv_bfloat16* bptr_or_null(const c10::optional<Tensor>& t) {
+  if (!t.has_value() || !t->defined() || t->numel() == 0) return nullptr;
+  TORCH_CHECK(t->scalar_type() == torch::kBFloat16 && t->is_cuda());
+  return reinterpret_cast<__nv_bfloat16*>(t->data_ptr());
+}
+static float* mfptr_or_null(const c10::optional<Tensor>& t) {
+  if (!t.has_value() || !t->defined() || t->numel() == 0) return nullptr;
+  TORCH_CHECK(t->scalar_type() == torch::kFloat32 && t->is_cuda());
+  return t->data_ptr<float>();
+}
+
+// grad_ptrs: list of int64 device addresses (one per rank; local first when single GPU)
+void fused_update(Tensor w, std::vector<int64_t> grad_ptrs, int64_t nparts, int64_t part_stride,
+                  c10::optional<Tensor> grad_out, c10::optional<Tensor> acc, c10::optional<Tensor> vel,
+                  Tensor hyper, c10::optional<Tensor> col_sums, int64_t flags, bool is_bias, int64_t rows,
+                  int64_t cols, c10::optional<Tensor> lp, int64_t ld, c10::optional<Tensor> lp_conv,
+                  int64_t taps, int64_t C, int64_t c_pad, std::vector<int64_t> peer_flags,
+                  int64_t epoch_ptr, int64_t rank, int64_t blocks) {
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32 && w.is_cuda() && w.is_contiguous());
+  TORCH_CHECK(grad_ptrs.size() >= 1 && grad_ptrs.size() <= 8);
+  const float* gp[8]; uint32_t* fl[8];
+  for (size_t i = 0; i < grad_ptrs.size(); ++i) gp[i] = reinterpret_cast<const float*>(grad_ptrs[i]);
+  bool multi = peer_flags.size() == grad_ptrs.size() && grad_ptrs.size() > 1;
+  if (multi) for (size_t i = 0; i < peer_flags.size(); ++i) fl[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  zn::launch_fused_update(w.data_ptr<float>(), gp, (int)grad_ptrs.size(), (int)nparts, part_stride,
+                          mfptr_or_null(grad_out), mfptr_or_null(acc), mfptr_or_null(vel),
+                          hyper.data_ptr<float>(), fptr_or_null(col_sums), (int)flags, is_bias ? 1 : 0,
+                          w.numel(), (int)rows, (int)cols, bptr_or_null(lp), (int)ld, bptr_or_null(lp_conv),
+                          (int)taps, (int)C, (int)c_pad, multi ? fl : nullptr,
+                          reinterpret_cast<uint32_t*>(epoch_ptr), (int)rank, (int)blocks, cur());
+  kcheck();
+}
+int64_t update_blocks(int64_t size) { return zn::fused_update_blocks(size); }
+void col_sums(Tensor w, Tensor out, int64_t rows, int64_t cols, bool transposed) {
+  zn::launch_col_sums(w.data_ptr<float>(), out.data_ptr<float>(), (int)rows, (int)cols, transposed ? 1 : 0, cur());
+  kcheck();
+}
+void refresh_shadows(Tensor w, int64_t rows, int64_t cols, c10::optional<Tensor> lp, int64_t ld,
+                     c10::optional<Tensor> lp_conv, int64_t taps, int64_t C, int64_t c_pad) {
+  zn::launch_refresh_shadows(w.data_ptr<float>(), w.numel(), (int)rows, (int)cols, bptr_or_null(lp), (int)ld,
+                             bptr_or_null(lp_conv), (int)taps, (int)C, (int)c_pad, cur());
+  kcheck();
+}
+
+// generic GEMM: out[M,N] = act(alpha * opA(a) opB(b) + bias) + beta*out ; engine: 0 simt, 1 umma
+// transa: A stored [K][lda]; transb: B stored [N][ldb] (i.e. "NT" when transb = 1)
+int64_t gemm(Tensor a, int64_t lda, bool transa, Tensor b, int64_t ldb, bool transb, Tensor out,
+             int64_t ldo, bool out_trans, int64_t M, int64_t N, int64_t K, c10::optional<Tensor> bias,
+             int64_t act, double alpha, double beta, int64_t splits, int64_t split_stride, int64_t engine) {
+  chk(a, "a"); chk(b, "b"); chk(out, "out");
+  if (engine == 1) {
+    TORCH_CHECK(is_bf16(a) && is_bf16(b), "tcgen05 path needs bf16 operands");
+    int r = zn::launch_gemm_umma(a.data_ptr(), lda, transa ? 1 : 0, b.data_ptr(), ldb, transb ? 0 : 1,
+                                 out.data_ptr(), is_bf16(out) ? 1 : 0, ldo, out_trans ? 1 : 0, (int)M,
+                                 (int)N, (int)K, fptr_or_null(bias), (int)act, (float)alpha, (float)beta,
+                                 (int)splits, split_stride, cur());
+    if (r == 0) kcheck();
+    return r;
+  }
+  zn::launch_gemm_simt(a.data_ptr(), is_bf16(a), lda, transa ? 1 : 0, b.data_ptr(), is_bf16(b), ldb,
+                       transb ? 1 : 0, out.data_ptr(), is_bf16(out), ldo, out_trans ? 1 : 0, (int)M, (int)N,
+                       (int)K, fptr_or_null(bias), (int)act, (float)alpha, (float)beta,
+                       (int)(splits < 1 ? 1 : splits), split_stride, cur());
+  kcheck();
+  return 0;
+}
+int64_t pick_splits(int64_t M, int64_t N, int64_t K, int64_t max_splits) {
+  return zn::umma_pick_splits((int)M, (int)N, (int)K, (int)max_splits);
+}
+
+// geometry vector: [N,H,W,C,OH,OW,F,KY,KX,SY,SX,PT,PL]
+int64_t conv_fprop(Tensor x, Tensor w, int64_t ldw, bool w_trans, c10::optional<Tensor> bias, Tensor out,
+                   std::vector<int64_t> g, int64_t act, int64_t engine) {
+  TORCH_CHECK(g.size() == 13);
+  int gi[13]; for (int i = 0; i < 13; ++i) gi[i] = (int)g[i];
+  if (engine == 1) {
+    TORCH_CHECK(is_bf16(x) && is_bf16(w));
+    int r = zn::launch_conv_fprop_umma(x.data_ptr(), w.data_ptr(), ldw, fptr_or_null(bias), out.data_ptr(),
+                                       is_bf16(out) ? 1 : 0, gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6],
+                                       gi[7], gi[8], gi[9], gi[10], gi[11], gi[12], (int)act, cur());
+    if (r == 0) kcheck();
+    return r;
+  }
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32);
+  zn::launch_conv_fprop_simt_raw(x.data_ptr(), is_bf16(x), w.data_ptr<float>(), ldw, w_trans ? 1 : 0,
+                                 fptr_or_null(bias), out.data_ptr(), is_bf16(out), gi, (int)act, cur());
+  kcheck();
+  return 0;
+}
+int64_t conv_dgrad(Tensor err_out, Tensor w, int64_t ldw, bool w_trans, Tensor err_in,
+                   std::vector<int64_t> g, double alpha, double beta, int64_t engine) {
+  TORCH_CHECK(g.size() == 13);
+  int gi[13]; for (int i = 0; i < 13; ++i) gi[i] = (int)g[i];
+  if (engine == 1) {
+    TORCH_CHECK(is_bf16(err_out) && is_bf16(w));
+    int r = zn::launch_conv_dgrad_umma(err_out.data_ptr(), w.data_ptr(), ldw, err_in.data_ptr(),
+                                       is_bf16(err_in) ? 1 : 0, gi[0], gi[1], gi[2], gi[3], gi[4], gi[5],
+                                       gi[6], gi[7], gi[8], gi[9], gi[10], gi[11], gi[12], (float)alpha,
+                                       (float)beta, cur());
+    if (r == 0) kcheck();
+    return r;
+  }
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32);
+  zn::launch_conv_dgrad_simt_raw(err_out.data_ptr(), is_bf16(err_out), w.data_ptr<float>(), ldw,
+                                 w_trans ? 1 : 0, err_in.data_ptr(), is_bf16(err_in), gi, (float)alpha,
+                                 (float)beta, cur());
+  kcheck();
+  return 0;
+}
+int64_t conv_wgrad(Tensor err_out, Tensor x, Tensor partials, int64_t splits, std::vector<int64_t> g,
+                   bool out_trans, int64_t engine) {
+  TORCH_CHECK(g.size() == 13 && partials.scalar_type() == torch::kFloat32);
+  int gi[13]; for (int i = 0; i < 13; ++i) gi[i] = (int)g[i];
+  if (engine == 1) {
+    TORCH_CHECK(is_bf16(err_out) && is_bf16(x) && !out_trans);
+    int r = zn::launch_conv_wgrad_umma(err_out.data_ptr(), x.data_ptr(), partials.data_ptr<float>(),
+                                       (int)splits, gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gi[7],
+                                       gi[8], gi[9], gi[10], gi[11], gi[12], cur());
+    if (r == 0) kcheck();
+    return r;
+  }
+  zn::launch_conv_wgrad_simt_raw(err_out.data_ptr(), is_bf16(err_out), x.data_ptr(), is_bf16(x),
+                                 partials.data_ptr<float>(), (int)splits, gi, out_trans ? 1 : 0, cur());
+  kcheck();
+  return 0;
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "znicz_b200 sm_100a kernels";
+  m.def("act_forward", &act_forward); m.def("act_backward", &act_backward);
+  m.def("colsum_slices", &colsum_slices); m.def("err_act_colsum", &err_act_colsum);
+  m.def("dropout_forward", &dropout_forward); m.def("binary_op", &binary_op);
+  m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
+  m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
+  m.def("mask_mul", &mask_mul); m.def("cast_copy", &cast_copy); m.def("scatter_offsets", &scatter_offsets);
+  m.def("pool_forward", &pool_forward); m.def("pool_backward", &pool_backward);
+  m.def("lrn_forward", &lrn_forward); m.def("lrn_backward", &lrn_backward);
+  m.def("softmax_rows", &softmax_rows); m.def("evaluate_softmax", &evaluate_softmax);
+  m.def("evaluate_mse", &evaluate_mse); m.def("mse_find_closest", &mse_find_closest);
+  m.def("fused_update", &fused_update); m.def("update_blocks", &update_blocks);
+  m.def("col_sums", &col_sums); m.def("refresh_shadows", &refresh_shadows);
+  m.def("gemm", &gemm); m.def("pick_splits", &pick_splits);
+  m.def("conv_fprop", &conv_fprop); m.def("conv_dgrad", &conv_dgrad); m.def("conv_wgrad", &conv_wgrad);
+}

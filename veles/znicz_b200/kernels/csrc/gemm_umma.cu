@@ -1,0 +1,513 @@
+// tcgen05 / TMEM / TMA GEMM family for sm_100a (bf16 operands, fp32 accumulate in TMEM).
+//
+//   D[M, N] = sum_k A[m, k] * B[n, k]      (one 128 x BLOCK_N tile per CTA, optional split-K)
+//
+// Operand sources (template):
+//   A_TMA_K   A stored [M][K] (K contiguous)  -> TMA box {64, 128}, K-major SW128 descriptor
+//   A_TMA_MN  A stored [K][M] (M contiguous)  -> TMA boxes {64, 64}, MN-major SW128 descriptor
+//   A_GATHER_K / A_GATHER_MN: implicit-GEMM convolution; producer warps gather NHWC patches
+//   (im2col of x, or the dgrad gather of err_out) as 16-byte chunks straight into the swizzled
+//   shared-memory tile — no im2col buffer in HBM (the reference unpacks 16 images at a time into
+//   a temp buffer and calls cuBLAS, /root/reference/conv.py:268-297, gd_conv.py:313-423).
+//   B_TMA_K   B stored [N][K];  B_TMA_MN  B stored [K][N].
+//
+// Warp roles (192 threads): warps 0-3 = gather producers (if any) then epilogue (TMEM -> regs ->
+// bias/activation/alpha-beta -> global); warp 4 = TMA producer; warp 5 = TMEM allocator + the
+// single thread that issues tcgen05.mma and commits to mbarriers. 4-stage smem ring.
+//
+// This covers: FC forward (TMA_K x TMA_K, fused bias+activation), FC dgrad (TMA_K x TMA_MN,
+// alpha/beta), FC wgrad (TMA_MN x TMA_MN), conv fprop (GATHER_K x TMA_K, fused bias+act),
+// conv dgrad (GATHER_K x TMA_MN, no atomics), conv wgrad (GATHER_MN x TMA_MN, split-K partials
+// that the fused update kernel sums in fixed order).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace zn {
+
+using namespace umma;
+
+enum { A_TMA_K = 0, A_TMA_MN = 1, A_GATHER_K = 2, A_GATHER_MN = 3 };
+enum { B_TMA_K = 0, B_TMA_MN = 1 };
+enum { G_NONE = 0, G_IM2COL = 1, G_DGRAD = 2 };
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // bf16 elements = 128 bytes = one SW128 row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * 128;
+
+struct ConvGeomU {
+  int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL;
+  int vec;   // 1 when 16-byte chunks never straddle a tap (C % 8 == 0 resp. F % 8 == 0)
+};
+
+struct GemmParams {
+  int M, N, K;                 // logical GEMM sizes (K = reduction)
+  int k_blocks_per_split;      // in BLOCK_K units
+  // epilogue
+  void* out; int out_bf16; long long ldo; int out_trans;
+  const float* bias; int act; float alpha, beta;
+  long long split_stride;      // > 0: fp32 partial [blockIdx.z][...]
+  // gather source
+  const __nv_bfloat16* gsrc; ConvGeomU g; int gather_kind;
+  int gK;                      // valid extent of the gathered K (fprop/dgrad) or M (wgrad) index
+};
+
+// ---- gather: 8 consecutive "inner" indices of one "pixel" -> 16 bytes ------------------------
+struct PixCtx { int n, y, x, valid; };
+
+__device__ __forceinline__ PixCtx decode_out_pixel(const ConvGeomU& g, int pix, int limit) {
+  PixCtx c; c.valid = pix < limit;
+  int p = c.valid ? pix : 0;
+  c.x = p % g.OW; int t = p / g.OW; c.y = t % g.OH; c.n = t / g.OH;
+  return c;
+}
+__device__ __forceinline__ PixCtx decode_in_pixel(const ConvGeomU& g, int pix, int limit) {
+  PixCtx c; c.valid = pix < limit;
+  int p = c.valid ? pix : 0;
+  c.x = p % g.W; int t = p / g.W; c.y = t % g.H; c.n = t / g.H;
+  return c;
+}
+__device__ __forceinline__ float im2col_elem(const __nv_bfloat16* x, const ConvGeomU& g,
+                                             const PixCtx& c, int kidx, int klimit) {
+  if (!c.valid || kidx >= klimit) return 0.f;
+  int ch = kidx % g.C; int tap = kidx / g.C; int kx = tap % g.KX; int ky = tap / g.KX;
+  int iy = c.y * g.SY - g.PT + ky, ix = c.x * g.SX - g.PL + kx;
+  if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
+  return __bfloat162float(x[(((long long)c.n * g.H + iy) * g.W + ix) * g.C + ch]);
+}
+__device__ __forceinline__ uint4 im2col_chunk(const __nv_bfloat16* x, const ConvGeomU& g,
+                                              const PixCtx& c, int kidx0, int klimit) {
+  uint4 z = make_uint4(0, 0, 0, 0);
+  if (!c.valid || kidx0 >= klimit) return z;
+  if (g.vec) {
+    int ch = kidx0 % g.C; int tap = kidx0 / g.C; int kx = tap % g.KX; int ky = tap / g.KX;
+    int iy = c.y * g.SY - g.PT + ky, ix = c.x * g.SX - g.PL + kx;
+    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return z;
+    return *reinterpret_cast<const uint4*>(x + (((long long)c.n * g.H + iy) * g.W + ix) * g.C + ch);
+  }
+  __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(im2col_elem(x, g, c, kidx0 + j, klimit));
+  return *reinterpret_cast<uint4*>(v);
+}
+__device__ __forceinline__ float dgrad_elem(const __nv_bfloat16* e, const ConvGeomU& g,
+                                            const PixCtx& c, int k, int klimit) {
+  if (!c.valid || k >= klimit) return 0.f;
+  int f = k % g.F; int tap = k / g.F; int kx = tap % g.KX; int ky = tap / g.KX;
+  int ty = c.y + g.PT - ky, tx = c.x + g.PL - kx;
+  if (ty < 0 || tx < 0 || (ty % g.SY) || (tx % g.SX)) return 0.f;
+  int oy = ty / g.SY, ox = tx / g.SX;
+  if (oy >= g.OH || ox >= g.OW) return 0.f;
+  return __bfloat162float(e[(((long long)c.n * g.OH + oy) * g.OW + ox) * g.F + f]);
+}
+__device__ __forceinline__ uint4 dgrad_chunk(const __nv_bfloat16* e, const ConvGeomU& g,
+                                             const PixCtx& c, int k0, int klimit) {
+  uint4 z = make_uint4(0, 0, 0, 0);
+  if (!c.valid || k0 >= klimit) return z;
+  if (g.vec) {
+    int f = k0 % g.F; int tap = k0 / g.F; int kx = tap % g.KX; int ky = tap / g.KX;
+    int ty = c.y + g.PT - ky, tx = c.x + g.PL - kx;
+    if (ty < 0 || tx < 0 || (ty % g.SY) || (tx % g.SX)) return z;
+    int oy = ty / g.SY, ox = tx / g.SX;
+    if (oy >= g.OH || ox >= g.OW) return z;
+    return *reinterpret_cast<const uint4*>(e + (((long long)c.n * g.OH + oy) * g.OW + ox) * g.F + f);
+  }
+  __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(dgrad_elem(e, g, c, k0 + j, klimit));
+  return *reinterpret_cast<uint4*>(v);
+}
+
+template <int BLOCK_N, int B_MODE>
+__host__ __device__ constexpr int b_bytes() {
+  return B_MODE == B_TMA_K ? BLOCK_N * 128 : ((BLOCK_N + 63) / 64) * 8192;
+}
+
+template <int BLOCK_N, int A_MODE, int B_MODE>
+__global__ void __launch_bounds__(192, 1)
+gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const GemmParams p) {
+  constexpr int B_BYTES = b_bytes<BLOCK_N, B_MODE>();
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr bool A_GATHER = (A_MODE == A_GATHER_K || A_MODE == A_GATHER_MN);
+  constexpr bool A_MN = (A_MODE == A_TMA_MN || A_MODE == A_GATHER_MN);
+  constexpr bool B_MN = (B_MODE == B_TMA_MN);
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr uint32_t TX_BYTES = (A_GATHER ? 0 : A_BYTES) + B_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  // 1024-byte aligned tile area (SWIZZLE_128B atoms are 1024 B)
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_begin = blockIdx.z * p.k_blocks_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
+  const int num_kb = max(0, kb_end - kb_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], (A_GATHER ? 128u : 0u) + 1u);
+      mbar_init(&empty_bar[s], 1u);
+    }
+    mbar_init(&tmem_full_bar, 1u);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    if (!A_GATHER) tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 5) {
+    tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const int k0 = (kb_begin + i) * BLOCK_K;
+        mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
+        if (A_MODE == A_TMA_K) {
+          tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
+        } else if (A_MODE == A_TMA_MN) {
+          tma_load_2d(sa, &tmap_a, &full_bar[s], m0, k0);
+          tma_load_2d(sa + 8192, &tmap_a, &full_bar[s], m0 + 64, k0);
+        }
+        if (B_MODE == B_TMA_K) {
+          tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < (BLOCK_N + 63) / 64; ++j)
+            tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[s], n0 + j * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // K-major: 16 bf16 = 32 B along the swizzled row. MN-major: 16 k-rows = 2 atoms.
+          const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024)
+                                   : make_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                   : make_smem_desc(sb + k * 32, 16, 1024);
+          mma_f16(tmem_base, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
+      }
+      mma_commit(&tmem_full_bar);           // accumulator complete
+    }
+  } else {
+    // ===================== gather producers (warps 0-3) =====================
+    if (A_GATHER) {
+      const int t = threadIdx.x;            // 0..127
+      if (A_MODE == A_GATHER_K) {
+        // tile row r = t is GEMM row m0 + t (a pixel); chunks run over the reduction index
+        const int m = m0 + t;
+        PixCtx ctx = (p.gather_kind == G_IM2COL) ? decode_out_pixel(p.g, m, p.M)
+                                                 : decode_in_pixel(p.g, m, p.M);
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+          const int k0 = (kb_begin + i) * BLOCK_K;
+          uint4 v[8];
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            v[c8] = (p.gather_kind == G_IM2COL)
+                        ? im2col_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK)
+                        : dgrad_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(sa + t * 128 + ((c8 ^ (t & 7)) << 4)) = v[c8];
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[s]);
+        }
+      } else {
+        // A_GATHER_MN (conv wgrad): tile = [64 reduction rows (pixels)][128 m (kidx)];
+        // thread -> reduction row kr = t % 64, 64-wide m block = t / 64 (8 chunks of 8 kidx)
+        const int kr = t & 63, mblk = t >> 6;
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+          const int pix = (kb_begin + i) * BLOCK_K + kr;
+          PixCtx ctx = decode_out_pixel(p.g, pix, p.K);
+          uint4 v[8];
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            v[c8] = im2col_chunk(p.gsrc, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(sa + mblk * 8192 + kr * 128 + ((c8 ^ (kr & 7)) << 4)) = v[c8];
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
+    // ===================== epilogue (warps 0-3) =====================
+    const int row = m0 + warp * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+      uint32_t r[32];
+      if (num_kb > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        if (CH == 32) {
+          tmem_ld_32x32(taddr, r);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_32x16(taddr, r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = r16[j];
+        }
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row < p.M) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const int n = n0 + c0 + j;
+          if (n >= p.N) break;
+          float v = __uint_as_float(r[j]);
+          const long long o = p.out_trans ? (long long)n * p.ldo + row : (long long)row * p.ldo + n;
+          if (p.split_stride > 0) {
+            reinterpret_cast<float*>(p.out)[(long long)blockIdx.z * p.split_stride + o] = v;
+          } else {
+            if (p.bias) v += p.bias[n];
+            v = act_fwd(p.act, v) * p.alpha;
+            if (p.out_bf16) {
+              __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
+              if (p.beta != 0.f) v += p.beta * __bfloat162float(*q);
+              *q = __float2bfloat16_rn(v);
+            } else {
+              float* q = reinterpret_cast<float*>(p.out) + o;
+              if (p.beta != 0.f) v += p.beta * *q;
+              *q = v;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dim `inner` (contiguous), outer dim `outer`, row pitch ld elements,
+// box {64, box_rows}, SWIZZLE_128B, OOB -> zeros.
+static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld,
+                    int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int BN, int AM, int BM>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
+                      cudaStream_t st) {
+  constexpr int smem = STAGES * (A_BYTES + b_bytes<BN, BM>()) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_umma_k<BN, AM, BM>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BLOCK_M - 1) / BLOCK_M, splits);
+  gemm_umma_k<BN, AM, BM><<<grid, 192, smem, st>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
+template <int AM, int BM>
+static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                     int splits, cudaStream_t st) {
+  switch (bn) {
+    case 16: return launch_cfg<16, AM, BM>(ta, tb, p, splits, st);
+    case 32: return launch_cfg<32, AM, BM>(ta, tb, p, splits, st);
+    case 64: return launch_cfg<64, AM, BM>(ta, tb, p, splits, st);
+    case 128: return launch_cfg<128, AM, BM>(ta, tb, p, splits, st);
+    default: return -2;
+  }
+}
+
+static int pick_bn(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : (N <= 64 ? 64 : 128)); }
+
+int umma_pick_splits(int M, int N, int K, int max_splits) {
+  int bn = pick_bn(N);
+  if (bn < 64) bn = 64;
+  long long tiles = (long long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
+  int kb = (K + BLOCK_K - 1) / BLOCK_K;
+  int s = (int)((148 + tiles - 1) / tiles);
+  if (s > kb) s = kb;
+  if (s > max_splits) s = max_splits;
+  return s < 1 ? 1 : s;
+}
+
+// Dense GEMM. a_mn = 0: A stored [M][lda] (K contiguous); 1: A stored [K][lda] (M contiguous).
+// b_mn = 0: B stored [N][ldb] (K contiguous); 1: B stored [K][ldb] (N contiguous).
+// Returns 0 on success; non-zero = not launched (caller must fall back loudly).
+int launch_gemm_umma(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn,
+                     void* out, int out_bf16, long long ldo, int out_trans, int M, int N, int K,
+                     const float* bias, int act, float alpha, float beta, int splits,
+                     long long split_stride, cudaStream_t st) {
+  if ((lda % 8) || (ldb % 8) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return -3;
+  CUtensorMap ta, tb;
+  int bn = pick_bn(N);
+  if (b_mn && bn < 64) bn = 64;
+  int r;
+  if (a_mn) r = make_map(&ta, a, M, K, lda, 64); else r = make_map(&ta, a, K, M, lda, BLOCK_M);
+  if (r) return r;
+  if (b_mn) r = make_map(&tb, b, N, K, ldb, 64); else r = make_map(&tb, b, K, N, ldb, bn);
+  if (r) return r;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (splits < 1) splits = 1;
+  p.k_blocks_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  p.out = out; p.out_bf16 = out_bf16; p.ldo = ldo; p.out_trans = out_trans;
+  p.bias = bias; p.act = act; p.alpha = alpha; p.beta = beta; p.split_stride = split_stride;
+  p.gather_kind = G_NONE;
+  if (!a_mn && !b_mn) return launch_bn<A_TMA_K, B_TMA_K>(bn, ta, tb, p, splits, st);
+  // MN-major B tiles are built from 64-wide swizzle atoms: never go below UMMA_N = 64 there
+  if (!a_mn && b_mn) return launch_bn<A_TMA_K, B_TMA_MN>(bn, ta, tb, p, splits, st);
+  if (a_mn && !b_mn) return launch_bn<A_TMA_MN, B_TMA_K>(bn, ta, tb, p, splits, st);
+  return launch_bn<A_TMA_MN, B_TMA_MN>(bn, ta, tb, p, splits, st);
+}
+
+static ConvGeomU geom(int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX,
+                      int PT, int PL, int vec) {
+  ConvGeomU g{N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, vec};
+  return g;
+}
+
+// out[pix, f] = act(im2col(x)[pix, :] . w_lp[f, :] + bias[f]); w_lp stored [F][ldw] bf16 (ldw % 8 == 0)
+int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const float* bias, void* out,
+                           int out_bf16, int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX,
+                           int SY, int SX, int PT, int PL, int act, cudaStream_t st) {
+  if ((ldw % 8) || ((uintptr_t)w_lp & 15) || ((uintptr_t)x & 15)) return -3;
+  int Kw = KY * KX * C;
+  CUtensorMap ta, tb;
+  int bn = pick_bn(F);
+  int r = make_map(&tb, w_lp, ldw, F, ldw, bn);
+  if (r) return r;
+  ta = tb;
+  GemmParams p{};
+  p.M = N * OH * OW; p.N = F; p.K = Kw;
+  p.k_blocks_per_split = (Kw + BLOCK_K - 1) / BLOCK_K;
+  p.out = out; p.out_bf16 = out_bf16; p.ldo = F; p.out_trans = 0;
+  p.bias = bias; p.act = act; p.alpha = 1.f; p.beta = 0.f; p.split_stride = 0;
+  p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
+  p.gather_kind = G_IM2COL; p.gK = Kw;
+  return launch_bn<A_GATHER_K, B_TMA_K>(bn, ta, tb, p, 1, st);
+}
+
+// err_in[ipix, c] = alpha * sum_{tap,f} gather(err_out) * wd_lp[(tap,f), c] + beta * err_in
+// wd_lp stored [KY*KX*F][ldc] bf16 (ldc % 8 == 0, zero padded columns)
+int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc, void* err_in,
+                           int ei_bf16, int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX,
+                           int SY, int SX, int PT, int PL, float alpha, float beta, cudaStream_t st) {
+  if ((ldc % 8) || ((uintptr_t)wd_lp & 15) || ((uintptr_t)err_out & 15)) return -3;
+  int Kd = KY * KX * F;
+  CUtensorMap ta, tb;
+  int bn = pick_bn(C);
+  if (bn < 64) bn = 64;
+  int r = make_map(&tb, wd_lp, ldc, Kd, ldc, 64);
+  if (r) return r;
+  ta = tb;
+  GemmParams p{};
+  p.M = N * H * W; p.N = C; p.K = Kd;
+  p.k_blocks_per_split = (Kd + BLOCK_K - 1) / BLOCK_K;
+  p.out = err_in; p.out_bf16 = ei_bf16; p.ldo = C; p.out_trans = 0;
+  p.bias = nullptr; p.act = 0; p.alpha = alpha; p.beta = beta; p.split_stride = 0;
+  p.gsrc = (const __nv_bfloat16*)err_out;
+  p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, F % 8 == 0);
+  p.gather_kind = G_DGRAD; p.gK = Kd;
+  return launch_bn<A_GATHER_K, B_TMA_MN>(bn, ta, tb, p, 1, st);
+}
+
+// partials[z][f][kidx] = sum_{pix in split z} err_out[pix, f] * im2col(x)[pix, kidx]
+// (computed as D[kidx, f] with the im2col operand on the 128-wide M side, stored transposed)
+int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, int splits, int N, int H,
+                           int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX, int PT,
+                           int PL, cudaStream_t st) {
+  if ((F % 8) || ((uintptr_t)err_out & 15) || ((uintptr_t)x & 15)) return -3;
+  int Kw = KY * KX * C, P = N * OH * OW;
+  CUtensorMap ta, tb;
+  int bn = pick_bn(F);
+  if (bn < 64) bn = 64;
+  int r = make_map(&tb, err_out, F, P, F, 64);
+  if (r) return r;
+  ta = tb;
+  GemmParams p{};
+  p.M = Kw; p.N = F; p.K = P;
+  int total_kb = (P + BLOCK_K - 1) / BLOCK_K;
+  if (splits < 1) splits = 1;
+  p.k_blocks_per_split = (total_kb + splits - 1) / splits;
+  p.out = partials; p.out_bf16 = 0; p.ldo = Kw; p.out_trans = 1;
+  p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.beta = 0.f; p.split_stride = (long long)F * Kw;
+  p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
+  p.gather_kind = G_IM2COL; p.gK = Kw;
+  return launch_bn<A_GATHER_MN, B_TMA_MN>(bn, ta, tb, p, splits, st);
+}
+
+}  // namespace zn

@@ -1,0 +1,203 @@
+// Fused SGD step (+ cross-GPU gradient reduction over peer memory).
+//
+// One kernel replaces the reference's weights_update / bias_update / compute_col_sums kernels
+// (/root/reference/cuda/all2all/gradient_descent/weights_update.cu:10, bias_update.cu:18,
+// cuda/weights_ortho.cu:14,41, cuda/gradient_descent.store_output.cu) AND the slave->master /
+// master->slave gradient and weight messages of the reference's data parallelism
+// (/root/reference/nn_units.py:644-694):
+//
+//   g    = sum over ranks r (fixed order) of sum over split-K partials p of grad[r][p][idx]
+//   gd   = -lr * (g + wd * ((1 - l1) * w + 0.5 * l1 * sign(w)) + ortho / rows * (colsum[col] - w))
+//   acc  = acc_beta * acc + acc_alpha * gd ; gd = gd_beta * gd + gd_alpha * acc      (optional)
+//   gd  += moment * vel ; vel = gd                                                     (optional)
+//   w   += gd                                                                          (optional)
+//   + bf16 shadow copies of w in the layouts the tcgen05 GEMM/conv kernels consume.
+//
+// In data-parallel mode grad[r] are *peer pointers* into the other GPUs' HBM (symmetric
+// memory over NVLink5/NVSwitch): every rank reads all ranks' gradient tiles in the same order,
+// so all replicas compute bit-identical weights with no NCCL call and no broadcast.
+// Cross-GPU ordering uses per-block flag words in symmetric memory (st.release.sys /
+// ld.acquire.sys), with the epoch counter kept in device memory so CUDA-graph replays work.
+#include "common.cuh"
+
+namespace zn {
+
+struct GradSources {
+  const float* ptr[8];   // per-rank base pointers (ptr[0] = local when nranks == 1)
+  int nranks;
+  int nparts;            // split-K partials per rank
+  long long part_stride; // elements between partials
+};
+
+struct ShadowSpec {
+  __nv_bfloat16* lp;       // [rows][ld] bf16 copy of w (row-major as w), may be null
+  int ld;
+  __nv_bfloat16* lp_conv;  // conv dgrad operand [tap][f][c_pad], may be null
+  int taps, C, c_pad;
+};
+
+struct PeerSync {
+  uint32_t* flags[8];      // flags[r] = rank r's flag array [max_blocks][8]
+  uint32_t* epoch;         // local [max_blocks]
+  int rank, nranks;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Block-level barrier across ranks: thread t < nranks signals rank t and waits for rank t.
+__device__ __forceinline__ void peer_barrier(const PeerSync& ps, uint32_t value) {
+  __syncthreads();
+  if ((int)threadIdx.x < ps.nranks) {
+    int peer = threadIdx.x;
+    st_release_sys(ps.flags[peer] + (size_t)blockIdx.x * 8 + ps.rank, value);
+    const uint32_t* mine = ps.flags[ps.rank] + (size_t)blockIdx.x * 8 + peer;
+    long long spins = 0;
+    while ((int)(ld_acquire_sys(mine) - value) < 0) {
+      if (++spins > (1LL << 31)) { __trap(); }
+    }
+  }
+  __syncthreads();
+}
+
+// hyper layout: see GradientDescentBase.HYPER_FIELDS
+template <bool MULTI>
+__global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __restrict__ grad_out,
+                               float* __restrict__ acc, float* __restrict__ vel,
+                               const float* __restrict__ hyper, const float* __restrict__ col_sums,
+                               int flags, int is_bias, long long size, int rows, int cols,
+                               ShadowSpec sh, PeerSync ps) {
+  __shared__ uint32_t s_epoch;
+  uint32_t epoch = 0;
+  if (MULTI) {
+    if (threadIdx.x == 0) s_epoch = ps.epoch[blockIdx.x] + 1;
+    __syncthreads();
+    epoch = s_epoch;
+    peer_barrier(ps, 2 * epoch - 1);   // every rank's gradient is complete and visible
+  }
+  const float lr = hyper[is_bias ? 9 : 0], wd = hyper[is_bias ? 10 : 1];
+  const float l1 = hyper[is_bias ? 11 : 2], moment = hyper[is_bias ? 12 : 3];
+  const float acc_alpha = hyper[4], acc_beta = hyper[5], gd_alpha = hyper[6], gd_beta = hyper[7];
+  const float ortho = hyper[8];
+  const bool apply = flags & 1, use_moment = flags & 2, use_acc = flags & 4;
+  const bool use_ortho = (flags & 8) && col_sums != nullptr;
+  const bool transposed = flags & 16;
+
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < size; i += stride) {
+    float g = 0.f;
+    for (int r = 0; r < gs.nranks; ++r) {
+      const float* base = gs.ptr[r] + i;
+      for (int p = 0; p < gs.nparts; ++p) g += base[(long long)p * gs.part_stride];
+    }
+    if (grad_out) grad_out[i] = g;
+    float wv = w[i];
+    float sgn = wv > 0.f ? 1.f : (wv < 0.f ? -1.f : 0.f);
+    float reg = wd * ((1.f - l1) * wv + 0.5f * l1 * sgn);
+    if (use_ortho) {
+      // weights [rows=Y][cols=H] (or stored transposed [H][Y]); col index = input index
+      int col = transposed ? (int)(i / rows) : (int)(i % cols);
+      int n_rows = transposed ? cols : rows;
+      reg += ortho / (float)(transposed ? rows : rows) * (col_sums[col] - wv);
+      (void)n_rows;
+    }
+    float gd = -lr * (g + reg);
+    if (use_acc) {
+      float a = (acc_beta != 0.f ? acc_beta * acc[i] : 0.f) + acc_alpha * gd;
+      acc[i] = a;
+      gd = gd * gd_beta + gd_alpha * a;
+    }
+    if (use_moment) { gd += vel[i] * moment; vel[i] = gd; }
+    if (apply) { wv += gd; w[i] = wv; }
+    if (sh.lp) {
+      int r = (int)(i / cols), c = (int)(i % cols);
+      sh.lp[(size_t)r * sh.ld + c] = __float2bfloat16_rn(wv);
+      if (sh.lp_conv) {
+        int tap = c / sh.C, ch = c % sh.C;      // w[f=r][tap][ch]
+        sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
+      }
+    }
+  }
+  if (MULTI) {
+    peer_barrier(ps, 2 * epoch);       // nobody still reads my gradient buffer
+    if (threadIdx.x == 0) ps.epoch[blockIdx.x] = epoch;
+  }
+}
+
+// column sums of W (pre-update) for the orthogonality regulariser: out[col] = sum_row w[row, col]
+__global__ void col_sums_k(const float* __restrict__ w, float* __restrict__ out, int rows, int cols,
+                           int transposed) {
+  // logical matrix [rows=Y][cols=H]; when transposed the storage is [H][Y]
+  int col = blockIdx.x * blockDim.y + threadIdx.y;
+  if (col >= cols) return;
+  float s = 0.f;
+  for (int r = threadIdx.x; r < rows; r += 32)
+    s += transposed ? w[(size_t)col * rows + r] : w[(size_t)r * cols + col];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) out[col] = s;
+}
+
+// shadow refresh without an update step (initialisation, rollback, weights from a snapshot)
+__global__ void refresh_shadows_k(const float* __restrict__ w, long long size, int rows, int cols,
+                                  ShadowSpec sh) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < size; i += stride) {
+    float wv = w[i];
+    int r = (int)(i / cols), c = (int)(i % cols);
+    if (sh.lp) sh.lp[(size_t)r * sh.ld + c] = __float2bfloat16_rn(wv);
+    if (sh.lp_conv) {
+      int tap = c / sh.C, ch = c % sh.C;
+      sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
+    }
+  }
+}
+
+int fused_update_blocks(long long size) {
+  long long b = (size + 1023) / 1024;   // >= 4 elements per thread
+  if (b < 1) b = 1;
+  if (b > 148) b = 148;
+  return (int)b;
+}
+
+void launch_fused_update(float* w, const float* const* grad_ptrs, int nranks, int nparts,
+                         long long part_stride, float* grad_out, float* acc, float* vel,
+                         const float* hyper, const float* col_sums, int flags, int is_bias,
+                         long long size, int rows, int cols, __nv_bfloat16* lp, int ld,
+                         __nv_bfloat16* lp_conv, int taps, int C, int c_pad,
+                         uint32_t* const* peer_flags, uint32_t* epoch, int rank, int blocks,
+                         cudaStream_t st) {
+  GradSources gs{};
+  for (int r = 0; r < nranks; ++r) gs.ptr[r] = grad_ptrs[r];
+  gs.nranks = nranks; gs.nparts = nparts; gs.part_stride = part_stride;
+  ShadowSpec sh{lp, ld, lp_conv, taps, C, c_pad};
+  PeerSync ps{};
+  ps.rank = rank; ps.nranks = nranks; ps.epoch = epoch;
+  if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
+  if (blocks <= 0) blocks = fused_update_blocks(size);
+  if (peer_flags && nranks > 1)
+    fused_update_k<true><<<blocks, 256, 0, st>>>(w, gs, grad_out, acc, vel, hyper, col_sums, flags,
+                                                  is_bias, size, rows, cols, sh, ps);
+  else
+    fused_update_k<false><<<blocks, 256, 0, st>>>(w, gs, grad_out, acc, vel, hyper, col_sums, flags,
+                                                   is_bias, size, rows, cols, sh, ps);
+}
+void launch_col_sums(const float* w, float* out, int rows, int cols, int transposed, cudaStream_t st) {
+  dim3 block(32, 8);
+  col_sums_k<<<(cols + 7) / 8, block, 0, st>>>(w, out, rows, cols, transposed);
+}
+void launch_refresh_shadows(const float* w, long long size, int rows, int cols, __nv_bfloat16* lp, int ld,
+                            __nv_bfloat16* lp_conv, int taps, int C, int c_pad, cudaStream_t st) {
+  ShadowSpec sh{lp, ld, lp_conv, taps, C, c_pad};
+  long long b = (size + 255) / 256; if (b > 592) b = 592; if (b < 1) b = 1;
+  refresh_shadows_k<<<(int)b, 256, 0, st>>>(w, size, rows, cols, sh);
+}
+
+}  // namespace zn

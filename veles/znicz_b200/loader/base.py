@@ -333,7 +333,7 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
                     tmp = torch.empty(pin.shape, dtype=pin.dtype, device=dst.device)
                     self.__dict__["_stage_%d_" % id(a)] = tmp
                 tmp.copy_(pin, non_blocking=True)
-                dst.copy_(tmp)
+                self.device.ext.cast_copy(tmp, dst)
             else:
                 dst.copy_(pin, non_blocking=True)
             a.dev_written()

@@ -52,6 +52,9 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         shape = (self.max_minibatch_size,) + tuple(self.original_data.shape[1:])
         if not self.minibatch_data or self.minibatch_data.shape != shape:
             self.minibatch_data.reset(numpy.zeros(shape, dtype=self.dtype))
+        if self.on_cuda:
+            from ..ops.nn_units import torch_act_dtype
+            self.minibatch_data.dev_dtype = torch_act_dtype()
         if self.has_labels and (
                 not self.minibatch_labels or
                 self.minibatch_labels.shape[0] != self.max_minibatch_size):
@@ -156,6 +159,9 @@ class FullBatchLoaderMSE(FullBatchLoader, LoaderMSEMixin):
         shape = (self.max_minibatch_size,) + tuple(self.original_targets.shape[1:])
         if not self.minibatch_targets or self.minibatch_targets.shape != shape:
             self.minibatch_targets.reset(numpy.zeros(shape, dtype=self.dtype))
+        if self.on_cuda:
+            from ..ops.nn_units import torch_act_dtype
+            self.minibatch_targets.dev_dtype = torch_act_dtype()
         self.targets_shape = tuple(self.original_targets.shape[1:])
 
     def analyze_dataset(self):

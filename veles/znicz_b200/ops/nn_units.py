@@ -402,6 +402,9 @@ class GradientDescentBase(AcceleratedUnit, metaclass=MatchingObject):
         self.hyper_dev_.copy_(self.hyper_host_, non_blocking=True)
         self.hyper_cache_ = vals
 
+    def cuda_prepare(self):
+        self.sync_hyper()
+
     def update_flags(self, for_bias=False):
         """Bit flags understood by the fused update kernel."""
         moment_arr = self.gradient_bias_with_moment if for_bias \

@@ -74,6 +74,9 @@ class EvaluatorBase(AcceleratedUnit, TriviallyDistributable,
             return None
         if not self.err_output or self.err_output.shape != self.output.shape:
             self.err_output.reset(numpy.zeros(self.output.shape, dtype))
+        if self.on_cuda:
+            from ..ops.nn_units import torch_act_dtype
+            self.err_output.dev_dtype = torch_act_dtype()
         self.init_vectors(self.output, self.err_output)
         return None
 
