@@ -23,8 +23,21 @@ class Device(object):
         return "<%s>" % type(self).__name__
 
 
+def _restore_device(backend):
+    """Unpickle hook: devices are process-local; re-acquire by backend name."""
+    if backend == "cuda":
+        try:
+            return get_device("cuda")
+        except Exception:
+            return NumpyDevice()
+    return NumpyDevice()
+
+
 class NumpyDevice(Device):
     backend_name = "numpy"
+
+    def __reduce__(self):
+        return (_restore_device, ("numpy",))
 
     def alloc_like(self, mem, dev_dtype=None):
         return None
@@ -56,6 +69,9 @@ class CUDADevice(Device):
         self.stream = torch.cuda.current_stream(self.torch_device)
         self.side_stream = torch.cuda.Stream(self.torch_device)
         self.copy_stream = torch.cuda.Stream(self.torch_device)
+
+    def __reduce__(self):
+        return (_restore_device, ("cuda",))
 
     def alloc_like(self, mem, dev_dtype=None):
         import torch

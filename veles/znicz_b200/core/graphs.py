@@ -42,7 +42,12 @@ def recorder():
 
 
 class _Captured(object):
-    __slots__ = ("graph", "reads", "writes")
+    __slots__ = ("graph", "reads", "writes", "n_kernels")
+
+
+def _launch_counters():
+    from ..kernels import api
+    return api.counters
 
 
 class GraphSegment(object):
@@ -90,6 +95,7 @@ class GraphSegment(object):
             for a in cap.writes:
                 a._state = _memory._UNMAPPED
             self.replays += 1
+            _launch_counters()["launches"] += cap.n_kernels
             return
         n = self._runs.get(key, 0)
         self._runs[key] = n + 1
@@ -98,6 +104,8 @@ class GraphSegment(object):
             return
         # capture
         rec = _Recorder()
+        counters = _launch_counters()
+        n0 = counters["launches"]
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         _active_recorder = rec
@@ -112,6 +120,7 @@ class GraphSegment(object):
         cap.graph = g
         cap.reads = rec.reads
         cap.writes = rec.writes
+        cap.n_kernels = counters["launches"] - n0
         self._graphs[key] = cap
         g.replay()   # the capture pass did not execute anything
         for a in cap.writes:

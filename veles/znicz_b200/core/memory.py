@@ -243,9 +243,28 @@ class Array(object):
         return self
 
     def _upload(self):
+        """Host → device through a persistent pinned staging buffer (asynchronous w.r.t.
+        the host, so run-ahead of the launch queue is preserved; the staging buffer is
+        only rewritten after the previous copy out of it has completed)."""
         import torch
         src = torch.from_numpy(self._mem)
-        self._devmem_.copy_(src)  # converts dtype if needed; sync w.r.t. host buffer
+        pin = self.__dict__.get("_pin_")
+        if pin is None or pin.shape != src.shape or pin.dtype != src.dtype:
+            if src.numel() * src.element_size() > (64 << 20):
+                self._devmem_.copy_(src)      # huge one-off uploads: plain copy
+                return
+            pin = torch.empty(src.shape, dtype=src.dtype).pin_memory()
+            self.__dict__["_pin_"] = pin
+            self.__dict__["_pin_evt_"] = torch.cuda.Event()
+        else:
+            self.__dict__["_pin_evt_"].synchronize()
+        pin.copy_(src)
+        dev = self._devmem_
+        if dev.dtype != pin.dtype:
+            dev.copy_(pin.to(dev.device, non_blocking=True))
+        else:
+            dev.copy_(pin, non_blocking=True)
+        self.__dict__["_pin_evt_"].record()
 
     def _download(self):
         import torch

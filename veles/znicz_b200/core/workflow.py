@@ -93,6 +93,7 @@ class Workflow(Unit):
         super().init_unpickled()
         self._queue_ = None
         self._restored_from_snapshot_ = None
+        self.step_hooks_ = []
 
     # -- container ------------------------------------------------------------
     def add_ref(self, unit):
@@ -189,13 +190,18 @@ class Workflow(Unit):
         self._is_initialized = True
         return None
 
-    def run(self):
-        """Run until the EndPoint fires (or ``stop()``)."""
+    def run(self, iterations=None):
+        """Run until the EndPoint fires (or ``stop()``). With ``iterations=K`` the loop
+        is paused after exactly K passes of the Repeater cycle (K minibatches); calling
+        ``run`` again continues with the next minibatch. ``step_hooks_`` (callables taking
+        the workflow) are invoked after every completed pass."""
         self._finished <<= False
         self._stopped = False
         self._run_started = time.time()
         q = collections.deque()
         self._queue_ = q
+        hooks = self.step_hooks_
+        count = 0
         try:
             sp = self.start_point
             sp._is_initialized = True
@@ -205,10 +211,17 @@ class Workflow(Unit):
             pop = q.popleft
             while q and not fin._value:
                 src, dst = pop()
+                if src is not sp and type(dst) is Repeater:
+                    count += 1
+                    for h in hooks:
+                        h(self)
+                    if iterations is not None and count >= iterations:
+                        break
                 dst._check_gate_and_run(src)
         finally:
             self._queue_ = None
         self._run_time += time.time() - self._run_started
+        return count
 
     def _check_gate_and_run(self, src):
         # nested workflow used as a unit

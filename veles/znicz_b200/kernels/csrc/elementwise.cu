@@ -58,6 +58,46 @@ __global__ void err_act_colsum_k(T* __restrict__ err_y, const T* __restrict__ y,
   }
 }
 
+// Vectorised variant for cols % 8 == 0: 256 threads = (256/groups) row lanes x groups of 8
+// columns; 16-byte loads/stores; per-block partial sums -> partial[blockIdx.x][cols].
+template <typename T>
+__global__ void __launch_bounds__(256) err_act_colsum_vec_k(T* __restrict__ err_y, const T* __restrict__ y,
+                                                         int rows, int cols, int act,
+                                                         float* __restrict__ partial) {
+  __shared__ float red[256][9];
+  const int groups = cols >> 3;                 // <= 256
+  const int lanes = 256 / groups;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (lane < lanes) {
+    for (int r = blockIdx.x * lanes + lane; r < rows; r += gridDim.x * lanes) {
+      size_t o = (size_t)r * cols + g * 8;
+      float e[8];
+      ld8(err_y + o, e);
+      if (act != ACT_LINEAR) {
+        float yv[8];
+        ld8(y + o, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] *= act_deriv(act, 0.f, yv[j]);
+        st8(err_y + o, e);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += e[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (partial && threadIdx.x < cols) {
+    const int c = threadIdx.x, gg = c >> 3, j = c & 7;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * groups + gg][j];
+    partial[(size_t)blockIdx.x * cols + c] = s;
+  }
+}
+
 template <typename T>
 __global__ void dropout_forward_k(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ mask,
                                   long long n, const int* __restrict__ rng, uint32_t threshold,
@@ -161,6 +201,29 @@ __global__ void gather_labels_k(const int* __restrict__ src, const int* __restri
   if (i < max_rows) dst[i] = i < count ? src[idx[i]] : -1;
 }
 
+// hdr = [count, class, epoch, pad, idx0, idx1, ...]; dst rows >= count are zero / label -1
+template <typename TS, typename TD>
+__global__ void gather_minibatch_k(const TS* __restrict__ src, const int* __restrict__ labels_src,
+                                   const int* __restrict__ hdr, TD* __restrict__ dst,
+                                   int* __restrict__ labels_dst, int max_rows, int row8) {
+  const int count = hdr[0];
+  const int* idx = hdr + 4;
+  const int total = max_rows * row8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / row8, c = i - r * row8;
+    float v[8];
+    if (r < count) {
+      ld8(src + ((size_t)idx[r] * row8 + c) * 8, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    st8(dst + (size_t)i * 8, v);
+  }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (labels_dst && t < max_rows) labels_dst[t] = t < count ? labels_src[idx[t]] : -1;
+}
+
 template <typename T>
 __global__ void mask_mul_k(T* __restrict__ w, const T* __restrict__ mask, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,9 +266,15 @@ void launch_act_backward(const void* ey, const void* x, const void* y, void* ex,
   DISPATCH_T(bf16, act_backward_k<T><<<grid_for(n), 256, 0, st>>>(
       (const T*)ey, (const T*)x, (const T*)y, (T*)ex, n, act, factor));
 }
-int err_act_colsum_slices(int rows) { int s = (rows + 63) / 64; return s < 1 ? 1 : (s > 64 ? 64 : s); }
+int err_act_colsum_slices(int rows) { int s = (rows + 63) / 64; return s < 1 ? 1 : (s > 128 ? 128 : s); }
 void launch_err_act_colsum(void* err_y, const void* y, int rows, int cols, int act, float* partial,
                            int slices, bool bf16, cudaStream_t st) {
+  if (cols % 8 == 0 && cols <= 256 && (((uintptr_t)err_y) & 15) == 0 &&
+      (y == nullptr || (((uintptr_t)y) & 15) == 0)) {
+    DISPATCH_T(bf16, err_act_colsum_vec_k<T><<<slices, 256, 0, st>>>((T*)err_y, (const T*)y, rows,
+                                                                       cols, act, partial));
+    return;
+  }
   dim3 grid((cols + 31) / 32, slices), block(32, 8);
   DISPATCH_T(bf16, err_act_colsum_k<T><<<grid, block, 0, st>>>((T*)err_y, (const T*)y, rows, cols, act,
                                                               partial));
@@ -244,6 +313,17 @@ void launch_gather_rows(const void* src, bool src_bf16, const int* idx, void* ds
   else if (!src_bf16 && dst_bf16) gather_rows_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
   else if (src_bf16 && dst_bf16) gather_rows_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
   else gather_rows_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (float*)dst, count, max_rows, row);
+}
+void launch_gather_minibatch(const void* src, bool src_bf16, const int* labels_src, const int* hdr,
+                             void* dst, bool dst_bf16, int* labels_dst, int max_rows, long long row,
+                             cudaStream_t st) {
+  int row8 = (int)(row / 8);
+  int g = grid_for((long long)max_rows * row8);
+  if (g * 256 < max_rows) g = (max_rows + 255) / 256;
+  if (!src_bf16 && dst_bf16) gather_minibatch_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8);
+  else if (!src_bf16) gather_minibatch_k<float, float><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8);
+  else if (dst_bf16) gather_minibatch_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8);
+  else gather_minibatch_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8);
 }
 void launch_gather_labels(const int* src, const int* idx, int* dst, int count, int max_rows,
                           cudaStream_t st) {

@@ -18,6 +18,7 @@ void launch_axpby_2d(const void*, int, int, void*, int, int, int, int, float, fl
 void launch_crop_nhwc(const void*, void*, int, int, int, int, int, int, int, int, int, bool, cudaStream_t);
 void launch_gather_rows(const void*, bool, const int*, void*, bool, int, int, long long, cudaStream_t);
 void launch_gather_labels(const int*, const int*, int*, int, int, cudaStream_t);
+void launch_gather_minibatch(const void*, bool, const int*, const int*, void*, bool, int*, int, long long, cudaStream_t);
 void launch_mask_mul(void*, const void*, long long, bool, cudaStream_t);
 void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
 void launch_scatter_offsets(const void*, const int*, void*, long long, bool, cudaStream_t);
@@ -150,6 +151,17 @@ void gather_rows(Tensor src, Tensor idx, Tensor dst, int64_t count) {
 void gather_labels(Tensor src, Tensor idx, Tensor dst, int64_t count) {
   zn::launch_gather_labels(src.data_ptr<int>(), idx.data_ptr<int>(), dst.data_ptr<int>(), (int)count,
                            (int)dst.size(0), cur());
+  kcheck();
+}
+void gather_minibatch(Tensor src, c10::optional<Tensor> labels_src, Tensor hdr, Tensor dst,
+                      c10::optional<Tensor> labels_dst) {
+  chk(src, "src"); chk(dst, "dst");
+  long long row = src.numel() / src.size(0);
+  TORCH_CHECK(row % 8 == 0, "gather_minibatch needs row % 8 == 0");
+  const int* ls = (labels_src.has_value() && labels_src->defined()) ? labels_src->data_ptr<int>() : nullptr;
+  int* ld = (labels_dst.has_value() && labels_dst->defined()) ? labels_dst->data_ptr<int>() : nullptr;
+  zn::launch_gather_minibatch(src.data_ptr(), is_bf16(src), ls, hdr.data_ptr<int>(), dst.data_ptr(),
+                              is_bf16(dst), ld, (int)dst.size(0), row, cur());
   kcheck();
 }
 void mask_mul(Tensor w, Tensor mask) {
@@ -376,6 +388,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_forward", &dropout_forward); m.def("binary_op", &binary_op);
   m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
+  m.def("gather_minibatch", &gather_minibatch);
   m.def("mask_mul", &mask_mul); m.def("cast_copy", &cast_copy); m.def("scatter_offsets", &scatter_offsets);
   m.def("pool_forward", &pool_forward); m.def("pool_backward", &pool_backward);
   m.def("lrn_forward", &lrn_forward); m.def("lrn_backward", &lrn_backward);

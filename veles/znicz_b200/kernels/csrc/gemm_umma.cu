@@ -123,8 +123,13 @@ __host__ __device__ constexpr int b_bytes() {
   return B_MODE == B_TMA_K ? BLOCK_N * 128 : ((BLOCK_N + 63) / 64) * 8192;
 }
 
+template <int BLOCK_N, int B_MODE>
+__host__ __device__ constexpr int min_ctas() {
+  return (2 * (STAGES * (A_BYTES + b_bytes<BLOCK_N, B_MODE>()) + 2048) <= 227 * 1024) ? 2 : 1;
+}
+
 template <int BLOCK_N, int A_MODE, int B_MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (min_ctas<BLOCK_N, B_MODE>()))
 gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
   constexpr int B_BYTES = b_bytes<BLOCK_N, B_MODE>();
@@ -230,42 +235,56 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int m = m0 + t;
         PixCtx ctx = (p.gather_kind == G_IM2COL) ? decode_out_pixel(p.g, m, p.M)
                                                  : decode_in_pixel(p.g, m, p.M);
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+        uint4 v[8];
+        auto load_k = [&](int i, uint4 (&dst)[8]) {
           const int k0 = (kb_begin + i) * BLOCK_K;
-          uint4 v[8];
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
-            v[c8] = (p.gather_kind == G_IM2COL)
-                        ? im2col_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK)
-                        : dgrad_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK);
+            dst[c8] = (p.gather_kind == G_IM2COL)
+                          ? im2col_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK)
+                          : dgrad_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK);
+        };
+        if (num_kb > 0) load_k(0, v);
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+          uint4 nv[8];
+          if (i + 1 < num_kb) load_k(i + 1, nv);      // issue the next stage's loads early
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
             *reinterpret_cast<uint4*>(sa + t * 128 + ((c8 ^ (t & 7)) << 4)) = v[c8];
           fence_proxy_async_smem();
           mbar_arrive(&full_bar[s]);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) v[c8] = nv[c8];
         }
       } else {
         // A_GATHER_MN (conv wgrad): tile = [64 reduction rows (pixels)][128 m (kidx)];
         // thread -> reduction row kr = t % 64, 64-wide m block = t / 64 (8 chunks of 8 kidx)
         const int kr = t & 63, mblk = t >> 6;
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+        uint4 v[8];
+        auto load_mn = [&](int i, uint4 (&dst)[8]) {
           const int pix = (kb_begin + i) * BLOCK_K + kr;
           PixCtx ctx = decode_out_pixel(p.g, pix, p.K);
-          uint4 v[8];
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
-            v[c8] = im2col_chunk(p.gsrc, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
+            dst[c8] = im2col_chunk(p.gsrc, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
+        };
+        if (num_kb > 0) load_mn(0, v);
+        for (int i = 0; i < num_kb; ++i) {
+          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+          uint4 nv[8];
+          if (i + 1 < num_kb) load_mn(i + 1, nv);
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
             *reinterpret_cast<uint4*>(sa + mblk * 8192 + kr * 128 + ((c8 ^ (kr & 7)) << 4)) = v[c8];
           fence_proxy_async_smem();
           mbar_arrive(&full_bar[s]);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) v[c8] = nv[c8];
         }
       }
     }

@@ -129,11 +129,163 @@ __global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict
   stf(err_in + i, s);
 }
 
+
+// ------------------------------------------------------------------ vectorised (C % 8 == 0)
+// thread = (output pixel, group of 8 channels): 16-byte loads, 32-bit index math.
+template <typename T>
+__global__ void pool_forward_vec_k(const T* __restrict__ in, T* __restrict__ out, int* __restrict__ offs,
+                                   PoolGeom g, int mode) {
+  const int C8 = g.C >> 3;
+  const int total = g.N * g.OH * g.OW * C8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = i % C8; int t = i / C8;
+  const int ox = t % g.OW; t /= g.OW; const int oy = t % g.OH; const int n = t / g.OH;
+  const int y1 = oy * g.SY, x1 = ox * g.SX;
+  const int y2 = min(y1 + g.KY, g.H), x2 = min(x1 + g.KX, g.W);
+  const int img = n * g.H * g.W * g.C + cg * 8;
+  float best[8]; int boff[8]; float key[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { best[j] = 0.f; boff[j] = 0; key[j] = -3.0e38f; }
+  for (int y = y1; y < y2; ++y)
+    for (int x = x1; x < x2; ++x) {
+      const int o = img + (y * g.W + x) * g.C;
+      float v[8];
+      ld8(in + o, v);
+      if (mode == POOL_AVG) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] += v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float k = (mode == POOL_MAXABS) ? fabsf(v[j]) : v[j];
+          if (k > key[j]) { key[j] = k; best[j] = v[j]; boff[j] = o + j; }
+        }
+      }
+    }
+  if (mode == POOL_AVG) {
+    const float inv = 1.f / (float)((y2 - y1) * (x2 - x1));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] *= inv;
+  } else {
+    int4* po = reinterpret_cast<int4*>(offs + (size_t)i * 8);
+    po[0] = make_int4(boff[0], boff[1], boff[2], boff[3]);
+    po[1] = make_int4(boff[4], boff[5], boff[6], boff[7]);
+  }
+  st8(out + (size_t)i * 8, best);
+}
+
+template <typename T>
+__global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __restrict__ offs,
+                                    T* __restrict__ err_in, PoolGeom g, int is_avg) {
+  const int C8 = g.C >> 3;
+  const int total = g.N * g.H * g.W * C8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cg = i % C8; int t = i / C8;
+  const int x = t % g.W; t /= g.W; const int y = t % g.H; const int n = t / g.H;
+  const int oy_hi = min(y / g.SY, g.OH - 1), ox_hi = min(x / g.SX, g.OW - 1);
+  const int oy_lo = (y - g.KY + 1 <= 0) ? 0 : (y - g.KY + g.SY) / g.SY;
+  const int ox_lo = (x - g.KX + 1 <= 0) ? 0 : (x - g.KX + g.SX) / g.SX;
+  const int self = i * 8;     // flat element index of channel 0 of this group
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    const int hy = min(oy * g.SY + g.KY, g.H) - oy * g.SY;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const int o = (((n * g.OH + oy) * g.OW + ox) * C8 + cg) * 8;
+      float e[8];
+      ld8(err_out + o, e);
+      if (is_avg) {
+        const int hx = min(ox * g.SX + g.KX, g.W) - ox * g.SX;
+        const float inv = 1.f / (float)(hy * hx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += e[j] * inv;
+      } else {
+        const int4* po = reinterpret_cast<const int4*>(offs + o);
+        const int4 a = po[0], b = po[1];
+        const int of[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (of[j] == self + j) s[j] += e[j];
+      }
+    }
+  }
+  st8(err_in + (size_t)i * 8, s);
+}
+
+// LRN, thread = (pixel, 8-channel group); needs 2*half <= 8
+template <typename T, int half>
+__global__ void lrn_vec_k(const T* __restrict__ x, const T* __restrict__ ey, T* __restrict__ out,
+                          int pixels, int C, float alpha, float beta, float k, int backward) {
+  const int C8 = C >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pixels * C8) return;
+  const int cg = i % C8; const int pix = i / C8;
+  const T* px = x + (size_t)pix * C;
+  float xv[24], ev[24];
+#pragma unroll
+  for (int q = 0; q < 24; ++q) { xv[q] = 0.f; ev[q] = 0.f; }
+  // local window [cg*8 - 8, cg*8 + 16)
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const int c0 = (cg - 1 + b) * 8;
+    if (c0 >= 0 && c0 < C) {
+      float tmp[8];
+      ld8(px + c0, tmp);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[b * 8 + j] = tmp[j];
+      if (backward) {
+        ld8(ey + (size_t)pix * C + c0, tmp);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ev[b * 8 + j] = tmp[j];
+      }
+    }
+  }
+  // s[q] for local positions q in [8 - half, 16 + half): window clipped to [0, C) == zeros outside
+  float res[8];
+  if (!backward) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = -half; d <= half; ++d) { const float v = xv[8 + j + d]; s += v * v; }
+      res[j] = xv[8 + j] * __powf(k + alpha * s, -beta);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.f, si = 1.f;
+#pragma unroll
+      for (int d = -half; d <= half; ++d) {
+        const int q = 8 + j + d;
+        const int cabs = cg * 8 + j + d;
+        if (cabs < 0 || cabs >= C) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int d2 = -half; d2 <= half; ++d2) { const float v = xv[q + d2]; s += v * v; }
+        s = k + alpha * s;
+        if (d == 0) si = s;
+        acc += ev[q] * xv[q] * __powf(s, -beta - 1.f);
+      }
+      res[j] = ev[8 + j] * __powf(si, -beta) - 2.f * alpha * beta * xv[8 + j] * acc;
+    }
+  }
+  st8(out + (size_t)i * 8, res);
+}
+
 void launch_pool_forward(const void* in, void* out, int* offs, int N, int H, int W, int C, int OH, int OW,
                          int KY, int KX, int SY, int SX, int mode, const int* rng, bool bf16,
                          cudaStream_t st) {
   PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX};
   long long total = (long long)N * OH * OW * C;
+  if (mode <= POOL_AVG && C % 8 == 0 && (long long)N * H * W * C < (1LL << 31) &&
+      (((uintptr_t)in | (uintptr_t)out | (uintptr_t)offs) & 15) == 0) {
+    int gridv = cdiv(total / 8, 256);
+    if (bf16) pool_forward_vec_k<__nv_bfloat16><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, offs, g, mode);
+    else pool_forward_vec_k<float><<<gridv, 256, 0, st>>>((const float*)in, (float*)out, offs, g, mode);
+    return;
+  }
   int grid = cdiv(total, 256);
   if (bf16) pool_forward_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, offs, g, mode, rng);
   else pool_forward_k<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, offs, g, mode, rng);
@@ -143,6 +295,13 @@ void launch_pool_backward(const void* err_out, const int* offs, void* err_in, in
                           cudaStream_t st) {
   PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX};
   long long total = (long long)N * H * W * C;
+  if (C % 8 == 0 && total < (1LL << 31) &&
+      (((uintptr_t)err_out | (uintptr_t)err_in | (uintptr_t)offs) & 15) == 0) {
+    int gridv = cdiv(total / 8, 256);
+    if (bf16) pool_backward_vec_k<__nv_bfloat16><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, is_avg);
+    else pool_backward_vec_k<float><<<gridv, 256, 0, st>>>((const float*)err_out, offs, (float*)err_in, g, is_avg);
+    return;
+  }
   int grid = cdiv(total, 256);
   if (is_avg) {
     if (bf16) pool_backward_avg_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)err_out, (__nv_bfloat16*)err_in, g);
@@ -194,12 +353,36 @@ __global__ void lrn_backward_k(const T* __restrict__ ey, const T* __restrict__ x
 
 void launch_lrn_forward(const void* x, void* y, long long pixels, int C, int n, float alpha, float beta,
                         float k, bool bf16, cudaStream_t st) {
+  if (C % 8 == 0 && (n / 2 == 1 || n / 2 == 2) && pixels * C < (1LL << 31) &&
+      (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    int gridv = cdiv(pixels * C / 8, 256);
+    if (n / 2 == 1) {
+      if (bf16) lrn_vec_k<__nv_bfloat16, 1><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, (int)pixels, C, alpha, beta, k, 0);
+      else lrn_vec_k<float, 1><<<gridv, 256, 0, st>>>((const float*)x, nullptr, (float*)y, (int)pixels, C, alpha, beta, k, 0);
+    } else {
+      if (bf16) lrn_vec_k<__nv_bfloat16, 2><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, (int)pixels, C, alpha, beta, k, 0);
+      else lrn_vec_k<float, 2><<<gridv, 256, 0, st>>>((const float*)x, nullptr, (float*)y, (int)pixels, C, alpha, beta, k, 0);
+    }
+    return;
+  }
   int grid = cdiv(pixels * C, 256);
   if (bf16) lrn_forward_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, pixels, C, n / 2, alpha, beta, k);
   else lrn_forward_k<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, pixels, C, n / 2, alpha, beta, k);
 }
 void launch_lrn_backward(const void* ey, const void* x, void* eh, long long pixels, int C, int n,
                          float alpha, float beta, float k, bool bf16, cudaStream_t st) {
+  if (C % 8 == 0 && (n / 2 == 1 || n / 2 == 2) && pixels * C < (1LL << 31) &&
+      (((uintptr_t)x | (uintptr_t)ey | (uintptr_t)eh) & 15) == 0) {
+    int gridv = cdiv(pixels * C / 8, 256);
+    if (n / 2 == 1) {
+      if (bf16) lrn_vec_k<__nv_bfloat16, 1><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
+      else lrn_vec_k<float, 1><<<gridv, 256, 0, st>>>((const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
+    } else {
+      if (bf16) lrn_vec_k<__nv_bfloat16, 2><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
+      else lrn_vec_k<float, 2><<<gridv, 256, 0, st>>>((const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
+    }
+    return;
+  }
   int grid = cdiv(pixels * C, 256);
   if (bf16) lrn_backward_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)ey, (const __nv_bfloat16*)x, (__nv_bfloat16*)eh, pixels, C, n / 2, alpha, beta, k);
   else lrn_backward_k<float><<<grid, 256, 0, st>>>((const float*)ey, (const float*)x, (float*)eh, pixels, C, n / 2, alpha, beta, k);

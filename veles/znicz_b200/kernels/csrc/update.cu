@@ -93,9 +93,18 @@ __global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __r
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < size; i += stride) {
     float g = 0.f;
-    for (int r = 0; r < gs.nranks; ++r) {
+    for (int r = 0; r < gs.nranks; ++r) {        // fixed rank order => bit-identical replicas
       const float* base = gs.ptr[r] + i;
-      for (int p = 0; p < gs.nparts; ++p) g += base[(long long)p * gs.part_stride];
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+      int p = 0;
+      for (; p + 4 <= gs.nparts; p += 4) {       // 4 loads in flight per rank
+        g0 += base[(long long)(p + 0) * gs.part_stride];
+        g1 += base[(long long)(p + 1) * gs.part_stride];
+        g2 += base[(long long)(p + 2) * gs.part_stride];
+        g3 += base[(long long)(p + 3) * gs.part_stride];
+      }
+      for (; p < gs.nparts; ++p) g0 += base[(long long)p * gs.part_stride];
+      g += (g0 + g1) + (g2 + g3);
     }
     if (grad_out) grad_out[i] = g;
     float wv = w[i];
@@ -161,7 +170,7 @@ __global__ void refresh_shadows_k(const float* __restrict__ w, long long size, i
 }
 
 int fused_update_blocks(long long size) {
-  long long b = (size + 1023) / 1024;   // >= 4 elements per thread
+  long long b = (size + 255) / 256;     // one element per thread up to one CTA per SM
   if (b < 1) b = 1;
   if (b > 148) b = 148;
   return (int)b;

@@ -241,6 +241,27 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
                 not self.class_lengths[VALID] and not self.class_lengths[TEST]:
             raise LoaderError("class_length for TRAIN dataset is invalid")
 
+    def shard(self, rank, world):
+        """Data-parallel sharding: rank r keeps every world-th sample of each class
+        (equal shard sizes, remainder dropped) — the synchronous equivalent of the master
+        handing different minibatches to different slaves."""
+        if world <= 1:
+            return
+        self.shuffled_indices.map_read()
+        full = self.shuffled_indices.mem
+        parts, start = [], 0
+        for i in range(3):
+            n = self.class_lengths[i]
+            keep = (n // world)
+            parts.append(full[start:start + keep * world][rank::world][:keep])
+            start += n
+            self.class_lengths[i] = keep
+        self.shuffled_indices.reset(numpy.concatenate(parts).astype(numpy.int32))
+        self._update_total_samples()
+        self.global_offset = 0
+        self.dp_rank, self.dp_world = rank, world
+        self.prng = prng.RandomGenerator(seed=977 + rank)
+
     # -- serving --------------------------------------------------------------------
     def shuffle(self):
         if self.shuffle_limit <= 0 or self.class_lengths[TRAIN] == 0:
@@ -267,6 +288,8 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
     def run(self):
         if self.global_offset == 0 or self.global_offset >= self.total_samples:
             self.shuffle()  # epoch start: reshuffle the train part
+        if self.on_cuda:
+            self._cuda_begin_step()
         cls, start, count = self._advance()
         self.minibatch_class = cls
         self.minibatch_size = count
@@ -311,37 +334,53 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
                           self.minibatch_indices)
         # device header: [minibatch_size, minibatch_class, epoch_number, reserved]
         self.header_dev_ = torch.zeros(4, dtype=torch.int32, device=dev.torch_device)
-        self._pinned_ = {
-            "header": torch.zeros(4, dtype=torch.int32).pin_memory()}
+        hdr = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._pinned_ = {"header": hdr, "header_np": hdr.numpy(), "slot": 0,
+                         "events": [torch.cuda.Event(), torch.cuda.Event()], "bufs": {}}
+        # double-buffered pinned staging: the Arrays' host memory *is* the pinned buffer, so
+        # fill_minibatch gathers straight into DMA-able memory (no extra host copy)
         for a in self._staged_arrays():
             t = torch.from_numpy(a.mem)
-            self._pinned_[id(a)] = torch.empty_like(t).pin_memory()
+            pair = [torch.zeros_like(t).pin_memory(), torch.zeros_like(t).pin_memory()]
+            self._pinned_["bufs"][id(a)] = (a, pair, [p.numpy() for p in pair])
         self.h2d_bytes_per_step = sum(
             a.mem.nbytes for a in self._staged_arrays()) + 16
+
+    def _cuda_begin_step(self):
+        """Flip to the other pinned staging slot (waiting for its previous H2D copy)."""
+        pd = self._pinned_
+        slot = pd["slot"] ^ 1
+        pd["slot"] = slot
+        pd["events"][slot].synchronize()
+        for a, pair, views in pd["bufs"].values():
+            a._mem = views[slot]
 
     def _cuda_serve(self):
         """Copy this step's minibatch host→device from pinned memory (async on the
         compute stream so the captured step graph that follows sees the data)."""
         import torch
-        for a in self._staged_arrays():
-            pin = self._pinned_[id(a)]
-            pin.copy_(torch.from_numpy(a.mem))
+        pd = self._pinned_
+        slot = pd["slot"]
+        for a, pair, views in pd["bufs"].values():
+            pin = pair[slot]
             dst = a.devmem
             if dst.dtype != pin.dtype:
-                tmp = self.__dict__.setdefault("_stage_%d_" % id(a), None)
+                key = "_stage_%d_" % id(a)
+                tmp = self.__dict__.get(key)
                 if tmp is None:
                     tmp = torch.empty(pin.shape, dtype=pin.dtype, device=dst.device)
-                    self.__dict__["_stage_%d_" % id(a)] = tmp
+                    self.__dict__[key] = tmp
                 tmp.copy_(pin, non_blocking=True)
                 self.device.ext.cast_copy(tmp, dst)
             else:
                 dst.copy_(pin, non_blocking=True)
             a.dev_written()
-        hdr = self._pinned_["header"]
-        hdr[0] = self.minibatch_size
-        hdr[1] = self.minibatch_class
-        hdr[2] = self.epoch_number
-        self.header_dev_.copy_(hdr, non_blocking=True)
+        hn = pd["header_np"]
+        hn[0] = self.minibatch_size
+        hn[1] = self.minibatch_class
+        hn[2] = self.epoch_number
+        self.header_dev_.copy_(pd["header"], non_blocking=True)
+        pd["events"][slot].record()
 
     # -- IDistributable: the master serves indices, the slaves read the data --------------
     def generate_data_for_slave(self, slave=None):

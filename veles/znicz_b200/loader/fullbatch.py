@@ -104,44 +104,71 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         idx = self.minibatch_indices.mem[:n]
         self.minibatch_data.map_invalidate()
         md = self.minibatch_data.mem
-        numpy.take(self.original_data.mem, idx, axis=0, out=md[:n])
+        numpy.take(self.original_data.mem, idx, axis=0, out=md[:n], mode="clip")
         if n < md.shape[0]:
             md[n:] = 0
         if self.has_labels:
             self.minibatch_labels.map_invalidate()
             ml = self.minibatch_labels.mem
-            numpy.take(self._mapped_original_labels.mem, idx, out=ml[:n])
+            numpy.take(self._mapped_original_labels.mem, idx, out=ml[:n], mode="clip")
             ml[n:] = -1
 
     # -- device-resident dataset ---------------------------------------------------------
+    def fill_indices(self, start, count):
+        super().fill_indices(start, count)
+        # dataset in HBM: only the indices travel, the rows are gathered on the device
+        return bool(self.on_device and self.on_cuda)
+
     def _cuda_setup(self):
         super()._cuda_setup()
         if self.on_device:
+            import torch
+            # only header + indices are staged per step; data/labels stay in HBM
+            self._pinned_["bufs"] = {}
             self.original_data.initialize(self.device)
             if self.has_labels:
                 self._mapped_original_labels.initialize(self.device)
-            self.h2d_bytes_per_step = self.minibatch_indices.mem.nbytes + 16
+            n = 4 + self.max_minibatch_size
+            self._hdr_idx_dev_ = torch.zeros(n, dtype=torch.int32,
+                                             device=self.device.torch_device)
+            self.header_dev_ = self._hdr_idx_dev_[:4]
+            pins = [torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._pinned_["hdr_idx"] = pins
+            self._pinned_["hdr_idx_np"] = [p.numpy() for p in pins]
+            self.h2d_bytes_per_step = n * 4
+            row = self.original_data.size // self.original_data.shape[0]
+            self._fused_gather_ = (row % 8 == 0)
 
     def _cuda_serve(self):
         if not self.on_device:
             return super()._cuda_serve()
-        import torch
-        # only the indices (+header) cross PCIe; rows are gathered in HBM
-        self.minibatch_indices.unmap()
+        pd = self._pinned_
+        slot = pd["slot"]
+        n = int(self.minibatch_size)
+        hn = pd["hdr_idx_np"][slot]
+        hn[0] = n
+        hn[1] = self.minibatch_class
+        hn[2] = self.epoch_number
+        hn[4:4 + self.max_minibatch_size] = self.minibatch_indices.mem
+        self._hdr_idx_dev_.copy_(pd["hdr_idx"][slot], non_blocking=True)
+        pd["events"][slot].record()
         ext = self.device.ext
-        ext.gather_rows(self.original_data.devmem, self.minibatch_indices.devmem,
-                        self.minibatch_data.devmem, int(self.minibatch_size))
+        labels = self.has_labels
+        if self._fused_gather_:
+            ext.gather_minibatch(
+                self.original_data.devmem,
+                self._mapped_original_labels.devmem if labels else None,
+                self._hdr_idx_dev_, self.minibatch_data.devmem,
+                self.minibatch_labels.devmem if labels else None)
+        else:
+            idx = self._hdr_idx_dev_[4:]
+            ext.gather_rows(self.original_data.devmem, idx, self.minibatch_data.devmem, n)
+            if labels:
+                ext.gather_labels(self._mapped_original_labels.devmem, idx,
+                                  self.minibatch_labels.devmem, n)
         self.minibatch_data.dev_written()
-        if self.has_labels:
-            ext.gather_labels(self._mapped_original_labels.devmem,
-                              self.minibatch_indices.devmem,
-                              self.minibatch_labels.devmem, int(self.minibatch_size))
+        if labels:
             self.minibatch_labels.dev_written()
-        hdr = self._pinned_["header"]
-        hdr[0] = self.minibatch_size
-        hdr[1] = self.minibatch_class
-        hdr[2] = self.epoch_number
-        self.header_dev_.copy_(hdr, non_blocking=True)
 
 
 class FullBatchLoaderMSE(FullBatchLoader, LoaderMSEMixin):
@@ -184,7 +211,7 @@ class FullBatchLoaderMSE(FullBatchLoader, LoaderMSEMixin):
         idx = self.minibatch_indices.mem[:n]
         self.minibatch_targets.map_invalidate()
         mt = self.minibatch_targets.mem
-        numpy.take(self.original_targets.mem, idx, axis=0, out=mt[:n])
+        numpy.take(self.original_targets.mem, idx, axis=0, out=mt[:n], mode="clip")
         mt[n:] = 0
 
     def _staged_arrays(self):

@@ -206,7 +206,7 @@ class ForwardMul(ActivationForward):
         if self._factor is None:
             self.input.map_read()
             mx = float(numpy.fabs(self.input.mem).max())
-            dp = getattr(self, "dp", None)
+            dp = getattr(self, "dp_", None)
             self.factor = 0.75 / mx if mx else 0.75
             if dp is not None and dp.world_size > 1:
                 self.factor = dp.all_reduce_scalar(self.factor, "min")

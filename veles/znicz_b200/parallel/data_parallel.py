@@ -47,16 +47,12 @@ class DataParallel(object):
         and broadcast rank 0's initial weights so replicas start identical."""
         from ..ops.nn_units import GradientDescentBase, Forward
         loader = workflow.real_loader
-        loader.dp_rank = self.rank
-        loader.dp_world = self.world_size
+        loader.shard(self.rank, self.world_size)
         for u in workflow.units:
             if isinstance(u, GradientDescentBase):
                 u.dp_ = self
-            if hasattr(u, "dp") and not isinstance(u, type(workflow)):
-                try:
-                    u.dp = self
-                except AttributeError:
-                    pass
+            if "dp_" in u.__dict__ and u is not workflow:
+                u.dp_ = self
         self.broadcast_parameters(
             [u for u in workflow.forwards if isinstance(u, Forward)])
         if self.device is not None and self.device.is_cuda and self.mode == "fused":

@@ -68,11 +68,11 @@ class DecisionBase(Unit, metaclass=DecisionsRegistry):
         self.snapshot_suffix = ""
         self.demand("last_minibatch", "minibatch_class", "class_lengths",
                     "epoch_number", "epoch_ended")
-        self.dp = None   # parallel.DataParallel context (set by the workflow)
 
     def init_unpickled(self):
         super().init_unpickled()
         self.epoch_timestamp_ = False
+        self.dp_ = None   # parallel.DataParallel context (set by the workflow)
 
     @property
     def max_epochs(self):
@@ -284,7 +284,7 @@ class DecisionGD(DecisionBase):
         self.gd_skip <<= (self.minibatch_class != TRAIN)
 
     def _reduce_across_ranks(self):
-        dp = self.dp
+        dp = self.dp_
         if dp is None or dp.world_size == 1:
             return
         dp.reduce_metrics(n_err=self.minibatch_n_err,

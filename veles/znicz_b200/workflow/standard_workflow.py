@@ -67,12 +67,12 @@ class StandardWorkflow(StandardWorkflowBase):
         self.decision_name = kwargs.get("decision_name")
         self.evaluator_name = kwargs.get("evaluator_name")
         self.use_graphs = kwargs.get("use_graphs", root.common.engine.get("graphs", True))
-        self.dp = None
         self.create_workflow()
 
     def init_unpickled(self):
         super().init_unpickled()
         self.segments_ = []
+        self.dp_ = None
 
     # -- names ---------------------------------------------------------------------------------
     @property
@@ -568,9 +568,9 @@ class StandardWorkflow(StandardWorkflowBase):
         dev = self.device
         if dev is not None and dev.is_cuda:
             from ..parallel import DataParallel
-            self.dp = DataParallel.from_env(dev)
-            if self.dp is not None:
-                self.dp.attach(self)
+            self.dp_ = DataParallel.from_env(dev)
+            if self.dp_ is not None:
+                self.dp_.attach(self)
             if self.use_graphs:
                 self._build_segments()
         return res
