@@ -53,68 +53,75 @@ struct GemmParams {
 };
 
 // ---- gather: 8 consecutive "inner" indices of one "pixel" -> 16 bytes ------------------------
-struct PixCtx { int n, y, x, valid; };
+// All div/mod of the reduction index is hoisted into a per-CTA shared-memory table built once:
+// vec mode   : ktab[k / 8] = (ky << 24) | (kx << 16) | c0     (16-byte chunks never straddle a tap)
+// scalar mode: ktab[k]     = (ky << 24) | (kx << 16) | c
+constexpr int KTAB = 2048;
 
-__device__ __forceinline__ PixCtx decode_out_pixel(const ConvGeomU& g, int pix, int limit) {
+struct PixCtx { const __nv_bfloat16* base; int y, x, valid; };
+
+__device__ __forceinline__ PixCtx decode_out_pixel(const __nv_bfloat16* src, const ConvGeomU& g,
+                                                   int pix, int limit) {
+  // im2col source = x [N,H,W,C]; (y, x) = top-left input coordinate of the patch
   PixCtx c; c.valid = pix < limit;
-  int p = c.valid ? pix : 0;
-  c.x = p % g.OW; int t = p / g.OW; c.y = t % g.OH; c.n = t / g.OH;
+  const int p = c.valid ? pix : 0;
+  const int ox = p % g.OW; const int t = p / g.OW; const int oy = t % g.OH; const int n = t / g.OH;
+  c.y = oy * g.SY - g.PT; c.x = ox * g.SX - g.PL;
+  c.base = src + (long long)n * g.H * g.W * g.C;
   return c;
 }
-__device__ __forceinline__ PixCtx decode_in_pixel(const ConvGeomU& g, int pix, int limit) {
+__device__ __forceinline__ PixCtx decode_in_pixel(const __nv_bfloat16* src, const ConvGeomU& g,
+                                                  int pix, int limit) {
+  // dgrad source = err_out [N,OH,OW,F]; (y, x) = input pixel + padding
   PixCtx c; c.valid = pix < limit;
-  int p = c.valid ? pix : 0;
-  c.x = p % g.W; int t = p / g.W; c.y = t % g.H; c.n = t / g.H;
+  const int p = c.valid ? pix : 0;
+  const int ix = p % g.W; const int t = p / g.W; const int iy = t % g.H; const int n = t / g.H;
+  c.y = iy + g.PT; c.x = ix + g.PL;
+  c.base = src + (long long)n * g.OH * g.OW * g.F;
   return c;
 }
-__device__ __forceinline__ float im2col_elem(const __nv_bfloat16* x, const ConvGeomU& g,
-                                             const PixCtx& c, int kidx, int klimit) {
-  if (!c.valid || kidx >= klimit) return 0.f;
-  int ch = kidx % g.C; int tap = kidx / g.C; int kx = tap % g.KX; int ky = tap / g.KX;
-  int iy = c.y * g.SY - g.PT + ky, ix = c.x * g.SX - g.PL + kx;
-  if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return 0.f;
-  return __bfloat162float(x[(((long long)c.n * g.H + iy) * g.W + ix) * g.C + ch]);
-}
-__device__ __forceinline__ uint4 im2col_chunk(const __nv_bfloat16* x, const ConvGeomU& g,
-                                              const PixCtx& c, int kidx0, int klimit) {
-  uint4 z = make_uint4(0, 0, 0, 0);
-  if (!c.valid || kidx0 >= klimit) return z;
-  if (g.vec) {
-    int ch = kidx0 % g.C; int tap = kidx0 / g.C; int kx = tap % g.KX; int ky = tap / g.KX;
-    int iy = c.y * g.SY - g.PT + ky, ix = c.x * g.SX - g.PL + kx;
-    if (iy < 0 || iy >= g.H || ix < 0 || ix >= g.W) return z;
-    return *reinterpret_cast<const uint4*>(x + (((long long)c.n * g.H + iy) * g.W + ix) * g.C + ch);
+__device__ __forceinline__ void build_ktab(int* ktab, const ConvGeomU& g, int kind, int klimit) {
+  const int inner = (kind == 1) ? g.C : g.F;      // G_IM2COL : G_DGRAD
+  const int step = g.vec ? 8 : 1;
+  const int n = min(KTAB, (klimit + step - 1) / step);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int k = e * step;
+    const int c = k % inner; const int tap = k / inner;
+    const int kx = tap % g.KX; const int ky = tap / g.KX;
+    ktab[e] = (ky << 24) | (kx << 16) | c;
   }
-  __nv_bfloat16 v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(im2col_elem(x, g, c, kidx0 + j, klimit));
-  return *reinterpret_cast<uint4*>(v);
 }
-__device__ __forceinline__ float dgrad_elem(const __nv_bfloat16* e, const ConvGeomU& g,
-                                            const PixCtx& c, int k, int klimit) {
-  if (!c.valid || k >= klimit) return 0.f;
-  int f = k % g.F; int tap = k / g.F; int kx = tap % g.KX; int ky = tap / g.KX;
-  int ty = c.y + g.PT - ky, tx = c.x + g.PL - kx;
-  if (ty < 0 || tx < 0 || (ty % g.SY) || (tx % g.SX)) return 0.f;
-  int oy = ty / g.SY, ox = tx / g.SX;
-  if (oy >= g.OH || ox >= g.OW) return 0.f;
-  return __bfloat162float(e[(((long long)c.n * g.OH + oy) * g.OW + ox) * g.F + f]);
+__device__ __forceinline__ const __nv_bfloat16* im2col_addr(const ConvGeomU& g, const PixCtx& c, int e) {
+  const int iy = c.y + (e >> 24), ix = c.x + ((e >> 16) & 0xff);
+  if ((unsigned)iy >= (unsigned)g.H || (unsigned)ix >= (unsigned)g.W) return nullptr;
+  return c.base + (iy * g.W + ix) * g.C + (e & 0xffff);
 }
-__device__ __forceinline__ uint4 dgrad_chunk(const __nv_bfloat16* e, const ConvGeomU& g,
-                                             const PixCtx& c, int k0, int klimit) {
+__device__ __forceinline__ const __nv_bfloat16* dgrad_addr(const ConvGeomU& g, const PixCtx& c, int e) {
+  int ty = c.y - (e >> 24), tx = c.x - ((e >> 16) & 0xff);
+  if (g.SY != 1 || g.SX != 1) {
+    if (ty < 0 || tx < 0 || (ty % g.SY) || (tx % g.SX)) return nullptr;
+    ty /= g.SY; tx /= g.SX;
+  }
+  if ((unsigned)ty >= (unsigned)g.OH || (unsigned)tx >= (unsigned)g.OW) return nullptr;
+  return c.base + (ty * g.OW + tx) * g.F + (e & 0xffff);
+}
+template <int KIND>
+__device__ __forceinline__ uint4 gather_chunk(const int* ktab, const ConvGeomU& g, const PixCtx& c,
+                                              int k0, int klimit) {
   uint4 z = make_uint4(0, 0, 0, 0);
   if (!c.valid || k0 >= klimit) return z;
   if (g.vec) {
-    int f = k0 % g.F; int tap = k0 / g.F; int kx = tap % g.KX; int ky = tap / g.KX;
-    int ty = c.y + g.PT - ky, tx = c.x + g.PL - kx;
-    if (ty < 0 || tx < 0 || (ty % g.SY) || (tx % g.SX)) return z;
-    int oy = ty / g.SY, ox = tx / g.SX;
-    if (oy >= g.OH || ox >= g.OW) return z;
-    return *reinterpret_cast<const uint4*>(e + (((long long)c.n * g.OH + oy) * g.OW + ox) * g.F + f);
+    const __nv_bfloat16* p = (KIND == 1) ? im2col_addr(g, c, ktab[k0 >> 3]) : dgrad_addr(g, c, ktab[k0 >> 3]);
+    return p ? *reinterpret_cast<const uint4*>(p) : z;
   }
   __nv_bfloat16 v[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(dgrad_elem(e, g, c, k0 + j, klimit));
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j;
+    const __nv_bfloat16* p = nullptr;
+    if (k < klimit) p = (KIND == 1) ? im2col_addr(g, c, ktab[k]) : dgrad_addr(g, c, ktab[k]);
+    v[j] = p ? *p : __float2bfloat16_rn(0.f);
+  }
   return *reinterpret_cast<uint4*>(v);
 }
 
@@ -146,6 +153,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ int ktab[A_GATHER ? KTAB : 1];
 
   // 1024-byte aligned tile area (SWIZZLE_128B atoms are 1024 B)
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
@@ -174,6 +182,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tmem_alloc(&tmem_base_smem, TMEM_COLS);
     tmem_relinquish();
   }
+  if (A_GATHER) build_ktab(ktab, p.g, p.gather_kind, p.gK);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -233,16 +242,16 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (A_MODE == A_GATHER_K) {
         // tile row r = t is GEMM row m0 + t (a pixel); chunks run over the reduction index
         const int m = m0 + t;
-        PixCtx ctx = (p.gather_kind == G_IM2COL) ? decode_out_pixel(p.g, m, p.M)
-                                                 : decode_in_pixel(p.g, m, p.M);
+        const PixCtx ctx = (p.gather_kind == G_IM2COL) ? decode_out_pixel(p.gsrc, p.g, m, p.M)
+                                                       : decode_in_pixel(p.gsrc, p.g, m, p.M);
         uint4 v[8];
         auto load_k = [&](int i, uint4 (&dst)[8]) {
           const int k0 = (kb_begin + i) * BLOCK_K;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
             dst[c8] = (p.gather_kind == G_IM2COL)
-                          ? im2col_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK)
-                          : dgrad_chunk(p.gsrc, p.g, ctx, k0 + c8 * 8, p.gK);
+                          ? gather_chunk<G_IM2COL>(ktab, p.g, ctx, k0 + c8 * 8, p.gK)
+                          : gather_chunk<G_DGRAD>(ktab, p.g, ctx, k0 + c8 * 8, p.gK);
         };
         if (num_kb > 0) load_k(0, v);
         for (int i = 0; i < num_kb; ++i) {
@@ -266,10 +275,10 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         uint4 v[8];
         auto load_mn = [&](int i, uint4 (&dst)[8]) {
           const int pix = (kb_begin + i) * BLOCK_K + kr;
-          PixCtx ctx = decode_out_pixel(p.g, pix, p.K);
+          const PixCtx ctx = decode_out_pixel(p.gsrc, p.g, pix, p.K);
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
-            dst[c8] = im2col_chunk(p.gsrc, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
+            dst[c8] = gather_chunk<G_IM2COL>(ktab, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
         };
         if (num_kb > 0) load_mn(0, v);
         for (int i = 0; i < num_kb; ++i) {
@@ -314,25 +323,44 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       if (row < p.M) {
+        const int nb = n0 + c0;
+        const bool fast = (p.split_stride == 0) && !p.out_trans && p.out_bf16 && p.beta == 0.f &&
+                          (nb + CH <= p.N) && ((p.ldo & 7) == 0);
+        if (fast) {
+          // bias + activation + bf16 pack: one 16-byte store per 8 outputs
+          __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + nb;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int n = n0 + c0 + j;
-          if (n >= p.N) break;
-          float v = __uint_as_float(r[j]);
-          const long long o = p.out_trans ? (long long)n * p.ldo + row : (long long)row * p.ldo + n;
-          if (p.split_stride > 0) {
-            reinterpret_cast<float*>(p.out)[(long long)blockIdx.z * p.split_stride + o] = v;
-          } else {
-            if (p.bias) v += p.bias[n];
-            v = act_fwd(p.act, v) * p.alpha;
-            if (p.out_bf16) {
-              __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
-              if (p.beta != 0.f) v += p.beta * __bfloat162float(*q);
-              *q = __float2bfloat16_rn(v);
+          for (int j8 = 0; j8 < CH; j8 += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float t = __uint_as_float(r[j8 + j]);
+              if (p.bias) t += __ldg(p.bias + nb + j8 + j);
+              v[j] = act_fwd(p.act, t) * p.alpha;
+            }
+            st8(q + j8, v);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int n = nb + j;
+            if (n >= p.N) break;
+            float v = __uint_as_float(r[j]);
+            const long long o = p.out_trans ? (long long)n * p.ldo + row : (long long)row * p.ldo + n;
+            if (p.split_stride > 0) {
+              reinterpret_cast<float*>(p.out)[(long long)blockIdx.z * p.split_stride + o] = v;
             } else {
-              float* q = reinterpret_cast<float*>(p.out) + o;
-              if (p.beta != 0.f) v += p.beta * *q;
-              *q = v;
+              if (p.bias) v += p.bias[n];
+              v = act_fwd(p.act, v) * p.alpha;
+              if (p.out_bf16) {
+                __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
+                if (p.beta != 0.f) v += p.beta * __bfloat162float(*q);
+                *q = __float2bfloat16_rn(v);
+              } else {
+                float* q = reinterpret_cast<float*>(p.out) + o;
+                if (p.beta != 0.f) v += p.beta * *q;
+                *q = v;
+              }
             }
           }
         }
@@ -465,6 +493,7 @@ int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const
                            int SY, int SX, int PT, int PL, int act, cudaStream_t st) {
   if ((ldw % 8) || ((uintptr_t)w_lp & 15) || ((uintptr_t)x & 15)) return -3;
   int Kw = KY * KX * C;
+  if ((C % 8 == 0 ? (Kw + 7) / 8 : Kw) > KTAB || KY > 255 || KX > 255) return -4;
   CUtensorMap ta, tb;
   int bn = pick_bn(F);
   int r = make_map(&tb, w_lp, ldw, F, ldw, bn);
@@ -487,6 +516,7 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
                            int SY, int SX, int PT, int PL, float alpha, float beta, cudaStream_t st) {
   if ((ldc % 8) || ((uintptr_t)wd_lp & 15) || ((uintptr_t)err_out & 15)) return -3;
   int Kd = KY * KX * F;
+  if ((F % 8 == 0 ? (Kd + 7) / 8 : Kd) > KTAB || KY > 255 || KX > 255) return -4;
   CUtensorMap ta, tb;
   int bn = pick_bn(C);
   if (bn < 64) bn = 64;
@@ -511,6 +541,7 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
                            int PL, cudaStream_t st) {
   if ((F % 8) || ((uintptr_t)err_out & 15) || ((uintptr_t)x & 15)) return -3;
   int Kw = KY * KX * C, P = N * OH * OW;
+  if ((C % 8 == 0 ? (Kw + 7) / 8 : Kw) > KTAB || KY > 255 || KX > 255) return -4;
   CUtensorMap ta, tb;
   int bn = pick_bn(F);
   if (bn < 64) bn = 64;
