@@ -489,3 +489,68 @@ def evaluate_mse(unit):
                              unit.batch_dev_, unit.n_err.dev)
         unit.n_err.dev_written()
         _launch()
+
+
+# ------------------------------------------------------------------------------------------
+# deconvolution (transposed conv = the conv dgrad / fprop / wgrad kernels with swapped roles)
+# ------------------------------------------------------------------------------------------
+def _deconv_geom(u):
+    """Geometry of the *equivalent convolution*: image = deconv output side."""
+    return [u._batch_size if hasattr(u, "_batch_size") else u._output_shape[0], u._sy, u._sx,
+            u._n_channels, u.input.shape[1], u.input.shape[2], u.n_kernels, u.ky, u.kx,
+            u.sliding[1], u.sliding[0], u.padding[1], u.padding[0]]
+
+
+def _rhits(unit, like):
+    """Reciprocal overlap map in the activation dtype (static for a geometry)."""
+    t = unit.__dict__.get("rhits_dev_")
+    if t is None or t.dtype != like.dtype:
+        unit.hits.map_read()
+        r = 1.0 / numpy.maximum(unit.hits.mem, 1).astype(numpy.float32)
+        t = torch.from_numpy(r).to(like.device).to(like.dtype).contiguous()
+        unit.__dict__["rhits_dev_"] = t
+    return t
+
+
+def deconv_forward(unit):
+    ext = _ext(unit)
+    x = unit.input.dev                       # [N, oy, ox, F] plays the role of err_out
+    out = unit.output.dev_out                # [N, sy, sx, C] plays the role of err_in
+    g = _deconv_geom(unit)
+    w = unit.weights.dev
+    alpha = 1.0 if unit.hits else float(unit.scale)
+    ext.conv_dgrad(x, w, w.shape[1], bool(unit.weights_transposed), out, g, alpha, 0.0, 0)
+    _launch()
+    if unit.hits:
+        ext.mask_mul(out, _rhits(unit, out))
+        _launch()
+
+
+def deconv_backward(unit):
+    ext = _ext(unit)
+    err = unit.err_output.dev                # [N, sy, sx, C]
+    if unit.unsafe_padding:
+        ext.mask_mul(err, _rhits(unit, err))
+    else:
+        ext.axpby_2d(err.view(err.shape[0], -1), 0, err.view(err.shape[0], -1), 0,
+                     err.numel() // err.shape[0], float(unit.scale), 0.0)
+    unit.err_output.dev_written()
+    _launch()
+    g = _deconv_geom(unit)
+    w = unit.weights.dev
+    f, kw = unit.n_kernels, unit._kernel_size
+    if unit.need_err_input:
+        ei = unit.err_input.dev_out
+        if unit.err_input_beta or unit.err_input_alpha != 1.0:
+            raise NotImplementedError("GDDeconv: err_input alpha/beta on the device path")
+        ext.conv_fprop(err, w, w.shape[1], bool(unit.weights_transposed), None, ei, g, 0, 0)
+        _launch()
+    if not (unit.need_gradient_weights and unit.weights):
+        return
+    pixels = unit.input.size // f
+    tiles = ((f + 63) // 64) * ((kw + 63) // 64)
+    splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
+    gbuf = _grad_buffer(unit, "wgrad", (splits, f, kw))
+    ext.conv_wgrad(unit.input.dev, err, gbuf, splits, g, bool(unit.weights_transposed), 0)
+    _launch()
+    _update(unit, False, gbuf, splits, f * kw, f, kw)

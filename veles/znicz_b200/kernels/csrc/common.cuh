@@ -70,6 +70,29 @@ __device__ __forceinline__ float act_fwd(int act, float s, float factor = 1.f, i
     default: return s;
   }
 }
+// The five layer activations that can sit in a GEMM/conv epilogue. Small code on purpose: the
+// generic act_fwd() drags sinf/cosf/logf slow paths into every unrolled epilogue element and
+// made the tcgen05 kernels ~45k SASS instructions (instruction-fetch bound).
+__device__ __forceinline__ float act_fwd5(int act, float s) {          // accurate (fp32 paths)
+  if (act == ACT_LINEAR) return s;
+  if (act == ACT_STRICT_RELU) return fmaxf(s, 0.f);
+  if (act == ACT_TANH) return 1.7159f * tanhf(0.6666f * s);
+  if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-s));
+  return s > 15.f ? s : log1pf(__expf(s));                             // ACT_RELU = softplus
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float act_fwd5_fast(int act, float s) {     // bf16-output epilogues
+  if (act == ACT_LINEAR) return s;
+  if (act == ACT_STRICT_RELU) return fmaxf(s, 0.f);
+  if (act == ACT_TANH) return 1.7159f * tanh_approx(0.6666f * s);
+  if (act == ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-s));
+  return s > 15.f ? s : __logf(1.f + __expf(s));
+}
+
 // derivative factor f'(.) given pre-activation x (may be unused) and output y
 __device__ __forceinline__ float act_deriv(int act, float x, float y, float factor = 1.f, int idx = 0) {
   switch (act) {

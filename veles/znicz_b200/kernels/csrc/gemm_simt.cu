@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) gemm_simt_k(AL A, BL B, Epilogue ep, int 
         continue;
       }
       if (ep.bias) v += ep.bias[n];
-      v = act_fwd(ep.act, v);
+      v = act_fwd5(ep.act, v);
       v *= ep.alpha;
       if (ep.out_bf16) {
         __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + o;

@@ -105,12 +105,12 @@ __device__ __forceinline__ const __nv_bfloat16* dgrad_addr(const ConvGeomU& g, c
   if ((unsigned)ty >= (unsigned)g.OH || (unsigned)tx >= (unsigned)g.OW) return nullptr;
   return c.base + (ty * g.OW + tx) * g.F + (e & 0xffff);
 }
-template <int KIND>
+template <int KIND, int VEC>
 __device__ __forceinline__ uint4 gather_chunk(const int* ktab, const ConvGeomU& g, const PixCtx& c,
                                               int k0, int klimit) {
   uint4 z = make_uint4(0, 0, 0, 0);
   if (!c.valid || k0 >= klimit) return z;
-  if (g.vec) {
+  if (VEC) {
     const __nv_bfloat16* p = (KIND == 1) ? im2col_addr(g, c, ktab[k0 >> 3]) : dgrad_addr(g, c, ktab[k0 >> 3]);
     return p ? *reinterpret_cast<const uint4*>(p) : z;
   }
@@ -130,12 +130,33 @@ __host__ __device__ constexpr int b_bytes() {
   return B_MODE == B_TMA_K ? BLOCK_N * 128 : ((BLOCK_N + 63) / 64) * 8192;
 }
 
+// generic (rare) epilogue element: split-K partials, transposed / fp32 / alpha-beta outputs.
+// Deliberately not inlined: keeps the unrolled epilogue small.
+__device__ __noinline__ void epi_store_slow(const GemmParams& p, int row, int n, float v, int z) {
+  const long long o = p.out_trans ? (long long)n * p.ldo + row : (long long)row * p.ldo + n;
+  if (p.split_stride > 0) {
+    reinterpret_cast<float*>(p.out)[(long long)z * p.split_stride + o] = v;
+    return;
+  }
+  if (p.bias) v += p.bias[n];
+  v = act_fwd5(p.act, v) * p.alpha;
+  if (p.out_bf16) {
+    __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
+    if (p.beta != 0.f) v += p.beta * __bfloat162float(*q);
+    *q = __float2bfloat16_rn(v);
+  } else {
+    float* q = reinterpret_cast<float*>(p.out) + o;
+    if (p.beta != 0.f) v += p.beta * *q;
+    *q = v;
+  }
+}
+
 template <int BLOCK_N, int B_MODE>
 __host__ __device__ constexpr int min_ctas() {
   return (2 * (STAGES * (A_BYTES + b_bytes<BLOCK_N, B_MODE>()) + 2048) <= 227 * 1024) ? 2 : 1;
 }
 
-template <int BLOCK_N, int A_MODE, int B_MODE>
+template <int BLOCK_N, int A_MODE, int B_MODE, int GKIND, int GVEC>
 __global__ void __launch_bounds__(192, (min_ctas<BLOCK_N, B_MODE>()))
 gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
@@ -182,7 +203,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tmem_alloc(&tmem_base_smem, TMEM_COLS);
     tmem_relinquish();
   }
-  if (A_GATHER) build_ktab(ktab, p.g, p.gather_kind, p.gK);
+  if (A_GATHER) build_ktab(ktab, p.g, GKIND, p.gK);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -242,29 +263,29 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (A_MODE == A_GATHER_K) {
         // tile row r = t is GEMM row m0 + t (a pixel); chunks run over the reduction index
         const int m = m0 + t;
-        const PixCtx ctx = (p.gather_kind == G_IM2COL) ? decode_out_pixel(p.gsrc, p.g, m, p.M)
-                                                       : decode_in_pixel(p.gsrc, p.g, m, p.M);
-        uint4 v[8];
-        auto load_k = [&](int i, uint4 (&dst)[8]) {
-          const int k0 = (kb_begin + i) * BLOCK_K;
+        const PixCtx ctx = (GKIND == G_IM2COL) ? decode_out_pixel(p.gsrc, p.g, m, p.M)
+                                               : decode_in_pixel(p.gsrc, p.g, m, p.M);
+        uint4 v[8], nv[8];
+        // software pipeline with ONE load site: iteration i issues the global loads of stage
+        // i + 1 and then publishes stage i (whose loads were issued one iteration earlier)
+#pragma unroll 1
+        for (int i = -1; i < num_kb; ++i) {
+          if (i + 1 < num_kb) {
+            const int k0 = (kb_begin + i + 1) * BLOCK_K;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            dst[c8] = (p.gather_kind == G_IM2COL)
-                          ? gather_chunk<G_IM2COL>(ktab, p.g, ctx, k0 + c8 * 8, p.gK)
-                          : gather_chunk<G_DGRAD>(ktab, p.g, ctx, k0 + c8 * 8, p.gK);
-        };
-        if (num_kb > 0) load_k(0, v);
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
-          uint4 nv[8];
-          if (i + 1 < num_kb) load_k(i + 1, nv);      // issue the next stage's loads early
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+            for (int c8 = 0; c8 < 8; ++c8)
+              nv[c8] = gather_chunk<GKIND, GVEC>(ktab, p.g, ctx, k0 + c8 * 8, p.gK);
+          }
+          if (i >= 0) {
+            const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            *reinterpret_cast<uint4*>(sa + t * 128 + ((c8 ^ (t & 7)) << 4)) = v[c8];
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[s]);
+            for (int c8 = 0; c8 < 8; ++c8)
+              *reinterpret_cast<uint4*>(sa + t * 128 + ((c8 ^ (t & 7)) << 4)) = v[c8];
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[s]);
+          }
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) v[c8] = nv[c8];
         }
@@ -272,26 +293,26 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // A_GATHER_MN (conv wgrad): tile = [64 reduction rows (pixels)][128 m (kidx)];
         // thread -> reduction row kr = t % 64, 64-wide m block = t / 64 (8 chunks of 8 kidx)
         const int kr = t & 63, mblk = t >> 6;
-        uint4 v[8];
-        auto load_mn = [&](int i, uint4 (&dst)[8]) {
-          const int pix = (kb_begin + i) * BLOCK_K + kr;
-          const PixCtx ctx = decode_out_pixel(p.gsrc, p.g, pix, p.K);
+        uint4 v[8], nv[8];
+#pragma unroll 1
+        for (int i = -1; i < num_kb; ++i) {
+          if (i + 1 < num_kb) {
+            const int pix = (kb_begin + i + 1) * BLOCK_K + kr;
+            const PixCtx ctx = decode_out_pixel(p.gsrc, p.g, pix, p.K);
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            dst[c8] = gather_chunk<G_IM2COL>(ktab, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
-        };
-        if (num_kb > 0) load_mn(0, v);
-        for (int i = 0; i < num_kb; ++i) {
-          const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
-          uint4 nv[8];
-          if (i + 1 < num_kb) load_mn(i + 1, nv);
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+            for (int c8 = 0; c8 < 8; ++c8)
+              nv[c8] = gather_chunk<G_IM2COL, GVEC>(ktab, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
+          }
+          if (i >= 0) {
+            const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8)
-            *reinterpret_cast<uint4*>(sa + mblk * 8192 + kr * 128 + ((c8 ^ (kr & 7)) << 4)) = v[c8];
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[s]);
+            for (int c8 = 0; c8 < 8; ++c8)
+              *reinterpret_cast<uint4*>(sa + mblk * 8192 + kr * 128 + ((c8 ^ (kr & 7)) << 4)) = v[c8];
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[s]);
+          }
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) v[c8] = nv[c8];
         }
@@ -336,32 +357,14 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int j = 0; j < 8; ++j) {
               float t = __uint_as_float(r[j8 + j]);
               if (p.bias) t += __ldg(p.bias + nb + j8 + j);
-              v[j] = act_fwd(p.act, t) * p.alpha;
+              v[j] = act_fwd5_fast(p.act, t) * p.alpha;
             }
             st8(q + j8, v);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
-            const int n = nb + j;
-            if (n >= p.N) break;
-            float v = __uint_as_float(r[j]);
-            const long long o = p.out_trans ? (long long)n * p.ldo + row : (long long)row * p.ldo + n;
-            if (p.split_stride > 0) {
-              reinterpret_cast<float*>(p.out)[(long long)blockIdx.z * p.split_stride + o] = v;
-            } else {
-              if (p.bias) v += p.bias[n];
-              v = act_fwd(p.act, v) * p.alpha;
-              if (p.out_bf16) {
-                __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
-                if (p.beta != 0.f) v += p.beta * __bfloat162float(*q);
-                *q = __float2bfloat16_rn(v);
-              } else {
-                float* q = reinterpret_cast<float*>(p.out) + o;
-                if (p.beta != 0.f) v += p.beta * *q;
-                *q = v;
-              }
-            }
+            if (nb + j < p.N) epi_store_slow(p, row, nb + j, __uint_as_float(r[j]), blockIdx.z);
           }
         }
       }
@@ -408,31 +411,40 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BN, int AM, int BM>
+template <int BN, int AM, int BM, int GK, int GV>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
                       cudaStream_t st) {
   constexpr int smem = STAGES * (A_BYTES + b_bytes<BN, BM>()) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_umma_k<BN, AM, BM>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_umma_k<BN, AM, BM, GK, GV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BLOCK_M - 1) / BLOCK_M, splits);
-  gemm_umma_k<BN, AM, BM><<<grid, 192, smem, st>>>(ta, tb, p);
+  gemm_umma_k<BN, AM, BM, GK, GV><<<grid, 192, smem, st>>>(ta, tb, p);
   return (int)cudaGetLastError();
 }
 
-template <int AM, int BM>
+// B K-major: BLOCK_N in {16, 32, 64, 128}; B MN-major: {64, 128}
+template <int AM, int BM, int GK, int GV>
 static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                      int splits, cudaStream_t st) {
-  switch (bn) {
-    case 16: return launch_cfg<16, AM, BM>(ta, tb, p, splits, st);
-    case 32: return launch_cfg<32, AM, BM>(ta, tb, p, splits, st);
-    case 64: return launch_cfg<64, AM, BM>(ta, tb, p, splits, st);
-    case 128: return launch_cfg<128, AM, BM>(ta, tb, p, splits, st);
-    default: return -2;
+  if constexpr (BM == B_TMA_K) {
+    switch (bn) {
+      case 16: return launch_cfg<16, AM, BM, GK, GV>(ta, tb, p, splits, st);
+      case 32: return launch_cfg<32, AM, BM, GK, GV>(ta, tb, p, splits, st);
+      case 64: return launch_cfg<64, AM, BM, GK, GV>(ta, tb, p, splits, st);
+      case 128: return launch_cfg<128, AM, BM, GK, GV>(ta, tb, p, splits, st);
+      default: return -2;
+    }
+  } else {
+    switch (bn) {
+      case 64: return launch_cfg<64, AM, BM, GK, GV>(ta, tb, p, splits, st);
+      case 128: return launch_cfg<128, AM, BM, GK, GV>(ta, tb, p, splits, st);
+      default: return -2;
+    }
   }
 }
 
@@ -474,11 +486,11 @@ int launch_gemm_umma(const void* a, long long lda, int a_mn, const void* b, long
   p.out = out; p.out_bf16 = out_bf16; p.ldo = ldo; p.out_trans = out_trans;
   p.bias = bias; p.act = act; p.alpha = alpha; p.beta = beta; p.split_stride = split_stride;
   p.gather_kind = G_NONE;
-  if (!a_mn && !b_mn) return launch_bn<A_TMA_K, B_TMA_K>(bn, ta, tb, p, splits, st);
+  if (!a_mn && !b_mn) return launch_bn<A_TMA_K, B_TMA_K, 0, 0>(bn, ta, tb, p, splits, st);
   // MN-major B tiles are built from 64-wide swizzle atoms: never go below UMMA_N = 64 there
-  if (!a_mn && b_mn) return launch_bn<A_TMA_K, B_TMA_MN>(bn, ta, tb, p, splits, st);
-  if (a_mn && !b_mn) return launch_bn<A_TMA_MN, B_TMA_K>(bn, ta, tb, p, splits, st);
-  return launch_bn<A_TMA_MN, B_TMA_MN>(bn, ta, tb, p, splits, st);
+  if (!a_mn && b_mn) return launch_bn<A_TMA_K, B_TMA_MN, 0, 0>(bn, ta, tb, p, splits, st);
+  if (a_mn && !b_mn) return launch_bn<A_TMA_MN, B_TMA_K, 0, 0>(bn, ta, tb, p, splits, st);
+  return launch_bn<A_TMA_MN, B_TMA_MN, 0, 0>(bn, ta, tb, p, splits, st);
 }
 
 static ConvGeomU geom(int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX,
@@ -506,7 +518,8 @@ int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const
   p.bias = bias; p.act = act; p.alpha = 1.f; p.beta = 0.f; p.split_stride = 0;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
-  return launch_bn<A_GATHER_K, B_TMA_K>(bn, ta, tb, p, 1, st);
+  if (C % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 1>(bn, ta, tb, p, 1, st);
+  return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 0>(bn, ta, tb, p, 1, st);
 }
 
 // err_in[ipix, c] = alpha * sum_{tap,f} gather(err_out) * wd_lp[(tap,f), c] + beta * err_in
@@ -531,7 +544,8 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
   p.gsrc = (const __nv_bfloat16*)err_out;
   p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, F % 8 == 0);
   p.gather_kind = G_DGRAD; p.gK = Kd;
-  return launch_bn<A_GATHER_K, B_TMA_MN>(bn, ta, tb, p, 1, st);
+  if (F % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 1>(bn, ta, tb, p, 1, st);
+  return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 0>(bn, ta, tb, p, 1, st);
 }
 
 // partials[z][f][kidx] = sum_{pix in split z} err_out[pix, f] * im2col(x)[pix, kidx]
@@ -557,7 +571,8 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
   p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.beta = 0.f; p.split_stride = (long long)F * Kw;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
-  return launch_bn<A_GATHER_MN, B_TMA_MN>(bn, ta, tb, p, splits, st);
+  if (C % 8 == 0) return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 1>(bn, ta, tb, p, splits, st);
+  return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 0>(bn, ta, tb, p, splits, st);
 }
 
 }  // namespace zn
