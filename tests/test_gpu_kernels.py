@@ -166,7 +166,7 @@ def test_fused_update_matches_reference_formula(ext):
     lp = torch.zeros(rows, 56, device=dev, dtype=torch.bfloat16)
     gout = torch.zeros(rows, cols, device=dev)
     ext.fused_update(w, [g.data_ptr()], 3, rows * cols, gout, acc, vel, hyper, cs,
-                     1 | 2 | 4 | 8, False, rows, cols, lp, 56, None, 0, 0, 0, [], 0, 0, 0)
+                     1 | 2 | 4 | 8, False, rows, cols, lp, 56, None, 0, 0, 0, [], 0, 0, 0, 0, 0)
     torch.cuda.synchronize()
     gs = g.sum(0)
     lr, wd, l1, mom, aa, ab, ga, gb, ortho = [float(v) for v in hyper[:9]]

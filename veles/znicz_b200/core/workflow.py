@@ -164,6 +164,11 @@ class Workflow(Unit):
         demands are not met yet) are re-queued until no progress is made."""
         snapshot = kwargs.get("snapshot", False)
         self._restored_from_snapshot_ = snapshot
+        if isinstance(kwargs.get("device"), str):      # "numpy" / "cuda" / "auto"
+            from .backends import get_device
+            kwargs["device"] = get_device(kwargs["device"])
+        if "device" in kwargs:
+            self.__dict__["device"] = kwargs["device"]
         pending = [u for u in self.units_in_dependency_order if u is not self]
         max_rounds = len(pending) + 2
         for _ in range(max_rounds):

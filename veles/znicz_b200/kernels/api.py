@@ -60,13 +60,27 @@ def lp_enabled(unit):
 
 
 def _shadow_spec(unit):
-    """(rows, cols, ld, conv?, taps, C, c_pad) of the weight matrix of a forward unit."""
+    """(rows, cols, ld, conv?, taps, C, c_pad) of the weight matrix of a forward unit.
+    For conv layers whose channel count is not a multiple of 8 (the first layer, C = 3) the
+    fprop shadow is stored channel-padded ``[F][tap][c_pad]`` so the implicit-GEMM gather can
+    move 16-byte chunks (see ``lp_cpad``)."""
     rows, cols = unit.weights.shape
     ld = _roundup(cols, 8)
     if hasattr(unit, "kx") and hasattr(unit, "n_kernels"):
         c = unit._n_channels
-        return rows, cols, ld, True, unit.kx * unit.ky, c, _roundup(c, 8)
+        taps = unit.kx * unit.ky
+        c_pad = _roundup(c, 8)
+        if c % 8:
+            ld = taps * c_pad
+        return rows, cols, ld, True, taps, c, c_pad
     return rows, cols, ld, False, 0, 0, 0
+
+
+def lp_cpad(unit):
+    """Channel padding of the fprop weight shadow / padded input (0 = none)."""
+    if hasattr(unit, "kx") and hasattr(unit, "n_kernels") and unit._n_channels % 8:
+        return _roundup(unit._n_channels, 8)
+    return 0
 
 
 def ensure_shadows(fwd):
@@ -86,7 +100,8 @@ def refresh_weight_shadows(fwd):
     ensure_shadows(fwd)
     rows, cols, ld, is_conv, taps, c, c_pad = _shadow_spec(fwd)
     _ext(fwd).refresh_shadows(fwd.weights.dev, rows, cols, fwd.weights_lp_, ld,
-                              fwd.weights_lp_t_ if is_conv else None, taps, c, c_pad)
+                              fwd.weights_lp_t_ if is_conv else None, taps, c, c_pad,
+                              lp_cpad(fwd))
     _launch()
 
 
@@ -141,7 +156,7 @@ def _grad_buffer(unit, name, shape):
     return _tmp(unit, name, shape, torch.float32)
 
 
-def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols):
+def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
     """Fused (cross-GPU reduce +) SGD step for weights or bias of a GD unit."""
     ext = _ext(unit)
     if is_bias:
@@ -158,11 +173,14 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols):
         _launch()
     fwd = unit.forward_unit
     lp = lp_conv = None
-    ld = taps = c = c_pad = 0
+    ld = taps = c = c_pad = cpad_lp = 0
     if not is_bias and fwd is not None and getattr(fwd, "weights_lp_", None) is not None:
         r_, c_, ld, is_conv, taps, c, c_pad = _shadow_spec(fwd)
         lp = fwd.weights_lp_
         lp_conv = fwd.weights_lp_t_ if is_conv else None
+        cpad_lp = lp_cpad(fwd)
+    elif g_cpad:
+        raise RuntimeError("channel-padded gradients need the forward unit's shadow spec")
     dp = unit.dp_
     if dp is not None and dp.symm is not None:
         ptrs, flag_ptrs, epoch_ptr, blocks = dp.symm.peers(unit, grad_buf)
@@ -173,7 +191,7 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols):
     ext.fused_update(wdev, ptrs, nparts, part_stride, gout.dev_out if gout else None,
                      acc.dev if acc else None, vel.dev if vel else None, unit.hyper_dev_,
                      colsums, flags, is_bias, rows, cols, lp, ld, lp_conv, taps, c, c_pad,
-                     flag_ptrs, epoch_ptr, rank, blocks)
+                     flag_ptrs, epoch_ptr, rank, blocks, cpad_lp, g_cpad)
     w.dev_written()
     if acc:
         acc.dev_written()
@@ -263,6 +281,14 @@ def conv_forward(unit):
     if lp_enabled(unit) and _is_bf16(x):
         ensure_shadows(unit)
         w = unit.weights_lp_
+        cp = lp_cpad(unit)
+        if cp:   # first layer: pad C -> 8 once, fprop and wgrad then gather 16-byte chunks
+            xp = _tmp(unit, "xpad", tuple(x.shape[:3]) + (cp,), x.dtype)
+            ext.pad_channels(x, xp, unit._n_channels, cp)
+            _launch()
+            x = xp
+            g = list(g)
+            g[3] = cp
         r = ext.conv_fprop(x, w, w.shape[1], False, bias, out, g, unit.ACT, 1)
         if r != 0:
             raise RuntimeError("%s: tcgen05 conv fprop refused (code %d)" % (unit, r))
@@ -311,7 +337,17 @@ def conv_backward(unit):
     if not need_w:
         return
     use_umma = lp_ok and f % 8 == 0
+    g_cp = 0
     if use_umma:
+        g_cp = lp_cpad(fwd)
+        if g_cp:
+            xp = fwd.__dict__.get("tmp_xpad_")
+            if xp is None:
+                raise RuntimeError("%s: padded input of the forward pass is missing" % unit)
+            x = xp
+            g = list(g)
+            g[3] = g_cp
+            kw = unit.kx * unit.ky * g_cp
         splits = int(ext.pick_splits(kw, f, pixels, _MAX_SPLITS))
     else:
         tiles = ((f + 63) // 64) * ((kw + 63) // 64)
@@ -324,7 +360,7 @@ def conv_backward(unit):
     else:
         ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0)
     _launch()
-    _update(unit, False, gbuf, splits, f * kw, f, kw)
+    _update(unit, False, gbuf, splits, f * kw, f, unit._kernel_size, g_cpad=g_cp)
     if need_b:
         _update(unit, True, parts, slices, f, 1, f)
 

@@ -224,6 +224,19 @@ __global__ void gather_minibatch_k(const TS* __restrict__ src, const int* __rest
   if (labels_dst && t < max_rows) labels_dst[t] = t < count ? labels_src[idx[t]] : -1;
 }
 
+// [P][C] -> [P][CP] (CP = 8-padded, zeros in the padding): first-layer channel padding so the
+// implicit-GEMM gather can use 16-byte chunks
+template <typename T>
+__global__ void pad_channels_k(const T* __restrict__ x, T* __restrict__ y, int pixels, int C, int CP) {
+  const int total = pixels * CP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int p = i / CP, c = i - p * CP;
+    T v; stf(&v, 0.f);
+    if (c < C) v = x[(size_t)p * C + c];
+    y[i] = v;
+  }
+}
+
 template <typename T>
 __global__ void mask_mul_k(T* __restrict__ w, const T* __restrict__ mask, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,6 +341,9 @@ void launch_gather_minibatch(const void* src, bool src_bf16, const int* labels_s
 void launch_gather_labels(const int* src, const int* idx, int* dst, int count, int max_rows,
                           cudaStream_t st) {
   gather_labels_k<<<(max_rows + 255) / 256, 256, 0, st>>>(src, idx, dst, count, max_rows);
+}
+void launch_pad_channels(const void* x, void* y, int pixels, int C, int CP, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, pad_channels_k<T><<<grid_for((long long)pixels * CP), 256, 0, st>>>((const T*)x, (T*)y, pixels, C, CP));
 }
 void launch_mask_mul(void* w, const void* mask, long long n, bool bf16, cudaStream_t st) {
   DISPATCH_T(bf16, mask_mul_k<T><<<grid_for(n), 256, 0, st>>>((T*)w, (const T*)mask, n));

@@ -20,6 +20,7 @@ void launch_gather_rows(const void*, bool, const int*, void*, bool, int, int, lo
 void launch_gather_labels(const int*, const int*, int*, int, int, cudaStream_t);
 void launch_gather_minibatch(const void*, bool, const int*, const int*, void*, bool, int*, int, long long, cudaStream_t);
 void launch_mask_mul(void*, const void*, long long, bool, cudaStream_t);
+void launch_pad_channels(const void*, void*, int, int, int, bool, cudaStream_t);
 void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
 void launch_scatter_offsets(const void*, const int*, void*, long long, bool, cudaStream_t);
 void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int, const int*, bool, cudaStream_t);
@@ -31,12 +32,14 @@ void launch_evaluate_softmax(const float*, const int*, const int*, void*, bool, 
 void launch_evaluate_mse(const void*, const void*, bool, void*, bool, const float*, int, int, const float*, int, float*, float*, cudaStream_t);
 void launch_mse_find_closest(const void*, bool, const float*, const int*, const float*, int, int, int, int*, cudaStream_t);
 int fused_update_blocks(long long size);
-void launch_fused_update(float*, const float* const*, int, int, long long, float*, float*, float*, const float*, const float*, int, int, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, uint32_t* const*, uint32_t*, int, int, cudaStream_t);
+void launch_fused_update(float*, const float* const*, int, int, long long, float*, float*, float*, const float*, const float*, int, int, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, uint32_t* const*, uint32_t*, int, int, int, int, cudaStream_t);
 void launch_col_sums(const float*, float*, int, int, int, cudaStream_t);
-void launch_refresh_shadows(const float*, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, cudaStream_t);
+void launch_refresh_shadows(const float*, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 void launch_gemm_simt(const void*, bool, long long, int, const void*, bool, long long, int, void*, bool, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
 struct ConvGeomS { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
 int umma_pick_splits(int, int, int, int);
+void launch_som_winners(const float*, const float*, int*, int*, int, int, int, int, cudaStream_t);
+void launch_som_update(const float*, float*, const float*, const int*, int, int, int, float, float, cudaStream_t);
 int launch_gemm_umma(const void*, long long, int, const void*, long long, int, void*, int, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
 int launch_conv_fprop_umma(const void*, const void*, long long, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_dgrad_umma(const void*, const void*, long long, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, float, float, cudaStream_t);
@@ -164,6 +167,11 @@ void gather_minibatch(Tensor src, c10::optional<Tensor> labels_src, Tensor hdr, 
                               is_bf16(dst), ld, (int)dst.size(0), row, cur());
   kcheck();
 }
+void pad_channels(Tensor x, Tensor y, int64_t C, int64_t CP) {
+  chk(x, "x"); same_dt(x, y);
+  zn::launch_pad_channels(x.data_ptr(), y.data_ptr(), (int)(x.numel() / C), (int)C, (int)CP, is_bf16(x), cur());
+  kcheck();
+}
 void mask_mul(Tensor w, Tensor mask) {
   chk(w, "w"); same_dt(w, mask);
   zn::launch_mask_mul(w.data_ptr(), mask.data_ptr(), w.numel(), is_bf16(w), cur());
@@ -271,7 +279,7 @@ void fused_update(Tensor w, std::vector<int64_t> grad_ptrs, int64_t nparts, int6
                   Tensor hyper, c10::optional<Tensor> col_sums, int64_t flags, bool is_bias, int64_t rows,
                   int64_t cols, c10::optional<Tensor> lp, int64_t ld, c10::optional<Tensor> lp_conv,
                   int64_t taps, int64_t C, int64_t c_pad, std::vector<int64_t> peer_flags,
-                  int64_t epoch_ptr, int64_t rank, int64_t blocks) {
+                  int64_t epoch_ptr, int64_t rank, int64_t blocks, int64_t lp_cpad, int64_t g_cpad) {
   TORCH_CHECK(w.scalar_type() == torch::kFloat32 && w.is_cuda() && w.is_contiguous());
   TORCH_CHECK(grad_ptrs.size() >= 1 && grad_ptrs.size() <= 8);
   const float* gp[8]; uint32_t* fl[8];
@@ -283,7 +291,8 @@ void fused_update(Tensor w, std::vector<int64_t> grad_ptrs, int64_t nparts, int6
                           hyper.data_ptr<float>(), fptr_or_null(col_sums), (int)flags, is_bias ? 1 : 0,
                           w.numel(), (int)rows, (int)cols, bptr_or_null(lp), (int)ld, bptr_or_null(lp_conv),
                           (int)taps, (int)C, (int)c_pad, multi ? fl : nullptr,
-                          reinterpret_cast<uint32_t*>(epoch_ptr), (int)rank, (int)blocks, cur());
+                          reinterpret_cast<uint32_t*>(epoch_ptr), (int)rank, (int)blocks, (int)lp_cpad,
+                          (int)g_cpad, cur());
   kcheck();
 }
 int64_t update_blocks(int64_t size) { return zn::fused_update_blocks(size); }
@@ -292,9 +301,9 @@ void col_sums(Tensor w, Tensor out, int64_t rows, int64_t cols, bool transposed)
   kcheck();
 }
 void refresh_shadows(Tensor w, int64_t rows, int64_t cols, c10::optional<Tensor> lp, int64_t ld,
-                     c10::optional<Tensor> lp_conv, int64_t taps, int64_t C, int64_t c_pad) {
+                     c10::optional<Tensor> lp_conv, int64_t taps, int64_t C, int64_t c_pad, int64_t lp_cpad) {
   zn::launch_refresh_shadows(w.data_ptr<float>(), w.numel(), (int)rows, (int)cols, bptr_or_null(lp), (int)ld,
-                             bptr_or_null(lp_conv), (int)taps, (int)C, (int)c_pad, cur());
+                             bptr_or_null(lp_conv), (int)taps, (int)C, (int)c_pad, (int)lp_cpad, cur());
   kcheck();
 }
 
@@ -381,7 +390,23 @@ int64_t conv_wgrad(Tensor err_out, Tensor x, Tensor partials, int64_t splits, st
   return 0;
 }
 
+void som_winners(Tensor x, Tensor w, Tensor argmins, c10::optional<Tensor> winners) {
+  TORCH_CHECK(x.scalar_type() == torch::kFloat32 && w.scalar_type() == torch::kFloat32);
+  int batch = (int)x.size(0), neurons = (int)w.size(0), len = (int)(w.numel() / w.size(0));
+  int* wp = (winners.has_value() && winners->defined()) ? winners->data_ptr<int>() : nullptr;
+  zn::launch_som_winners(x.data_ptr<float>(), w.data_ptr<float>(), argmins.data_ptr<int>(), wp, batch,
+                         neurons, len, wp ? 1 : 0, cur());
+  kcheck();
+}
+void som_update(Tensor x, Tensor w, Tensor coords, Tensor argmins, double sigma, double gmult) {
+  int batch = (int)x.size(0), neurons = (int)w.size(0), len = (int)(w.numel() / w.size(0));
+  zn::launch_som_update(x.data_ptr<float>(), w.data_ptr<float>(), coords.data_ptr<float>(),
+                        argmins.data_ptr<int>(), batch, neurons, len, (float)sigma, (float)gmult, cur());
+  kcheck();
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("som_winners", &som_winners); m.def("som_update", &som_update);
   m.doc() = "znicz_b200 sm_100a kernels";
   m.def("act_forward", &act_forward); m.def("act_backward", &act_backward);
   m.def("colsum_slices", &colsum_slices); m.def("err_act_colsum", &err_act_colsum);
@@ -389,7 +414,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
   m.def("gather_minibatch", &gather_minibatch);
-  m.def("mask_mul", &mask_mul); m.def("cast_copy", &cast_copy); m.def("scatter_offsets", &scatter_offsets);
+  m.def("mask_mul", &mask_mul); m.def("pad_channels", &pad_channels); m.def("cast_copy", &cast_copy); m.def("scatter_offsets", &scatter_offsets);
   m.def("pool_forward", &pool_forward); m.def("pool_backward", &pool_backward);
   m.def("lrn_forward", &lrn_forward); m.def("lrn_backward", &lrn_backward);
   m.def("softmax_rows", &softmax_rows); m.def("evaluate_softmax", &evaluate_softmax);

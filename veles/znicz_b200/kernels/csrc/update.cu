@@ -27,11 +27,13 @@ struct GradSources {
   int nranks;
   int nparts;            // split-K partials per rank
   long long part_stride; // elements between partials
+  int g_cpad;            // > 0: gradient rows are [tap][g_cpad] channel-padded (first conv layer)
 };
 
 struct ShadowSpec {
   __nv_bfloat16* lp;       // [rows][ld] bf16 copy of w (row-major as w), may be null
   int ld;
+  int lp_cpad;             // > 0: lp rows are [tap][lp_cpad] channel-padded
   __nv_bfloat16* lp_conv;  // conv dgrad operand [tap][f][c_pad], may be null
   int taps, C, c_pad;
 };
@@ -92,9 +94,15 @@ __global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __r
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < size; i += stride) {
+    long long gi = i;
+    if (gs.g_cpad > 0) {
+      const int r_ = (int)(i / cols), c_ = (int)(i % cols);
+      const int tap_ = c_ / sh.C, ch_ = c_ - tap_ * sh.C;
+      gi = ((long long)r_ * sh.taps + tap_) * gs.g_cpad + ch_;
+    }
     float g = 0.f;
     for (int r = 0; r < gs.nranks; ++r) {        // fixed rank order => bit-identical replicas
-      const float* base = gs.ptr[r] + i;
+      const float* base = gs.ptr[r] + gi;
       float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
       int p = 0;
       for (; p + 4 <= gs.nparts; p += 4) {       // 4 loads in flight per rank
@@ -127,7 +135,9 @@ __global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __r
     if (apply) { wv += gd; w[i] = wv; }
     if (sh.lp) {
       int r = (int)(i / cols), c = (int)(i % cols);
-      sh.lp[(size_t)r * sh.ld + c] = __float2bfloat16_rn(wv);
+      int lc = c;
+      if (sh.lp_cpad > 0) { int tap = c / sh.C; lc = tap * sh.lp_cpad + (c - tap * sh.C); }
+      sh.lp[(size_t)r * sh.ld + lc] = __float2bfloat16_rn(wv);
       if (sh.lp_conv) {
         int tap = c / sh.C, ch = c % sh.C;      // w[f=r][tap][ch]
         sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
@@ -161,7 +171,9 @@ __global__ void refresh_shadows_k(const float* __restrict__ w, long long size, i
   for (; i < size; i += stride) {
     float wv = w[i];
     int r = (int)(i / cols), c = (int)(i % cols);
-    if (sh.lp) sh.lp[(size_t)r * sh.ld + c] = __float2bfloat16_rn(wv);
+    int lc = c;
+    if (sh.lp_cpad > 0) { int tap = c / sh.C; lc = tap * sh.lp_cpad + (c - tap * sh.C); }
+    if (sh.lp) sh.lp[(size_t)r * sh.ld + lc] = __float2bfloat16_rn(wv);
     if (sh.lp_conv) {
       int tap = c / sh.C, ch = c % sh.C;
       sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
@@ -182,11 +194,11 @@ void launch_fused_update(float* w, const float* const* grad_ptrs, int nranks, in
                          long long size, int rows, int cols, __nv_bfloat16* lp, int ld,
                          __nv_bfloat16* lp_conv, int taps, int C, int c_pad,
                          uint32_t* const* peer_flags, uint32_t* epoch, int rank, int blocks,
-                         cudaStream_t st) {
+                         int lp_cpad, int g_cpad, cudaStream_t st) {
   GradSources gs{};
   for (int r = 0; r < nranks; ++r) gs.ptr[r] = grad_ptrs[r];
-  gs.nranks = nranks; gs.nparts = nparts; gs.part_stride = part_stride;
-  ShadowSpec sh{lp, ld, lp_conv, taps, C, c_pad};
+  gs.nranks = nranks; gs.nparts = nparts; gs.part_stride = part_stride; gs.g_cpad = g_cpad;
+  ShadowSpec sh{lp, ld, lp_cpad, lp_conv, taps, C, c_pad};
   PeerSync ps{};
   ps.rank = rank; ps.nranks = nranks; ps.epoch = epoch;
   if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
@@ -203,8 +215,9 @@ void launch_col_sums(const float* w, float* out, int rows, int cols, int transpo
   col_sums_k<<<(cols + 7) / 8, block, 0, st>>>(w, out, rows, cols, transposed);
 }
 void launch_refresh_shadows(const float* w, long long size, int rows, int cols, __nv_bfloat16* lp, int ld,
-                            __nv_bfloat16* lp_conv, int taps, int C, int c_pad, cudaStream_t st) {
-  ShadowSpec sh{lp, ld, lp_conv, taps, C, c_pad};
+                            __nv_bfloat16* lp_conv, int taps, int C, int c_pad, int lp_cpad,
+                            cudaStream_t st) {
+  ShadowSpec sh{lp, ld, lp_cpad, lp_conv, taps, C, c_pad};
   long long b = (size + 255) / 256; if (b > 592) b = 592; if (b < 1) b = 1;
   refresh_shadows_k<<<(int)b, 256, 0, st>>>(w, size, rows, cols, sh);
 }
