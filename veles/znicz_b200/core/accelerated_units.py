@@ -51,6 +51,9 @@ class AcceleratedUnit(Unit):
     def initialize(self, device=None, **kwargs):
         if device is None:
             device = self.device or NumpyDevice()
+        elif isinstance(device, str):
+            from .backends import get_device
+            device = get_device(device)
         self.device = device
         if self.on_cuda:
             self.ext_ = device.ext
