@@ -180,3 +180,94 @@ def test_fused_update_matches_reference_formula(ext):
     assert _rel(vel, gd) < 1e-5
     assert _rel(w, w0 + gd) < 1e-5
     assert _rel(lp[:, :cols], (w0 + gd)) < 1e-2
+
+
+def test_multi_update_matches_per_tensor_update(ext):
+    """The whole-network step kernel must be bit-compatible (fixed summation order aside)
+    with the per-tensor fused update: weights with ortho + split-K partials, a conv tensor
+    with channel-padded gradients and both bf16 shadows, and a bias with 128 partials that
+    takes the lane-cooperative path."""
+    torch.manual_seed(11)
+    dev = "cuda"
+    hyper = torch.tensor([0.1, 0.01, 0.3, 0.9, 0.5, 0.25, 0.75, 0.8, 0.002,
+                          0.2, 0.0, 0.0, 0.7, 0, 0, 0], device=dev)
+
+    def P(t):
+        return 0 if t is None else t.data_ptr()
+    specs = []
+    # (rows, cols, nparts, flags, is_bias, conv(taps, C, c_pad, lp_cpad, g_cpad), lanes)
+    specs.append(dict(rows=37, cols=53, nparts=3, flags=1 | 2 | 4 | 8, bias=False, conv=None,
+                      lanes=2))
+    specs.append(dict(rows=32, cols=75, nparts=22, flags=1 | 2 | 8, bias=False,
+                      conv=(25, 3, 8, 8, 8), lanes=16))
+    specs.append(dict(rows=1, cols=32, nparts=128, flags=1 | 2, bias=True, conv=None, lanes=32))
+    specs.append(dict(rows=64, cols=800, nparts=5, flags=1 | 2 | 8, bias=False,
+                      conv=(25, 32, 32, 0, 0), lanes=1))
+    ref, new, descs = [], [], []
+    for sp in specs:
+        rows, cols = sp["rows"], sp["cols"]
+        conv = sp["conv"]
+        g_cpad = conv[4] if conv else 0
+        gcols = conv[0] * g_cpad if g_cpad else cols
+        w = torch.randn(rows, cols, device=dev)
+        g = torch.randn(sp["nparts"], rows, gcols, device=dev)
+        acc = torch.randn(rows, cols, device=dev) if sp["flags"] & 4 else None
+        vel = torch.randn(rows, cols, device=dev)
+        ld = ((cols + 7) // 8) * 8
+        taps = C = c_pad = lp_cpad = 0
+        lp_conv = None
+        if conv:
+            taps, C, c_pad, lp_cpad, _ = conv
+            if lp_cpad:
+                ld = taps * lp_cpad
+        lp = None if sp["bias"] else torch.zeros(rows, ld, device=dev, dtype=torch.bfloat16)
+        if conv:
+            lp_conv = torch.zeros(taps * rows, c_pad, device=dev, dtype=torch.bfloat16)
+        two = []
+        for _ in range(2):
+            two.append(dict(w=w.clone(), acc=None if acc is None else acc.clone(),
+                            vel=vel.clone(), gout=torch.zeros(rows, cols, device=dev),
+                            cs=torch.zeros(cols, device=dev),
+                            lp=None if lp is None else lp.clone(),
+                            lp_conv=None if lp_conv is None else lp_conv.clone()))
+        a, b = two
+        if sp["flags"] & 8:
+            ext.col_sums(a["w"], a["cs"], rows, cols, False)
+        ext.fused_update(a["w"], [g.data_ptr()], sp["nparts"], rows * gcols, a["gout"], a["acc"],
+                         a["vel"], hyper, a["cs"] if sp["flags"] & 8 else None, sp["flags"],
+                         sp["bias"], rows, cols, a["lp"], ld, a["lp_conv"], taps, C, c_pad,
+                         [], 0, 0, 0, lp_cpad, g_cpad)
+        descs.append([P(b["w"]), P(b["gout"]), P(b["acc"]), P(b["vel"]), P(hyper),
+                      P(b["cs"]) if sp["flags"] & 8 else 0, g.data_ptr(), 0, 0, 0, 0, 0, 0, 0,
+                      rows * gcols, rows * cols, sp["nparts"], g_cpad, sp["flags"],
+                      1 if sp["bias"] else 0, rows, cols, sp["lanes"], 1,
+                      P(b["lp"]), ld, lp_cpad, P(b["lp_conv"]), taps, C, c_pad])
+        ref.append(a)
+        new.append(b)
+        sp["g"] = g
+    packed, tiles = ext.multi_update_table(descs)
+    table = packed.cuda()
+    sync = torch.zeros(2, dtype=torch.int32, device=dev)
+    for _ in range(1):
+        ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync)
+    torch.cuda.synchronize()
+    assert int(sync[0]) == 0 and int(sync[1]) == 1      # one grid barrier generation
+    for a, b, sp in zip(ref, new, specs):
+        for k in ("w", "vel", "gout", "acc"):
+            if a[k] is None:
+                continue
+            assert _rel(b[k], a[k]) < 2e-6, (sp["rows"], sp["cols"], k)
+        for k in ("lp", "lp_conv"):
+            if a[k] is not None:
+                assert _rel(b[k].float(), a[k].float()) < 1e-2, (sp["rows"], k)
+                assert float(b[k].float().abs().sum()) > 0
+    # disabled tensors must be left alone; a second launch must work (barrier re-arms)
+    descs[0][23] = 0
+    packed, tiles2 = ext.multi_update_table(descs)
+    assert tiles2 == tiles
+    table.copy_(packed)
+    w_before = new[0]["w"].clone()
+    ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync)
+    torch.cuda.synchronize()
+    assert torch.equal(new[0]["w"], w_before)
+    assert int(sync[1]) == 2

@@ -79,3 +79,39 @@ def test_mnist_lenet_gpu(compute):
         assert wf.decision.best_n_err_pt[1] < 25.0, wf.decision.best_n_err_pt
     finally:
         root.common.engine.compute_type = "fp32"
+
+
+def test_fused_step_equals_per_layer_updates():
+    """One whole-network step launch == per-tensor update launches (same weights after a few
+    minibatches, fp32 so the comparison is tight)."""
+    results = []
+    from veles.znicz_b200.core import prng
+    for fused in (False, True):
+        root.common.engine.fused_step = fused
+        prng.get(1).seed(1234)
+        prng.get(2).seed(5678)
+        try:
+            wf = cifar.build(
+                layers=_fast_layers(), use_graphs=False,
+                loader_config={"minibatch_size": 20, "n_train": 200, "n_valid": 40,
+                               "normalization_type": "internal_mean", "noise": 0.3},
+                decision_config={"max_epochs": 1, "fail_iterations": 10},
+                snapshotter_config={"prefix": "cifar_fs", "interval": 100,
+                                    "time_interval": 1e9})
+            wf.initialize(device="cuda")
+            assert (wf.fused_step_ is not None) == fused
+            wf.run()
+            if fused:
+                assert wf.fused_step_.launches == 10      # one per train minibatch
+            ws = []
+            for f in wf.forwards:
+                if getattr(f, "weights", None):
+                    f.weights.map_read()
+                    f.bias.map_read()
+                    ws.append((f.weights.mem.copy(), f.bias.mem.copy()))
+            results.append(ws)
+        finally:
+            root.common.engine.fused_step = True
+    for (wa, ba), (wb, bb) in zip(*results):
+        assert numpy.abs(wa - wb).max() <= 1e-4 * max(1.0, numpy.abs(wa).max())
+        assert numpy.abs(ba - bb).max() <= 1e-4 * max(1.0, numpy.abs(ba).max())

@@ -166,11 +166,13 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
         w, gout = unit.weights, unit.gradient_weights
         acc, vel = unit.accumulated_gradient_weights, unit.gradient_weights_with_moment
     flags = unit.update_flags(for_bias=is_bias)
+    step = unit.step_
     colsums = None
     if not is_bias and unit.factor_ortho:
         colsums = unit.col_sums.dev_out
-        ext.col_sums(w.dev, colsums, rows, cols, bool(unit.weights_transposed))
-        _launch()
+        if step is None:
+            ext.col_sums(w.dev, colsums, rows, cols, bool(unit.weights_transposed))
+            _launch()
     fwd = unit.forward_unit
     lp = lp_conv = None
     ld = taps = c = c_pad = cpad_lp = 0
@@ -188,16 +190,36 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
     else:
         ptrs, flag_ptrs, epoch_ptr, blocks, rank = [grad_buf.data_ptr()], [], 0, 0, 0
     wdev = w.dev
-    ext.fused_update(wdev, ptrs, nparts, part_stride, gout.dev_out if gout else None,
-                     acc.dev if acc else None, vel.dev if vel else None, unit.hyper_dev_,
-                     colsums, flags, is_bias, rows, cols, lp, ld, lp_conv, taps, c, c_pad,
-                     flag_ptrs, epoch_ptr, rank, blocks, cpad_lp, g_cpad)
+    gout_dev = gout.dev_out if gout else None
+    acc_dev = acc.dev if acc else None
+    vel_dev = vel.dev if vel else None
+    if step is not None:
+        # deferred: the whole-network step kernel applies it (ops/fused_step.py)
+        size = wdev.numel()
+        total_parts = nparts * len(ptrs)
+        lanes = 1
+        if size <= 16384:
+            while lanes * 2 <= min(32, total_parts if len(ptrs) == 1 else nparts):
+                lanes *= 2
+        p = lambda t: 0 if t is None else int(t.data_ptr())
+        fields = ([p(wdev), p(gout_dev), p(acc_dev), p(vel_dev), p(unit.hyper_dev_),
+                   p(colsums)] + [int(x) for x in ptrs] + [0] * (8 - len(ptrs)) +
+                  [int(part_stride), int(size), int(nparts), int(g_cpad), int(flags),
+                   1 if is_bias else 0, int(rows), int(cols), lanes, 1,
+                   p(lp), int(ld), int(cpad_lp), p(lp_conv), int(taps), int(c), int(c_pad)])
+        step.submit(unit, is_bias, fields,
+                    (wdev, gout_dev, acc_dev, vel_dev, colsums, lp, lp_conv, grad_buf),
+                    grad_buf.data_ptr())
+    else:
+        ext.fused_update(wdev, ptrs, nparts, part_stride, gout_dev, acc_dev, vel_dev,
+                         unit.hyper_dev_, colsums, flags, is_bias, rows, cols, lp, ld, lp_conv,
+                         taps, c, c_pad, flag_ptrs, epoch_ptr, rank, blocks, cpad_lp, g_cpad)
+        _launch()
     w.dev_written()
     if acc:
         acc.dev_written()
     if vel:
         vel.dev_written()
-    _launch()
     if dp is not None and dp.symm is None and dp.world_size > 1:
         raise RuntimeError("data-parallel GD without symmetric buffers is not wired")
 

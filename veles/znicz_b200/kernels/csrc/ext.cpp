@@ -34,6 +34,9 @@ void launch_mse_find_closest(const void*, bool, const float*, const int*, const 
 int fused_update_blocks(long long size);
 void launch_fused_update(float*, const float* const*, int, int, long long, float*, float*, float*, const float*, const float*, int, int, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, uint32_t* const*, uint32_t*, int, int, int, int, cudaStream_t);
 void launch_col_sums(const float*, float*, int, int, int, cudaStream_t);
+size_t multi_update_desc_size();
+int multi_update_pack(const long long*, int, void*, int);
+void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, cudaStream_t);
 void launch_refresh_shadows(const float*, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 void launch_gemm_simt(const void*, bool, long long, int, const void*, bool, long long, int, void*, bool, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
 struct ConvGeomS { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
@@ -296,6 +299,35 @@ void fused_update(Tensor w, std::vector<int64_t> grad_ptrs, int64_t nparts, int6
   kcheck();
 }
 int64_t update_blocks(int64_t size) { return zn::fused_update_blocks(size); }
+
+// Whole-network step table. Each descriptor is 31 int64 fields:
+// [w, grad_out, acc, vel, hyper, col_sums, grad[0..7], part_stride, size, nparts, g_cpad, flags,
+//  is_bias, rows, cols, lanes, enabled, lp, ld, lp_cpad, lp_conv, taps, C, c_pad]
+// Returns (packed CPU uint8 tensor [n * desc_size], total_tiles).
+std::tuple<Tensor, int64_t> multi_update_table(std::vector<std::vector<int64_t>> descs) {
+  const size_t ds = zn::multi_update_desc_size();
+  Tensor out = torch::zeros({(int64_t)(descs.size() * ds)}, torch::dtype(torch::kUInt8));
+  int tiles = 0;
+  for (size_t i = 0; i < descs.size(); ++i) {
+    TORCH_CHECK(descs[i].size() == 31, "descriptor must have 31 fields");
+    std::vector<long long> f(descs[i].begin(), descs[i].end());
+    tiles += zn::multi_update_pack(f.data(), 31, out.data_ptr<uint8_t>() + i * ds, tiles);
+  }
+  return std::make_tuple(out, (int64_t)tiles);
+}
+void multi_update(Tensor table, int64_t n, int64_t total_tiles, bool has_ortho,
+                  std::vector<int64_t> peer_flags, int64_t epoch_ptr, int64_t rank, Tensor gridsync) {
+  TORCH_CHECK(table.is_cuda() && table.scalar_type() == torch::kUInt8);
+  TORCH_CHECK(gridsync.is_cuda() && gridsync.scalar_type() == torch::kInt32 && gridsync.numel() >= 2);
+  uint32_t* fl[8];
+  const int nranks = peer_flags.size() > 1 ? (int)peer_flags.size() : 1;
+  TORCH_CHECK(nranks <= 8);
+  for (int i = 0; i < nranks && peer_flags.size() > 1; ++i) fl[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  zn::launch_multi_update(table.data_ptr(), (int)n, (int)total_tiles, has_ortho ? 1 : 0, nranks,
+                          nranks > 1 ? fl : nullptr, reinterpret_cast<uint32_t*>(epoch_ptr), (int)rank,
+                          reinterpret_cast<unsigned*>(gridsync.data_ptr<int32_t>()), cur());
+  kcheck();
+}
 void col_sums(Tensor w, Tensor out, int64_t rows, int64_t cols, bool transposed) {
   zn::launch_col_sums(w.data_ptr<float>(), out.data_ptr<float>(), (int)rows, (int)cols, transposed ? 1 : 0, cur());
   kcheck();
@@ -420,6 +452,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("softmax_rows", &softmax_rows); m.def("evaluate_softmax", &evaluate_softmax);
   m.def("evaluate_mse", &evaluate_mse); m.def("mse_find_closest", &mse_find_closest);
   m.def("fused_update", &fused_update); m.def("update_blocks", &update_blocks);
+  m.def("multi_update_table", &multi_update_table); m.def("multi_update", &multi_update);
   m.def("col_sums", &col_sums); m.def("refresh_shadows", &refresh_shadows);
   m.def("gemm", &gemm); m.def("pick_splits", &pick_splits);
   m.def("conv_fprop", &conv_fprop); m.def("conv_dgrad", &conv_dgrad); m.def("conv_wgrad", &conv_wgrad);

@@ -19,6 +19,7 @@
 // Cross-GPU ordering uses per-block flag words in symmetric memory (st.release.sys /
 // ld.acquire.sys), with the epoch counter kept in device memory so CUDA-graph replays work.
 #include "common.cuh"
+#include <string.h>
 
 namespace zn {
 
@@ -179,6 +180,269 @@ __global__ void refresh_shadows_k(const float* __restrict__ w, long long size, i
       sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Whole-network step: ONE launch applies the (cross-GPU reduced) SGD step to every parameter
+// tensor of the model. Replaces ~2 launches per layer (weights, bias) + the col_sums launches
+// with a single persistent kernel, and in data-parallel mode pays ONE cross-GPU flag barrier
+// per training step instead of one per tensor.
+//
+//   phase 0  signal peers "my gradients are complete" (they are: stream order)
+//   phase 1  column sums of the pre-update weights for tensors with the ortho regulariser
+//   ------   grid barrier (generation counter in device memory; graph-replay safe)
+//   phase 2  wait for the peers' signals, then tiles of 256 elements round-robin over blocks:
+//            sum over ranks and split-K partials (LANES threads cooperate per element when the
+//            partial count is large and the tensor small), SGD step, bf16 shadows
+//   phase 3  peer barrier "nobody still reads my gradient buffers"
+// ------------------------------------------------------------------------------------------
+struct TensorDesc {
+  float* w; float* grad_out; float* acc; float* vel;
+  const float* hyper; float* col_sums;
+  const float* grad[8];
+  long long part_stride, size;
+  int nparts, g_cpad, flags, is_bias, rows, cols, lanes, enabled;
+  ShadowSpec sh;
+  int tile_begin, n_tiles;
+};
+
+struct GridSync { unsigned* count; unsigned* gen; };
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_barrier(GridSync gs) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned my_gen = ld_acquire_gpu(gs.gen);   // cannot advance before I arrive
+    __threadfence();
+    const unsigned old = atomicAdd(gs.count, 1u);
+    if (old == gridDim.x - 1) {
+      *gs.count = 0u;
+      __threadfence();
+      atomicAdd(gs.gen, 1u);
+    } else {
+      long long spins = 0;
+      while (ld_acquire_gpu(gs.gen) == my_gen) {
+        if (++spins > (1LL << 31)) { __trap(); }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void multi_col_sums(const TensorDesc& d) {
+  // logical matrix [rows = Y][cols = H]; out[col] = sum over rows. 256 threads.
+  __shared__ float red[8][33];
+  const int tid = threadIdx.x;
+  if (d.flags & 16) {          // stored transposed [H][Y]: a warp per column, lanes over rows
+    const int lane = tid & 31, wib = tid >> 5;
+    for (int col = blockIdx.x * 8 + wib; col < d.cols; col += gridDim.x * 8) {
+      float s = 0.f;
+      for (int r = lane; r < d.rows; r += 32) s += d.w[(size_t)col * d.rows + r];
+      s = warp_sum(s);
+      if (lane == 0) d.col_sums[col] = s;
+    }
+    return;
+  }
+  const int cx = tid & 31, ry = tid >> 5;
+  const int n_cb = (d.cols + 31) / 32;
+  for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
+    const int col = cb * 32 + cx;
+    float s0 = 0.f, s1 = 0.f;
+    if (col < d.cols) {
+      int r = ry;
+      for (; r + 8 < d.rows; r += 16) {
+        s0 += d.w[(size_t)r * d.cols + col];
+        s1 += d.w[(size_t)(r + 8) * d.cols + col];
+      }
+      if (r < d.rows) s0 += d.w[(size_t)r * d.cols + col];
+    }
+    red[ry][cx] = s0 + s1;
+    __syncthreads();
+    if (ry == 0 && col < d.cols) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][cx];     // fixed order
+      d.col_sums[col] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, int nranks) {
+  const int L = d.lanes;                         // power of two, <= 32
+  const int tid = threadIdx.x;
+  const int lane = tid & (L - 1);
+  const int ept = 256 / L;                       // elements per tile
+  const long long i = (long long)tile * ept + tid / L;
+  const bool valid = i < d.size;
+  const int is_bias = d.is_bias;
+  float g = 0.f;
+  if (valid) {
+    long long gi = i;
+    if (d.g_cpad > 0) {
+      const int r_ = (int)(i / d.cols), c_ = (int)(i % d.cols);
+      const int tap_ = c_ / d.sh.C, ch_ = c_ - tap_ * d.sh.C;
+      gi = ((long long)r_ * d.sh.taps + tap_) * d.g_cpad + ch_;
+    }
+    for (int r = 0; r < nranks; ++r) {           // fixed rank order => bit-identical replicas
+      const float* base = d.grad[r] + gi;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+      int p = lane;
+      for (; p + 7 * L < d.nparts; p += 8 * L) { // 8 loads in flight
+        a0 += base[(long long)(p + 0 * L) * d.part_stride];
+        a1 += base[(long long)(p + 1 * L) * d.part_stride];
+        a2 += base[(long long)(p + 2 * L) * d.part_stride];
+        a3 += base[(long long)(p + 3 * L) * d.part_stride];
+        a4 += base[(long long)(p + 4 * L) * d.part_stride];
+        a5 += base[(long long)(p + 5 * L) * d.part_stride];
+        a6 += base[(long long)(p + 6 * L) * d.part_stride];
+        a7 += base[(long long)(p + 7 * L) * d.part_stride];
+      }
+      for (; p < d.nparts; p += L) a0 += base[(long long)p * d.part_stride];
+      g += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    }
+  }
+  for (int o = L >> 1; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  if (!valid || lane != 0) return;
+
+  const float* hyper = d.hyper;
+  const float lr = hyper[is_bias ? 9 : 0], wd = hyper[is_bias ? 10 : 1];
+  const float l1 = hyper[is_bias ? 11 : 2], moment = hyper[is_bias ? 12 : 3];
+  const float acc_alpha = hyper[4], acc_beta = hyper[5], gd_alpha = hyper[6], gd_beta = hyper[7];
+  const float ortho = hyper[8];
+  const int flags = d.flags;
+  const bool apply = flags & 1, use_moment = flags & 2, use_acc = flags & 4;
+  const bool use_ortho = (flags & 8) && d.col_sums != nullptr;
+  const bool transposed = flags & 16;
+  const int rows = d.rows, cols = d.cols;
+
+  if (d.grad_out) d.grad_out[i] = g;
+  float wv = d.w[i];
+  const float sgn = wv > 0.f ? 1.f : (wv < 0.f ? -1.f : 0.f);
+  float reg = wd * ((1.f - l1) * wv + 0.5f * l1 * sgn);
+  if (use_ortho) {
+    const int col = transposed ? (int)(i / rows) : (int)(i % cols);
+    reg += ortho / (float)rows * (d.col_sums[col] - wv);
+  }
+  float gd = -lr * (g + reg);
+  if (use_acc) {
+    const float a = (acc_beta != 0.f ? acc_beta * d.acc[i] : 0.f) + acc_alpha * gd;
+    d.acc[i] = a;
+    gd = gd * gd_beta + gd_alpha * a;
+  }
+  if (use_moment) { gd += d.vel[i] * moment; d.vel[i] = gd; }
+  if (apply) { wv += gd; d.w[i] = wv; }
+  const ShadowSpec& sh = d.sh;
+  if (sh.lp) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    int lc = c;
+    if (sh.lp_cpad > 0) { const int tap = c / sh.C; lc = tap * sh.lp_cpad + (c - tap * sh.C); }
+    sh.lp[(size_t)r * sh.ld + lc] = __float2bfloat16_rn(wv);
+    if (sh.lp_conv) {
+      const int tap = c / sh.C, ch = c % sh.C;
+      sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int has_ortho,
+               PeerSync ps, GridSync gsync) {
+  __shared__ uint32_t s_epoch;
+  __shared__ TensorDesc s_desc;
+  const bool multi = ps.nranks > 1;
+  uint32_t epoch = 0;
+  if (multi) {
+    if (threadIdx.x == 0) s_epoch = ps.epoch[blockIdx.x] + 1;
+    __syncthreads();
+    epoch = s_epoch;
+    if ((int)threadIdx.x < ps.nranks)              // phase 0: signal only, wait later
+      st_release_sys(ps.flags[threadIdx.x] + (size_t)blockIdx.x * 8 + ps.rank, 2 * epoch - 1);
+  }
+  if (has_ortho) {
+    for (int t = 0; t < n; ++t) {
+      if (!table[t].enabled || table[t].is_bias || !(table[t].flags & 8) || !table[t].col_sums)
+        continue;
+      __syncthreads();
+      if (threadIdx.x < sizeof(TensorDesc) / 4)
+        reinterpret_cast<uint32_t*>(&s_desc)[threadIdx.x] =
+            reinterpret_cast<const uint32_t*>(&table[t])[threadIdx.x];
+      __syncthreads();
+      multi_col_sums(s_desc);
+    }
+    grid_barrier(gsync);
+  }
+  if (multi) {
+    if ((int)threadIdx.x < ps.nranks) {
+      const uint32_t* mine = ps.flags[ps.rank] + (size_t)blockIdx.x * 8 + threadIdx.x;
+      const uint32_t value = 2 * epoch - 1;
+      long long spins = 0;
+      while ((int)(ld_acquire_sys(mine) - value) < 0) {
+        if (++spins > (1LL << 31)) { __trap(); }
+      }
+    }
+    __syncthreads();
+  }
+  int cur = -1;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int t = cur < 0 ? 0 : cur;
+    while (t + 1 < n && tile >= table[t].tile_begin + table[t].n_tiles) ++t;   // uniform
+    if (t != cur) {
+      __syncthreads();
+      if (threadIdx.x < sizeof(TensorDesc) / 4)
+        reinterpret_cast<uint32_t*>(&s_desc)[threadIdx.x] =
+            reinterpret_cast<const uint32_t*>(&table[t])[threadIdx.x];
+      __syncthreads();
+      cur = t;
+    }
+    if (s_desc.enabled) multi_tile(s_desc, tile - s_desc.tile_begin, ps.nranks);
+  }
+  if (multi) {
+    peer_barrier(ps, 2 * epoch);       // nobody still reads my gradient buffers
+    if (threadIdx.x == 0) ps.epoch[blockIdx.x] = epoch;
+  }
+}
+
+size_t multi_update_desc_size() { return sizeof(TensorDesc); }
+
+// fields: see ext.cpp::multi_update_table. Returns the number of tiles.
+int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begin) {
+  TensorDesc d{};
+  d.w = (float*)f[0]; d.grad_out = (float*)f[1]; d.acc = (float*)f[2]; d.vel = (float*)f[3];
+  d.hyper = (const float*)f[4]; d.col_sums = (float*)f[5];
+  for (int r = 0; r < 8; ++r) d.grad[r] = (const float*)f[6 + r];
+  d.part_stride = f[14]; d.size = f[15];
+  d.nparts = (int)f[16]; d.g_cpad = (int)f[17]; d.flags = (int)f[18]; d.is_bias = (int)f[19];
+  d.rows = (int)f[20]; d.cols = (int)f[21]; d.lanes = (int)f[22]; d.enabled = (int)f[23];
+  d.sh.lp = (__nv_bfloat16*)f[24]; d.sh.ld = (int)f[25]; d.sh.lp_cpad = (int)f[26];
+  d.sh.lp_conv = (__nv_bfloat16*)f[27]; d.sh.taps = (int)f[28]; d.sh.C = (int)f[29];
+  d.sh.c_pad = (int)f[30];
+  if (d.lanes < 1) d.lanes = 1;
+  const int ept = 256 / d.lanes;
+  d.tile_begin = tile_begin;
+  d.n_tiles = (int)((d.size + ept - 1) / ept);
+  memcpy(out, &d, sizeof(d));
+  (void)n_fields;
+  return d.n_tiles;
+}
+
+void launch_multi_update(const void* table, int n, int total_tiles, int has_ortho, int nranks,
+                         uint32_t* const* peer_flags, uint32_t* epoch, int rank, unsigned* gridsync,
+                         cudaStream_t st) {
+  PeerSync ps{};
+  ps.rank = rank; ps.nranks = (peer_flags && nranks > 1) ? nranks : 1; ps.epoch = epoch;
+  if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
+  GridSync gs{gridsync, gridsync + 1};
+  int blocks = total_tiles < 296 ? total_tiles : 296;
+  if (ps.nranks > 1 && blocks > 148) blocks = 148;   // flag arrays are sized for 148 blocks
+  if (blocks < 1) blocks = 1;
+  multi_update_k<<<blocks, 256, 0, st>>>((const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs);
 }
 
 int fused_update_blocks(long long size) {

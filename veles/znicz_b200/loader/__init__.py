@@ -3,3 +3,5 @@ from .base import (Loader, LoaderMSEMixin, UserLoaderRegistry, TEST, VALID, TRAI
                    CLASS_NAME, LoaderError)
 from .fullbatch import FullBatchLoader, FullBatchLoaderMSE  # noqa
 from . import synthetic  # noqa  (registers the synthetic_* loaders)
+from . import image  # noqa  (registers the *file_image loaders)
+from . import saver  # noqa  (registers minibatches_loader)

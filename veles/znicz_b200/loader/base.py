@@ -190,6 +190,7 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
         self.testing_mode = bool(self.testing)
         if not snapshot or not self.total_samples:
             self.load_data()
+            self.on_data_loaded()
             self._update_total_samples()
             if self.testing_mode:
                 self.shuffle_limit = 0
@@ -202,6 +203,7 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
         else:
             if not self._data_loaded():
                 self.load_data()
+                self.on_data_loaded()
             self._update_total_samples()
         self.max_minibatch_size = min(
             self.max_minibatch_size, max(self.class_lengths) or self.max_minibatch_size)
@@ -225,6 +227,10 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
 
     def _data_loaded(self):
         return True
+
+    def on_data_loaded(self):
+        """Hook between ``load_data`` and the offsets computation (validation carving)."""
+        pass
 
     def analyze_dataset(self):
         pass
@@ -458,3 +464,4 @@ class LoaderWithValidationRatio(object):
             return
         self.class_lengths[VALID] += delta
         self.class_lengths[TRAIN] -= delta
+        return delta

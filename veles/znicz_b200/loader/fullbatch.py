@@ -34,6 +34,7 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         self.original_labels = []
         self.on_device = kwargs.get("on_device", False)
         self.validation_ratio = kwargs.get("validation_ratio", None)
+        self.validation_seed = kwargs.get("validation_seed", 0x5EED)
         self._mapped_original_labels = Array()
         self._normalized = False
 
@@ -43,6 +44,26 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
 
     def _data_loaded(self):
         return bool(self.original_data)
+
+    def on_data_loaded(self):
+        """``validation_ratio``: shuffle VALID+TRAIN with a fixed seed (the dataset is
+        usually sorted by label) and move the class boundary."""
+        if not self.validation_ratio:
+            return
+        start = self.class_lengths[TEST]
+        n = self.class_lengths[VALID] + self.class_lengths[TRAIN]
+        before = self.class_lengths[VALID]
+        self.resize_validation()
+        if self.class_lengths[VALID] == before:
+            return
+        perm = numpy.random.RandomState(self.validation_seed).permutation(n) + start
+        for arr in (self.original_data, getattr(self, "original_targets", None)):
+            if arr is not None and arr:
+                arr.mem[start:start + n] = arr.mem[perm]
+        if len(self.original_labels):
+            labels = list(self.original_labels)
+            labels[start:start + n] = [labels[i] for i in perm]
+            self.original_labels = labels
 
     @property
     def dtype(self):

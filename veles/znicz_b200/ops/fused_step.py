@@ -1,0 +1,140 @@
+"""Whole-network optimizer step: one kernel launch per training step.
+
+The reference launches one weights_update + one bias_update kernel per layer
+(/root/reference/nn_units.py:560-642, cuda/gradient_descent_common.cu) and, when
+distributed, ships every layer's weights through the master
+(/root/reference/nn_units.py:644-694). Here every GD unit only *produces* its local
+gradient (split-K partials of the tcgen05 wgrad kernels, column-sum partials for the
+bias); a ``FusedStep`` attached to the workflow collects the parameter tensors into a
+descriptor table in HBM and, right after the last GD unit of the backward chain, launches
+``csrc/update.cu::multi_update_k`` once: cross-GPU reduction over NVLink peer pointers +
+split-K reduction + L1/L2/ortho regularisation + accumulation + momentum + apply + bf16
+operand shadows for *all* tensors, with a single cross-GPU flag barrier per step.
+
+Deferring the updates to the end of the chain is numerically identical to the reference
+order because every layer's err_input is computed from pre-update weights in both.
+"""
+from __future__ import annotations
+
+import torch
+
+from ..kernels import api
+
+
+def _ptr(t):
+    return 0 if t is None else int(t.data_ptr())
+
+
+class _Entry(object):
+    __slots__ = ("unit", "is_bias", "fields", "keep", "touched", "grad_ptr")
+
+
+class FusedStep(object):
+    def __init__(self, device, dp=None):
+        self.device = device
+        self.dp = dp
+        self.entries = []
+        self.index = {}
+        self.table = None
+        self.total_tiles = 0
+        self.has_ortho = False
+        self.dirty = True
+        self.enabled = []
+        self.gridsync = torch.zeros(2, dtype=torch.int32, device=device.torch_device)
+        self.flag_ptrs, self.epoch_ptr = [], 0
+        self.launches = 0
+        if dp is not None and dp.symm is not None:
+            self.flag_ptrs, self.epoch_ptr = dp.symm.sync_state("fused_step")
+
+    # -- wiring ------------------------------------------------------------------------------
+    @classmethod
+    def attach(cls, workflow, dp=None):
+        """Defer the updates of every CUDA GD unit of ``workflow`` and flush them after the
+        last unit of the backward chain."""
+        from .nn_units import GradientDescentBase
+        chain = [u for u in reversed(workflow.gds) if u is not None]
+        if not chain or not all(getattr(u, "on_cuda", False) for u in chain):
+            return None
+        fs = cls(workflow.device, dp)
+        for u in chain:
+            if isinstance(u, GradientDescentBase) and u.weights:
+                u.step_ = fs
+        last = chain[-1]
+        inner = last._backend_run_
+
+        def run_and_flush():
+            inner()
+            fs.flush()
+        last.__dict__["_backend_run_"] = run_and_flush
+        fs.last_unit = last
+        return fs
+
+    # -- registration (called by api._update in deferred mode) -----------------------------------
+    def submit(self, unit, is_bias, fields, keep, grad_ptr):
+        key = (id(unit), bool(is_bias))
+        e = self.index.get(key)
+        if e is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedStep: new tensor registered during graph capture")
+            e = _Entry()
+            e.unit, e.is_bias = unit, bool(is_bias)
+            self.index[key] = e
+            self.entries.append(e)
+            e.fields = None
+        if e.fields != fields:
+            if e.fields is not None and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedStep: %s changed buffers during graph capture" % unit)
+            e.fields = list(fields)
+            self.dirty = True
+        e.keep = keep
+        e.grad_ptr = grad_ptr
+        e.touched = True
+
+    def refresh_flags(self, unit):
+        """Host-side hook (GD ``cuda_prepare``): flags are baked into the table."""
+        for is_bias in (False, True):
+            e = self.index.get((id(unit), is_bias))
+            if e is not None and e.fields is not None:
+                f = unit.update_flags(for_bias=is_bias)
+                if e.fields[18] != f:
+                    e.fields[18] = f
+                    self.dirty = True
+        if self.dirty and self.table is not None and not torch.cuda.is_current_stream_capturing():
+            self._upload()
+
+    def _upload(self):
+        descs = []
+        for e in self.entries:
+            f = list(e.fields)
+            f[23] = 1 if e.touched else 0
+            descs.append(f)
+        packed, tiles = self.device.ext.multi_update_table(descs)
+        if self.table is None or self.table.numel() != packed.numel():
+            self.table = torch.empty(packed.numel(), dtype=torch.uint8,
+                                     device=self.device.torch_device)
+        self.table.copy_(packed)
+        self.total_tiles = int(tiles)
+        self.enabled = [bool(e.touched) for e in self.entries]
+        self.has_ortho = any((e.fields[18] & 8) and e.fields[5] and not e.is_bias
+                             for e in self.entries)
+        self.dirty = False
+
+    # -- the launch ------------------------------------------------------------------------------
+    def flush(self):
+        if not self.entries:
+            return
+        touched = [bool(e.touched) for e in self.entries]
+        if not any(touched):
+            return
+        if self.dirty or touched != self.enabled:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedStep: table changed during graph capture")
+            self._upload()
+        dp = self.dp
+        self.device.ext.multi_update(self.table, len(self.entries), self.total_tiles,
+                                     self.has_ortho, self.flag_ptrs, self.epoch_ptr,
+                                     dp.rank if dp is not None else 0, self.gridsync)
+        api._launch()
+        self.launches += 1
+        for e in self.entries:
+            e.touched = False

@@ -315,6 +315,7 @@ class GradientDescentBase(AcceleratedUnit, metaclass=MatchingObject):
         self.hyper_host_ = None
         self.hyper_cache_ = None
         self.dp_ = None   # data-parallel context (parallel.DataParallel) or None
+        self.step_ = None  # whole-network FusedStep collecting this unit's updates, or None
 
     @property
     def current_batch_size(self):
@@ -404,6 +405,8 @@ class GradientDescentBase(AcceleratedUnit, metaclass=MatchingObject):
 
     def cuda_prepare(self):
         self.sync_hyper()
+        if self.step_ is not None:
+            self.step_.refresh_flags(self)
 
     def update_flags(self, for_bias=False):
         """Bit flags understood by the fused update kernel."""

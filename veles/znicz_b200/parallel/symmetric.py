@@ -63,6 +63,21 @@ class SymmetricGradients(object):
         dist.barrier()
         return b.tensor.view(*shape)
 
+    def sync_state(self, key):
+        """(flag ptrs per rank, local epoch ptr) for a kernel that synchronises across
+        ranks on its own (the whole-network FusedStep)."""
+        b = self._bufs.get(("sync", key))
+        if b is None:
+            b = _Buf()
+            b.flags, fh = self._alloc(MAX_BLOCKS * 8, torch.int32)
+            b.flags.zero_()
+            b.flag_ptrs = [int(p) for p in fh.buffer_ptrs]
+            b.epoch = torch.zeros(MAX_BLOCKS, dtype=torch.int32, device=self.device)
+            self._bufs[("sync", key)] = b
+            torch.cuda.synchronize()
+            dist.barrier()
+        return b.flag_ptrs, b.epoch.data_ptr()
+
     def peers(self, unit, grad_buf):
         """(grad ptrs per rank, flag ptrs per rank, local epoch ptr, blocks)."""
         b = self._bufs[grad_buf.data_ptr()]

@@ -73,6 +73,7 @@ class StandardWorkflow(StandardWorkflowBase):
         super().init_unpickled()
         self.segments_ = []
         self.dp_ = None
+        self.fused_step_ = None
 
     # -- names ---------------------------------------------------------------------------------
     @property
@@ -571,6 +572,10 @@ class StandardWorkflow(StandardWorkflowBase):
             self.dp_ = DataParallel.from_env(dev)
             if self.dp_ is not None:
                 self.dp_.attach(self)
+            self.fused_step_ = None
+            if root.common.engine.get("fused_step", True):
+                from ..ops.fused_step import FusedStep
+                self.fused_step_ = FusedStep.attach(self, self.dp_)
             if self.use_graphs:
                 self._build_segments()
         return res
