@@ -320,28 +320,42 @@ class FullBatchAutoLabelFileImageLoaderMSE(FullBatchLoaderMSE, ImageOptionsMixin
         self.original_targets.reset(ct[idx])
 
 
-class AutoLabelFileImageLoader(Loader, ImageOptionsMixin):
-    """Streaming loader: only file names are kept; each minibatch is decoded on demand
-    (datasets that do not fit in host memory). Normalisation statistics are gathered from
-    a bounded random subset of TRAIN (``analysis_samples``)."""
-    MAPPING = "auto_label_file_image"
+class ImageLoaderBase(Loader):
+    """Streaming image loader in terms of three callbacks (the reference's ``IImageLoader``:
+    /root/reference/loader/loader_lmdb.py:76-104, loader_stl.py:96-116):
+
+      ``get_keys(class_index)``   → list of opaque keys of that class
+      ``get_image_data(key)``     → HWC array
+      ``get_image_label(key)``    → raw label
+
+    Only keys are kept in memory; each minibatch is decoded on demand. Normalisation
+    statistics come from a bounded random subset of TRAIN (``analysis_samples``)."""
+    hide_from_registry = True
 
     def __init__(self, workflow, **kwargs):
         super().__init__(workflow, **kwargs)
-        self._init_image_options(kwargs)
         self.analysis_samples = kwargs.get("analysis_samples", 1024)
+        self.mirror = kwargs.get("mirror", False)
         self.keys = []
         self.key_labels = []
         self.sample_shape = None
+
+    def get_keys(self, index):
+        raise NotImplementedError
+
+    def get_image_data(self, key):
+        raise NotImplementedError
+
+    def get_image_label(self, key):
+        raise NotImplementedError
 
     def _data_loaded(self):
         return bool(self.keys)
 
     def load_data(self):
         self.keys, raw = [], []
-        for cls, paths in ((TEST, self.test_paths), (VALID, self.validation_paths),
-                           (TRAIN, self.train_paths)):
-            ks = self.scan_files(paths)
+        for cls in (TEST, VALID, TRAIN):
+            ks = list(self.get_keys(cls))
             self.class_lengths[cls] = len(ks)
             self.keys.extend(ks)
             raw.extend(self.get_image_label(k) for k in ks)
@@ -351,7 +365,7 @@ class AutoLabelFileImageLoader(Loader, ImageOptionsMixin):
         self.labels_mapping = {l: i for i, l in enumerate(uniq)}
         self.reversed_labels_mapping = uniq
         self.key_labels = numpy.array([self.labels_mapping[l] for l in raw], numpy.int32)
-        self.sample_shape = self.decode(self.keys[-1]).shape
+        self.sample_shape = self.get_image_data(self.keys[-1]).shape
 
     @property
     def has_labels(self):
@@ -375,8 +389,8 @@ class AutoLabelFileImageLoader(Loader, ImageOptionsMixin):
         if not self.class_lengths[TRAIN]:
             start = 0
         pick = numpy.random.RandomState(1).permutation(n)[:self.analysis_samples] + start
-        sample = numpy.stack([self.decode(self.keys[i]) for i in pick]).astype(numpy.float32)
-        norm.analyze(sample)
+        sample = numpy.stack([self.get_image_data(self.keys[i]) for i in pick])
+        norm.analyze(sample.astype(numpy.float32))
 
     def fill_minibatch(self):
         n = self.minibatch_size
@@ -384,7 +398,7 @@ class AutoLabelFileImageLoader(Loader, ImageOptionsMixin):
         self.minibatch_data.map_invalidate()
         self.minibatch_labels.map_invalidate()
         md, ml = self.minibatch_data.mem, self.minibatch_labels.mem
-        raw = numpy.stack([self.decode(self.keys[i]) for i in idx]).astype(md.dtype)
+        raw = numpy.stack([self.get_image_data(self.keys[i]) for i in idx]).astype(md.dtype)
         if self.mirror == "random" and self.minibatch_class == TRAIN:
             flip = self.prng.randint(0, 2, n).astype(bool) if hasattr(self.prng, "randint") \
                 else numpy.random.randint(0, 2, n).astype(bool)
@@ -395,3 +409,40 @@ class AutoLabelFileImageLoader(Loader, ImageOptionsMixin):
         md[n:] = 0
         ml[:n] = self.key_labels[idx]
         ml[n:] = -1
+
+
+class FullBatchImageLoaderBase(FullBatchLoader):
+    """Full-batch counterpart of ``ImageLoaderBase`` (same three callbacks)."""
+    hide_from_registry = True
+
+    get_keys = ImageLoaderBase.get_keys
+    get_image_data = ImageLoaderBase.get_image_data
+    get_image_label = ImageLoaderBase.get_image_label
+
+    def load_data(self):
+        chunks, labels = [], []
+        for cls in (TEST, VALID, TRAIN):
+            ks = list(self.get_keys(cls))
+            self.class_lengths[cls] = len(ks)
+            chunks.extend(self.get_image_data(k) for k in ks)
+            labels.extend(self.get_image_label(k) for k in ks)
+        if not chunks:
+            raise LoaderError("no images found")
+        self.original_data.reset(numpy.stack(chunks))
+        self.original_labels = labels
+
+
+class AutoLabelFileImageLoader(ImageOptionsMixin, ImageLoaderBase):
+    """Streaming file loader: label = directory name (or ``label_regexp``)."""
+    MAPPING = "auto_label_file_image"
+
+    def __init__(self, workflow, **kwargs):
+        super().__init__(workflow, **kwargs)
+        self._init_image_options(kwargs)
+
+    def get_keys(self, index):
+        return self.scan_files((self.test_paths, self.validation_paths,
+                                self.train_paths)[index])
+
+    def get_image_data(self, key):
+        return self.decode(key)
