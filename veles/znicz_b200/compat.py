@@ -28,6 +28,18 @@ ALIASES = {
     "veles.loader": _B + "loader",
     "veles.loader.base": _B + "loader.base",
     "veles.loader.fullbatch": _B + "loader.fullbatch",
+    "veles.loader.image": _B + "loader.image",
+    "veles.loader.file_image": _B + "loader.image",
+    "veles.loader.fullbatch_image": _B + "loader.image",
+    "veles.loader.saver": _B + "loader.saver",
+    "veles.genetics": _B + "core.genetics",
+    "veles.launcher": _B + "launcher",
+    "veles.plotting_units": _B + "utils.plotting_units",
+    "veles.downloader": _B + "utils.downloader",
+    "veles.publishing": _B + "utils.publishing",
+    "veles.interaction": _B + "utils.interaction",
+    "veles.mean_disp_normalizer": _B + "utils.mean_disp_normalizer",
+    "veles.input_joiner": _B + "core.input_joiner",
     # znicz units
     "veles.znicz": _B[:-1],
     "veles.znicz.nn_units": _B + "ops.nn_units",
@@ -65,6 +77,11 @@ ALIASES = {
     "veles.znicz.nn_plotting_units": _B + "utils.nn_plotting_units",
     "veles.znicz.diversity": _B + "utils.diversity",
     "veles.znicz.loader": _B + "loader",
+    "veles.znicz.loader.loader_lmdb": _B + "loader.loader_lmdb",
+    "veles.znicz.loader.loader_stl": _B + "loader.loader_stl",
+    "veles.znicz.loader.imagenet_loader": _B + "loader.imagenet_loader",
+    "veles.znicz.loader.caffe": _B + "loader.caffe",
+    "veles.znicz.loader.caffe.protobuf2": _B + "loader.caffe.protobuf2",
 }
 
 
