@@ -57,6 +57,16 @@ class Config(object):
     def __iter__(self):
         return iter(self.__content__.items())
 
+    # mapping protocol, so ``dict(node)`` / ``**node`` work on config sub-trees
+    def keys(self):
+        return self.__content__.keys()
+
+    def values(self):
+        return self.__content__.values()
+
+    def items(self):
+        return self.__content__.items()
+
     # -- helpers ------------------------------------------------------------
     def update(self, value=None, **kwargs):
         if value is None:

@@ -81,7 +81,7 @@ class Weights2D(_PILPlotter):
         src = self.input if self.get_shape_from is None else self.get_shape_from
         n_channels = 1
         shape = src.shape if isinstance(src, Array) else tuple(
-            (s.shape[-1] if isinstance(s, Array) else s) for s in src)
+            ((s.shape[-1] if s else None) if isinstance(s, Array) else s) for s in src)
         if isinstance(src, Array):
             if len(shape) < 2:
                 return None, None, None
@@ -99,6 +99,8 @@ class Weights2D(_PILPlotter):
             sx, sy = shape
         else:
             sx, sy, n_channels = shape[-2], shape[-3], shape[-1]
+        if n_channels is None or sx is None or sy is None:
+            return None, None, None
         return int(n_channels), int(sx), int(sy)
 
     def prepare_pics(self, inp, transposed):

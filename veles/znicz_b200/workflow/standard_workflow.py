@@ -420,13 +420,20 @@ class StandardWorkflow(StandardWorkflowBase):
             prev = (p,)
         return self.err_y_plotter[-1]
 
+    def _has_weights(self, i):
+        """Only conv and fully connected layers are plotted
+        (/root/reference/standard_workflow.py:899-903)."""
+        from ..ops.all2all import All2All
+        from ..ops.conv import Conv
+        return isinstance(self.forwards[i], (Conv, All2All))
+
     def link_multi_hist_plotter(self, weights_input, *parents):
         from ..utils import plotting_units as pu
         self.multi_hist_plotter = []
         prev = parents
         for i, (unit, layer) in enumerate(
                 zip(self._get_weights_source_units(weights_input), self.layers)):
-            if unit is None or not getattr(unit, weights_input, None):
+            if unit is None or not self._has_weights(i):
                 continue
             p = pu.MultiHistogram(self, name="Histogram %s %d" % (weights_input, i + 1))
             p.link_attrs(unit, ("input", weights_input))
@@ -441,13 +448,14 @@ class StandardWorkflow(StandardWorkflowBase):
         self.weights_plotter = []
         prev = parents
         for i, unit in enumerate(self._get_weights_source_units(weights_input)):
-            if unit is None or not getattr(unit, weights_input, None):
+            if unit is None or not self._has_weights(i):
                 continue
             p = Weights2D(self, name="%s %d" % (weights_input, i + 1),
                           **self.dictify(self.config.weights_plotter))
             p.link_attrs(unit, ("input", weights_input))
             if hasattr(self.forwards[i], "kx"):
-                p.get_shape_from = [self.forwards[i].kx, self.forwards[i].ky, None]
+                p.get_shape_from = [self.forwards[i].kx, self.forwards[i].ky,
+                                    self.forwards[i].input]
             p.link_from(*prev)
             p.gate_skip = ~self.decision.epoch_ended
             self.weights_plotter.append(p)
@@ -459,7 +467,7 @@ class StandardWorkflow(StandardWorkflowBase):
         self.similar_weights_plotter = []
         prev = parents
         for i, unit in enumerate(self._get_weights_source_units(weights_input)):
-            if unit is None or not getattr(unit, weights_input, None):
+            if unit is None or not self._has_weights(i):
                 continue
             p = SimilarWeights2D(self, name="similar %s %d" % (weights_input, i + 1),
                                  **self.dictify(self.config.similar_weights_plotter))
