@@ -74,3 +74,82 @@ def test_video_ae(tmp_path):
     assert wf.forwards[-1].output.shape[1:] == (18, 32)
     wf.run()
     assert bool(wf.decision.complete) and wf.decision.best_mse[2] is not None
+
+
+def test_wine_relu():
+    from veles.znicz_b200.models import wine_relu
+    wf = wine_relu.build(decision_config={"max_epochs": 25, "fail_iterations": 50},
+                         snapshotter_config={"prefix": "wr", "interval": 1000,
+                                             "time_interval": 1e9})
+    assert type(wf.forwards[0]).__name__ == "All2AllRELU"
+    wf.initialize(device="numpy")
+    wf.run()
+    assert wf.decision.best_n_err_pt[2] < 15.0
+
+
+def test_mnist_simple_with_diff_stats():
+    import pickle
+    from veles.znicz_b200.models import mnist_simple
+    root.mnist_simple.decision.max_epochs = 3
+    wf = mnist_simple.build(loader_name="synthetic_mnist", layers=[30, 10],
+                            loader_config={"minibatch_size": 20, "n_train": 200,
+                                           "n_valid": 60, "noise": 0.3})
+    wf.initialize(device="numpy")
+    wf.run()
+    assert wf.decision.best_n_err_pt[1] < 30.0
+    assert wf.diff_stats.size > 0 and wf.slaves_plotter.records
+    with open(wf.diff_stats.file_name, "rb") as f:
+        stats = pickle.load(f)
+    assert any("gradient_weights" in v for v in stats.values())
+    assert len(wf.plt[1].values) >= 3
+
+
+def test_stl10_workflow(tmp_path):
+    pytest.importorskip("cv2")
+    from veles.znicz_b200.models import stl10
+    rs = numpy.random.RandomState(7)
+    (tmp_path / "class_names.txt").write_text("a b c\n")
+    protos = rs.randint(0, 255, (3, 3, 96, 96))
+    for stem, n in (("train", 24), ("test", 9)):
+        y = rs.randint(1, 4, n).astype(numpy.uint8)
+        x = numpy.clip(protos[y - 1] + rs.randn(n, 3, 96, 96) * 20, 0, 255).astype(numpy.uint8)
+        x.tofile(str(tmp_path / (stem + "_X.bin")))
+        y.tofile(str(tmp_path / (stem + "_y.bin")))
+    wf = stl10.build(loader_config={"directory": str(tmp_path), "minibatch_size": 8,
+                                    "scale": (32, 32), "normalization_type": "internal_mean"},
+                     decision_config={"max_epochs": 1, "fail_iterations": 5},
+                     snapshotter_config={"prefix": "stl_t", "interval": 1000,
+                                         "time_interval": 1e9})
+    wf.initialize(device="numpy")
+    assert wf.loader.original_data.shape == (33, 32, 32, 3)
+    assert wf.forwards[-1].output.shape == (8, 3)
+    wf.run()
+    assert bool(wf.decision.complete)
+
+
+def test_mnist_rbm_workflow():
+    from veles.znicz_b200.models import mnist_rbm
+    wf = mnist_rbm.build(minibatch_size=32, n_samples=96, h_size=40, max_epochs=3,
+                         learning_rate=0.05)
+    wf.initialize(device="numpy")
+    w0 = wf.forwards[1].weights.mem.copy()
+    wf.run()
+    assert bool(wf.decision.complete)
+    assert numpy.abs(wf.forwards[1].weights.mem - w0).max() > 1e-5
+    assert numpy.isfinite(wf.forwards[1].weights.mem).all()
+
+
+def test_mnist_ae_workflow():
+    from veles.znicz_b200.models import mnist_ae
+    wf = mnist_ae.build(loader_name="synthetic_mnist", max_epochs=3, learning_rate=0.0005,
+                        loader_config={"minibatch_size": 10, "n_train": 60, "n_valid": 20,
+                                       "noise": 0.3, "normalization_type": "linear"})
+    wf.initialize(device="numpy")
+    assert wf.deconv.output.shape == wf.loader.minibatch_data.shape
+    assert wf.deconv.weights is wf.conv.weights or \
+        wf.deconv.weights.mem is wf.conv.weights.mem
+    w0 = wf.conv.weights.mem.copy()
+    wf.run()
+    assert bool(wf.decision.complete)
+    assert numpy.abs(wf.conv.weights.mem - w0).max() > 0
+    assert wf.plt[2].pics and wf.plt[-1].pics

@@ -22,6 +22,7 @@ class STL10FullBatchLoader(FullBatchImageLoaderBase):
         super().__init__(workflow, **kwargs)
         self.directory = kwargs["directory"]
         self.size = tuple(kwargs.get("size", self.SIZE))
+        self.scale = kwargs.get("scale")        # (w, h) served size, None = native
 
     def init_unpickled(self):
         super().init_unpickled()
@@ -58,4 +59,8 @@ class STL10FullBatchLoader(FullBatchImageLoaderBase):
 
     def get_image_data(self, key):
         planes = self._open(key[0])[0][key[1]]        # [c][col][row]
-        return numpy.ascontiguousarray(planes.transpose(2, 1, 0))
+        img = numpy.ascontiguousarray(planes.transpose(2, 1, 0))
+        if self.scale is not None and tuple(self.scale) != (img.shape[1], img.shape[0]):
+            from .image import fit_image
+            img = fit_image(img, tuple(self.scale))
+        return img

@@ -305,8 +305,17 @@ class EvaluatorRBM(AcceleratedWorkflow):
         self.rec.link_attrs(self, "weights")
         self.rec.link_attrs(self, ("bias", "vbias"))
         self.mse.link_attrs(self, "target", "batch_size")
-        self.demand("input", "weights", "target", "vbias", "batch_size")
+        # the evaluator owns the visible bias (/root/reference/rbm_units.py:518-545); callers
+        # may still link an external one over it
+        self.vbias = Array(numpy.zeros(int(numpy.prod(kwargs["bias_shape"])),
+                                       dtype=numpy.float32))
+        self.demand("input", "weights", "target", "batch_size")
 
     @property
     def metrics(self):
         return self.mse.metrics
+
+    @property
+    def output(self):
+        """The reconstruction of the visible layer."""
+        return self.rec.output

@@ -252,3 +252,34 @@ class ImmediatePlotter(Plotter):
         for c, st in zip(self.curves, self.input_styles or ["k-"] * len(self.curves)):
             ax.plot(c, st)
         self._savefig(fig)
+
+
+class SlaveStats(Plotter):
+    """Per-worker throughput table (``veles.plotting_units.SlaveStats`` in
+    /root/reference/tests/research/MnistSimple/mnist.py:180). In the one-process-per-GPU
+    design a "slave" is a data-parallel rank: each run records
+    (rank, world_size, minibatches seen, wall seconds since the previous record)."""
+
+    def __init__(self, workflow, **kwargs):
+        kwargs.setdefault("name", "Slave Stats")
+        super().__init__(workflow, **kwargs)
+        self.records = []
+        self._count = 0
+        self._last = None
+
+    def record(self):
+        import time
+        now = time.time()
+        self._count += 1
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.records.append((rank, world, self._count,
+                             0.0 if self._last is None else now - self._last))
+        self._last = now
+        if len(self.records) > 4096:
+            del self.records[:2048]
+
+    def redraw(self):
+        if self.records:
+            r = self.records[-1]
+            self.info("rank %d/%d: %d minibatches, last step %.4f s", *r)
