@@ -153,3 +153,88 @@ def test_mnist_ae_workflow():
     assert bool(wf.decision.complete)
     assert numpy.abs(wf.conv.weights.mem - w0).max() > 0
     assert wf.plt[2].pics and wf.plt[-1].pics
+
+
+def _tiny_imagenet(tmp_path, n_val=8, n_train=24, side=40, n_classes=4):
+    import json
+    import pickle
+    rs = numpy.random.RandomState(3)
+    n = n_val + n_train
+    labels = rs.randint(0, n_classes, n)
+    protos = rs.randint(0, 255, (n_classes, side, side, 3))
+    samples = numpy.clip(protos[labels] + rs.randn(n, side, side, 3) * 25, 0, 255) \
+        .astype(numpy.uint8)
+    samples.tofile(str(tmp_path / "samples.dat"))
+    with open(tmp_path / "labels.pickle", "wb") as f:
+        pickle.dump([("n%03d" % l, int(l)) for l in labels], f)
+    with open(tmp_path / "count.json", "w") as f:
+        json.dump({"test": 0, "val": n_val, "train": n_train}, f)
+    mean = samples[n_val:].mean(axis=0)
+    with open(tmp_path / "matrixes.pickle", "wb") as f:
+        pickle.dump([mean, numpy.ones_like(mean, dtype=numpy.float32) / 64], f)
+    return dict(sx=side, sy=side, crop_size_sx=32, crop_size_sy=32, mirror=True, channels=3,
+                minibatch_size=8, normalization_type="none",
+                original_labels_filename=str(tmp_path / "labels.pickle"),
+                count_samples_filename=str(tmp_path / "count.json"),
+                samples_filename=str(tmp_path / "samples.dat"),
+                matrixes_filename=str(tmp_path / "matrixes.pickle"))
+
+
+def _shrink(layers, n_classes, div=16, fc=32):
+    """Same topology, far fewer kernels/neurons so the CPU test stays quick."""
+    out = []
+    for l in layers:
+        l = dict(l)
+        if "->" in l:
+            fwd = dict(l["->"])
+            if "n_kernels" in fwd:
+                fwd["n_kernels"] = max(4, fwd["n_kernels"] // div)
+                if fwd["kx"] == 11:
+                    fwd.update(kx=5, ky=5, sliding=(2, 2))
+            if "output_sample_shape" in fwd:
+                fwd["output_sample_shape"] = n_classes if l["type"] == "softmax" else fc
+            l["->"] = fwd
+        out.append(l)
+    return out
+
+
+def test_alexnet_family_topologies():
+    from veles.znicz_b200.models import alexnet
+    a, n, v = alexnet.alexnet_layers(), alexnet.nin_layers(), alexnet.vgga_layers()
+    assert [l["type"] for l in a].count("conv_str") == 5
+    assert [l["type"] for l in a].count("zero_filter") == 4
+    assert [l["type"] for l in n].count("conv") == 12 and n[-2]["type"] == "avg_pooling"
+    assert [l["type"] for l in v].count("conv_str") == 13
+    assert [l["type"] for l in v].count("max_pooling") == 5
+    assert a[0]["->"]["sliding"] == (4, 4) and a[-1]["->"]["output_sample_shape"] == 1000
+
+
+def test_alexnet_workflow_tiny(tmp_path):
+    from veles.znicz_b200.models import alexnet
+    loader = _tiny_imagenet(tmp_path)
+    layers = _shrink(alexnet.alexnet_layers(), 4, div=16)
+    # the 3/2 pools of the real net need >= 3x3 maps: use padding-friendly small maps
+    wf = alexnet.build(
+        loader_config=loader, layers=layers,
+        decision_config={"max_epochs": 2, "fail_iterations": 10},
+        snapshotter_config={"prefix": "alex_t", "interval": 1000, "time_interval": 1e9},
+        lr_adjuster_config={"lr_policy_name": "arbitrary_step",
+                            "bias_lr_policy_name": "arbitrary_step",
+                            "lr_parameters": {"lrs_with_lengths": [(1, 3), (0.1, 100)]},
+                            "bias_lr_parameters": {"lrs_with_lengths": [(1, 3), (0.1, 100)]}})
+    wf.initialize(device="numpy")
+    names = [type(f).__name__ for f in wf.forwards]
+    assert names.count("ZeroFiller") == 4 and names.count("DropoutForward") == 2
+    lr0 = wf.gds[0].learning_rate
+    wf.run()
+    assert bool(wf.decision.complete)
+    assert wf.gds[0].learning_rate < lr0                 # arbitrary_step kicked in
+    # grouping: conv2 only sees its own half of the input channels
+    conv2 = [f for f in wf.forwards if f.name == "conv_str2_forward"][0]
+    w = conv2.weights.mem.reshape(conv2.n_kernels, conv2.ky, conv2.kx, -1)
+    # the mask zeroes kernel % g == channel % g (/root/reference/weights_zerofilling.py:95-98)
+    k_idx = numpy.arange(conv2.n_kernels)[:, None] % 2
+    c_idx = numpy.arange(w.shape[-1])[None, :] % 2
+    off = (k_idx == c_idx)[:, None, None, :]
+    assert numpy.all(w[numpy.broadcast_to(off, w.shape)] == 0)
+    assert numpy.any(w[numpy.broadcast_to(~off, w.shape)] != 0)
