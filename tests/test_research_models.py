@@ -238,3 +238,76 @@ def test_alexnet_workflow_tiny(tmp_path):
     off = (k_idx == c_idx)[:, None, None, :]
     assert numpy.all(w[numpy.broadcast_to(off, w.shape)] == 0)
     assert numpy.any(w[numpy.broadcast_to(~off, w.shape)] != 0)
+
+
+def test_imagenet_ae_stages_and_fine_tuning(tmp_path):
+    """Greedy AE pre-training: stage 1 → (snapshot) → stack stage 2 → (snapshot) →
+    fine tuning as a softmax classifier; encoder weights carry over between stages."""
+    import glob
+    from veles.znicz_b200.core.snapshotter import SnapshotterToFile
+    from veles.znicz_b200.models import imagenet_ae
+    loader = _tiny_imagenet(tmp_path, side=24)
+    for k in ("crop_size_sx", "crop_size_sy", "mirror"):
+        loader.pop(k)
+    layers = [
+        {"type": "ae_begin"},
+        {"name": "conv1", "type": "conv",
+         "->": {"n_kernels": 6, "kx": 5, "ky": 5, "sliding": (1, 1), "include_bias": False,
+                "weights_filling": "gaussian", "weights_stddev": 0.05},
+         "<-": {"learning_rate": 1e-5, "learning_rate_ft": 1e-3, "weights_decay": 0.0}},
+        {"name": "pool1", "type": "stochastic_abs_pooling",
+         "->": {"kx": 2, "ky": 2, "sliding": (2, 2)}},
+        {"type": "ae_end"},
+        {"name": "mul1", "type": "activation_mul"},
+        {"type": "ae_begin"},
+        {"name": "conv2", "type": "conv",
+         "->": {"n_kernels": 8, "kx": 3, "ky": 3, "sliding": (1, 1), "include_bias": False,
+                "weights_filling": "gaussian", "weights_stddev": 0.05},
+         "<-": {"learning_rate": 1e-5, "learning_rate_ft": 1e-3, "weights_decay": 0.0}},
+        {"type": "ae_end"},
+        {"name": "fc3", "type": "all2all_tanh", "->": {"output_sample_shape": 16},
+         "<-": {"learning_rate": 1e-2, "learning_rate_ft": 1e-2}},
+        {"name": "softmax4", "type": "softmax", "<-": {"learning_rate": 1e-2}}]
+    blocks, inter, tail = imagenet_ae.split_layers(layers)
+    assert [len(b) for b in blocks] == [2, 1] and len(inter[1]) == 1 and len(tail) == 2
+    snap_dir = str(tmp_path / "snaps")
+    wf = imagenet_ae.build(
+        loader_name="imagenet_loader_base", loader_config=loader, layers=layers,
+        decision_mse_config={"max_epochs": 2, "fail_iterations": 10},
+        decision_gd_config={"max_epochs": 2, "fail_iterations": 10},
+        snapshotter_config={"prefix": "iae", "interval": 1, "time_interval": 0,
+                            "directory": snap_dir, "compression": ""})
+    wf.initialize(device="numpy")
+    assert [type(f).__name__ for f in wf.forwards] == ["Conv", "StochasticAbsPoolingDepooling"]
+    assert len(wf.decoder) == 1 and wf.decoder[0][0].weights.mem is wf.forwards[0].weights.mem
+    w_before = wf.forwards[0].weights.mem.copy()
+    wf.run()
+    assert bool(wf.decision.complete)
+    w1 = wf.forwards[0].weights.mem.copy()
+    assert numpy.abs(w1 - w_before).max() > 0
+    snaps = sorted(f for f in glob.glob(os.path.join(snap_dir, "iae*.pickle"))
+                   if not os.path.islink(f))
+    assert snaps
+    # -- restore → graph surgery stacks block 2 ------------------------------------------
+    wf2 = SnapshotterToFile.import_file(snaps[-1])
+    wf2.workflow = imagenet_ae.DummyLauncherFactory()
+    w1 = wf2.forwards[0].weights.mem.copy()        # the snapshot holds the best epoch
+    wf2.initialize(device="numpy", snapshot=True)
+    assert wf2.stage == 1
+    assert [type(f).__name__ for f in wf2.forwards] == [
+        "Conv", "StochasticAbsPooling", "ForwardMul", "Conv"]
+    numpy.testing.assert_array_equal(wf2.forwards[0].weights.mem, w1)
+    assert all(g.forward_unit is not wf2.forwards[0] for g in wf2.gds)   # block 1 is frozen
+    wf2.run()
+    numpy.testing.assert_array_equal(wf2.forwards[0].weights.mem, w1)
+    # -- fine tuning ---------------------------------------------------------------------
+    wf2.switch_to_fine_tuning()
+    wf2.initialize(device="numpy")
+    assert type(wf2.forwards[-1]).__name__ == "All2AllSoftmax"
+    assert wf2.forwards[-1].output.shape[1] == 4
+    assert len(wf2.gds) == 6 and wf2.gds[0].learning_rate == 1e-2
+    conv_gd = [g for g in wf2.gds if g.forward_unit is wf2.forwards[0]][0]
+    assert conv_gd.learning_rate == 1e-3                  # learning_rate_ft applied
+    wf2.run()
+    assert bool(wf2.decision.complete)
+    assert numpy.abs(wf2.forwards[0].weights.mem - w1).max() > 0

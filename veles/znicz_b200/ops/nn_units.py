@@ -346,6 +346,9 @@ class GradientDescentBase(AcceleratedUnit, metaclass=MatchingObject):
                 self._ensure_like(self.accumulated_gradient_weights, self.weights)
             if self.gradient_moment or not self.is_standalone:
                 self._ensure_like(self.gradient_weights_with_moment, self.weights)
+        if self.include_bias and not self.bias:
+            # the forward unit was built with include_bias=False: nothing to train
+            self.include_bias = False
         b_ok = self.need_gradient_weights and self.include_bias and self.bias
         if b_ok:
             self._ensure_like(self.gradient_bias, self.bias)
