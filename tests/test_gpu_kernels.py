@@ -271,3 +271,63 @@ def test_multi_update_matches_per_tensor_update(ext):
     torch.cuda.synchronize()
     assert torch.equal(new[0]["w"], w_before)
     assert int(sync[1]) == 2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n_out,act,softmax", [(10, 0, True), (7, 1, False), (16, 3, False),
+                                               (3, 4, False)])
+def test_fc_small_forward(ext, dtype, n_out, act, softmax):
+    torch.manual_seed(n_out)
+    dev = "cuda"
+    batch, n_in = 37, 1000
+    x = torch.randn(batch, n_in, device=dev).to(dtype)
+    w = torch.randn(n_out, n_in, device=dev) * 0.05
+    b = torch.randn(n_out, device=dev)
+    out = torch.full((batch, n_out), float("nan"), device=dev,
+                     dtype=torch.float32 if softmax else dtype)
+    mi = torch.full((batch,), -1, device=dev, dtype=torch.int32)
+    ext.fc_small_forward(x, w, b, out, mi if softmax else None, batch, n_in, n_out, act, softmax)
+    torch.cuda.synchronize()
+    z = x.float() @ w.t() + b
+    if softmax:
+        ref = torch.softmax(z, dim=1)
+        assert torch.equal(mi.long(), z.argmax(dim=1))
+    else:
+        ref = {1: lambda t: 1.7159 * torch.tanh(0.6666 * t), 3: torch.relu,
+               4: torch.sigmoid}[act](z)
+    assert _rel(out.float(), ref) < (1e-5 if dtype == torch.float32 and softmax else 2e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n_out,act", [(10, 0), (7, 1), (16, 3)])
+def test_fc_small_backward(ext, dtype, n_out, act):
+    torch.manual_seed(100 + n_out)
+    dev = "cuda"
+    batch, n_in, bsplit = 53, 520, 4
+    x = torch.randn(batch, n_in, device=dev).to(dtype)
+    w = torch.randn(n_out, n_in, device=dev) * 0.05
+    y = torch.randn(batch, n_out, device=dev).to(dtype)
+    err = torch.randn(batch, n_out, device=dev).to(dtype)
+    ei = torch.randn(batch, n_in, device=dev).to(dtype)
+    ei0, err0 = ei.clone(), err.clone()
+    gw = torch.full((bsplit, n_out, n_in), float("nan"), device=dev)
+    gb = torch.full((bsplit, n_out), float("nan"), device=dev)
+    alpha, beta = 0.75, 0.5
+    ext.fc_small_backward(err, y if act else None, x, w, ei, gw, gb, batch, n_in, n_out, act,
+                          alpha, beta, bsplit)
+    torch.cuda.synchronize()
+    yf = y.float()
+    d = {0: torch.ones_like(yf), 1: yf * yf * (-0.388484177) + 1.14381894,
+         3: (yf > 0).float()}[act]
+    e = err0.float() * d
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    if act:
+        assert _rel(err.float(), e) < tol
+    e_used = err.float() if act else e          # the kernel works from the fp32 product
+    assert _rel(ei.float(), alpha * (e @ w) + beta * ei0.float()) < tol
+    assert _rel(gw.sum(0), e.t() @ x.float()) < tol
+    assert _rel(gb.sum(0), e.sum(0)) < tol
+    # optional outputs
+    ext.fc_small_backward(err0.clone(), y if act else None, x, w, None, None, None, batch, n_in,
+                          n_out, act, 1.0, 0.0, 2)
+    torch.cuda.synchronize()

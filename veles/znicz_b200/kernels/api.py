@@ -121,6 +121,13 @@ def fc_forward(unit, softmax=False):
         out = unit.output.dev_out
     use_lp = lp_enabled(unit) and _is_bf16(x) and n_in % 8 == 0
     act = ACT_LINEAR if softmax else unit.ACT
+    if _fc_small_ok(unit, n_out) and act <= 4:
+        # few outputs: one launch does GEMV x n_out + bias + activation (+ softmax + arg-max)
+        ext.fc_small_forward(x, unit.weights.dev, bias, unit.output.dev_out,
+                             unit.max_idx.dev_out if softmax else None, batch, n_in, n_out,
+                             act, bool(softmax))
+        _launch()
+        return
     if use_lp:
         ensure_shadows(unit)
         w = unit.weights_lp_
@@ -140,6 +147,15 @@ def fc_forward(unit, softmax=False):
     if softmax:
         ext.softmax_rows(out, unit.output.dev_out, unit.max_idx.dev_out)
         _launch()
+
+
+FC_SMALL_MAX_OUT = 16
+
+
+def _fc_small_ok(unit, n_out):
+    """Few-output FC layers use the dedicated kernels of csrc/fc_small.cu."""
+    return (n_out <= FC_SMALL_MAX_OUT and not unit.weights_transposed and unit.weights and
+            unit.weights.dev.dtype == torch.float32)
 
 
 def _bias_partials(unit, rows, cols):
@@ -233,6 +249,29 @@ def fc_backward(unit):
     n_in = x.numel() // batch
     need_w = unit.need_gradient_weights and unit.weights
     need_b = need_w and unit.include_bias and unit.bias
+    if (_fc_small_ok(unit, n_out) and unit.ACT <= 4 and err.dtype == x.dtype and
+            (unit.ACT == ACT_LINEAR or unit.output.dev.dtype == err.dtype)):
+        # whole GD step of a few-output layer in one launch (+ the deferred update)
+        bsplit = max(1, min(8, batch // 16))
+        gbuf = _grad_buffer(unit, "wgrad", (bsplit,) + tuple(unit.weights.shape)) \
+            if need_w else None
+        parts = _grad_buffer(unit, "bias_parts", (bsplit, n_out)) if need_b else None
+        ei = None
+        if unit.need_err_input:
+            ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
+        ext.fc_small_backward(err, unit.output.dev if unit.ACT != ACT_LINEAR else None, x,
+                              unit.weights.dev, ei, gbuf, parts, batch, n_in, n_out, unit.ACT,
+                              float(unit.err_input_alpha), float(unit.err_input_beta), bsplit)
+        if unit.ACT != ACT_LINEAR:
+            unit.err_output.dev_written()
+        if ei is not None:
+            unit.err_input.dev_written()
+        _launch()
+        if need_w:
+            _update(unit, False, gbuf, bsplit, n_out * n_in, n_out, n_in)
+        if need_b:
+            _update(unit, True, parts, bsplit, n_out, 1, n_out)
+        return
     # 1. err_output *= f'(output) fused with the bias-gradient column sums
     if unit.ACT != ACT_LINEAR or need_b:
         parts = None

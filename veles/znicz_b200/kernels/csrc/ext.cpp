@@ -34,6 +34,9 @@ void launch_mse_find_closest(const void*, bool, const float*, const int*, const 
 int fused_update_blocks(long long size);
 void launch_fused_update(float*, const float* const*, int, int, long long, float*, float*, float*, const float*, const float*, int, int, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, uint32_t* const*, uint32_t*, int, int, int, int, cudaStream_t);
 void launch_col_sums(const float*, float*, int, int, int, cudaStream_t);
+int fc_small_max_out();
+void launch_fc_small_forward(const void*, bool, const float*, const float*, void*, float*, int*, int, int, int, int, int, cudaStream_t);
+void launch_fc_small_backward(void*, const void*, const void*, bool, const float*, void*, float*, float*, int, int, int, int, float, float, int, cudaStream_t);
 size_t multi_update_desc_size();
 int multi_update_pack(const long long*, int, void*, int);
 void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, cudaStream_t);
@@ -339,6 +342,61 @@ void refresh_shadows(Tensor w, int64_t rows, int64_t cols, c10::optional<Tensor>
   kcheck();
 }
 
+// FC layers with n_out <= fc_small_max_out(): see csrc/fc_small.cu
+int64_t fc_small_max_out() { return zn::fc_small_max_out(); }
+void fc_small_forward(Tensor x, Tensor w, c10::optional<Tensor> bias, Tensor out, c10::optional<Tensor> max_idx,
+                      int64_t batch, int64_t n_in, int64_t n_out, int64_t act, bool softmax) {
+  chk(x, "x"); chk(out, "out");
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32 && w.is_cuda() && w.is_contiguous(), "weights must be fp32");
+  TORCH_CHECK(n_out <= zn::fc_small_max_out() && w.numel() == n_out * n_in);
+  TORCH_CHECK(x.numel() >= batch * n_in && out.numel() >= batch * n_out);
+  const bool out_f32 = out.scalar_type() == torch::kFloat32;
+  TORCH_CHECK(out_f32 || out.scalar_type() == x.scalar_type(), "output dtype must be fp32 or match the input");
+  int* mi = nullptr;
+  if (max_idx.has_value() && max_idx->defined()) {
+    TORCH_CHECK(max_idx->scalar_type() == torch::kInt32 && max_idx->numel() >= batch);
+    mi = max_idx->data_ptr<int>();
+  }
+  const bool xb = is_bf16(x);
+  // fp32 output of a bf16 input goes through out_f; same-dtype output through out_t
+  void* out_t = (out_f32 && xb) ? nullptr : out.data_ptr();
+  float* out_f = (out_f32 && xb) ? out.data_ptr<float>() : nullptr;
+  if (!xb) { out_t = out.data_ptr(); out_f = nullptr; }
+  zn::launch_fc_small_forward(x.data_ptr(), xb, w.data_ptr<float>(), fptr_or_null(bias), out_t, out_f, mi,
+                              (int)batch, (int)n_in, (int)n_out, (int)act, softmax ? 1 : 0, cur());
+  kcheck();
+}
+void fc_small_backward(Tensor err, c10::optional<Tensor> y, Tensor x, Tensor w, c10::optional<Tensor> err_in,
+                       c10::optional<Tensor> gw_parts, c10::optional<Tensor> gb_parts, int64_t batch,
+                       int64_t n_in, int64_t n_out, int64_t act, double alpha, double beta, int64_t bsplit) {
+  chk(err, "err"); chk(x, "x");
+  same_dt(err, x);
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32 && w.is_cuda() && w.is_contiguous());
+  TORCH_CHECK(n_out <= zn::fc_small_max_out() && bsplit >= 1);
+  TORCH_CHECK(act >= 0 && act <= 4, "fc_small_backward supports linear/tanh/relu/strict relu/sigmoid");
+  const void* yp = nullptr;
+  if (act != 0) {
+    TORCH_CHECK(y.has_value() && y->defined(), "activation derivative needs the output");
+    same_dt(err, *y);
+    yp = y->data_ptr();
+  }
+  void* eip = nullptr;
+  if (err_in.has_value() && err_in->defined()) { same_dt(err, *err_in); eip = err_in->data_ptr(); }
+  float* gw = nullptr; float* gb = nullptr;
+  if (gw_parts.has_value() && gw_parts->defined()) {
+    TORCH_CHECK(gw_parts->scalar_type() == torch::kFloat32 && gw_parts->numel() >= bsplit * n_out * n_in);
+    gw = gw_parts->data_ptr<float>();
+  }
+  if (gb_parts.has_value() && gb_parts->defined()) {
+    TORCH_CHECK(gb_parts->scalar_type() == torch::kFloat32 && gb_parts->numel() >= bsplit * n_out);
+    gb = gb_parts->data_ptr<float>();
+  }
+  zn::launch_fc_small_backward(err.data_ptr(), yp, x.data_ptr(), is_bf16(err), w.data_ptr<float>(), eip, gw, gb,
+                               (int)batch, (int)n_in, (int)n_out, (int)act, (float)alpha, (float)beta,
+                               (int)bsplit, cur());
+  kcheck();
+}
+
 // generic GEMM: out[M,N] = act(alpha * opA(a) opB(b) + bias) + beta*out ; engine: 0 simt, 1 umma
 // transa: A stored [K][lda]; transb: B stored [N][ldb] (i.e. "NT" when transb = 1)
 int64_t gemm(Tensor a, int64_t lda, bool transa, Tensor b, int64_t ldb, bool transb, Tensor out,
@@ -454,6 +512,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fused_update", &fused_update); m.def("update_blocks", &update_blocks);
   m.def("multi_update_table", &multi_update_table); m.def("multi_update", &multi_update);
   m.def("col_sums", &col_sums); m.def("refresh_shadows", &refresh_shadows);
+  m.def("fc_small_max_out", &fc_small_max_out); m.def("fc_small_forward", &fc_small_forward);
+  m.def("fc_small_backward", &fc_small_backward);
   m.def("gemm", &gemm); m.def("pick_splits", &pick_splits);
   m.def("conv_fprop", &conv_fprop); m.def("conv_dgrad", &conv_dgrad); m.def("conv_wgrad", &conv_wgrad);
 }
