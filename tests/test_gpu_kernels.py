@@ -93,6 +93,9 @@ CONV_CASES = [
     (2, 12, 12, 64, 88, 5, 5, (0, 0, 0, 0), (1, 1)),    # MNIST conv2-like
     (2, 15, 13, 8, 16, 3, 2, (1, 0, 2, 1), (2, 1)),     # odd geometry
     (2, 27, 27, 16, 24, 11, 11, (0, 0, 0, 0), (4, 4)),  # AlexNet conv1-like stride 4
+    (2, 9, 9, 128, 128, 3, 3, (1, 1, 1, 1), (1, 1)),    # 64-channel slices of one tap (tpk = 1)
+    (3, 20, 20, 8, 32, 5, 5, (2, 2, 2, 2), (1, 1)),     # channel-padded first layer (tpk = 8)
+    (2, 10, 10, 16, 16, 3, 3, (1, 1, 1, 1), (1, 1)),    # tpk = 4, dgrad with F = 16
 ]
 
 
@@ -321,9 +324,7 @@ def test_fc_small_backward(ext, dtype, n_out, act):
          3: (yf > 0).float()}[act]
     e = err0.float() * d
     tol = 1e-5 if dtype == torch.float32 else 2e-2
-    if act:
-        assert _rel(err.float(), e) < tol
-    e_used = err.float() if act else e          # the kernel works from the fp32 product
+    assert torch.equal(err, err0)               # err_output is read-only for the kernel
     assert _rel(ei.float(), alpha * (e @ w) + beta * ei0.float()) < tol
     assert _rel(gw.sum(0), e.t() @ x.float()) < tol
     assert _rel(gb.sum(0), e.sum(0)) < tol
@@ -331,3 +332,32 @@ def test_fc_small_backward(ext, dtype, n_out, act):
     ext.fc_small_backward(err0.clone(), y if act else None, x, w, None, None, None, batch, n_in,
                           n_out, act, 1.0, 0.0, 2)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode,c", [(0, 32), (2, 32), (0, 5), (2, 5)])
+def test_pooling_fused_activation(ext, dtype, mode, c):
+    """max / avg pooling with strict ReLU folded in (forward) and f'(y) folded into the
+    backward gather == pooling followed by a separate ReLU."""
+    torch.manual_seed(mode * 10 + c)
+    dev = "cuda"
+    n, h, w, k, s = 3, 9, 9, 3, 2
+    oh = ow = (h - k + s - 1) // s + 1 if (h - k) % s else (h - k) // s + 1
+    oh = ow = -(-(h - k) // s) + 1
+    x = torch.randn(n, h, w, c, device=dev).to(dtype)
+    out_f = torch.empty(n, oh, ow, c, device=dev, dtype=dtype)
+    out_p = torch.empty_like(out_f)
+    offs_f = torch.zeros(n, oh, ow, c, device=dev, dtype=torch.int32)
+    offs_p = torch.zeros_like(offs_f)
+    ext.pool_forward(x, out_f, offs_f, oh, ow, k, k, s, s, mode, None, 3)
+    ext.pool_forward(x, out_p, offs_p, oh, ow, k, k, s, s, mode, None, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, torch.relu(out_p)) and torch.equal(offs_f, offs_p)
+    err = torch.randn(n, oh, ow, c, device=dev).to(dtype)
+    ei_f = torch.empty_like(x)
+    ei_p = torch.empty_like(x)
+    ext.pool_backward(err, offs_f, ei_f, oh, ow, k, k, s, s, mode == 2, out_f, 3)
+    masked = (err.float() * (out_f.float() > 0)).to(dtype)
+    ext.pool_backward(masked, offs_p, ei_p, oh, ow, k, k, s, s, mode == 2, None, 0)
+    torch.cuda.synchronize()
+    assert _rel(ei_f.float(), ei_p.float()) < (1e-6 if dtype == torch.float32 else 1e-2)

@@ -115,3 +115,42 @@ def test_fused_step_equals_per_layer_updates():
     for (wa, ba), (wb, bb) in zip(*results):
         assert numpy.abs(wa - wb).max() <= 1e-4 * max(1.0, numpy.abs(wa).max())
         assert numpy.abs(ba - bb).max() <= 1e-4 * max(1.0, numpy.abs(ba).max())
+
+
+def test_activation_fusion_equals_separate_units():
+    """conv→relu / maxpool→relu / conv→relu folded into the producers' kernels must train
+    exactly like the stand-alone activation units (fp32, eager)."""
+    from veles.znicz_b200.core import prng
+    results, counts = [], []
+    for fuse in (False, True):
+        root.common.engine.fuse_activations = fuse
+        prng.get(1).seed(1234)
+        prng.get(2).seed(5678)
+        try:
+            wf = cifar.build(
+                layers=_fast_layers(), use_graphs=False,
+                loader_config={"minibatch_size": 20, "n_train": 200, "n_valid": 40,
+                               "normalization_type": "internal_mean", "noise": 0.3},
+                decision_config={"max_epochs": 1, "fail_iterations": 10},
+                snapshotter_config={"prefix": "cifar_fa", "interval": 100,
+                                    "time_interval": 1e9})
+            wf.initialize(device="cuda")
+            counts.append(wf.fused_activations_)
+            from veles.znicz_b200.kernels import api
+            n0 = api.counters["launches"]
+            wf.run()
+            launches = api.counters["launches"] - n0
+            ws = []
+            for f in wf.forwards:
+                if getattr(f, "weights", None):
+                    f.weights.map_read()
+                    ws.append(f.weights.mem.copy())
+            results.append((ws, launches, wf.decision.epoch_n_err[2]))
+        finally:
+            root.common.engine.fuse_activations = True
+    assert counts == [0, 3]
+    (wa, la, ea), (wb, lb, eb) = results
+    assert lb < la                       # six fewer launches per training step
+    for a, b in zip(wa, wb):
+        assert numpy.abs(a - b).max() <= 2e-4 * max(1.0, numpy.abs(a).max())
+    assert ea == eb

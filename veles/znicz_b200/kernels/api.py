@@ -120,7 +120,7 @@ def fc_forward(unit, softmax=False):
     else:
         out = unit.output.dev_out
     use_lp = lp_enabled(unit) and _is_bf16(x) and n_in % 8 == 0
-    act = ACT_LINEAR if softmax else unit.ACT
+    act = ACT_LINEAR if softmax else eff_act(unit)
     if _fc_small_ok(unit, n_out) and act <= 4:
         # few outputs: one launch does GEMV x n_out + bias + activation (+ softmax + arg-max)
         ext.fc_small_forward(x, unit.weights.dev, bias, unit.output.dev_out,
@@ -147,6 +147,16 @@ def fc_forward(unit, softmax=False):
     if softmax:
         ext.softmax_rows(out, unit.output.dev_out, unit.max_idx.dev_out)
         _launch()
+
+
+def fused_act(unit):
+    """Activation code folded into this unit by the workflow fusion pass (0 = none)."""
+    return int(getattr(unit, "fused_act_", 0) or 0)
+
+
+def eff_act(unit):
+    """The activation a GEMM-like unit applies: its own or the one fused behind it."""
+    return fused_act(unit) or unit.ACT
 
 
 FC_SMALL_MAX_OUT = 16
@@ -249,8 +259,8 @@ def fc_backward(unit):
     n_in = x.numel() // batch
     need_w = unit.need_gradient_weights and unit.weights
     need_b = need_w and unit.include_bias and unit.bias
-    if (_fc_small_ok(unit, n_out) and unit.ACT <= 4 and err.dtype == x.dtype and
-            (unit.ACT == ACT_LINEAR or unit.output.dev.dtype == err.dtype)):
+    if (_fc_small_ok(unit, n_out) and eff_act(unit) <= 4 and err.dtype == x.dtype and
+            (eff_act(unit) == ACT_LINEAR or unit.output.dev.dtype == err.dtype)):
         # whole GD step of a few-output layer in one launch (+ the deferred update)
         bsplit = max(1, min(8, batch // 16))
         gbuf = _grad_buffer(unit, "wgrad", (bsplit,) + tuple(unit.weights.shape)) \
@@ -259,11 +269,9 @@ def fc_backward(unit):
         ei = None
         if unit.need_err_input:
             ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
-        ext.fc_small_backward(err, unit.output.dev if unit.ACT != ACT_LINEAR else None, x,
-                              unit.weights.dev, ei, gbuf, parts, batch, n_in, n_out, unit.ACT,
+        ext.fc_small_backward(err, unit.output.dev if eff_act(unit) != ACT_LINEAR else None, x,
+                              unit.weights.dev, ei, gbuf, parts, batch, n_in, n_out, eff_act(unit),
                               float(unit.err_input_alpha), float(unit.err_input_beta), bsplit)
-        if unit.ACT != ACT_LINEAR:
-            unit.err_output.dev_written()
         if ei is not None:
             unit.err_input.dev_written()
         _launch()
@@ -273,14 +281,14 @@ def fc_backward(unit):
             _update(unit, True, parts, bsplit, n_out, 1, n_out)
         return
     # 1. err_output *= f'(output) fused with the bias-gradient column sums
-    if unit.ACT != ACT_LINEAR or need_b:
+    if eff_act(unit) != ACT_LINEAR or need_b:
         parts = None
         if need_b:
             slices, parts = _bias_partials(unit, batch, n_out)
-        y = unit.output.dev if unit.ACT != ACT_LINEAR else None
+        y = unit.output.dev if eff_act(unit) != ACT_LINEAR else None
         if y is not None and y.dtype != err.dtype:
             raise RuntimeError("%s: output/err_output dtype mismatch" % unit)
-        ext.err_act_colsum(err, y, batch, n_out, unit.ACT, parts)
+        ext.err_act_colsum(err, y, batch, n_out, eff_act(unit), parts)
         unit.err_output.dev_written()
         _launch()
     lp_ok = (lp_enabled(unit) and _is_bf16(err) and _is_bf16(x) and
@@ -350,13 +358,13 @@ def conv_forward(unit):
             x = xp
             g = list(g)
             g[3] = cp
-        r = ext.conv_fprop(x, w, w.shape[1], False, bias, out, g, unit.ACT, 1)
+        r = ext.conv_fprop(x, w, w.shape[1], False, bias, out, g, eff_act(unit), 1)
         if r != 0:
             raise RuntimeError("%s: tcgen05 conv fprop refused (code %d)" % (unit, r))
     else:
         w = unit.weights.dev
         ld = w.shape[1]
-        ext.conv_fprop(x, w, ld, bool(unit.weights_transposed), bias, out, g, unit.ACT, 0)
+        ext.conv_fprop(x, w, ld, bool(unit.weights_transposed), bias, out, g, eff_act(unit), 0)
     _launch()
 
 
@@ -370,12 +378,12 @@ def conv_backward(unit):
     kw = unit._kernel_size
     need_w = unit.need_gradient_weights and unit.weights
     need_b = need_w and unit.include_bias and unit.bias
-    if unit.ACT != ACT_LINEAR or need_b:
+    if eff_act(unit) != ACT_LINEAR or need_b:
         parts = None
         if need_b:
             slices, parts = _bias_partials(unit, pixels, f)
-        y = unit.output.dev if unit.ACT != ACT_LINEAR else None
-        ext.err_act_colsum(err, y, pixels, f, unit.ACT, parts)
+        y = unit.output.dev if eff_act(unit) != ACT_LINEAR else None
+        ext.err_act_colsum(err, y, pixels, f, eff_act(unit), parts)
         unit.err_output.dev_written()
         _launch()
     fwd = unit.forward_unit
@@ -442,11 +450,11 @@ def pooling_forward(unit):
     rng = getattr(unit, "rng_dev_", None)
     if mode >= 5:
         ext.pool_forward(x, None, offs, oy, ox, unit.ky, unit.kx, unit.sliding[1],
-                         unit.sliding[0], mode, rng)
+                         unit.sliding[0], mode, rng, 0)
         unit.input.dev_written()
     else:
         ext.pool_forward(x, unit.output.dev_out, offs, oy, ox, unit.ky, unit.kx,
-                         unit.sliding[1], unit.sliding[0], mode, rng)
+                         unit.sliding[1], unit.sliding[0], mode, rng, fused_act(unit))
     _launch()
 
 
@@ -457,8 +465,11 @@ def pooling_backward(unit):
     offs = None if is_avg else unit.input_offset.dev
     err = unit.err_output.dev
     ei = unit.err_input.dev_out
+    act = fused_act(unit)
+    y = unit.output.dev if act else None
     ext.pool_backward(err.view(ei.shape[0], oy, ox, ei.shape[3]), offs, ei, oy, ox, unit.ky,
-                      unit.kx, unit.sliding[1], unit.sliding[0], is_avg)
+                      unit.kx, unit.sliding[1], unit.sliding[0], is_avg,
+                      y.view(ei.shape[0], oy, ox, ei.shape[3]) if act else None, act)
     _launch()
 
 

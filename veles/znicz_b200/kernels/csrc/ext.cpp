@@ -23,8 +23,8 @@ void launch_mask_mul(void*, const void*, long long, bool, cudaStream_t);
 void launch_pad_channels(const void*, void*, int, int, int, bool, cudaStream_t);
 void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
 void launch_scatter_offsets(const void*, const int*, void*, long long, bool, cudaStream_t);
-void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int, const int*, bool, cudaStream_t);
-void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, cudaStream_t);
+void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int, const int*, bool, int, cudaStream_t);
+void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, const void*, int, cudaStream_t);
 void launch_lrn_forward(const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
 void launch_lrn_backward(const void*, const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
 void launch_softmax_rows(const void*, bool, float*, int*, int, int, cudaStream_t);
@@ -38,6 +38,7 @@ int fc_small_max_out();
 void launch_fc_small_forward(const void*, bool, const float*, const float*, void*, float*, int*, int, int, int, int, int, cudaStream_t);
 void launch_fc_small_backward(void*, const void*, const void*, bool, const float*, void*, float*, float*, int, int, int, int, float, float, int, cudaStream_t);
 size_t multi_update_desc_size();
+int multi_update_max_tensors();
 int multi_update_pack(const long long*, int, void*, int);
 void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, cudaStream_t);
 void launch_refresh_shadows(const float*, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, int, cudaStream_t);
@@ -196,8 +197,10 @@ void scatter_offsets(Tensor in, Tensor offs, Tensor out) {
   kcheck();
 }
 void pool_forward(Tensor in, c10::optional<Tensor> out, c10::optional<Tensor> offs, int64_t OH, int64_t OW,
-                  int64_t KY, int64_t KX, int64_t SY, int64_t SX, int64_t mode, c10::optional<Tensor> rng) {
+                  int64_t KY, int64_t KX, int64_t SY, int64_t SX, int64_t mode, c10::optional<Tensor> rng,
+                  int64_t act) {
   chk(in, "in");
+  TORCH_CHECK(act >= 0 && act <= 4 && (act == 0 || mode <= 2), "fused activation: max/maxabs/avg pooling only");
   void* op = (out.has_value() && out->defined()) ? out->data_ptr() : nullptr;
   int* fp = (offs.has_value() && offs->defined()) ? offs->data_ptr<int>() : nullptr;
   const int* rp = (rng.has_value() && rng->defined()) ? rng->data_ptr<int>() : nullptr;
@@ -205,17 +208,25 @@ void pool_forward(Tensor in, c10::optional<Tensor> out, c10::optional<Tensor> of
   TORCH_CHECK(mode < 3 || rp, "rng required for stochastic pooling");
   zn::launch_pool_forward(in.data_ptr(), op, fp, (int)in.size(0), (int)in.size(1), (int)in.size(2),
                           (int)in.size(3), (int)OH, (int)OW, (int)KY, (int)KX, (int)SY, (int)SX, (int)mode,
-                          rp, is_bf16(in), cur());
+                          rp, is_bf16(in), (int)act, cur());
   kcheck();
 }
 void pool_backward(Tensor err_out, c10::optional<Tensor> offs, Tensor err_in, int64_t OH, int64_t OW,
-                   int64_t KY, int64_t KX, int64_t SY, int64_t SX, bool is_avg) {
+                   int64_t KY, int64_t KX, int64_t SY, int64_t SX, bool is_avg, c10::optional<Tensor> yact,
+                   int64_t act) {
   chk(err_out, "err_out"); same_dt(err_out, err_in);
+  const void* yp = nullptr;
+  if (act != 0) {
+    TORCH_CHECK(act >= 1 && act <= 4 && yact.has_value() && yact->defined(), "fused activation needs the output");
+    same_dt(err_out, *yact);
+    TORCH_CHECK(yact->numel() == err_out.numel());
+    yp = yact->data_ptr();
+  }
   const int* fp = (offs.has_value() && offs->defined()) ? offs->data_ptr<int>() : nullptr;
   TORCH_CHECK(is_avg || fp, "offsets required");
   zn::launch_pool_backward(err_out.data_ptr(), fp, err_in.data_ptr(), (int)err_in.size(0), (int)err_in.size(1),
                            (int)err_in.size(2), (int)err_in.size(3), (int)OH, (int)OW, (int)KY, (int)KX,
-                           (int)SY, (int)SX, is_avg ? 1 : 0, is_bf16(err_out), cur());
+                           (int)SY, (int)SX, is_avg ? 1 : 0, is_bf16(err_out), yp, (int)act, cur());
   kcheck();
 }
 void lrn_forward(Tensor x, Tensor y, int64_t n, double alpha, double beta, double k) {
@@ -309,6 +320,8 @@ int64_t update_blocks(int64_t size) { return zn::fused_update_blocks(size); }
 // Returns (packed CPU uint8 tensor [n * desc_size], total_tiles).
 std::tuple<Tensor, int64_t> multi_update_table(std::vector<std::vector<int64_t>> descs) {
   const size_t ds = zn::multi_update_desc_size();
+  TORCH_CHECK((int)descs.size() <= zn::multi_update_max_tensors(),
+              "multi_update handles at most ", zn::multi_update_max_tensors(), " tensors per launch");
   Tensor out = torch::zeros({(int64_t)(descs.size() * ds)}, torch::dtype(torch::kUInt8));
   int tiles = 0;
   for (size_t i = 0; i < descs.size(); ++i) {
@@ -510,7 +523,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("softmax_rows", &softmax_rows); m.def("evaluate_softmax", &evaluate_softmax);
   m.def("evaluate_mse", &evaluate_mse); m.def("mse_find_closest", &mse_find_closest);
   m.def("fused_update", &fused_update); m.def("update_blocks", &update_blocks);
-  m.def("multi_update_table", &multi_update_table); m.def("multi_update", &multi_update);
+  m.def("multi_update_table", &multi_update_table);
+  m.def("multi_update_max_tensors", []() { return (int64_t)zn::multi_update_max_tensors(); }); m.def("multi_update", &multi_update);
   m.def("col_sums", &col_sums); m.def("refresh_shadows", &refresh_shadows);
   m.def("fc_small_max_out", &fc_small_max_out); m.def("fc_small_forward", &fc_small_forward);
   m.def("fc_small_backward", &fc_small_backward);

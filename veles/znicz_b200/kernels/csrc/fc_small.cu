@@ -72,7 +72,7 @@ fc_small_forward_k(const T* __restrict__ x, const float* __restrict__ w,
 // grid = (ceil(n_in / 128), bsplit); thread = one input index k, a contiguous batch range.
 template <typename T>
 __global__ void __launch_bounds__(128)
-fc_small_backward_k(T* __restrict__ err, const T* __restrict__ y, const T* __restrict__ x,
+fc_small_backward_k(const T* __restrict__ err, const T* __restrict__ y, const T* __restrict__ x,
                     const float* __restrict__ w, T* __restrict__ err_in,
                     float* __restrict__ gw_parts, float* __restrict__ gb_parts, int batch, int n_in,
                     int n_out, int act, float alpha, float beta, int need_ei, int need_gw) {
@@ -89,10 +89,9 @@ fc_small_backward_k(T* __restrict__ err, const T* __restrict__ y, const T* __res
     if (o < n_out) {
       const size_t idx = (size_t)(b0 + r) * n_out + o;
       e = ldf(err + idx);
-      if (act != ACT_LINEAR) {
-        e *= act_deriv(act, 0.f, ldf(y + idx));
-        if (blockIdx.x == 0) stf(err + idx, e);     // the reference updates err_output in place
-      }
+      // err_output itself is left untouched (the reference scales it in place, but nothing
+      // downstream reads it and an in-place write would race with the other CTAs' reads)
+      if (act != ACT_LINEAR) e *= act_deriv(act, 0.f, ldf(y + idx));
     }
     s_err[i] = e;
   }
@@ -157,10 +156,10 @@ void launch_fc_small_backward(void* err, const void* y, const void* x, bool bf16
   const int need_ei = err_in != nullptr, need_gw = gw_parts != nullptr;
   if (bf16)
     fc_small_backward_k<__nv_bfloat16><<<grid, 128, smem, st>>>(
-        (__nv_bfloat16*)err, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)err_in,
+        (const __nv_bfloat16*)err, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)err_in,
         gw_parts, gb_parts, batch, n_in, n_out, act, alpha, beta, need_ei, need_gw);
   else
-    fc_small_backward_k<float><<<grid, 128, smem, st>>>((float*)err, (const float*)y, (const float*)x, w,
+    fc_small_backward_k<float><<<grid, 128, smem, st>>>((const float*)err, (const float*)y, (const float*)x, w,
                                                         (float*)err_in, gw_parts, gb_parts, batch, n_in,
                                                         n_out, act, alpha, beta, need_ei, need_gw);
 }

@@ -38,6 +38,9 @@ constexpr int A_BYTES = BLOCK_M * 128;
 struct ConvGeomU {
   int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL;
   int vec;   // 1 when 16-byte chunks never straddle a tap (C % 8 == 0 resp. F % 8 == 0)
+  // tap mode (GVEC == 2): a 64-wide block of the reduction index covers ``tpk`` whole taps
+  // (inner = 64 / tpk channels each) or a 64-channel slice of one tap (tpk == 1, inner % 64 == 0)
+  int tpk, ntaps, inner;
 };
 
 struct GemmParams {
@@ -81,6 +84,11 @@ __device__ __forceinline__ PixCtx decode_in_pixel(const __nv_bfloat16* src, cons
   return c;
 }
 __device__ __forceinline__ void build_ktab(int* ktab, const ConvGeomU& g, int kind, int klimit) {
+  if (g.tpk > 0) {                                // tap mode: ktab[tap] = (ky << 8) | kx
+    for (int e = threadIdx.x; e < g.ntaps; e += blockDim.x)
+      ktab[e] = ((e / g.KX) << 8) | (e % g.KX);
+    return;
+  }
   const int inner = (kind == 1) ? g.C : g.F;      // G_IM2COL : G_DGRAD
   const int step = g.vec ? 8 : 1;
   const int n = min(KTAB, (klimit + step - 1) / step);
@@ -123,6 +131,54 @@ __device__ __forceinline__ uint4 gather_chunk(const int* ktab, const ConvGeomU& 
     v[j] = p ? *p : __float2bfloat16_rn(0.f);
   }
   return *reinterpret_cast<uint4*>(v);
+}
+
+// Tap-mode gather: the 8 chunks (64 reduction indices starting at k0, k0 % 64 == 0) of one pixel.
+// One table lookup + one bounds check + one address per *tap*; the chunks of a tap are
+// consecutive 16-byte loads. ~6 instructions per chunk instead of ~100 for the generic path.
+template <int KIND, int TPK>
+__device__ __forceinline__ void gather_taps(uint4 (&nv)[8], const int* ttab, const ConvGeomU& g,
+                                            const PixCtx& c, int k0) {
+  constexpr int CPT = 8 / TPK;
+  int tap0, c0;
+  if (TPK == 1) { tap0 = k0 / g.inner; c0 = k0 - tap0 * g.inner; }
+  else { tap0 = (k0 >> 6) * TPK; c0 = 0; }
+  const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int j = 0; j < TPK; ++j) {
+    const int tap = tap0 + j;
+    bool ok = c.valid && tap < g.ntaps;
+    const int e = ttab[ok ? tap : 0];
+    const int ky = e >> 8, kx = e & 0xff;
+    int off;
+    if (KIND == G_IM2COL) {
+      const int iy = c.y + ky, ix = c.x + kx;
+      ok = ok && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+      off = (iy * g.W + ix) * g.C;
+    } else {                                      // dgrad, unit stride only
+      const int ty = c.y - ky, tx = c.x - kx;
+      ok = ok && (unsigned)ty < (unsigned)g.OH && (unsigned)tx < (unsigned)g.OW;
+      off = (ty * g.OW + tx) * g.F;
+    }
+    const uint4* ptr = reinterpret_cast<const uint4*>(c.base + (ok ? off + c0 : 0));
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) nv[j * CPT + q] = ok ? ptr[q] : z;
+  }
+}
+template <int KIND, int GVEC>
+__device__ __forceinline__ void gather_row(uint4 (&nv)[8], const int* ktab, const ConvGeomU& g,
+                                           const PixCtx& c, int k0, int klimit) {
+  if (GVEC == 2) {
+    switch (g.tpk) {
+      case 1: gather_taps<KIND, 1>(nv, ktab, g, c, k0); break;
+      case 2: gather_taps<KIND, 2>(nv, ktab, g, c, k0); break;
+      case 4: gather_taps<KIND, 4>(nv, ktab, g, c, k0); break;
+      default: gather_taps<KIND, 8>(nv, ktab, g, c, k0); break;
+    }
+  } else {
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) nv[c8] = gather_chunk<KIND, GVEC>(ktab, g, c, k0 + c8 * 8, klimit);
+  }
 }
 
 template <int BLOCK_N, int B_MODE>
@@ -272,9 +328,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int i = -1; i < num_kb; ++i) {
           if (i + 1 < num_kb) {
             const int k0 = (kb_begin + i + 1) * BLOCK_K;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
-              nv[c8] = gather_chunk<GKIND, GVEC>(ktab, p.g, ctx, k0 + c8 * 8, p.gK);
+            gather_row<GKIND, GVEC>(nv, ktab, p.g, ctx, k0, p.gK);
           }
           if (i >= 0) {
             const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
@@ -299,9 +353,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (i + 1 < num_kb) {
             const int pix = (kb_begin + i + 1) * BLOCK_K + kr;
             const PixCtx ctx = decode_out_pixel(p.gsrc, p.g, pix, p.K);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8)
-              nv[c8] = gather_chunk<G_IM2COL, GVEC>(ktab, p.g, ctx, m0 + mblk * 64 + c8 * 8, p.gK);
+            gather_row<G_IM2COL, GVEC>(nv, ktab, p.g, ctx, m0 + mblk * 64, p.gK);
           }
           if (i >= 0) {
             const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
@@ -495,8 +547,18 @@ int launch_gemm_umma(const void* a, long long lda, int a_mn, const void* b, long
 
 static ConvGeomU geom(int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX,
                       int PT, int PL, int vec) {
-  ConvGeomU g{N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, vec};
+  ConvGeomU g{N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, vec, 0, KY * KX, 0};
   return g;
+}
+// Enable the tap-mode gather when the inner (channel) extent tiles a 64-wide reduction block.
+static bool set_tap_mode(ConvGeomU& g, int inner, bool dgrad) {
+  g.tpk = 0; g.inner = inner;
+  if (!g.vec || (inner % 8) || g.KY * g.KX > KTAB) return false;
+  if (dgrad && (g.SY != 1 || g.SX != 1)) return false;
+  if (inner >= 64) { if (inner % 64) return false; g.tpk = 1; return true; }
+  if (64 % inner) return false;
+  g.tpk = 64 / inner;
+  return true;
 }
 
 // out[pix, f] = act(im2col(x)[pix, :] . w_lp[f, :] + bias[f]); w_lp stored [F][ldw] bf16 (ldw % 8 == 0)
@@ -518,6 +580,7 @@ int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const
   p.bias = bias; p.act = act; p.alpha = 1.f; p.beta = 0.f; p.split_stride = 0;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
+  if (set_tap_mode(p.g, C, false)) return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 2>(bn, ta, tb, p, 1, st);
   if (C % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 1>(bn, ta, tb, p, 1, st);
   return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 0>(bn, ta, tb, p, 1, st);
 }
@@ -544,6 +607,7 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
   p.gsrc = (const __nv_bfloat16*)err_out;
   p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, F % 8 == 0);
   p.gather_kind = G_DGRAD; p.gK = Kd;
+  if (set_tap_mode(p.g, F, true)) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 2>(bn, ta, tb, p, 1, st);
   if (F % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 1>(bn, ta, tb, p, 1, st);
   return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 0>(bn, ta, tb, p, 1, st);
 }
@@ -571,6 +635,7 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
   p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.beta = 0.f; p.split_stride = (long long)F * Kw;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
+  if (set_tap_mode(p.g, C, false)) return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 2>(bn, ta, tb, p, splits, st);
   if (C % 8 == 0) return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 1>(bn, ta, tb, p, splits, st);
   return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 0>(bn, ta, tb, p, splits, st);
 }

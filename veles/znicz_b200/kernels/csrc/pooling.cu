@@ -10,7 +10,9 @@ namespace zn {
 enum PoolMode { POOL_MAX = 0, POOL_MAXABS = 1, POOL_AVG = 2, POOL_STOCH = 3, POOL_STOCH_ABS = 4,
                 POOL_STOCH_DEPOOL = 5, POOL_STOCH_ABS_DEPOOL = 6 };
 
-struct PoolGeom { int N, H, W, C, OH, OW, KY, KX, SY, SX; };
+// act: activation fused behind the pooling (0 = none; forward applies f, backward multiplies the
+// incoming error by f'(y) with y = the pooled+activated output)
+struct PoolGeom { int N, H, W, C, OH, OW, KY, KX, SY, SX; int act; };
 
 template <typename T>
 __global__ void pool_forward_k(const T* __restrict__ in, T* __restrict__ out, int* __restrict__ offs,
@@ -27,7 +29,7 @@ __global__ void pool_forward_k(const T* __restrict__ in, T* __restrict__ out, in
     float s = 0.f;
     for (int y = y1; y < y2; ++y)
       for (int x = x1; x < x2; ++x) s += ldf(base + ((size_t)y * g.W + x) * g.C);
-    stf(out + i, s / (float)((y2 - y1) * (x2 - x1)));
+    stf(out + i, act_fwd5(g.act, s / (float)((y2 - y1) * (x2 - x1))));
     return;
   }
   bool use_abs = (mode == POOL_MAXABS || mode == POOL_STOCH_ABS || mode == POOL_STOCH_ABS_DEPOOL);
@@ -82,14 +84,14 @@ __global__ void pool_forward_k(const T* __restrict__ in, T* __restrict__ out, in
         if ((int)o != best_off) stf(wbase + o, 0.f);
       }
   } else {
-    stf(out + i, best_v);
+    stf(out + i, act_fwd5(g.act, best_v));
   }
 }
 
 // err_in[n,y,x,c] = sum over windows covering (y,x) of err_out[window] * [offs[window]==self]
 template <typename T>
 __global__ void pool_backward_max_k(const T* __restrict__ err_out, const int* __restrict__ offs,
-                                    T* __restrict__ err_in, PoolGeom g) {
+                                    T* __restrict__ err_in, PoolGeom g, const T* __restrict__ yact) {
   long long total = (long long)g.N * g.H * g.W * g.C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -103,13 +105,15 @@ __global__ void pool_backward_max_k(const T* __restrict__ err_out, const int* __
   for (int oy = oy_lo; oy <= oy_hi; ++oy)
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
       size_t o = (((size_t)n * g.OH + oy) * g.OW + ox) * g.C + c;
-      if (offs[o] == (int)i) s += ldf(err_out + o);
+      if (offs[o] == (int)i)
+        s += ldf(err_out + o) * (g.act ? act_deriv(g.act, 0.f, ldf(yact + o)) : 1.f);
     }
   stf(err_in + i, s);
 }
 
 template <typename T>
-__global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict__ err_in, PoolGeom g) {
+__global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict__ err_in, PoolGeom g,
+                                    const T* __restrict__ yact) {
   long long total = (long long)g.N * g.H * g.W * g.C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -123,7 +127,8 @@ __global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict
     int hy = min(oy * g.SY + g.KY, g.H) - oy * g.SY;
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
       int hx = min(ox * g.SX + g.KX, g.W) - ox * g.SX;
-      s += ldf(err_out + (((size_t)n * g.OH + oy) * g.OW + ox) * g.C + c) / (float)(hy * hx);
+      const size_t o = (((size_t)n * g.OH + oy) * g.OW + ox) * g.C + c;
+      s += ldf(err_out + o) * (g.act ? act_deriv(g.act, 0.f, ldf(yact + o)) : 1.f) / (float)(hy * hx);
     }
   }
   stf(err_in + i, s);
@@ -172,12 +177,17 @@ __global__ void pool_forward_vec_k(const T* __restrict__ in, T* __restrict__ out
     po[0] = make_int4(boff[0], boff[1], boff[2], boff[3]);
     po[1] = make_int4(boff[4], boff[5], boff[6], boff[7]);
   }
+  if (g.act) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = act_fwd5(g.act, best[j]);
+  }
   st8(out + (size_t)i * 8, best);
 }
 
 template <typename T>
 __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __restrict__ offs,
-                                    T* __restrict__ err_in, PoolGeom g, int is_avg) {
+                                    T* __restrict__ err_in, PoolGeom g, int is_avg,
+                                    const T* __restrict__ yact) {
   const int C8 = g.C >> 3;
   const int total = g.N * g.H * g.W * C8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,6 +207,12 @@ __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __
       const int o = (((n * g.OH + oy) * g.OW + ox) * C8 + cg) * 8;
       float e[8];
       ld8(err_out + o, e);
+      if (g.act) {
+        float yv[8];
+        ld8(yact + o, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] *= act_deriv(g.act, 0.f, yv[j]);
+      }
       if (is_avg) {
         const int hx = min(ox * g.SX + g.KX, g.W) - ox * g.SX;
         const float inv = 1.f / (float)(hy * hx);
@@ -275,9 +291,9 @@ __global__ void lrn_vec_k(const T* __restrict__ x, const T* __restrict__ ey, T* 
 }
 
 void launch_pool_forward(const void* in, void* out, int* offs, int N, int H, int W, int C, int OH, int OW,
-                         int KY, int KX, int SY, int SX, int mode, const int* rng, bool bf16,
+                         int KY, int KX, int SY, int SX, int mode, const int* rng, bool bf16, int act,
                          cudaStream_t st) {
-  PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX};
+  PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX, act};
   long long total = (long long)N * OH * OW * C;
   if (mode <= POOL_AVG && C % 8 == 0 && (long long)N * H * W * C < (1LL << 31) &&
       (((uintptr_t)in | (uintptr_t)out | (uintptr_t)offs) & 15) == 0) {
@@ -292,23 +308,23 @@ void launch_pool_forward(const void* in, void* out, int* offs, int N, int H, int
 }
 void launch_pool_backward(const void* err_out, const int* offs, void* err_in, int N, int H, int W, int C,
                           int OH, int OW, int KY, int KX, int SY, int SX, int is_avg, bool bf16,
-                          cudaStream_t st) {
-  PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX};
+                          const void* yact, int act, cudaStream_t st) {
+  PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX, yact ? act : 0};
   long long total = (long long)N * H * W * C;
   if (C % 8 == 0 && total < (1LL << 31) &&
-      (((uintptr_t)err_out | (uintptr_t)err_in | (uintptr_t)offs) & 15) == 0) {
+      (((uintptr_t)err_out | (uintptr_t)err_in | (uintptr_t)offs | (uintptr_t)yact) & 15) == 0) {
     int gridv = cdiv(total / 8, 256);
-    if (bf16) pool_backward_vec_k<__nv_bfloat16><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, is_avg);
-    else pool_backward_vec_k<float><<<gridv, 256, 0, st>>>((const float*)err_out, offs, (float*)err_in, g, is_avg);
+    if (bf16) pool_backward_vec_k<__nv_bfloat16><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, is_avg, (const __nv_bfloat16*)yact);
+    else pool_backward_vec_k<float><<<gridv, 256, 0, st>>>((const float*)err_out, offs, (float*)err_in, g, is_avg, (const float*)yact);
     return;
   }
   int grid = cdiv(total, 256);
   if (is_avg) {
-    if (bf16) pool_backward_avg_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)err_out, (__nv_bfloat16*)err_in, g);
-    else pool_backward_avg_k<float><<<grid, 256, 0, st>>>((const float*)err_out, (float*)err_in, g);
+    if (bf16) pool_backward_avg_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)err_out, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
+    else pool_backward_avg_k<float><<<grid, 256, 0, st>>>((const float*)err_out, (float*)err_in, g, (const float*)yact);
   } else {
-    if (bf16) pool_backward_max_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g);
-    else pool_backward_max_k<float><<<grid, 256, 0, st>>>((const float*)err_out, offs, (float*)err_in, g);
+    if (bf16) pool_backward_max_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
+    else pool_backward_max_k<float><<<grid, 256, 0, st>>>((const float*)err_out, offs, (float*)err_in, g, (const float*)yact);
   }
 }
 

@@ -208,6 +208,7 @@ struct TensorDesc {
 };
 
 struct GridSync { unsigned* count; unsigned* gen; };
+constexpr int MU_MAX_TENSORS = 48;
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -293,18 +294,21 @@ __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, int nr
     for (int r = 0; r < nranks; ++r) {           // fixed rank order => bit-identical replicas
       const float* base = d.grad[r] + gi;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
-      int p = lane;
-      for (; p + 7 * L < d.nparts; p += 8 * L) { // 8 loads in flight
-        a0 += base[(long long)(p + 0 * L) * d.part_stride];
-        a1 += base[(long long)(p + 1 * L) * d.part_stride];
-        a2 += base[(long long)(p + 2 * L) * d.part_stride];
-        a3 += base[(long long)(p + 3 * L) * d.part_stride];
-        a4 += base[(long long)(p + 4 * L) * d.part_stride];
-        a5 += base[(long long)(p + 5 * L) * d.part_stride];
-        a6 += base[(long long)(p + 6 * L) * d.part_stride];
-        a7 += base[(long long)(p + 7 * L) * d.part_stride];
+      // 8 predicated loads in flight per round (the remainder is not serialised: out-of-range
+      // slots load nothing and add 0, the summation order stays fixed)
+      for (int p = lane; p < d.nparts; p += 8 * L) {
+        const long long st = d.part_stride;
+        const float* b = base + (long long)p * st;
+        const int left = d.nparts - p;
+        a0 += b[0];
+        a1 += (1 * L < left) ? b[(long long)(1 * L) * st] : 0.f;
+        a2 += (2 * L < left) ? b[(long long)(2 * L) * st] : 0.f;
+        a3 += (3 * L < left) ? b[(long long)(3 * L) * st] : 0.f;
+        a4 += (4 * L < left) ? b[(long long)(4 * L) * st] : 0.f;
+        a5 += (5 * L < left) ? b[(long long)(5 * L) * st] : 0.f;
+        a6 += (6 * L < left) ? b[(long long)(6 * L) * st] : 0.f;
+        a7 += (7 * L < left) ? b[(long long)(7 * L) * st] : 0.f;
       }
-      for (; p < d.nparts; p += L) a0 += base[(long long)p * d.part_stride];
       g += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     }
   }
@@ -355,26 +359,29 @@ __global__ void __launch_bounds__(256)
 multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int has_ortho,
                PeerSync ps, GridSync gsync) {
   __shared__ uint32_t s_epoch;
-  __shared__ TensorDesc s_desc;
+  __shared__ TensorDesc s_table[MU_MAX_TENSORS];     // the whole table: no dependent global loads
   const bool multi = ps.nranks > 1;
   uint32_t epoch = 0;
   if (multi) {
     if (threadIdx.x == 0) s_epoch = ps.epoch[blockIdx.x] + 1;
-    __syncthreads();
+  }
+  {
+    const int words = n * (int)(sizeof(TensorDesc) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(table);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_table);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (multi) {
     epoch = s_epoch;
     if ((int)threadIdx.x < ps.nranks)              // phase 0: signal only, wait later
       st_release_sys(ps.flags[threadIdx.x] + (size_t)blockIdx.x * 8 + ps.rank, 2 * epoch - 1);
   }
   if (has_ortho) {
     for (int t = 0; t < n; ++t) {
-      if (!table[t].enabled || table[t].is_bias || !(table[t].flags & 8) || !table[t].col_sums)
-        continue;
-      __syncthreads();
-      if (threadIdx.x < sizeof(TensorDesc) / 4)
-        reinterpret_cast<uint32_t*>(&s_desc)[threadIdx.x] =
-            reinterpret_cast<const uint32_t*>(&table[t])[threadIdx.x];
-      __syncthreads();
-      multi_col_sums(s_desc);
+      const TensorDesc& d = s_table[t];
+      if (!d.enabled || d.is_bias || !(d.flags & 8) || !d.col_sums) continue;
+      multi_col_sums(d);
     }
     grid_barrier(gsync);
   }
@@ -389,19 +396,11 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
     }
     __syncthreads();
   }
-  int cur = -1;
+  int t = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    int t = cur < 0 ? 0 : cur;
-    while (t + 1 < n && tile >= table[t].tile_begin + table[t].n_tiles) ++t;   // uniform
-    if (t != cur) {
-      __syncthreads();
-      if (threadIdx.x < sizeof(TensorDesc) / 4)
-        reinterpret_cast<uint32_t*>(&s_desc)[threadIdx.x] =
-            reinterpret_cast<const uint32_t*>(&table[t])[threadIdx.x];
-      __syncthreads();
-      cur = t;
-    }
-    if (s_desc.enabled) multi_tile(s_desc, tile - s_desc.tile_begin, ps.nranks);
+    while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;   // uniform
+    const TensorDesc& d = s_table[t];
+    if (d.enabled) multi_tile(d, tile - d.tile_begin, ps.nranks);
   }
   if (multi) {
     peer_barrier(ps, 2 * epoch);       // nobody still reads my gradient buffers
@@ -410,6 +409,7 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
 }
 
 size_t multi_update_desc_size() { return sizeof(TensorDesc); }
+int multi_update_max_tensors() { return MU_MAX_TENSORS; }
 
 // fields: see ext.cpp::multi_update_table. Returns the number of tiles.
 int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begin) {

@@ -15,7 +15,7 @@ void launch_gemm_simt(const void*, bool, long long, int, const void*, bool, long
 void launch_conv_fprop_simt_raw(const void*, bool, const float*, long long, int, const float*, void*, bool,
                                 const int*, int, cudaStream_t);
 void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int,
-                         const int*, bool, cudaStream_t);
+                         const int*, bool, int, cudaStream_t);
 void launch_lrn_forward(const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
 void launch_act_forward(const void*, void*, long long, int, float, bool, cudaStream_t);
 void launch_softmax_rows(const void*, bool, float*, int*, int, int, cudaStream_t);
@@ -78,7 +78,7 @@ std::vector<float> Engine::run_cuda(const float* input, const Shape4& in) {
       int g[13] = {s.n, s.h, s.w, s.c, o.h, o.w, o.c, u.ky, u.kx, u.sy, u.sx, u.pad[1], u.pad[0]};
       zn::launch_conv_fprop_simt_raw(x, false, cuda_->w[i], u.weights.shape[1], 0, cuda_->b[i], y, false, g, (int)u.act, st);
     } else if (u.kind == "pool") {
-      zn::launch_pool_forward(x, y, cuda_->ibuf, s.n, s.h, s.w, s.c, o.h, o.w, u.ky, u.kx, u.sy, u.sx, u.pool_mode, nullptr, false, st);
+      zn::launch_pool_forward(x, y, cuda_->ibuf, s.n, s.h, s.w, s.c, o.h, o.w, u.ky, u.kx, u.sy, u.sx, u.pool_mode, nullptr, false, 0, st);
     } else if (u.kind == "lrn") {
       zn::launch_lrn_forward(x, y, s.size() / s.c, s.c, u.n, u.alpha, u.beta, u.k, false, st);
     } else if (u.kind == "act") {

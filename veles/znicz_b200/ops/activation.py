@@ -89,10 +89,21 @@ class ActivationForward(Forward, Activation):
     MAPPING = set()
     hide_from_registry = True
 
+    def init_unpickled(self):
+        super().init_unpickled()
+        # set by workflow/fusion.py: the producing unit applies this activation in its own
+        # kernel epilogue; this unit then only aliases ``output`` to ``input``
+        self.fused_into_ = None
+
     def initialize(self, device=None, **kwargs):
         if not self.input:
             return True
         super().initialize(device=device, **kwargs)
+        if self.fused_into_ is not None and self.on_cuda:
+            self.output = self.input
+            return None
+        if self.output is self.input:       # restored from a snapshot of a fused run
+            self.output = Array()
         self.make_output(self.input.shape, self.input.dtype)
         self.output.dev_dtype = self.input.dev_dtype
         self.init_vectors(self.input, self.output)
@@ -108,6 +119,8 @@ class ActivationForward(Forward, Activation):
         self.output.mem[...] = act_forward_numpy(self.CODE, self.input.mem, self.factor)
 
     def cuda_run(self):
+        if self.fused_into_ is not None:
+            return
         from ..kernels import api
         api.activation_forward(self)
 
@@ -127,10 +140,21 @@ class ActivationBackward(GradientDescentBase, Activation):
         super().__init__(workflow, **kwargs)
         self.demand("output")
 
+    def init_unpickled(self):
+        super().init_unpickled()
+        self.fused_into_ = None     # see ActivationForward.fused_into_
+
     def initialize(self, device=None, **kwargs):
         if not self.err_output or not self.input:
             return True
-        return super().initialize(device=device, **kwargs)
+        if self.err_input is not None and self.err_input is self.err_output and \
+                self.fused_into_ is None:
+            self.err_input = Array()        # restored from a snapshot of a fused run
+        r = super().initialize(device=device, **kwargs)
+        if self.fused_into_ is not None and self.on_cuda:
+            # the consumer GD unit multiplies by f'(y) itself: pass the error through
+            self.err_input = self.err_output
+        return r
 
     @property
     def factor(self):
@@ -146,6 +170,8 @@ class ActivationBackward(GradientDescentBase, Activation):
             self.input.mem, self.output.mem.reshape(self.input.shape), self.factor)
 
     def cuda_run(self):
+        if self.fused_into_ is not None:
+            return
         from ..kernels import api
         api.activation_backward(self)
 

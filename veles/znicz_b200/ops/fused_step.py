@@ -40,6 +40,8 @@ class FusedStep(object):
         self.has_ortho = False
         self.dirty = True
         self.enabled = []
+        self.tables = []
+        self.chunks = []
         self.gridsync = torch.zeros(2, dtype=torch.int32, device=device.torch_device)
         self.flag_ptrs, self.epoch_ptr = [], 0
         self.launches = 0
@@ -103,20 +105,29 @@ class FusedStep(object):
             self._upload()
 
     def _upload(self):
+        """(Re)build the descriptor table(s); more than ``multi_update_max_tensors`` tensors
+        are split over several launches."""
+        ext = self.device.ext
+        cap = int(ext.multi_update_max_tensors())
         descs = []
         for e in self.entries:
             f = list(e.fields)
             f[23] = 1 if e.touched else 0
             descs.append(f)
-        packed, tiles = self.device.ext.multi_update_table(descs)
-        if self.table is None or self.table.numel() != packed.numel():
-            self.table = torch.empty(packed.numel(), dtype=torch.uint8,
-                                     device=self.device.torch_device)
-        self.table.copy_(packed)
-        self.total_tiles = int(tiles)
+        self.chunks = []
+        for i in range(0, len(descs), cap):
+            part = descs[i:i + cap]
+            packed, tiles = ext.multi_update_table(part)
+            old = self.tables[len(self.chunks)] if len(self.chunks) < len(self.tables) else None
+            if old is None or old.numel() != packed.numel():
+                old = torch.empty(packed.numel(), dtype=torch.uint8,
+                                  device=self.device.torch_device)
+            old.copy_(packed)
+            ortho = any((f[18] & 8) and f[5] and not f[19] for f in part)
+            self.chunks.append((old, len(part), int(tiles), ortho))
+        self.tables = [c[0] for c in self.chunks]
+        self.table = self.tables[0] if self.tables else None
         self.enabled = [bool(e.touched) for e in self.entries]
-        self.has_ortho = any((e.fields[18] & 8) and e.fields[5] and not e.is_bias
-                             for e in self.entries)
         self.dirty = False
 
     # -- the launch ------------------------------------------------------------------------------
@@ -131,10 +142,10 @@ class FusedStep(object):
                 raise RuntimeError("FusedStep: table changed during graph capture")
             self._upload()
         dp = self.dp
-        self.device.ext.multi_update(self.table, len(self.entries), self.total_tiles,
-                                     self.has_ortho, self.flag_ptrs, self.epoch_ptr,
-                                     dp.rank if dp is not None else 0, self.gridsync)
-        api._launch()
+        for table, n, tiles, ortho in self.chunks:
+            self.device.ext.multi_update(table, n, tiles, ortho, self.flag_ptrs, self.epoch_ptr,
+                                         dp.rank if dp is not None else 0, self.gridsync)
+            api._launch()
         self.launches += 1
         for e in self.entries:
             e.touched = False

@@ -1,0 +1,75 @@
+"""Graph-level activation fusion for the CUDA backend.
+
+The reference configs spell activations as separate layers (``conv`` → ``activation_str``,
+``max_pooling`` → ``activation_str`` in cifar_caffe_config.py:86-144); the reference then
+runs one elementwise kernel per activation in each direction. On B200 these kernels are
+pure HBM round trips, so before the units are initialised this pass folds every
+*stand-alone* tanh / softplus / strict-ReLU / sigmoid activation into its producer:
+
+  forward   the producer (conv / fully connected with linear activation, max / maxabs / avg
+            pooling) applies f in its kernel epilogue; the activation unit aliases its
+            ``output`` to its ``input`` and launches nothing;
+  backward  the producer's GD unit multiplies the incoming error by f'(y) in the kernel it
+            runs anyway (``err_act_colsum`` for conv/FC, the pooling backward gather); the
+            activation's GD unit aliases ``err_input`` to ``err_output``.
+
+All four functions have derivatives expressible through the output y alone, so aliasing
+input and output loses nothing. The unit graph, the layer DSL, snapshots and
+``package_export`` are unchanged — only launches disappear. ``root.common.engine.
+fuse_activations = False`` switches the pass off.
+"""
+from __future__ import annotations
+
+from ..core.config import root
+from ..ops.activation import ActivationBackward, ActivationForward
+from ..ops.all2all import All2All, All2AllSoftmax
+from ..ops.conv import Conv
+from ..ops.pooling import AvgPooling, MaxAbsPooling, MaxPooling
+
+FUSABLE_CODES = (1, 2, 3, 4)       # tanh, softplus, strict relu, sigmoid
+
+
+def _producer_ok(p):
+    if isinstance(p, All2AllSoftmax):
+        return False
+    if isinstance(p, (Conv, All2All)):
+        return p.ACT == 0 and not getattr(p, "weights_transposed", False)
+    return type(p) in (MaxPooling, MaxAbsPooling, AvgPooling)
+
+
+def clear(workflow):
+    for u in list(workflow.forwards) + [g for g in workflow.gds if g is not None]:
+        if "fused_act_" in u.__dict__:
+            u.__dict__["fused_act_"] = 0
+        if getattr(u, "fused_into_", None) is not None:
+            u.fused_into_ = None
+
+
+def fuse_activations(workflow, device):
+    """Returns the number of activation layers folded away."""
+    clear(workflow)
+    if device is None or not device.is_cuda or \
+            not root.common.engine.get("fuse_activations", True):
+        return 0
+    fwds = list(workflow.forwards)
+    gds = list(workflow.gds)
+    have_gds = len(gds) == len(fwds) and any(g is not None for g in gds)
+    n = 0
+    for i in range(1, len(fwds)):
+        a, p = fwds[i], fwds[i - 1]
+        if not isinstance(a, ActivationForward) or a.CODE not in FUSABLE_CODES:
+            continue
+        if not _producer_ok(p) or getattr(a, "force_numpy", False) or \
+                getattr(p, "force_numpy", False):
+            continue
+        if have_gds:
+            ga, gp = gds[i], gds[i - 1]
+            if not isinstance(ga, ActivationBackward) or gp is None or \
+                    getattr(gp, "force_numpy", False) or getattr(ga, "force_numpy", False):
+                continue
+            gp.__dict__["fused_act_"] = a.CODE
+            ga.fused_into_ = gp
+        p.__dict__["fused_act_"] = a.CODE
+        a.fused_into_ = p
+        n += 1
+    return n

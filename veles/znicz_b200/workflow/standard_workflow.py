@@ -573,6 +573,11 @@ class StandardWorkflow(StandardWorkflowBase):
 
     # -- B200: CUDA-graph segments + data parallel -------------------------------------------------
     def initialize(self, device=None, **kwargs):
+        if device is None or isinstance(device, str):
+            from ..core.backends import get_device
+            device = get_device(device)
+        from . import fusion
+        self.fused_activations_ = fusion.fuse_activations(self, device)
         res = super().initialize(device=device, **kwargs)
         dev = self.device
         if dev is not None and dev.is_cuda:
