@@ -361,3 +361,32 @@ def test_pooling_fused_activation(ext, dtype, mode, c):
     ext.pool_backward(masked, offs_p, ei_p, oh, ow, k, k, s, s, mode == 2, None, 0)
     torch.cuda.synchronize()
     assert _rel(ei_f.float(), ei_p.float()) < (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("src_dt,dst_dt", [(torch.float32, torch.bfloat16),
+                                           (torch.float32, torch.float32)])
+def test_gather_minibatch_with_channel_padding(ext, src_dt, dst_dt):
+    """Device-resident dataset → minibatch (+ labels) and, in the same launch, the
+    channel-padded (3 → 8) copy the first conv layer's vector gather consumes."""
+    torch.manual_seed(5)
+    dev = "cuda"
+    total, rows, count = 50, 12, 9
+    data = torch.randn(total, 8, 8, 3, device=dev).to(src_dt)
+    labels = torch.randint(0, 10, (total,), device=dev, dtype=torch.int32)
+    idx = torch.randperm(total, device=dev)[:rows].to(torch.int32)
+    hdr = torch.cat([torch.tensor([count, 2, 0, 0], device=dev, dtype=torch.int32), idx])
+    dst = torch.full((rows, 8, 8, 3), float("nan"), device=dev, dtype=dst_dt)
+    pad = torch.full((rows, 8, 8, 8), float("nan"), device=dev, dtype=dst_dt)
+    ldst = torch.full((rows,), -7, device=dev, dtype=torch.int32)
+    ext.gather_minibatch(data, labels, hdr, dst, ldst, pad, 3)
+    torch.cuda.synchronize()
+    ref = data[idx.long()].to(dst_dt)
+    ref[count:] = 0
+    assert torch.equal(dst, ref)
+    assert torch.equal(pad[..., :3], ref) and float(pad[..., 3:].abs().sum()) == 0.0
+    assert torch.equal(ldst[:count], labels[idx.long()][:count]) and bool((ldst[count:] == -1).all())
+    # without the padded copy
+    dst2 = torch.empty_like(dst)
+    ext.gather_minibatch(data, labels, hdr, dst2, ldst, None, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(dst2, ref)

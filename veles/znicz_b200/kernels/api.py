@@ -262,7 +262,7 @@ def fc_backward(unit):
     if (_fc_small_ok(unit, n_out) and eff_act(unit) <= 4 and err.dtype == x.dtype and
             (eff_act(unit) == ACT_LINEAR or unit.output.dev.dtype == err.dtype)):
         # whole GD step of a few-output layer in one launch (+ the deferred update)
-        bsplit = max(1, min(8, batch // 16))
+        bsplit = max(1, min(16, batch // 8))
         gbuf = _grad_buffer(unit, "wgrad", (bsplit,) + tuple(unit.weights.shape)) \
             if need_w else None
         parts = _grad_buffer(unit, "bias_parts", (bsplit, n_out)) if need_b else None
@@ -352,9 +352,17 @@ def conv_forward(unit):
         w = unit.weights_lp_
         cp = lp_cpad(unit)
         if cp:   # first layer: pad C -> 8 once, fprop and wgrad then gather 16-byte chunks
-            xp = _tmp(unit, "xpad", tuple(x.shape[:3]) + (cp,), x.dtype)
-            ext.pad_channels(x, xp, unit._n_channels, cp)
-            _launch()
+            shape = tuple(x.shape[:3]) + (cp,)
+            ready = unit.input.__dict__.get("padded_dev_") if cp == 8 else None
+            if ready is not None and tuple(ready.shape) == shape and ready.dtype == x.dtype:
+                xp = ready           # the loader's gather kernel already produced it
+                unit.__dict__["tmp_xpad_"] = xp
+            else:
+                if cp == 8:
+                    unit.input.__dict__["pad_request_"] = cp
+                xp = _tmp(unit, "xpad", shape, x.dtype)
+                ext.pad_channels(x, xp, unit._n_channels, cp)
+                _launch()
             x = xp
             g = list(g)
             g[3] = cp

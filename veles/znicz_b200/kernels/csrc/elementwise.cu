@@ -205,10 +205,28 @@ __global__ void gather_labels_k(const int* __restrict__ src, const int* __restri
 template <typename TS, typename TD>
 __global__ void gather_minibatch_k(const TS* __restrict__ src, const int* __restrict__ labels_src,
                                    const int* __restrict__ hdr, TD* __restrict__ dst,
-                                   int* __restrict__ labels_dst, int max_rows, int row8) {
+                                   int* __restrict__ labels_dst, int max_rows, int row8,
+                                   TD* __restrict__ dst_pad, int C, int CP) {
   const int count = hdr[0];
   const int* idx = hdr + 4;
   const int total = max_rows * row8;
+  if (dst_pad) {
+    // second copy with the channels padded C -> CP (= 8): the first conv layer's tcgen05 gather
+    // then moves whole 16-byte pixels (replaces a separate pad_channels launch)
+    const int pixels = row8 * 8 / C;
+    const int ptotal = max_rows * pixels;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ptotal; i += gridDim.x * blockDim.x) {
+      const int r = i / pixels, px = i - r * pixels;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (r < count) {
+        const TS* s = src + (size_t)idx[r] * row8 * 8 + (size_t)px * C;
+        for (int j = 0; j < C; ++j) v[j] = ldf(s + j);
+      }
+      st8(dst_pad + (size_t)i * 8, v);
+    }
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / row8, c = i - r * row8;
     float v[8];
@@ -329,14 +347,14 @@ void launch_gather_rows(const void* src, bool src_bf16, const int* idx, void* ds
 }
 void launch_gather_minibatch(const void* src, bool src_bf16, const int* labels_src, const int* hdr,
                              void* dst, bool dst_bf16, int* labels_dst, int max_rows, long long row,
-                             cudaStream_t st) {
+                             void* dst_pad, int C, int CP, cudaStream_t st) {
   int row8 = (int)(row / 8);
   int g = grid_for((long long)max_rows * row8);
   if (g * 256 < max_rows) g = (max_rows + 255) / 256;
-  if (!src_bf16 && dst_bf16) gather_minibatch_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8);
-  else if (!src_bf16) gather_minibatch_k<float, float><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8);
-  else if (dst_bf16) gather_minibatch_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8);
-  else gather_minibatch_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8);
+  if (!src_bf16 && dst_bf16) gather_minibatch_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8, (__nv_bfloat16*)dst_pad, C, CP);
+  else if (!src_bf16) gather_minibatch_k<float, float><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8, (float*)dst_pad, C, CP);
+  else if (dst_bf16) gather_minibatch_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8, (__nv_bfloat16*)dst_pad, C, CP);
+  else gather_minibatch_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8, (float*)dst_pad, C, CP);
 }
 void launch_gather_labels(const int* src, const int* idx, int* dst, int count, int max_rows,
                           cudaStream_t st) {

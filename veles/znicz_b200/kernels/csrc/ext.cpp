@@ -18,7 +18,7 @@ void launch_axpby_2d(const void*, int, int, void*, int, int, int, int, float, fl
 void launch_crop_nhwc(const void*, void*, int, int, int, int, int, int, int, int, int, bool, cudaStream_t);
 void launch_gather_rows(const void*, bool, const int*, void*, bool, int, int, long long, cudaStream_t);
 void launch_gather_labels(const int*, const int*, int*, int, int, cudaStream_t);
-void launch_gather_minibatch(const void*, bool, const int*, const int*, void*, bool, int*, int, long long, cudaStream_t);
+void launch_gather_minibatch(const void*, bool, const int*, const int*, void*, bool, int*, int, long long, void*, int, int, cudaStream_t);
 void launch_mask_mul(void*, const void*, long long, bool, cudaStream_t);
 void launch_pad_channels(const void*, void*, int, int, int, bool, cudaStream_t);
 void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
@@ -164,14 +164,21 @@ void gather_labels(Tensor src, Tensor idx, Tensor dst, int64_t count) {
   kcheck();
 }
 void gather_minibatch(Tensor src, c10::optional<Tensor> labels_src, Tensor hdr, Tensor dst,
-                      c10::optional<Tensor> labels_dst) {
+                      c10::optional<Tensor> labels_dst, c10::optional<Tensor> dst_pad, int64_t C) {
   chk(src, "src"); chk(dst, "dst");
   long long row = src.numel() / src.size(0);
+  void* pad = nullptr;
+  if (dst_pad.has_value() && dst_pad->defined()) {
+    same_dt(dst, *dst_pad);
+    TORCH_CHECK(C >= 1 && C < 8 && row % C == 0 && dst_pad->numel() == dst.size(0) * (row / C) * 8,
+                "padded minibatch must be [rows][pixels][8]");
+    pad = dst_pad->data_ptr();
+  }
   TORCH_CHECK(row % 8 == 0, "gather_minibatch needs row % 8 == 0");
   const int* ls = (labels_src.has_value() && labels_src->defined()) ? labels_src->data_ptr<int>() : nullptr;
   int* ld = (labels_dst.has_value() && labels_dst->defined()) ? labels_dst->data_ptr<int>() : nullptr;
   zn::launch_gather_minibatch(src.data_ptr(), is_bf16(src), ls, hdr.data_ptr<int>(), dst.data_ptr(),
-                              is_bf16(dst), ld, (int)dst.size(0), row, cur());
+                              is_bf16(dst), ld, (int)dst.size(0), row, pad, (int)C, 8, cur());
   kcheck();
 }
 void pad_channels(Tensor x, Tensor y, int64_t C, int64_t CP) {

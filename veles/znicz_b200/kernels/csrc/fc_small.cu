@@ -29,11 +29,15 @@ fc_small_forward_k(const T* __restrict__ x, const float* __restrict__ w,
   float acc[FCS_MAX_OUT];
 #pragma unroll
   for (int o = 0; o < FCS_MAX_OUT; ++o) acc[o] = 0.f;
+  // rows >= n_out re-read the last valid row (result ignored): branch-free, all 16 loads of an
+  // iteration are independent and two iterations are in flight
+  const int last = n_out - 1;
+#pragma unroll 2
   for (int k = tid; k < n_in; k += 128) {
     const float xv = ldf(xr + k);
 #pragma unroll
     for (int o = 0; o < FCS_MAX_OUT; ++o)
-      if (o < n_out) acc[o] = fmaf(xv, w[(size_t)o * n_in + k], acc[o]);
+      acc[o] = fmaf(xv, __ldg(w + (size_t)min(o, last) * n_in + k), acc[o]);
   }
 #pragma unroll
   for (int o = 0; o < FCS_MAX_OUT; ++o) {
@@ -109,6 +113,7 @@ fc_small_backward_k(const T* __restrict__ err, const T* __restrict__ y, const T*
     wv[o] = (need_ei && o < n_out) ? w[(size_t)o * n_in + k] : 0.f;
     g[o] = 0.f;
   }
+#pragma unroll 4
   for (int r = 0; r < rows; ++r) {
     const float* e = s_err + r * FCS_MAX_OUT;
     const size_t xi = (size_t)(b0 + r) * n_in + k;

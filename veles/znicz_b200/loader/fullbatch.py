@@ -176,11 +176,24 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         ext = self.device.ext
         labels = self.has_labels
         if self._fused_gather_:
+            # a first conv layer with C % 8 != 0 asks for a channel-padded copy
+            # (``pad_request_`` on the Array, kernels/api.py::conv_forward): produce it here
+            md = self.minibatch_data
+            pad, c = None, 0
+            cp = md.__dict__.get("pad_request_")
+            if cp and md.devmem.dim() == 4 and md.devmem.shape[3] < 8:
+                pad = md.__dict__.get("padded_dev_")
+                shape = tuple(md.devmem.shape[:3]) + (8,)
+                if pad is None or tuple(pad.shape) != shape or pad.dtype != md.devmem.dtype:
+                    import torch
+                    pad = torch.zeros(shape, dtype=md.devmem.dtype, device=md.devmem.device)
+                    md.__dict__["padded_dev_"] = pad
+                c = int(md.devmem.shape[3])
             ext.gather_minibatch(
                 self.original_data.devmem,
                 self._mapped_original_labels.devmem if labels else None,
-                self._hdr_idx_dev_, self.minibatch_data.devmem,
-                self.minibatch_labels.devmem if labels else None)
+                self._hdr_idx_dev_, md.devmem,
+                self.minibatch_labels.devmem if labels else None, pad, c)
         else:
             idx = self._hdr_idx_dev_[4:]
             ext.gather_rows(self.original_data.devmem, idx, self.minibatch_data.devmem, n)
