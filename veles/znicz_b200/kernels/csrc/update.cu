@@ -209,6 +209,7 @@ struct TensorDesc {
 
 struct GridSync { unsigned* count; unsigned* gen; };
 constexpr int MU_MAX_TENSORS = 48;
+constexpr int MU_MAX_PEER_BLOCKS = 296;     // size of the cross-GPU flag / epoch arrays
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -236,23 +237,26 @@ __device__ __forceinline__ void grid_barrier(GridSync gs) {
   __syncthreads();
 }
 
-__device__ __forceinline__ void multi_col_sums(const TensorDesc& d) {
+// ``base`` rotates the block -> work mapping so that consecutive tensors land on different
+// blocks (the column-block lists of all tensors together are shorter than the grid).
+__device__ __forceinline__ int multi_col_sums(const TensorDesc& d, int base) {
   // logical matrix [rows = Y][cols = H]; out[col] = sum over rows. 256 threads.
   __shared__ float red[8][33];
   const int tid = threadIdx.x;
+  const int vb = (int)((blockIdx.x + gridDim.x - (unsigned)base % gridDim.x) % gridDim.x);
   if (d.flags & 16) {          // stored transposed [H][Y]: a warp per column, lanes over rows
     const int lane = tid & 31, wib = tid >> 5;
-    for (int col = blockIdx.x * 8 + wib; col < d.cols; col += gridDim.x * 8) {
+    for (int col = vb * 8 + wib; col < d.cols; col += gridDim.x * 8) {
       float s = 0.f;
       for (int r = lane; r < d.rows; r += 32) s += d.w[(size_t)col * d.rows + r];
       s = warp_sum(s);
       if (lane == 0) d.col_sums[col] = s;
     }
-    return;
+    return (d.cols + 7) / 8;
   }
   const int cx = tid & 31, ry = tid >> 5;
   const int n_cb = (d.cols + 31) / 32;
-  for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
+  for (int cb = vb; cb < n_cb; cb += gridDim.x) {
     const int col = cb * 32 + cx;
     float s0 = 0.f, s1 = 0.f;
     if (col < d.cols) {
@@ -273,6 +277,7 @@ __device__ __forceinline__ void multi_col_sums(const TensorDesc& d) {
     }
     __syncthreads();
   }
+  return n_cb;
 }
 
 __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, int nranks) {
@@ -355,7 +360,7 @@ __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, int nr
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int has_ortho,
                PeerSync ps, GridSync gsync) {
   __shared__ uint32_t s_epoch;
@@ -378,10 +383,11 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
       st_release_sys(ps.flags[threadIdx.x] + (size_t)blockIdx.x * 8 + ps.rank, 2 * epoch - 1);
   }
   if (has_ortho) {
+    int cs_base = 0;
     for (int t = 0; t < n; ++t) {
       const TensorDesc& d = s_table[t];
       if (!d.enabled || d.is_bias || !(d.flags & 8) || !d.col_sums) continue;
-      multi_col_sums(d);
+      cs_base += multi_col_sums(d, cs_base);
     }
     grid_barrier(gsync);
   }
@@ -439,8 +445,9 @@ void launch_multi_update(const void* table, int n, int total_tiles, int has_orth
   ps.rank = rank; ps.nranks = (peer_flags && nranks > 1) ? nranks : 1; ps.epoch = epoch;
   if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
   GridSync gs{gridsync, gridsync + 1};
-  int blocks = total_tiles < 296 ? total_tiles : 296;
-  if (ps.nranks > 1 && blocks > 148) blocks = 148;   // flag arrays are sized for 148 blocks
+  // latency-bound kernel: 4 CTAs of 256 threads per SM (all co-resident: the grid barrier needs it)
+  int blocks = total_tiles < 592 ? total_tiles : 592;
+  if (ps.nranks > 1 && blocks > MU_MAX_PEER_BLOCKS) blocks = MU_MAX_PEER_BLOCKS;
   if (blocks < 1) blocks = 1;
   multi_update_k<<<blocks, 256, 0, st>>>((const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs);
 }
