@@ -1,0 +1,39 @@
+"""Host-side data-parallel logic on CPU: two gloo processes (SURVEY §2.6 replacement of the
+master/slave exchange). Replicas must start identical (broadcast), see disjoint shards, apply
+identical summed gradients (bit-identical weights afterwards) and agree on reduced metrics."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_two_rank_gloo_training(tmp_path):
+    env = dict(os.environ, PYTHONPATH=REPO, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(REPO, "tests", "dp_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = [json.load(open(tmp_path / ("rank%d.json" % i))) for i in range(2)]
+    assert res[0]["world"] == 2 and res[1]["world"] == 2
+    # every rank serves half of each class
+    assert res[0]["train_len"] == 40 and res[1]["train_len"] == 40
+    assert res[0]["valid_len"] == 20 and res[1]["valid_len"] == 20
+    # replicas end bit-identical although they were initialised with different seeds
+    assert res[0]["checksum"] == res[1]["checksum"]
+    assert res[0]["absmax"] == res[1]["absmax"]
+    # metrics were all-reduced: both ranks report the same whole-job numbers
+    assert res[0]["epoch_n_err"] == res[1]["epoch_n_err"]
+    assert res[0]["best_valid_err_pt"] == res[1]["best_valid_err_pt"]
+    assert res[0]["best_valid_err_pt"] < 50.0

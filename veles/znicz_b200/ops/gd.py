@@ -106,6 +106,11 @@ class GDCommon(nn_units.GradientDescentBase):
             if a:
                 a.map_write()
         grad_vec.map_read()
+        dp = self.dp_
+        if dp is not None and dp.world_size > 1:
+            # host-side counterpart of the fused cross-GPU reduction: sum over ranks
+            grad_vec.map_write()
+            dp.all_reduce_numpy(grad_vec.mem)
         lr = self.learning_rate_bias if is_bias else self.learning_rate
         factor_l12 = self.weights_decay_bias if is_bias else self.weights_decay
         l1_vs_l2 = self.l1_vs_l2_bias if is_bias else self.l1_vs_l2

@@ -580,6 +580,13 @@ class StandardWorkflow(StandardWorkflowBase):
         self.fused_activations_ = fusion.fuse_activations(self, device)
         res = super().initialize(device=device, **kwargs)
         dev = self.device
+        if dev is not None and not dev.is_cuda:
+            # CPU multi-process runs (gloo): same sharding / metric reduction, gradients are
+            # all-reduced on the host inside the numpy GD step
+            from ..parallel import DataParallel
+            self.dp_ = DataParallel.from_env(dev)
+            if self.dp_ is not None:
+                self.dp_.attach(self)
         if dev is not None and dev.is_cuda:
             from ..parallel import DataParallel
             self.dp_ = DataParallel.from_env(dev)
