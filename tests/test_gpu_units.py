@@ -191,3 +191,22 @@ def test_stochastic_pooling_gpu_valid():
     # chosen elements are positive whenever the window has a positive element
     win_max = x.reshape(2, 4, 2, 4, 2, 16).max(axis=(2, 4))
     assert ((f.output.mem > 0) | (win_max <= 0)).all()
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+@pytest.mark.parametrize("seq", [True, False])
+def test_lstm_sequence(compute, seq):
+    from veles.znicz_b200.ops import lstm_seq
+    x = RS.uniform(-1, 1, (16, 6, 24)).astype(numpy.float32)        # [batch, T, features]
+    _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x,
+             {"output_sample_shape": 40, "weights_stddev": 0.2, "return_sequences": seq},
+             {"gradient_moment": 0.0, "gradient_moment_bias": 0.0},
+             extra=("gates", "cells", "hidden", "xh"), compute=compute,
+             tol=None if compute == "fp32" else 8e-2)
+    # odd sizes: (I + H) % 8 != 0 -> SIMT GEMMs even in bf16 mode
+    x = RS.uniform(-1, 1, (5, 3, 7)).astype(numpy.float32)
+    _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x,
+             {"output_sample_shape": 6, "weights_stddev": 0.3, "return_sequences": seq},
+             {"gradient_moment": 0.0, "gradient_moment_bias": 0.0},
+             extra=("gates", "cells", "hidden", "xh"), compute=compute,
+             tol=None if compute == "fp32" else 8e-2)

@@ -670,3 +670,130 @@ def deconv_backward(unit):
     ext.conv_wgrad(unit.input.dev, err, gbuf, splits, g, bool(unit.weights_transposed), 0)
     _launch()
     _update(unit, False, gbuf, splits, f * kw, f, kw)
+
+
+# ------------------------------------------------------------------------------------------
+# LSTM over a sequence (ops/lstm_seq.py)
+# ------------------------------------------------------------------------------------------
+def _lstm_gemm_nt(ext, unit, a, w_lp, w_f32, out, m, n, k, bias, beta):
+    """out[m, n] = a[m, k] . W[n, k]^T (+ bias) (+ beta * out); tcgen05 when a is bf16."""
+    if w_lp is not None and _is_bf16(a) and k % 8 == 0:
+        r = ext.gemm(a, k, False, w_lp, w_lp.shape[1], True, out, n, False, m, n, k, bias,
+                     ACT_LINEAR, 1.0, beta, 1, 0, 1)
+        if r != 0:
+            raise RuntimeError("%s: tcgen05 LSTM GEMM refused (code %d)" % (unit, r))
+    else:
+        ext.gemm(a, k, False, w_f32, k, True, out, n, False, m, n, k, bias, ACT_LINEAR, 1.0,
+                 beta, 1, 0, 0)
+    _launch()
+
+
+def lstm_seq_forward(unit):
+    ext = _ext(unit)
+    x = unit.input.dev                       # [B, T, I]
+    b, t, i = x.shape
+    h = unit.hidden_size
+    xh = unit.xh.dev_out                     # [T + 1, B, I + H]
+    gates = unit.gates.dev_out
+    cells = unit.cells.dev_out
+    hidden = unit.hidden.dev_out
+    out = unit.output.dev_out
+    w = unit.weights.dev
+    w_lp = None
+    if lp_enabled(unit) and _is_bf16(x) and (i + h) % 8 == 0:
+        ensure_shadows(unit)
+        w_lp = unit.weights_lp_
+    bias = unit.bias.dev if unit.include_bias and unit.bias else None
+    # [x_t] part of every step's operand in one strided copy; h_{-1} = 0
+    xh_flat = xh.view((t + 1) * b, i + h)
+    for s in range(t):
+        ext.axpby_2d(x.view(b, t * i), s * i, xh[s], 0, i, 1.0, 0.0)
+        _launch()
+    ext.axpby_2d(xh[0], i, xh[0], i, h, 0.0, 0.0)
+    _launch()
+    z = _tmp(unit, "z", (b, 4 * h), torch.float32)
+    seq = unit.return_sequences
+    for s in range(t):
+        _lstm_gemm_nt(ext, unit, xh[s], w_lp, w, z, b, 4 * h, i + h, bias, 0.0)
+        ext.lstm_cell_fwd(z, cells[s - 1] if s else None, cells[s], gates[s],
+                          hidden, s * b * h, h, xh, (s + 1) * b * (i + h) + i, i + h, b, h)
+        _launch()
+    # the unit's output: the whole sequence [B, T, H] or the last step [B, H]
+    if seq:
+        for s in range(t):
+            ext.axpby_2d(hidden[s], 0, out.view(b, t * h), s * h, h, 1.0, 0.0)
+            _launch()
+    else:
+        ext.axpby_2d(hidden[t - 1], 0, out, 0, h, 1.0, 0.0)
+        _launch()
+    del xh_flat
+
+
+def lstm_seq_backward(unit):
+    ext = _ext(unit)
+    gates = unit.gates.dev
+    cells = unit.cells.dev
+    xh = unit.xh.dev
+    t, b, h4 = gates.shape
+    h = h4 // 4
+    i = xh.shape[2] - h
+    err = unit.err_output.dev
+    seq = err.dim() == 3
+    dz = unit.dz.dev_out                    # [T, B, 4H] compute dtype
+    w = unit.weights.dev
+    fwd = unit.forward_unit
+    w_lp = getattr(fwd, "weights_lp_", None) if (lp_enabled(unit) and _is_bf16(dz)) else None
+    dxh = _tmp(unit, "dxh", (b, i + h), dz.dtype)
+    dc = [_tmp(unit, "dc0", (b, h), torch.float32), _tmp(unit, "dc1", (b, h), torch.float32)]
+    need_ei = unit.need_err_input
+    ei = None
+    if need_ei:
+        ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
+    for s in range(t - 1, -1, -1):
+        if seq:
+            e_t, e_off, lde = err, s * h, t * h
+        else:
+            e_t, e_off, lde = (err, 0, h) if s == t - 1 else (None, 0, 0)
+        ext.lstm_cell_bwd(e_t, e_off, lde, dxh if s < t - 1 else None, i, i + h,
+                          dc[(s + 1) & 1] if s < t - 1 else None, gates[s], cells[s],
+                          cells[s - 1] if s else None, dc[s & 1], dz[s], b, h)
+        _launch()
+        if s > 0 or need_ei:
+            # [dx_t | dh_{t-1}] = dz_t . W      (B = W stored [K = 4H][N = I + H], MN-major)
+            if w_lp is not None and h4 % 8 == 0:
+                r = ext.gemm(dz[s], h4, False, w_lp, w_lp.shape[1], False, dxh, i + h, False,
+                             b, i + h, h4, None, 0, 1.0, 0.0, 1, 0, 1)
+                if r != 0:
+                    raise RuntimeError("%s: tcgen05 LSTM dgrad refused (code %d)" % (unit, r))
+            else:
+                ext.gemm(dz[s], h4, False, w, i + h, False, dxh, i + h, False, b, i + h, h4,
+                         None, 0, 1.0, 0.0, 1, 0, 0)
+            _launch()
+            if need_ei:
+                ext.axpby_2d(dxh, 0, ei.view(b, t * i), s * i, i,
+                             float(unit.err_input_alpha), float(unit.err_input_beta))
+                _launch()
+    if need_ei:
+        unit.err_input.dev_written()
+    if not (unit.need_gradient_weights and unit.weights):
+        return
+    # gradW[4H, I + H] = dZ^T . XH over all T * B rows: one GEMM
+    rows = t * b
+    dz2 = dz.view(rows, h4)
+    xh2 = xh[:t].reshape(rows, i + h) if not xh[:t].is_contiguous() else xh[:t].view(rows, i + h)
+    gbuf = _grad_buffer(unit, "wgrad", (1, h4, i + h))
+    if w_lp is not None and h4 % 8 == 0 and (i + h) % 8 == 0:
+        r = ext.gemm(dz2, h4, True, xh2, i + h, False, gbuf, i + h, False, h4, i + h, rows,
+                     None, 0, 1.0, 0.0, 1, 0, 1)
+        if r != 0:
+            raise RuntimeError("%s: tcgen05 LSTM wgrad refused (code %d)" % (unit, r))
+    else:
+        ext.gemm(dz2, h4, True, xh2, i + h, False, gbuf, i + h, False, h4, i + h, rows, None, 0,
+                 1.0, 0.0, 1, 0, 0)
+    _launch()
+    _update(unit, False, gbuf, 1, 0, h4, i + h)
+    if unit.include_bias and unit.bias:
+        slices, parts = _bias_partials(unit, rows, h4)
+        ext.err_act_colsum(dz2, None, rows, h4, ACT_LINEAR, parts)
+        _launch()
+        _update(unit, True, parts, slices, h4, 1, h4)

@@ -379,3 +379,82 @@ void launch_scatter_offsets(const void* in, const int* offs, void* out, long lon
 }
 
 }  // namespace zn
+
+// ------------------------------------------------------------------------------------------
+// LSTM sequence cell kernels (ops/lstm_seq.py). Gate pre-activations z = [i | f | g | o]
+// (each H wide, fp32) come from one GEMM per time step; the cell update is one fused launch:
+//   i = sigma(z_i), f = sigma(z_f), g = A tanh(B z_g), o = sigma(z_o)
+//   c = i * g + f * c_prev ;  h = o * A tanh(B c)          (A = 1.7159, B = 0.6666: the
+//   reference's scaled tanh, /root/reference/lstm.py:75-108 + all2all.py:271-296)
+// h is written twice: to the output sequence slot and into the [x | h] operand of step t + 1.
+namespace zn {
+
+template <typename T>
+__global__ void lstm_cell_fwd_k(const float* __restrict__ z, const float* __restrict__ c_prev,
+                                float* __restrict__ c, float* __restrict__ gates,
+                                T* __restrict__ h_out, long long ldh, T* __restrict__ h_next,
+                                long long ldn, int batch, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * H) return;
+  const int b = i / H, j = i - b * H;
+  const float* zr = z + (size_t)b * 4 * H;
+  const float ig = 1.f / (1.f + __expf(-zr[j]));
+  const float fg = 1.f / (1.f + __expf(-zr[H + j]));
+  const float gg = 1.7159f * tanhf(0.6666f * zr[2 * H + j]);
+  const float og = 1.f / (1.f + __expf(-zr[3 * H + j]));
+  const float cv = ig * gg + fg * (c_prev ? c_prev[i] : 0.f);
+  const float tc = 1.7159f * tanhf(0.6666f * cv);
+  const float hv = og * tc;
+  c[i] = cv;
+  float* gr = gates + (size_t)b * 4 * H;
+  gr[j] = ig; gr[H + j] = fg; gr[2 * H + j] = gg; gr[3 * H + j] = og;
+  stf(h_out + (size_t)b * ldh + j, hv);
+  if (h_next) stf(h_next + (size_t)b * ldn + j, hv);
+}
+
+// dh = err_h (from above, may be null) + dh_rec (from step t + 1 through W_h, may be null)
+// dz (fp32 + compute-dtype copy for the GEMMs), dc_prev = dc * f
+template <typename T>
+__global__ void lstm_cell_bwd_k(const T* __restrict__ err_h, long long lde,
+                                const T* __restrict__ dh_rec, long long ldr,
+                                const float* __restrict__ dc_next, const float* __restrict__ gates,
+                                const float* __restrict__ c, const float* __restrict__ c_prev,
+                                float* __restrict__ dc_prev, T* __restrict__ dz, int batch, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * H) return;
+  const int b = i / H, j = i - b * H;
+  float dh = 0.f;
+  if (err_h) dh += ldf(err_h + (size_t)b * lde + j);
+  if (dh_rec) dh += ldf(dh_rec + (size_t)b * ldr + j);
+  const float* gr = gates + (size_t)b * 4 * H;
+  const float ig = gr[j], fg = gr[H + j], gg = gr[2 * H + j], og = gr[3 * H + j];
+  const float tc = 1.7159f * tanhf(0.6666f * c[i]);
+  const float dtc = tc * tc * (-0.388484177f) + 1.14381894f;     // d(A tanh(B c)) / dc
+  float dc = dh * og * dtc + (dc_next ? dc_next[i] : 0.f);
+  const float cp = c_prev ? c_prev[i] : 0.f;
+  T* dr = dz + (size_t)b * 4 * H;
+  stf(dr + j, dc * gg * ig * (1.f - ig));
+  stf(dr + H + j, dc * cp * fg * (1.f - fg));
+  stf(dr + 2 * H + j, dc * ig * (gg * gg * (-0.388484177f) + 1.14381894f));
+  stf(dr + 3 * H + j, dh * tc * og * (1.f - og));
+  dc_prev[i] = dc * fg;
+}
+
+void launch_lstm_cell_fwd(const float* z, const float* c_prev, float* c, float* gates, void* h_out,
+                          long long ldh, void* h_next, long long ldn, int batch, int H, bool bf16,
+                          cudaStream_t st) {
+  const int g = (batch * H + 255) / 256;
+  DISPATCH_T(bf16, lstm_cell_fwd_k<T><<<g, 256, 0, st>>>(z, c_prev, c, gates, (T*)h_out, ldh,
+                                                         (T*)h_next, ldn, batch, H));
+}
+void launch_lstm_cell_bwd(const void* err_h, long long lde, const void* dh_rec, long long ldr,
+                          const float* dc_next, const float* gates, const float* c,
+                          const float* c_prev, float* dc_prev, void* dz, int batch, int H, bool bf16,
+                          cudaStream_t st) {
+  const int g = (batch * H + 255) / 256;
+  DISPATCH_T(bf16, lstm_cell_bwd_k<T><<<g, 256, 0, st>>>((const T*)err_h, lde, (const T*)dh_rec, ldr,
+                                                         dc_next, gates, c, c_prev, dc_prev, (T*)dz,
+                                                         batch, H));
+}
+
+}  // namespace zn

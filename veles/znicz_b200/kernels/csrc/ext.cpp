@@ -34,6 +34,8 @@ void launch_mse_find_closest(const void*, bool, const float*, const int*, const 
 int fused_update_blocks(long long size);
 void launch_fused_update(float*, const float* const*, int, int, long long, float*, float*, float*, const float*, const float*, int, int, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, uint32_t* const*, uint32_t*, int, int, int, int, cudaStream_t);
 void launch_col_sums(const float*, float*, int, int, int, cudaStream_t);
+void launch_lstm_cell_fwd(const float*, const float*, float*, float*, void*, long long, void*, long long, int, int, bool, cudaStream_t);
+void launch_lstm_cell_bwd(const void*, long long, const void*, long long, const float*, const float*, const float*, const float*, float*, void*, int, int, bool, cudaStream_t);
 int fc_small_max_out();
 void launch_fc_small_forward(const void*, bool, const float*, const float*, void*, float*, int*, int, int, int, int, int, cudaStream_t);
 void launch_fc_small_backward(void*, const void*, const void*, bool, const float*, void*, float*, float*, int, int, int, int, float, float, int, cudaStream_t);
@@ -362,6 +364,47 @@ void refresh_shadows(Tensor w, int64_t rows, int64_t cols, c10::optional<Tensor>
   kcheck();
 }
 
+// LSTM sequence cell (ops/lstm_seq.py). Strided destinations are given as base tensor + element
+// offset + leading dimension.
+static inline size_t esz(const Tensor& t) { return (size_t)t.element_size(); }
+void lstm_cell_fwd(Tensor z, c10::optional<Tensor> c_prev, Tensor c, Tensor gates, Tensor h_out,
+                   int64_t h_off, int64_t ldh, c10::optional<Tensor> h_next, int64_t n_off, int64_t ldn,
+                   int64_t batch, int64_t H) {
+  TORCH_CHECK(z.scalar_type() == torch::kFloat32 && c.scalar_type() == torch::kFloat32 &&
+              gates.scalar_type() == torch::kFloat32 && z.is_cuda());
+  TORCH_CHECK(z.numel() >= batch * 4 * H && gates.numel() >= batch * 4 * H && c.numel() >= batch * H);
+  chk(h_out, "h_out");
+  void* hn = nullptr;
+  if (h_next.has_value() && h_next->defined()) {
+    same_dt(h_out, *h_next);
+    hn = static_cast<char*>(h_next->data_ptr()) + n_off * esz(*h_next);
+  }
+  zn::launch_lstm_cell_fwd(z.data_ptr<float>(), fptr_or_null(c_prev), c.data_ptr<float>(),
+                           gates.data_ptr<float>(), static_cast<char*>(h_out.data_ptr()) + h_off * esz(h_out),
+                           ldh, hn, ldn, (int)batch, (int)H, is_bf16(h_out), cur());
+  kcheck();
+}
+void lstm_cell_bwd(c10::optional<Tensor> err_h, int64_t e_off, int64_t lde, c10::optional<Tensor> dh_rec,
+                   int64_t r_off, int64_t ldr, c10::optional<Tensor> dc_next, Tensor gates, Tensor c,
+                   c10::optional<Tensor> c_prev, Tensor dc_prev, Tensor dz, int64_t batch, int64_t H) {
+  chk(dz, "dz");
+  TORCH_CHECK(gates.scalar_type() == torch::kFloat32 && c.scalar_type() == torch::kFloat32 &&
+              dc_prev.scalar_type() == torch::kFloat32);
+  const void* ep = nullptr; const void* rp = nullptr;
+  if (err_h.has_value() && err_h->defined()) {
+    same_dt(dz, *err_h);
+    ep = static_cast<const char*>(err_h->data_ptr()) + e_off * esz(*err_h);
+  }
+  if (dh_rec.has_value() && dh_rec->defined()) {
+    same_dt(dz, *dh_rec);
+    rp = static_cast<const char*>(dh_rec->data_ptr()) + r_off * esz(*dh_rec);
+  }
+  zn::launch_lstm_cell_bwd(ep, lde, rp, ldr, fptr_or_null(dc_next), gates.data_ptr<float>(),
+                           c.data_ptr<float>(), fptr_or_null(c_prev), dc_prev.data_ptr<float>(),
+                           dz.data_ptr(), (int)batch, (int)H, is_bf16(dz), cur());
+  kcheck();
+}
+
 // FC layers with n_out <= fc_small_max_out(): see csrc/fc_small.cu
 int64_t fc_small_max_out() { return zn::fc_small_max_out(); }
 void fc_small_forward(Tensor x, Tensor w, c10::optional<Tensor> bias, Tensor out, c10::optional<Tensor> max_idx,
@@ -533,6 +576,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("multi_update_table", &multi_update_table);
   m.def("multi_update_max_tensors", []() { return (int64_t)zn::multi_update_max_tensors(); }); m.def("multi_update", &multi_update);
   m.def("col_sums", &col_sums); m.def("refresh_shadows", &refresh_shadows);
+  m.def("lstm_cell_fwd", &lstm_cell_fwd); m.def("lstm_cell_bwd", &lstm_cell_bwd);
   m.def("fc_small_max_out", &fc_small_max_out); m.def("fc_small_forward", &fc_small_forward);
   m.def("fc_small_backward", &fc_small_backward);
   m.def("gemm", &gemm); m.def("pick_splits", &pick_splits);

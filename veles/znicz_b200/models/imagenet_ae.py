@@ -277,6 +277,7 @@ class ImagenetAEWorkflow(StandardWorkflow):
             attrs.update(ConvolutionalBase.CONV_ATTRS)
         if isinstance(g, GDPooling):
             attrs.update(GDPooling.POOL_ATTRS)
+        attrs.update(getattr(fwd, "GD_LINK_ATTRS", ()))
         g.link_attrs(fwd, *[a for a in sorted(attrs) if hasattr(fwd, a)])
         g.forward_unit = fwd
         return g

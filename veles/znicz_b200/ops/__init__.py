@@ -12,3 +12,4 @@ for _m in ("deconv", "gd_deconv", "lstm", "kohonen", "rbm_units", "rprop_gd",
     except ModuleNotFoundError as _e:   # module not written yet in this round
         if _m not in str(_e):
             raise
+from . import lstm_seq  # noqa: F401

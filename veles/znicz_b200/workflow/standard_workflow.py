@@ -209,6 +209,7 @@ class StandardWorkflow(StandardWorkflowBase):
                 try_link_attrs.update(ConvolutionalBase.CONV_ATTRS)
             if isinstance(unit, GDPooling):
                 try_link_attrs.update(GDPooling.POOL_ATTRS)
+            try_link_attrs.update(getattr(self.forwards[i], "GD_LINK_ATTRS", ()))
             attrs = [a for a in sorted(try_link_attrs) if hasattr(self.forwards[i], a)]
             unit.link_attrs(self.forwards[i], *attrs)
             unit.forward_unit = self.forwards[i]
