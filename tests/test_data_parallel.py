@@ -37,3 +37,31 @@ def test_two_rank_gloo_training(tmp_path):
     assert res[0]["epoch_n_err"] == res[1]["epoch_n_err"]
     assert res[0]["best_valid_err_pt"] == res[1]["best_valid_err_pt"]
     assert res[0]["best_valid_err_pt"] < 50.0
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("compute,mode", [("fp32", "eager"), ("bf16", "graphs")])
+def test_two_gpu_fused_reduce_update(tmp_path, compute, mode):
+    """Fused cross-GPU reduce + update over NVLink peer pointers (no NCCL on the step path):
+    replicas must stay bit-identical and learn."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, PYTHONPATH=REPO)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(REPO, "tests", "dp_worker_gpu.py"), str(tmp_path), compute, mode]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = [json.load(open(tmp_path / ("gpu_rank%d.json" % i))) for i in range(2)]
+    assert res[0]["world"] == 2 and res[0]["fused_symm"] and res[1]["fused_symm"]
+    assert res[0]["finite"] and res[1]["finite"]
+    assert res[0]["train_len"] == 200 and res[1]["train_len"] == 200
+    assert res[0]["checksum"] == res[1]["checksum"]        # bit-identical replicas
+    assert res[0]["abssum"] == res[1]["abssum"]
+    assert res[0]["step_launches"] == 30                   # 10 minibatches x 3 epochs per rank
+    assert res[0]["epoch_n_err"] == res[1]["epoch_n_err"]
+    assert res[0]["best_valid_err_pt"] < 60.0
