@@ -311,3 +311,69 @@ def test_imagenet_ae_stages_and_fine_tuning(tmp_path):
     wf2.run()
     assert bool(wf2.decision.complete)
     assert numpy.abs(wf2.forwards[0].weights.mem - w1).max() > 0
+
+
+def test_hands_and_channels(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from veles.znicz_b200.models import image_classifiers as ic
+    rs = numpy.random.RandomState(8)
+    # Hands: headerless .raw grey images in Training/<class>/ and Testing/<class>/
+    for split, n in (("Training", 12), ("Testing", 4)):
+        for ci, cname in enumerate(("Positive", "Negative")):
+            d = tmp_path / "hands" / split / cname
+            os.makedirs(d)
+            for k in range(n):
+                img = (rs.rand(16, 16) * 60).astype(numpy.uint8)
+                img[:, 8 * ci:8 * ci + 8] += 150          # bright left / right half
+                img.tofile(str(d / ("h%02d.raw" % k)))
+    wf = ic.build_hands(
+        loader_config=dict(root.hands.loader.to_dict(), minibatch_size=8, raw_shape=(16, 16),
+                           train_paths=[str(tmp_path / "hands" / "Training")],
+                           validation_paths=[str(tmp_path / "hands" / "Testing")]),
+        decision_config={"max_epochs": 12, "fail_iterations": 20},
+        image_saver_config={"out_dirs": [str(tmp_path / ("hs%d" % i)) for i in range(3)]},
+        snapshotter_config={"prefix": "hands_t", "interval": 1000, "time_interval": 1e9})
+    wf.initialize(device="numpy")
+    assert wf.loader.original_data.shape == (32, 16, 16, 1)
+    wf.run()
+    assert wf.decision.best_n_err_pt[1] < 30.0
+    # TvChannels: HSV + Sobel channel, aspect-preserving scale on a background
+    for ci, cname in enumerate(("first", "second", "third")):
+        d = tmp_path / "channels" / cname
+        os.makedirs(d)
+        for k in range(8):
+            img = numpy.full((30, 50, 3), 30, numpy.uint8)
+            cv2.circle(img, (10 + 12 * ci, 15), 6, (40 + 90 * ci, 200 - 60 * ci, 90), -1)
+            img = numpy.clip(img + rs.randn(30, 50, 3) * 6, 0, 255).astype(numpy.uint8)
+            cv2.imwrite(str(d / ("c%02d.png" % k)), img)
+    wf = ic.build_channels(
+        loader_config=dict(root.channels.loader.to_dict(), minibatch_size=6, scale=(32, 32),
+                           train_paths=[str(tmp_path / "channels")]),
+        layers=[{"name": "fc_tanh1", "type": "all2all_tanh", "->": {"output_sample_shape": 16},
+                 "<-": {"learning_rate": 0.01, "weights_decay": 0.0}},
+                {"name": "fc_softmax2", "type": "softmax",
+                 "<-": {"learning_rate": 0.01, "weights_decay": 0.0}}],
+        decision_config={"max_epochs": 6, "fail_iterations": 10},
+        image_saver_config={"out_dirs": [str(tmp_path / ("cs%d" % i)) for i in range(3)]},
+        snapshotter_config={"prefix": "chan_t", "interval": 1000, "time_interval": 1e9})
+    wf.initialize(device="numpy")
+    assert wf.loader.original_data.shape[1:] == (32, 32, 4)       # HSV + sobel
+    wf.run()
+    assert bool(wf.decision.complete)
+
+
+def test_spam_kohonen(tmp_path):
+    from veles.znicz_b200.models import spam_kohonen as sk
+    path = sk.generate_dataset(str(tmp_path / "spam.txt.xz"), n=160, n_lemmas=24)
+    out = str(tmp_path / "classified.txt")
+    root.spam_kohonen.forward.shape = (4, 4)
+    wf = sk.build(file=path, ids=True, classes=True, minibatch_size=40, epochs=5,
+                  export_file=out)
+    wf.initialize(device="numpy")
+    assert wf.loader.original_data.shape[0] == 160 and len(wf.loader.ids) == 160
+    wf.run()
+    assert bool(wf.decision.complete)
+    lines = open(out).read().split("\n")
+    assert len([l for l in lines if l]) == 160 and lines[0].startswith("msg")
+    # the two synthetic topics occupy different regions of the map
+    assert wf.validator.fitness > 0.6

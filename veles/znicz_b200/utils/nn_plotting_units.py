@@ -344,9 +344,13 @@ class KohonenValidationResults(KohonenGridBase):
     def record(self):
         hits = numpy.array(_host(self.input)).ravel()
         owner = {}
-        for label, neurons in enumerate(self.result):
+        res = self.result
+        pairs = res.items() if isinstance(res, dict) else enumerate(res)
+        labels = {}
+        for label, neurons in pairs:
+            idx = labels.setdefault(label, len(labels))
             for n in neurons:
-                owner[int(n)] = label
+                owner[int(n)] = idx
         fbn = self.fitness_by_neuron
         self.cells = [[(owner.get(y * self.width + x), int(hits[y * self.width + x]),
                         float(fbn[y * self.width + x]) if len(fbn) > y * self.width + x
