@@ -120,3 +120,43 @@ def test_demo_kohonen(tmp_path):
     assert numpy.abs(wf.trainer.weights.mem - w0).max() > 1e-3
     assert wf.plotters[0].hits is not None and wf.plotters[0].hits.sum() == 200
     assert wf.plotters[2].link_values is not None
+
+
+def test_forward_from_snapshot_on_new_images(tmp_path):
+    """Train the MNIST FC sample briefly, then classify image files with the restored
+    workflow in testing mode (samples/MNIST/mnist_forward.py equivalent)."""
+    import glob
+    import cv2
+    from veles.znicz_b200.models import mnist, mnist_forward
+    wf = mnist.build(
+        layers=mnist.fc_layers(), loader_name="synthetic_mnist",
+        loader_config={"minibatch_size": 20, "n_train": 300, "n_valid": 60, "noise": 0.3,
+                       "normalization_type": "linear"},
+        decision_config={"max_epochs": 4, "fail_iterations": 10},
+        snapshotter_config={"prefix": "mnist_fw", "interval": 1, "time_interval": 0,
+                            "compression": "", "directory": str(tmp_path / "snap")})
+    wf.initialize(device="numpy")
+    wf.run()
+    snaps = sorted(f for f in glob.glob(str(tmp_path / "snap" / "mnist_fw*.pickle"))
+                   if not os.path.islink(f))
+    assert snaps
+    # "new pictures": a few validation samples written as PNG files under <label>/ dirs
+    ld = wf.loader
+    ld.original_data.map_read()
+    truth = []
+    for k in range(12):
+        img = ld.original_data.mem[k, :, :, 0]
+        lbl = ld.original_labels[k]
+        d = tmp_path / "pics" / str(lbl)
+        os.makedirs(d, exist_ok=True)
+        u8 = ((img - img.min()) / (img.max() - img.min()) * 255).astype(numpy.uint8)
+        cv2.imwrite(str(d / ("p%02d.png" % k)), u8)
+        truth.append(lbl)
+    out = str(tmp_path / "result.json")
+    fwf, results = mnist_forward.forward_from_snapshot(
+        snaps[-1], [str(tmp_path / "pics")], result_file=out, device="numpy")
+    assert fwf.loader.class_lengths[0] == 12 and bool(fwf.decision.complete)
+    assert "Output" in results and os.path.exists(out)
+    probs = numpy.asarray(fwf.evaluator.merged_output)
+    assert probs.shape == (12, 10)
+    numpy.testing.assert_allclose(probs.sum(axis=1), 1.0, rtol=1e-4)
