@@ -179,3 +179,27 @@ def test_imagenet_loaders(tmp_path):
     aug.run()
     aug.run()                      # TRAIN minibatch: random crops stay in bounds
     assert aug.minibatch_class == 2 and numpy.isfinite(aug.minibatch_data.mem).all()
+
+
+def test_preparation_imagenet_roundtrip(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from veles.znicz_b200.loader.imagenet_loader import ImagenetLoader
+    from veles.znicz_b200.utils import preparation_imagenet as prep
+    rs = numpy.random.RandomState(4)
+    for split, n in (("train", 5), ("val", 2)):
+        for label in ("n01", "n02", "n03"):
+            d = tmp_path / "src" / split / label
+            os.makedirs(d)
+            for k in range(n):
+                img = rs.randint(0, 255, (20 + k, 30, 3)).astype(numpy.uint8)
+                cv2.imwrite(str(d / ("im%d.png" % k)), img)
+    info = prep.prepare(str(tmp_path / "src"), str(tmp_path / "out"), size=16, workers=2)
+    assert info["samples"] == 21 and info["labels"] == 3
+    wf = DummyWorkflow()
+    ld = ImagenetLoader(wf, minibatch_size=4, crop_size_sx=12, crop_size_sy=12, mirror=True,
+                        **info["loader_config"])
+    ld.initialize(device="numpy")
+    assert list(ld.class_lengths) == [0, 6, 15] and ld.unique_labels_count == 3
+    assert ld.has_mean_file and ld.mean.shape == (16, 16, 3)
+    ld.run()
+    assert ld.minibatch_data.shape == (4, 12, 12, 3) and numpy.isfinite(ld.minibatch_data.mem).all()
