@@ -62,6 +62,8 @@ def test_two_gpu_fused_reduce_update(tmp_path, compute, mode):
     assert res[0]["train_len"] == 200 and res[1]["train_len"] == 200
     assert res[0]["checksum"] == res[1]["checksum"]        # bit-identical replicas
     assert res[0]["abssum"] == res[1]["abssum"]
-    assert res[0]["step_launches"] == 30                   # 10 minibatches x 3 epochs per rank
+    # 10 minibatches x 3 epochs per rank; under CUDA graphs only the eager warm-up and capture
+    # passes go through python
+    assert res[0]["step_launches"] == (30 if mode == "eager" else 3)
     assert res[0]["epoch_n_err"] == res[1]["epoch_n_err"]
     assert res[0]["best_valid_err_pt"] < 60.0

@@ -248,11 +248,12 @@ def test_multi_update_matches_per_tensor_update(ext):
         ref.append(a)
         new.append(b)
         sp["g"] = g
-    packed, tiles = ext.multi_update_table(descs)
+    packed, tiles, red = ext.multi_update_table(descs, 0)
+    assert red == sum(d[15] for d in descs)
     table = packed.cuda()
     sync = torch.zeros(2, dtype=torch.int32, device=dev)
     for _ in range(1):
-        ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync)
+        ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync, [])
     torch.cuda.synchronize()
     assert int(sync[0]) == 0 and int(sync[1]) == 1      # one grid barrier generation
     for a, b, sp in zip(ref, new, specs):
@@ -266,11 +267,11 @@ def test_multi_update_matches_per_tensor_update(ext):
                 assert float(b[k].float().abs().sum()) > 0
     # disabled tensors must be left alone; a second launch must work (barrier re-arms)
     descs[0][23] = 0
-    packed, tiles2 = ext.multi_update_table(descs)
+    packed, tiles2, _ = ext.multi_update_table(descs, 0)
     assert tiles2 == tiles
     table.copy_(packed)
     w_before = new[0]["w"].clone()
-    ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync)
+    ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync, [])
     torch.cuda.synchronize()
     assert torch.equal(new[0]["w"], w_before)
     assert int(sync[1]) == 2

@@ -41,8 +41,8 @@ void launch_fc_small_forward(const void*, bool, const float*, const float*, void
 void launch_fc_small_backward(void*, const void*, const void*, bool, const float*, void*, float*, float*, int, int, int, int, float, float, int, cudaStream_t);
 size_t multi_update_desc_size();
 int multi_update_max_tensors();
-int multi_update_pack(const long long*, int, void*, int);
-void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, cudaStream_t);
+int multi_update_pack(const long long*, int, void*, int, long long);
+void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, float* const*, cudaStream_t);
 void launch_refresh_shadows(const float*, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 void launch_gemm_simt(const void*, bool, long long, int, const void*, bool, long long, int, void*, bool, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
 struct ConvGeomS { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
@@ -327,30 +327,38 @@ int64_t update_blocks(int64_t size) { return zn::fused_update_blocks(size); }
 // [w, grad_out, acc, vel, hyper, col_sums, grad[0..7], part_stride, size, nparts, g_cpad, flags,
 //  is_bias, rows, cols, lanes, enabled, lp, ld, lp_cpad, lp_conv, taps, C, c_pad]
 // Returns (packed CPU uint8 tensor [n * desc_size], total_tiles).
-std::tuple<Tensor, int64_t> multi_update_table(std::vector<std::vector<int64_t>> descs) {
+std::tuple<Tensor, int64_t, int64_t> multi_update_table(std::vector<std::vector<int64_t>> descs, int64_t red_base) {
   const size_t ds = zn::multi_update_desc_size();
   TORCH_CHECK((int)descs.size() <= zn::multi_update_max_tensors(),
               "multi_update handles at most ", zn::multi_update_max_tensors(), " tensors per launch");
   Tensor out = torch::zeros({(int64_t)(descs.size() * ds)}, torch::dtype(torch::kUInt8));
   int tiles = 0;
+  long long red = red_base;
   for (size_t i = 0; i < descs.size(); ++i) {
     TORCH_CHECK(descs[i].size() == 31, "descriptor must have 31 fields");
     std::vector<long long> f(descs[i].begin(), descs[i].end());
-    tiles += zn::multi_update_pack(f.data(), 31, out.data_ptr<uint8_t>() + i * ds, tiles);
+    tiles += zn::multi_update_pack(f.data(), 31, out.data_ptr<uint8_t>() + i * ds, tiles, red);
+    red += f[15];        // size: one fp32 slot per element in the cross-GPU reduction buffer
   }
-  return std::make_tuple(out, (int64_t)tiles);
+  return std::make_tuple(out, (int64_t)tiles, (int64_t)red);
 }
 void multi_update(Tensor table, int64_t n, int64_t total_tiles, bool has_ortho,
-                  std::vector<int64_t> peer_flags, int64_t epoch_ptr, int64_t rank, Tensor gridsync) {
+                  std::vector<int64_t> peer_flags, int64_t epoch_ptr, int64_t rank, Tensor gridsync,
+                  std::vector<int64_t> red_ptrs) {
   TORCH_CHECK(table.is_cuda() && table.scalar_type() == torch::kUInt8);
   TORCH_CHECK(gridsync.is_cuda() && gridsync.scalar_type() == torch::kInt32 && gridsync.numel() >= 2);
   uint32_t* fl[8];
   const int nranks = peer_flags.size() > 1 ? (int)peer_flags.size() : 1;
   TORCH_CHECK(nranks <= 8);
   for (int i = 0; i < nranks && peer_flags.size() > 1; ++i) fl[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  float* rp[8] = {nullptr};
+  if (nranks > 1) {
+    TORCH_CHECK((int)red_ptrs.size() == nranks, "data-parallel multi_update needs the reduction buffers");
+    for (int i = 0; i < nranks; ++i) rp[i] = reinterpret_cast<float*>(red_ptrs[i]);
+  }
   zn::launch_multi_update(table.data_ptr(), (int)n, (int)total_tiles, has_ortho ? 1 : 0, nranks,
                           nranks > 1 ? fl : nullptr, reinterpret_cast<uint32_t*>(epoch_ptr), (int)rank,
-                          reinterpret_cast<unsigned*>(gridsync.data_ptr<int32_t>()), cur());
+                          reinterpret_cast<unsigned*>(gridsync.data_ptr<int32_t>()), nranks > 1 ? rp : nullptr, cur());
   kcheck();
 }
 void col_sums(Tensor w, Tensor out, int64_t rows, int64_t cols, bool transposed) {

@@ -205,9 +205,11 @@ struct TensorDesc {
   int nparts, g_cpad, flags, is_bias, rows, cols, lanes, enabled;
   ShadowSpec sh;
   int tile_begin, n_tiles;
+  long long red_off;          // offset of this tensor in the cross-GPU reduction buffer
 };
 
 struct GridSync { unsigned* count; unsigned* gen; };
+struct RedBufs { float* ptr[8]; int nranks, rank; };
 constexpr int MU_MAX_TENSORS = 48;
 constexpr int MU_MAX_PEER_BLOCKS = 296;     // size of the cross-GPU flag / epoch arrays
 
@@ -280,7 +282,12 @@ __device__ __forceinline__ int multi_col_sums(const TensorDesc& d, int base) {
   return n_cb;
 }
 
-__device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, int nranks) {
+// MODE 0: single GPU (partials -> update). Data-parallel runs split the tile in two so that only
+// ONE fp32 value per element crosses NVLink instead of every split-K partial of every rank:
+// MODE 1: sum this rank's partials into its slot of the symmetric reduction buffer;
+// MODE 2 (after the cross-GPU flag barrier): sum the ranks' slots in fixed order and update.
+template <int MODE>
+__device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, const RedBufs& rb) {
   const int L = d.lanes;                         // power of two, <= 32
   const int tid = threadIdx.x;
   const int lane = tid & (L - 1);
@@ -289,36 +296,40 @@ __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, int nr
   const bool valid = i < d.size;
   const int is_bias = d.is_bias;
   float g = 0.f;
-  if (valid) {
+  if (MODE == 2) {
+    if (valid && lane == 0) {
+      for (int r = 0; r < rb.nranks; ++r) g += rb.ptr[r][d.red_off + i];   // fixed rank order
+    }
+  } else if (valid) {
     long long gi = i;
     if (d.g_cpad > 0) {
       const int r_ = (int)(i / d.cols), c_ = (int)(i % d.cols);
       const int tap_ = c_ / d.sh.C, ch_ = c_ - tap_ * d.sh.C;
       gi = ((long long)r_ * d.sh.taps + tap_) * d.g_cpad + ch_;
     }
-    for (int r = 0; r < nranks; ++r) {           // fixed rank order => bit-identical replicas
-      const float* base = d.grad[r] + gi;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
-      // 8 predicated loads in flight per round (the remainder is not serialised: out-of-range
-      // slots load nothing and add 0, the summation order stays fixed)
-      for (int p = lane; p < d.nparts; p += 8 * L) {
-        const long long st = d.part_stride;
-        const float* b = base + (long long)p * st;
-        const int left = d.nparts - p;
-        a0 += b[0];
-        a1 += (1 * L < left) ? b[(long long)(1 * L) * st] : 0.f;
-        a2 += (2 * L < left) ? b[(long long)(2 * L) * st] : 0.f;
-        a3 += (3 * L < left) ? b[(long long)(3 * L) * st] : 0.f;
-        a4 += (4 * L < left) ? b[(long long)(4 * L) * st] : 0.f;
-        a5 += (5 * L < left) ? b[(long long)(5 * L) * st] : 0.f;
-        a6 += (6 * L < left) ? b[(long long)(6 * L) * st] : 0.f;
-        a7 += (7 * L < left) ? b[(long long)(7 * L) * st] : 0.f;
-      }
-      g += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    const float* base = d.grad[0] + gi;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+    // 8 predicated loads in flight per round (the remainder is not serialised: out-of-range
+    // slots load nothing and add 0, the summation order stays fixed)
+    for (int p = lane; p < d.nparts; p += 8 * L) {
+      const long long st = d.part_stride;
+      const float* b = base + (long long)p * st;
+      const int left = d.nparts - p;
+      a0 += b[0];
+      a1 += (1 * L < left) ? b[(long long)(1 * L) * st] : 0.f;
+      a2 += (2 * L < left) ? b[(long long)(2 * L) * st] : 0.f;
+      a3 += (3 * L < left) ? b[(long long)(3 * L) * st] : 0.f;
+      a4 += (4 * L < left) ? b[(long long)(4 * L) * st] : 0.f;
+      a5 += (5 * L < left) ? b[(long long)(5 * L) * st] : 0.f;
+      a6 += (6 * L < left) ? b[(long long)(6 * L) * st] : 0.f;
+      a7 += (7 * L < left) ? b[(long long)(7 * L) * st] : 0.f;
     }
+    g = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
   }
-  for (int o = L >> 1; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  if (MODE != 2)
+    for (int o = L >> 1; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
   if (!valid || lane != 0) return;
+  if (MODE == 1) { rb.ptr[rb.rank][d.red_off + i] = g; return; }
 
   const float* hyper = d.hyper;
   const float lr = hyper[is_bias ? 9 : 0], wd = hyper[is_bias ? 10 : 1];
@@ -362,7 +373,7 @@ __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, int nr
 
 __global__ void __launch_bounds__(256, 4)
 multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int has_ortho,
-               PeerSync ps, GridSync gsync) {
+               PeerSync ps, GridSync gsync, RedBufs rb) {
   __shared__ uint32_t s_epoch;
   __shared__ TensorDesc s_table[MU_MAX_TENSORS];     // the whole table: no dependent global loads
   const bool multi = ps.nranks > 1;
@@ -377,11 +388,7 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  if (multi) {
-    epoch = s_epoch;
-    if ((int)threadIdx.x < ps.nranks)              // phase 0: signal only, wait later
-      st_release_sys(ps.flags[threadIdx.x] + (size_t)blockIdx.x * 8 + ps.rank, 2 * epoch - 1);
-  }
+  if (multi) epoch = s_epoch;
   if (has_ortho) {
     int cs_base = 0;
     for (int t = 0; t < n; ++t) {
@@ -389,27 +396,32 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
       if (!d.enabled || d.is_bias || !(d.flags & 8) || !d.col_sums) continue;
       cs_base += multi_col_sums(d, cs_base);
     }
-    grid_barrier(gsync);
   }
   if (multi) {
-    if ((int)threadIdx.x < ps.nranks) {
-      const uint32_t* mine = ps.flags[ps.rank] + (size_t)blockIdx.x * 8 + threadIdx.x;
-      const uint32_t value = 2 * epoch - 1;
-      long long spins = 0;
-      while ((int)(ld_acquire_sys(mine) - value) < 0) {
-        if (++spins > (1LL << 31)) { __trap(); }
-      }
+    // phase A: this block's tiles, local split-K reduction -> my slot of the reduction buffer
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;
+      const TensorDesc& d = s_table[t];
+      if (d.enabled) multi_tile<1>(d, tile - d.tile_begin, rb);
     }
-    __syncthreads();
+    // every rank maps tile -> block identically, so block b only needs block b of each peer:
+    // publish (release, after the CTA barrier inside peer_barrier) and wait
+    peer_barrier(ps, 2 * epoch - 1);
   }
-  int t = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;   // uniform
-    const TensorDesc& d = s_table[t];
-    if (d.enabled) multi_tile(d, tile - d.tile_begin, ps.nranks);
+  if (has_ortho) grid_barrier(gsync);    // col_sums of all tensors complete before any update
+  {
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;   // uniform
+      const TensorDesc& d = s_table[t];
+      if (!d.enabled) continue;
+      if (multi) multi_tile<2>(d, tile - d.tile_begin, rb);
+      else multi_tile<0>(d, tile - d.tile_begin, rb);
+    }
   }
   if (multi) {
-    peer_barrier(ps, 2 * epoch);       // nobody still reads my gradient buffers
+    peer_barrier(ps, 2 * epoch);       // nobody still reads my slot of the reduction buffer
     if (threadIdx.x == 0) ps.epoch[blockIdx.x] = epoch;
   }
 }
@@ -418,7 +430,7 @@ size_t multi_update_desc_size() { return sizeof(TensorDesc); }
 int multi_update_max_tensors() { return MU_MAX_TENSORS; }
 
 // fields: see ext.cpp::multi_update_table. Returns the number of tiles.
-int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begin) {
+int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begin, long long red_off) {
   TensorDesc d{};
   d.w = (float*)f[0]; d.grad_out = (float*)f[1]; d.acc = (float*)f[2]; d.vel = (float*)f[3];
   d.hyper = (const float*)f[4]; d.col_sums = (float*)f[5];
@@ -433,6 +445,7 @@ int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begi
   const int ept = 256 / d.lanes;
   d.tile_begin = tile_begin;
   d.n_tiles = (int)((d.size + ept - 1) / ept);
+  d.red_off = red_off;
   memcpy(out, &d, sizeof(d));
   (void)n_fields;
   return d.n_tiles;
@@ -440,7 +453,7 @@ int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begi
 
 void launch_multi_update(const void* table, int n, int total_tiles, int has_ortho, int nranks,
                          uint32_t* const* peer_flags, uint32_t* epoch, int rank, unsigned* gridsync,
-                         cudaStream_t st) {
+                         float* const* red_ptrs, cudaStream_t st) {
   PeerSync ps{};
   ps.rank = rank; ps.nranks = (peer_flags && nranks > 1) ? nranks : 1; ps.epoch = epoch;
   if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
@@ -449,7 +462,10 @@ void launch_multi_update(const void* table, int n, int total_tiles, int has_orth
   int blocks = total_tiles < 592 ? total_tiles : 592;
   if (ps.nranks > 1 && blocks > MU_MAX_PEER_BLOCKS) blocks = MU_MAX_PEER_BLOCKS;
   if (blocks < 1) blocks = 1;
-  multi_update_k<<<blocks, 256, 0, st>>>((const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs);
+  RedBufs rb{};
+  rb.nranks = ps.nranks; rb.rank = rank;
+  if (red_ptrs) for (int r = 0; r < nranks; ++r) rb.ptr[r] = red_ptrs[r];
+  multi_update_k<<<blocks, 256, 0, st>>>((const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs, rb);
 }
 
 int fused_update_blocks(long long size) {

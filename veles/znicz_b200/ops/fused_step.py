@@ -42,6 +42,8 @@ class FusedStep(object):
         self.enabled = []
         self.tables = []
         self.chunks = []
+        self.red_ptrs = []
+        self.red_numel = 0
         self.gridsync = torch.zeros(2, dtype=torch.int32, device=device.torch_device)
         self.flag_ptrs, self.epoch_ptr = [], 0
         self.launches = 0
@@ -115,9 +117,10 @@ class FusedStep(object):
             f[23] = 1 if e.touched else 0
             descs.append(f)
         self.chunks = []
+        red = 0
         for i in range(0, len(descs), cap):
             part = descs[i:i + cap]
-            packed, tiles = ext.multi_update_table(part)
+            packed, tiles, red = ext.multi_update_table(part, red)
             old = self.tables[len(self.chunks)] if len(self.chunks) < len(self.tables) else None
             if old is None or old.numel() != packed.numel():
                 old = torch.empty(packed.numel(), dtype=torch.uint8,
@@ -127,6 +130,12 @@ class FusedStep(object):
             self.chunks.append((old, len(part), int(tiles), ortho))
         self.tables = [c[0] for c in self.chunks]
         self.table = self.tables[0] if self.tables else None
+        if self.dp is not None and self.dp.symm is not None and red > self.red_numel:
+            # one fp32 slot per parameter in symmetric memory: ranks publish their locally
+            # reduced gradients here, peers read them over NVLink (collective allocation:
+            # all ranks build identical tables in the same step)
+            self.red_ptrs = self.dp.symm.reduction_buffer("fused_step_red", int(red))
+            self.red_numel = int(red)
         self.enabled = [bool(e.touched) for e in self.entries]
         self.dirty = False
 
@@ -144,7 +153,8 @@ class FusedStep(object):
         dp = self.dp
         for table, n, tiles, ortho in self.chunks:
             self.device.ext.multi_update(table, n, tiles, ortho, self.flag_ptrs, self.epoch_ptr,
-                                         dp.rank if dp is not None else 0, self.gridsync)
+                                         dp.rank if dp is not None else 0, self.gridsync,
+                                         self.red_ptrs)
             api._launch()
         self.launches += 1
         for e in self.entries:

@@ -63,6 +63,18 @@ class SymmetricGradients(object):
         dist.barrier()
         return b.tensor.view(*shape)
 
+    def reduction_buffer(self, key, numel):
+        """fp32 buffer of ``numel`` elements in symmetric memory → per-rank base pointers."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("symmetric buffers must be created before graph capture")
+        t, h = self._alloc(numel, torch.float32)
+        t.zero_()
+        self._bufs[("red", key, numel)] = (t, h)
+        self.bytes += numel * 4
+        torch.cuda.synchronize()
+        dist.barrier()
+        return [int(p) for p in h.buffer_ptrs]
+
     def sync_state(self, key):
         """(flag ptrs per rank, local epoch ptr) for a kernel that synchronises across
         ranks on its own (the whole-network FusedStep)."""
