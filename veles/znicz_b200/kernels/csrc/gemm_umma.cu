@@ -165,6 +165,54 @@ __device__ __forceinline__ void gather_taps(uint4 (&nv)[8], const int* ttab, con
     for (int q = 0; q < CPT; ++q) nv[j * CPT + q] = ok ? ptr[q] : z;
   }
 }
+// Asynchronous variant: the same taps, but every 16-byte chunk is an LDGSTS (cp.async) straight
+// into its swizzled shared-memory slot (row_base + ((c8 ^ sw) << 4)); out-of-image chunks are
+// zero-filled by the copy itself. No registers are staged and the thread never waits for global
+// memory: the stage's full-barrier gets this thread's arrival when its copies have landed, so
+// up to STAGES k-blocks of gathers are in flight per thread.
+template <int KIND, int TPK>
+__device__ __forceinline__ void gather_taps_async(uint32_t row_base, int sw, const int* ttab,
+                                                  const ConvGeomU& g, const PixCtx& c, int k0) {
+  constexpr int CPT = 8 / TPK;
+  int tap0, c0;
+  if (TPK == 1) { tap0 = k0 / g.inner; c0 = k0 - tap0 * g.inner; }
+  else { tap0 = (k0 >> 6) * TPK; c0 = 0; }
+#pragma unroll
+  for (int j = 0; j < TPK; ++j) {
+    const int tap = tap0 + j;
+    bool ok = c.valid && tap < g.ntaps;
+    const int e = ttab[ok ? tap : 0];
+    const int ky = e >> 8, kx = e & 0xff;
+    int off;
+    if (KIND == G_IM2COL) {
+      const int iy = c.y + ky, ix = c.x + kx;
+      ok = ok && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+      off = (iy * g.W + ix) * g.C;
+    } else {
+      const int ty = c.y - ky, tx = c.x - kx;
+      ok = ok && (unsigned)ty < (unsigned)g.OH && (unsigned)tx < (unsigned)g.OW;
+      off = (ty * g.OW + tx) * g.F;
+    }
+    const __nv_bfloat16* ptr = c.base + (ok ? off + c0 : 0);
+    const uint32_t nbytes = ok ? 16u : 0u;
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+      const int c8 = j * CPT + q;
+      cp_async_16(row_base + (uint32_t)((c8 ^ sw) << 4), ptr + q * 8, nbytes);
+    }
+  }
+}
+template <int KIND>
+__device__ __forceinline__ void gather_row_async(uint32_t row_base, int sw, const int* ktab,
+                                                 const ConvGeomU& g, const PixCtx& c, int k0) {
+  switch (g.tpk) {
+    case 1: gather_taps_async<KIND, 1>(row_base, sw, ktab, g, c, k0); break;
+    case 2: gather_taps_async<KIND, 2>(row_base, sw, ktab, g, c, k0); break;
+    case 4: gather_taps_async<KIND, 4>(row_base, sw, ktab, g, c, k0); break;
+    default: gather_taps_async<KIND, 8>(row_base, sw, ktab, g, c, k0); break;
+  }
+}
+
 template <int KIND, int GVEC>
 __device__ __forceinline__ void gather_row(uint4 (&nv)[8], const int* ktab, const ConvGeomU& g,
                                            const PixCtx& c, int k0, int klimit) {
@@ -296,6 +344,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (A_GATHER && GVEC == 2) fence_proxy_async_smem();   // LDGSTS data -> async proxy
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
         const uint32_t sb = sa + A_BYTES;
@@ -321,6 +370,18 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int m = m0 + t;
         const PixCtx ctx = (GKIND == G_IM2COL) ? decode_out_pixel(p.gsrc, p.g, m, p.M)
                                                : decode_in_pixel(p.gsrc, p.g, m, p.M);
+        if (GVEC == 2) {
+          // asynchronous gather: issue the LDGSTS of a stage as soon as its slot is free; the
+          // stage's full barrier is armed by the copies themselves
+#pragma unroll 1
+          for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const uint32_t row_base = smem_u32(tiles + (size_t)s * STAGE_BYTES) + t * 128;
+            gather_row_async<GKIND>(row_base, t & 7, ktab, p.g, ctx, (kb_begin + i) * BLOCK_K);
+            cp_async_mbar_arrive_noinc(&full_bar[s]);
+          }
+        } else {
         uint4 v[8], nv[8];
         // software pipeline with ONE load site: iteration i issues the global loads of stage
         // i + 1 and then publishes stage i (whose loads were issued one iteration earlier)
@@ -343,10 +404,24 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) v[c8] = nv[c8];
         }
+        }
       } else {
         // A_GATHER_MN (conv wgrad): tile = [64 reduction rows (pixels)][128 m (kidx)];
         // thread -> reduction row kr = t % 64, 64-wide m block = t / 64 (8 chunks of 8 kidx)
         const int kr = t & 63, mblk = t >> 6;
+        if (GVEC == 2) {
+#pragma unroll 1
+          for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int pix = (kb_begin + i) * BLOCK_K + kr;
+            const PixCtx ctx = decode_out_pixel(p.gsrc, p.g, pix, p.K);
+            const uint32_t row_base =
+                smem_u32(tiles + (size_t)s * STAGE_BYTES) + mblk * 8192 + kr * 128;
+            gather_row_async<G_IM2COL>(row_base, kr & 7, ktab, p.g, ctx, m0 + mblk * 64);
+            cp_async_mbar_arrive_noinc(&full_bar[s]);
+          }
+        } else {
         uint4 v[8], nv[8];
 #pragma unroll 1
         for (int i = -1; i < num_kb; ++i) {
@@ -367,6 +442,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) v[c8] = nv[c8];
+        }
         }
       }
     }

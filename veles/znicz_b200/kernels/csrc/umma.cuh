@@ -46,6 +46,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) { __trap(); }   // ~2 s at 2 GHz
   }
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc),
+               "r"(src_bytes)
+               : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all prior cp.async of this thread landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA / tensor core reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
