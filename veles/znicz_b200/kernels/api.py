@@ -177,8 +177,10 @@ def _bias_partials(unit, rows, cols):
 def _grad_buffer(unit, name, shape):
     """fp32 gradient staging buffer; lives in symmetric memory when data-parallel."""
     dp = unit.dp_
-    if dp is not None and dp.symm is not None:
+    if dp is not None and dp.symm is not None and getattr(unit, "step_", None) is None:
         return dp.symm.buffer(unit, name, shape)
+    # with the whole-network FusedStep only the locally reduced gradient crosses NVLink (through
+    # the step's own symmetric slot), so the split-K partials live in ordinary HBM
     return _tmp(unit, name, shape, torch.float32)
 
 
@@ -210,7 +212,7 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
     elif g_cpad:
         raise RuntimeError("channel-padded gradients need the forward unit's shadow spec")
     dp = unit.dp_
-    if dp is not None and dp.symm is not None:
+    if dp is not None and dp.symm is not None and step is None:
         ptrs, flag_ptrs, epoch_ptr, blocks = dp.symm.peers(unit, grad_buf)
         rank = dp.rank
     else:

@@ -211,7 +211,7 @@ struct TensorDesc {
 struct GridSync { unsigned* count; unsigned* gen; };
 struct RedBufs { float* ptr[8]; int nranks, rank; };
 constexpr int MU_MAX_TENSORS = 48;
-constexpr int MU_MAX_PEER_BLOCKS = 296;     // size of the cross-GPU flag / epoch arrays
+constexpr int MU_MAX_PEER_BLOCKS = 592;     // size of the cross-GPU flag / epoch arrays
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;

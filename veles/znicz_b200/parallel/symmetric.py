@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-MAX_BLOCKS = 296     # csrc/update.cu::MU_MAX_PEER_BLOCKS
+MAX_BLOCKS = 592     # csrc/update.cu::MU_MAX_PEER_BLOCKS
 
 
 class _Buf(object):
