@@ -154,3 +154,35 @@ def test_activation_fusion_equals_separate_units():
     for a, b in zip(wa, wb):
         assert numpy.abs(a - b).max() <= 2e-4 * max(1.0, numpy.abs(a).max())
     assert ea == eb
+
+
+@pytest.mark.parametrize("family", ["alexnet", "nin", "vgga"])
+def test_imagenet_models_step_on_gpu(family):
+    """Full-size AlexNet (grouped) / NiN / 13-conv VGG, bf16, a few training steps on synthetic
+    227x227 (224 for VGG) images: exercises stride-4 11x11 convs on the channel-padded path,
+    3x3/1x1 convs with 64..1024 channels, 9216x4096 FC layers, dropout, LRN, ZeroFiller."""
+    from veles.znicz_b200.models import alexnet
+    root.common.engine.compute_type = "bf16"
+    try:
+        side = 224 if family == "vgga" else 227
+        layers = {"alexnet": alexnet.alexnet_layers, "nin": alexnet.nin_layers,
+                  "vgga": alexnet.vgga_layers}[family](n_classes=20)
+        wf = alexnet.build(
+            loader_name="synthetic_imagenet", layers=layers,
+            loader_config={"minibatch_size": 8, "shape": (side, side, 3), "n_classes": 20,
+                           "n_train": 24, "n_valid": 8, "noise": 0.3,
+                           "normalization_type": "internal_mean"},
+            decision_config={"max_epochs": 1, "fail_iterations": 5},
+            snapshotter_config={"prefix": "inet_g", "interval": 1000, "time_interval": 1e9})
+        wf.initialize(device="cuda")
+        wf.run()
+        assert bool(wf.decision.complete)
+        for f in wf.forwards:
+            if getattr(f, "weights", None):
+                f.weights.map_read()
+                assert numpy.isfinite(f.weights.mem).all(), f.name
+        wf.forwards[-1].output.map_read()
+        out = wf.forwards[-1].output.mem
+        assert numpy.isfinite(out).all() and abs(float(out[0].sum()) - 1.0) < 1e-2
+    finally:
+        root.common.engine.compute_type = "fp32"

@@ -52,8 +52,10 @@ def fuse_activations(workflow, device):
             not root.common.engine.get("fuse_activations", True):
         return 0
     fwds = list(workflow.forwards)
-    gds = list(workflow.gds)
-    have_gds = len(gds) == len(fwds) and any(g is not None for g in gds)
+    gds = [g for g in workflow.gds if g is not None]
+    # GD units are matched through ``forward_unit`` (layers without a GD, e.g. zero_filter,
+    # make the two lists differ in length)
+    gd_of = {id(g.forward_unit): g for g in gds if getattr(g, "forward_unit", None) is not None}
     n = 0
     for i in range(1, len(fwds)):
         a, p = fwds[i], fwds[i - 1]
@@ -62,8 +64,8 @@ def fuse_activations(workflow, device):
         if not _producer_ok(p) or getattr(a, "force_numpy", False) or \
                 getattr(p, "force_numpy", False):
             continue
-        if have_gds:
-            ga, gp = gds[i], gds[i - 1]
+        if gds:
+            ga, gp = gd_of.get(id(a)), gd_of.get(id(p))
             if not isinstance(ga, ActivationBackward) or gp is None or \
                     getattr(gp, "force_numpy", False) or getattr(ga, "force_numpy", False):
                 continue
