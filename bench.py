@@ -180,9 +180,13 @@ def main():
         return 0
     if args.impl == "baseline":
         # reference-equivalent decomposition inside this repo: fp32, exact SIMT GEMM/conv
-        # kernels, one python-driven launch per op (no CUDA graphs)
+        # kernels, one python-driven launch per reference kernel (no CUDA graphs, per-tensor
+        # update launches, stand-alone activation units)
         args.dtype = "fp32"
         args.no_graphs = True
+        from veles.znicz_b200.core.config import root as _root
+        _root.common.engine.fused_step = False
+        _root.common.engine.fuse_activations = False
     if args.warmup < 3:
         args.warmup = 3
     if world > 1:
