@@ -209,7 +209,9 @@ struct TensorDesc {
 };
 
 struct GridSync { unsigned* count; unsigned* gen; };
-struct RedBufs { float* ptr[8]; int nranks, rank; };
+// half > 0: the reduction buffer is double buffered (slot parity alternates every step), which
+// makes the trailing cross-GPU barrier unnecessary; chunks = launches per step
+struct RedBufs { float* ptr[8]; int nranks, rank; long long half; int chunks; };
 constexpr int MU_MAX_TENSORS = 48;
 constexpr int MU_MAX_PEER_BLOCKS = 592;     // size of the cross-GPU flag / epoch arrays
 
@@ -287,7 +289,8 @@ __device__ __forceinline__ int multi_col_sums(const TensorDesc& d, int base) {
 // MODE 1: sum this rank's partials into its slot of the symmetric reduction buffer;
 // MODE 2 (after the cross-GPU flag barrier): sum the ranks' slots in fixed order and update.
 template <int MODE>
-__device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, const RedBufs& rb) {
+__device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, const RedBufs& rb,
+                                           long long poff) {
   const int L = d.lanes;                         // power of two, <= 32
   const int tid = threadIdx.x;
   const int lane = tid & (L - 1);
@@ -298,7 +301,7 @@ __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, const 
   float g = 0.f;
   if (MODE == 2) {
     if (valid && lane == 0) {
-      for (int r = 0; r < rb.nranks; ++r) g += rb.ptr[r][d.red_off + i];   // fixed rank order
+      for (int r = 0; r < rb.nranks; ++r) g += rb.ptr[r][poff + d.red_off + i];   // fixed rank order
     }
   } else if (valid) {
     long long gi = i;
@@ -329,7 +332,7 @@ __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, const 
   if (MODE != 2)
     for (int o = L >> 1; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
   if (!valid || lane != 0) return;
-  if (MODE == 1) { rb.ptr[rb.rank][d.red_off + i] = g; return; }
+  if (MODE == 1) { rb.ptr[rb.rank][poff + d.red_off + i] = g; return; }
 
   const float* hyper = d.hyper;
   const float lr = hyper[is_bias ? 9 : 0], wd = hyper[is_bias ? 10 : 1];
@@ -389,6 +392,8 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
   }
   __syncthreads();
   if (multi) epoch = s_epoch;
+  const long long poff =
+      (multi && rb.half > 0 && (((epoch - 1) / (uint32_t)max(rb.chunks, 1)) & 1u)) ? rb.half : 0;
   if (has_ortho) {
     int cs_base = 0;
     for (int t = 0; t < n; ++t) {
@@ -403,7 +408,7 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;
       const TensorDesc& d = s_table[t];
-      if (d.enabled) multi_tile<1>(d, tile - d.tile_begin, rb);
+      if (d.enabled) multi_tile<1>(d, tile - d.tile_begin, rb, poff);
     }
     // every rank maps tile -> block identically, so block b only needs block b of each peer:
     // publish (release, after the CTA barrier inside peer_barrier) and wait
@@ -416,12 +421,15 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
       while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;   // uniform
       const TensorDesc& d = s_table[t];
       if (!d.enabled) continue;
-      if (multi) multi_tile<2>(d, tile - d.tile_begin, rb);
-      else multi_tile<0>(d, tile - d.tile_begin, rb);
+      if (multi) multi_tile<2>(d, tile - d.tile_begin, rb, poff);
+      else multi_tile<0>(d, tile - d.tile_begin, rb, poff);
     }
   }
   if (multi) {
-    peer_barrier(ps, 2 * epoch);       // nobody still reads my slot of the reduction buffer
+    // single-buffered slots: wait until nobody still reads mine. Double-buffered slots need no
+    // trailing barrier: a rank can be at most one step ahead (the phase barrier of step k + 1
+    // is passed only after every peer finished reading step k), and step k + 1 uses the other half.
+    if (rb.half <= 0) peer_barrier(ps, 2 * epoch);
     if (threadIdx.x == 0) ps.epoch[blockIdx.x] = epoch;
   }
 }
@@ -453,7 +461,7 @@ int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begi
 
 void launch_multi_update(const void* table, int n, int total_tiles, int has_ortho, int nranks,
                          uint32_t* const* peer_flags, uint32_t* epoch, int rank, unsigned* gridsync,
-                         float* const* red_ptrs, cudaStream_t st) {
+                         float* const* red_ptrs, long long red_half, int chunks, cudaStream_t st) {
   PeerSync ps{};
   ps.rank = rank; ps.nranks = (peer_flags && nranks > 1) ? nranks : 1; ps.epoch = epoch;
   if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
@@ -463,7 +471,7 @@ void launch_multi_update(const void* table, int n, int total_tiles, int has_orth
   if (ps.nranks > 1 && blocks > MU_MAX_PEER_BLOCKS) blocks = MU_MAX_PEER_BLOCKS;
   if (blocks < 1) blocks = 1;
   RedBufs rb{};
-  rb.nranks = ps.nranks; rb.rank = rank;
+  rb.nranks = ps.nranks; rb.rank = rank; rb.half = red_half; rb.chunks = chunks;
   if (red_ptrs) for (int r = 0; r < nranks; ++r) rb.ptr[r] = red_ptrs[r];
   multi_update_k<<<blocks, 256, 0, st>>>((const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs, rb);
 }

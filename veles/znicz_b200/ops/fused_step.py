@@ -134,7 +134,8 @@ class FusedStep(object):
             # one fp32 slot per parameter in symmetric memory: ranks publish their locally
             # reduced gradients here, peers read them over NVLink (collective allocation:
             # all ranks build identical tables in the same step)
-            self.red_ptrs = self.dp.symm.reduction_buffer("fused_step_red", int(red))
+            # double buffered: step parity selects the half, so no trailing barrier is needed
+            self.red_ptrs = self.dp.symm.reduction_buffer("fused_step_red", 2 * int(red))
             self.red_numel = int(red)
         self.enabled = [bool(e.touched) for e in self.entries]
         self.dirty = False
@@ -154,7 +155,8 @@ class FusedStep(object):
         for table, n, tiles, ortho in self.chunks:
             self.device.ext.multi_update(table, n, tiles, ortho, self.flag_ptrs, self.epoch_ptr,
                                          dp.rank if dp is not None else 0, self.gridsync,
-                                         self.red_ptrs)
+                                         self.red_ptrs, self.red_numel if self.red_ptrs else 0,
+                                         len(self.chunks))
             api._launch()
         self.launches += 1
         for e in self.entries:
