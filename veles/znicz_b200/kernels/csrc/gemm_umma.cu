@@ -32,7 +32,7 @@ enum { G_NONE = 0, G_IM2COL = 1, G_DGRAD = 2 };
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 elements = 128 bytes = one SW128 row
-constexpr int STAGES = 4;
+constexpr int STAGES_DEFAULT = 4;   // deep (8-stage) variant: see launch_cfg
 constexpr int A_BYTES = BLOCK_M * 128;
 
 struct ConvGeomU {
@@ -53,6 +53,9 @@ struct GemmParams {
   // gather source
   const __nv_bfloat16* gsrc; ConvGeomU g; int gather_kind;
   int gK;                      // valid extent of the gathered K (fprop/dgrad) or M (wgrad) index
+  // A_GATHER_K only: consecutive 128-row tiles streamed through ONE pipeline per CTA, each with
+  // its own TMEM columns (amortises prologue / epilogue latency for short-K convolutions)
+  int mt;
 };
 
 // ---- gather: 8 consecutive "inner" indices of one "pixel" -> 16 bytes ------------------------
@@ -255,13 +258,13 @@ __device__ __noinline__ void epi_store_slow(const GemmParams& p, int row, int n,
   }
 }
 
-template <int BLOCK_N, int B_MODE>
+template <int BLOCK_N, int B_MODE, int STAGES>
 __host__ __device__ constexpr int min_ctas() {
   return (2 * (STAGES * (A_BYTES + b_bytes<BLOCK_N, B_MODE>()) + 2048) <= 227 * 1024) ? 2 : 1;
 }
 
-template <int BLOCK_N, int A_MODE, int B_MODE, int GKIND, int GVEC>
-__global__ void __launch_bounds__(192, (min_ctas<BLOCK_N, B_MODE>()))
+template <int BLOCK_N, int A_MODE, int B_MODE, int GKIND, int GVEC, int STAGES>
+__global__ void __launch_bounds__(192, (min_ctas<BLOCK_N, B_MODE, STAGES>()))
 gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
   constexpr int B_BYTES = b_bytes<BLOCK_N, B_MODE>();
@@ -285,7 +288,13 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const int mt_cfg = (A_MODE == A_GATHER_K && p.mt > 1) ? p.mt : 1;
+  const int m_tiles_total = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int mtile0 = blockIdx.y * mt_cfg;
+  const int ntiles = min(mt_cfg, m_tiles_total - mtile0);       // tiles this CTA streams (>= 1)
+  const int m0 = mtile0 * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  uint32_t tmem_cols = TMEM_COLS;                                 // power of two >= 32
+  while (tmem_cols < (uint32_t)(BLOCK_N * mt_cfg)) tmem_cols <<= 1;
   const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_begin = blockIdx.z * p.k_blocks_per_split;
   const int kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
@@ -304,7 +313,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 5) {
-    tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tmem_alloc(&tmem_base_smem, tmem_cols);
     tmem_relinquish();
   }
   if (A_GATHER) build_ktab(ktab, p.g, GKIND, p.gK);
@@ -316,8 +325,9 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+      for (int gi = 0; gi < num_kb * ntiles; ++gi) {
+        const int i = gi % num_kb;
+        const int s = gi % STAGES; const uint32_t ph = (gi / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
@@ -341,8 +351,10 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+      for (int gi = 0; gi < num_kb * ntiles; ++gi) {
+        const int i = gi % num_kb;
+        const uint32_t d_tmem = tmem_base + (uint32_t)((gi / num_kb) * BLOCK_N);
+        const int s = gi % STAGES; const uint32_t ph = (gi / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         if (A_GATHER && GVEC == 2) fence_proxy_async_smem();   // LDGSTS data -> async proxy
         tc_fence_after();
@@ -355,7 +367,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                    : make_smem_desc(sa + k * 32, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
                                    : make_smem_desc(sb + k * 32, 16, 1024);
-          mma_f16(tmem_base, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          mma_f16(d_tmem, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
       }
@@ -367,7 +379,9 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int t = threadIdx.x;            // 0..127
       if (A_MODE == A_GATHER_K) {
         // tile row r = t is GEMM row m0 + t (a pixel); chunks run over the reduction index
-        const int m = m0 + t;
+        for (int tj = 0; tj < ntiles; ++tj) {
+        const int m = m0 + tj * BLOCK_M + t;
+        const int gbase = tj * num_kb;           // position of this tile in the stage sequence
         const PixCtx ctx = (GKIND == G_IM2COL) ? decode_out_pixel(p.gsrc, p.g, m, p.M)
                                                : decode_in_pixel(p.gsrc, p.g, m, p.M);
         if (GVEC == 2) {
@@ -375,7 +389,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           // stage's full barrier is armed by the copies themselves
 #pragma unroll 1
           for (int i = 0; i < num_kb; ++i) {
-            const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+            const int s = (gbase + i) % STAGES; const uint32_t ph = ((gbase + i) / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             const uint32_t row_base = smem_u32(tiles + (size_t)s * STAGE_BYTES) + t * 128;
             gather_row_async<GKIND>(row_base, t & 7, ktab, p.g, ctx, (kb_begin + i) * BLOCK_K);
@@ -392,7 +406,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             gather_row<GKIND, GVEC>(nv, ktab, p.g, ctx, k0, p.gK);
           }
           if (i >= 0) {
-            const int s = i % STAGES; const uint32_t ph = (i / STAGES) & 1;
+            const int s = (gbase + i) % STAGES; const uint32_t ph = ((gbase + i) / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
 #pragma unroll
@@ -405,6 +419,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int c8 = 0; c8 < 8; ++c8) v[c8] = nv[c8];
         }
         }
+        }   // tiles of this CTA
       } else {
         // A_GATHER_MN (conv wgrad): tile = [64 reduction rows (pixels)][128 m (kidx)];
         // thread -> reduction row kr = t % 64, 64-wide m block = t / 64 (8 chunks of 8 kidx)
@@ -447,17 +462,20 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
     // ===================== epilogue (warps 0-3) =====================
-    const int row = m0 + warp * 32 + lane;
     if (num_kb > 0) {
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
     }
     constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
 #pragma unroll 1
+    for (int tj = 0; tj < ntiles; ++tj) {
+    const int row = m0 + tj * BLOCK_M + warp * 32 + lane;
+#pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
       uint32_t r[32];
       if (num_kb > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                               (uint32_t)(tj * BLOCK_N + c0);
         if (CH == 32) {
           tmem_ld_32x32(taddr, r);
         } else {
@@ -497,12 +515,13 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
+    }   // tiles of this CTA
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -539,20 +558,37 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BN, int AM, int BM, int GK, int GV>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
-                      cudaStream_t st) {
-  constexpr int smem = STAGES * (A_BYTES + b_bytes<BN, BM>()) + 1024;
+template <int BN, int AM, int BM, int GK, int GV, int NS>
+static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+                         cudaStream_t st) {
+  constexpr int smem = NS * (A_BYTES + b_bytes<BN, BM>()) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_umma_k<BN, AM, BM, GK, GV>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_umma_k<BN, AM, BM, GK, GV, NS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BLOCK_M - 1) / BLOCK_M, splits);
-  gemm_umma_k<BN, AM, BM, GK, GV><<<grid, 192, smem, st>>>(ta, tb, p);
+  gemm_umma_k<BN, AM, BM, GK, GV, NS><<<grid, 192, smem, st>>>(ta, tb, p);
   return (int)cudaGetLastError();
+}
+
+template <int BN, int AM, int BM, int GK, int GV>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
+                      cudaStream_t st) {
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int mt = (AM == A_GATHER_K && p.mt > 1) ? p.mt : 1;
+  dim3 grid((p.N + BN - 1) / BN, (m_tiles + mt - 1) / mt, splits);
+  // Grids that leave one CTA (or none) per SM cannot hide the gather latency by co-residency:
+  // give those CTAs an 8-deep ring instead (asynchronous LDGSTS producers only, and only when
+  // the K loop is long enough to use it).
+  constexpr bool deep_ok = (GV == 2) && (8 * (A_BYTES + b_bytes<BN, BM>()) + 2048 <= 227 * 1024);
+  if constexpr (deep_ok) {
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    const int kb = p.k_blocks_per_split;
+    if (ctas <= 160 && kb >= 8) return launch_stages<BN, AM, BM, GK, GV, 8>(ta, tb, p, grid, st);
+  }
+  return launch_stages<BN, AM, BM, GK, GV, STAGES_DEFAULT>(ta, tb, p, grid, st);
 }
 
 // B K-major: BLOCK_N in {16, 32, 64, 128}; B MN-major: {64, 128}
@@ -626,6 +662,17 @@ static ConvGeomU geom(int N, int H, int W, int C, int OH, int OW, int F, int KY,
   ConvGeomU g{N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, vec, 0, KY * KX, 0};
   return g;
 }
+// Tiles streamed per CTA (GemmParams::mt): only when the grid would otherwise need more than one
+// wave at two CTAs per SM, and never so many that fewer than one CTA per SM remains.
+static int pick_mt(int M, int N, int bn) {
+  const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const long long n_tiles = (N + bn - 1) / bn;
+  int mt = 1;
+  while (mt < 4 && bn * mt * 2 <= 256 && (m_tiles * n_tiles) / (mt * 2) >= 148 &&
+         m_tiles * n_tiles > 296)
+    mt *= 2;
+  return mt;
+}
 // Enable the tap-mode gather when the inner (channel) extent tiles a 64-wide reduction block.
 static bool set_tap_mode(ConvGeomU& g, int inner, bool dgrad) {
   g.tpk = 0; g.inner = inner;
@@ -656,6 +703,7 @@ int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const
   p.bias = bias; p.act = act; p.alpha = 1.f; p.beta = 0.f; p.split_stride = 0;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
+  p.mt = pick_mt(p.M, p.N, bn);
   if (set_tap_mode(p.g, C, false)) return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 2>(bn, ta, tb, p, 1, st);
   if (C % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 1>(bn, ta, tb, p, 1, st);
   return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 0>(bn, ta, tb, p, 1, st);
@@ -683,6 +731,7 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
   p.gsrc = (const __nv_bfloat16*)err_out;
   p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, F % 8 == 0);
   p.gather_kind = G_DGRAD; p.gK = Kd;
+  p.mt = pick_mt(p.M, p.N, bn);
   if (set_tap_mode(p.g, F, true)) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 2>(bn, ta, tb, p, 1, st);
   if (F % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 1>(bn, ta, tb, p, 1, st);
   return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 0>(bn, ta, tb, p, 1, st);
