@@ -84,19 +84,43 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def build_workflow(streaming, compute, graphs, n_train):
+MODELS = {
+    # name: (per-GPU batch, description)
+    "cifar_caffe": (100, "cifar_caffe (conv32-5/maxpool3s2/relu/LRN/conv32-5/relu/avgpool/LRN/"
+                         "conv64-5/relu/avgpool/softmax10)"),
+    "mnist_conv": (6, "mnist_conv_config (conv64-5/mp2/conv87-5/mp2/fc791-softplus/softmax10)"),
+    "alexnet": (128, "AlexNet 227x227x3 (5 conv, 2-group zero_filter, LRN, 3 FC, dropout)"),
+}
+
+
+def build_workflow(streaming, compute, graphs, n_train, model="cifar_caffe"):
     from veles.znicz_b200.core.config import root
-    from veles.znicz_b200.models import cifar
     root.common.engine.compute_type = compute
     root.common.disable.snapshotting = True
-    wf = cifar.build(
+    batch = MODELS[model][0]
+    common = dict(
         use_graphs=graphs,
-        loader_config={"minibatch_size": BATCH, "n_train": n_train, "n_valid": 0, "n_test": 0,
-                       "normalization_type": "internal_mean", "on_device": not streaming,
-                       "shuffle_limit": 2000000000},
         decision_config={"max_epochs": 1000000000, "fail_iterations": 1000000},
         snapshotter_config={"prefix": "bench", "interval": 1000000, "time_interval": 1e9})
-    return wf
+    if model == "cifar_caffe":
+        from veles.znicz_b200.models import cifar
+        return cifar.build(
+            loader_config={"minibatch_size": batch, "n_train": n_train, "n_valid": 0,
+                           "n_test": 0, "normalization_type": "internal_mean",
+                           "on_device": not streaming, "shuffle_limit": 2000000000}, **common)
+    if model == "mnist_conv":
+        from veles.znicz_b200.models import mnist
+        return mnist.build(
+            layers=mnist.conv_layers(), loader_name="synthetic_mnist",
+            loader_config={"minibatch_size": batch, "n_train": min(n_train, 60000),
+                           "n_valid": 0, "n_test": 0, "normalization_type": "linear",
+                           "on_device": not streaming, "shuffle_limit": 2000000000}, **common)
+    from veles.znicz_b200.models import alexnet
+    return alexnet.build(
+        loader_name="synthetic_imagenet", layers=alexnet.alexnet_layers(1000),
+        loader_config={"minibatch_size": batch, "n_train": min(n_train, 1024), "n_valid": 0,
+                       "n_test": 0, "n_classes": 1000, "normalization_type": "internal_mean",
+                       "on_device": not streaming, "shuffle_limit": 2000000000}, **common)
 
 
 def run_arm(args, streaming):
@@ -104,7 +128,7 @@ def run_arm(args, streaming):
     import torch.distributed as dist
     from veles.znicz_b200.kernels import api
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wf = build_workflow(streaming, args.dtype, not args.no_graphs, args.n_train)
+    wf = build_workflow(streaming, args.dtype, not args.no_graphs, args.n_train, args.model)
     wf.initialize(device="cuda")
     dev = wf.device
     reader = None
@@ -166,6 +190,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--n-train", type=int, default=50000)
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--model", default="cifar_caffe", choices=sorted(MODELS),
+                    help="cifar_caffe is the north-star config; the others are extra data points")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,24 +222,27 @@ def main():
     if rank != 0:
         return 0
     n = max(world, 1)
-    images = args.steps * BATCH * n
+    batch = MODELS[args.model][0]
+    images = args.steps * batch * n
     value = images / (main_res["ms_dev"] / 1e3)
     out = {
-        "metric": "CIFAR-10 caffe-conv training images/sec (whole job, device-timed, max over ranks)",
+        "metric": {"cifar_caffe": "CIFAR-10 caffe-conv", "mnist_conv": "MNIST conv",
+                   "alexnet": "AlexNet"}[args.model] +
+                  " training images/sec (whole job, device-timed, max over ranks)",
         "value": round(value, 1), "unit": "images/s", "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(main_res["ms_dev"] / args.steps, 5),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "impl": "znicz_b200" if args.impl == "b200" else "baseline(in-repo, reference-equivalent)",
-        "config": {"model": "cifar_caffe (conv32-5/maxpool3s2/relu/LRN/conv32-5/relu/avgpool/LRN/"
-                            "conv64-5/relu/avgpool/softmax10)",
-                   "global_batch": BATCH * n, "per_gpu_batch": BATCH, "seq_len": None,
-                   "image": "32x32x3", "parallelism": "dp%d" % n,
+        "config": {"model": MODELS[args.model][1],
+                   "global_batch": batch * n, "per_gpu_batch": batch, "seq_len": None,
+                   "image": {"cifar_caffe": "32x32x3", "mnist_conv": "28x28x1",
+                             "alexnet": "227x227x3"}[args.model], "parallelism": "dp%d" % n,
                    "optimizer": "SGD momentum 0.9 + L2 5e-4 + factor_ortho 1e-3, "
                                 "arbitrary_step LR",
                    "cuda_graphs": not args.no_graphs,
-                   "l2": "inputs larger than L2: 50000x32x32x3 fp32 dataset (614 MB) resident "
-                         "in HBM, random minibatch rows gathered each step"},
+                   "l2": "inputs larger than L2: the whole fp32 dataset (614 MB for 50000x32x32x3) "
+                         "is resident in HBM, random minibatch rows gathered each step"},
         "clocks": {k: main_res["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
         "gpu_launches": main_res["launches"],
     }
