@@ -21,6 +21,7 @@
 // that the fused update kernel sums in fixed order).
 #include "common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace zn {
 
@@ -56,6 +57,7 @@ struct GemmParams {
   // A_GATHER_K only: consecutive 128-row tiles streamed through ONE pipeline per CTA, each with
   // its own TMEM columns (amortises prologue / epilogue latency for short-K convolutions)
   int mt;
+  int dbg;                     // experiments: 1 = producers skip the gather, 2 = skip the MMAs
 };
 
 // ---- gather: 8 consecutive "inner" indices of one "pixel" -> 16 bytes ------------------------
@@ -367,7 +369,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                    : make_smem_desc(sa + k * 32, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
                                    : make_smem_desc(sb + k * 32, 16, 1024);
-          mma_f16(d_tmem, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          if (!(p.dbg & 2)) mma_f16(d_tmem, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
       }
@@ -392,7 +394,8 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int s = (gbase + i) % STAGES; const uint32_t ph = ((gbase + i) / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             const uint32_t row_base = smem_u32(tiles + (size_t)s * STAGE_BYTES) + t * 128;
-            gather_row_async<GKIND>(row_base, t & 7, ktab, p.g, ctx, (kb_begin + i) * BLOCK_K);
+            if (!(p.dbg & 1))
+              gather_row_async<GKIND>(row_base, t & 7, ktab, p.g, ctx, (kb_begin + i) * BLOCK_K);
             cp_async_mbar_arrive_noinc(&full_bar[s]);
           }
         } else {
@@ -574,8 +577,14 @@ static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
 }
 
 template <int BN, int AM, int BM, int GK, int GV>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits,
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, int splits,
                       cudaStream_t st) {
+  GemmParams p = p_in;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("ZNICZ_UMMA_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int mt = (AM == A_GATHER_K && p.mt > 1) ? p.mt : 1;
   dim3 grid((p.N + BN - 1) / BN, (m_tiles + mt - 1) / mt, splits);
@@ -586,7 +595,11 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   if constexpr (deep_ok) {
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     const int kb = p.k_blocks_per_split;
-    if (ctas <= 160 && kb >= 8) return launch_stages<BN, AM, BM, GK, GV, 8>(ta, tb, p, grid, st);
+    // measured neutral on B200 for the CIFAR shapes (the per-k-block cost is not pipeline depth):
+    // opt-in with ZNICZ_UMMA_DEEP=1
+    static int deep = -1;
+    if (deep < 0) { const char* e = getenv("ZNICZ_UMMA_DEEP"); deep = e ? atoi(e) : 0; }
+    if (deep && ctas <= 160 && kb >= 8) return launch_stages<BN, AM, BM, GK, GV, 8>(ta, tb, p, grid, st);
   }
   return launch_stages<BN, AM, BM, GK, GV, STAGES_DEFAULT>(ta, tb, p, grid, st);
 }
@@ -667,8 +680,13 @@ static ConvGeomU geom(int N, int H, int W, int C, int OH, int OW, int F, int KY,
 static int pick_mt(int M, int N, int bn) {
   const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const long long n_tiles = (N + bn - 1) / bn;
+  // Measured on B200 (CIFAR conv1 fprop, 800 tiles, K = 200): streaming 4 tiles through one CTA
+  // is *slower* (36 us) than 800 independent CTAs (32.7 us) - CTA-level parallelism beats
+  // prologue amortisation - so the mode stays opt-in (ZNICZ_UMMA_MT=2|4) for experiments.
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("ZNICZ_UMMA_MT"); forced = e ? atoi(e) : 1; }
   int mt = 1;
-  while (mt < 4 && bn * mt * 2 <= 256 && (m_tiles * n_tiles) / (mt * 2) >= 148 &&
+  while (mt < forced && mt < 4 && bn * mt * 2 <= 256 && (m_tiles * n_tiles) / (mt * 2) >= 148 &&
          m_tiles * n_tiles > 296)
     mt *= 2;
   return mt;
