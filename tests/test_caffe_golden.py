@@ -1,0 +1,143 @@
+"""Cross-framework golden data: Caffe blob dumps shipped with the reference
+(/root/reference/tests/functional/data/*.txt, read-only test oracles) vs our numpy units —
+the reference's ``tests/functional/test_caffe.py`` strategy ("cross-framework golden
+data"). The dump format: ``<name>[\\tnum:N\\tchannels:C\\theight:H\\twidth:W]`` followed by
+``num:i`` / ``channels:c`` headers and H tab-separated rows per channel plane."""
+import os
+
+import numpy
+import pytest
+
+from veles.znicz_b200.core.config import root
+from veles.znicz_b200.core.memory import Array
+from veles.znicz_b200.core.workflow import DummyWorkflow
+from veles.znicz_b200.ops import conv, gd_conv, gd_pooling, normalization, pooling
+
+DATA = "/root/reference/tests/functional/data"
+pytestmark = pytest.mark.skipif(not os.path.isdir(DATA), reason="reference golden data absent")
+
+
+def read_blob(lines, name, shape=None):
+    """→ float64 array [num, height, width, channels] (NHWC) of blob ``name``."""
+    start = None
+    for i, line in enumerate(lines):
+        parts = line.rstrip("\n").split("\t")
+        if parts[0].strip() == name:
+            dims = dict(p.split(":") for p in parts[1:] if ":" in p)
+            if len(dims) >= 4:
+                shape = (int(dims["num"]), int(dims["height"]), int(dims["width"]),
+                         int(dims["channels"]))
+            start = i + 1
+            break
+    assert start is not None and shape is not None, name
+    n, h, w, c = shape
+    out = numpy.zeros(shape, numpy.float64)
+    cur = start
+    for pic in range(n):
+        assert lines[cur].strip().split(":") == ["num", str(pic)], lines[cur]
+        cur += 1
+        for ch in range(c):
+            assert lines[cur].strip().split(":") == ["channels", str(ch)]
+            cur += 1
+            for y in range(h):
+                out[pic, y, :, ch] = [float(v) for v in lines[cur].split()]
+                cur += 1
+    return out
+
+
+def _lines(name):
+    with open(os.path.join(DATA, name)) as f:
+        return f.readlines()
+
+
+def _rel(a, b):
+    return float(numpy.abs(a - b).sum() / max(numpy.abs(b).sum(), 1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _double():
+    root.common.engine.precision_type = "double"
+    yield
+    root.common.engine.precision_type = "float"
+
+
+def _conv_unit(wf, bottom, weights, n_kernels):
+    u = conv.Conv(wf, kx=5, ky=5, padding=(2, 2, 2, 2), sliding=(1, 1), n_kernels=n_kernels)
+    u.input = Array(bottom.copy())
+    u.initialize(device="numpy")
+    u.weights.mem[:] = weights.reshape(n_kernels, -1)
+    u.bias.mem[:] = 0
+    u.run()
+    return u
+
+
+def test_conv_forward_matches_caffe():
+    lines = _lines("conv.txt")
+    bottom = read_blob(lines, "bottom", (2, 32, 32, 3))
+    weights = read_blob(lines, "weights", (2, 5, 5, 3))
+    top = read_blob(lines, "top", (2, 32, 32, 2))
+    u = _conv_unit(DummyWorkflow(), bottom, weights, 2)
+    assert _rel(u.output.mem, top) < 1e-2      # dumps carry 6 decimals of ~1e-4 weights
+
+
+def test_conv_backward_matches_caffe():
+    lines = _lines("conv_grad.txt")
+    bottom = read_blob(lines, "bottom", (2, 32, 32, 3))
+    weights = read_blob(lines, "weights", (2, 5, 5, 3))
+    top = read_blob(lines, "top", (2, 32, 32, 2))
+    top_err = read_blob(lines, "top_diff", (2, 32, 32, 2))
+    bot_err = read_blob(lines, "bottom_diff", (2, 32, 32, 3))
+    wf = DummyWorkflow()
+    u = _conv_unit(wf, bottom, weights, 2)
+    assert _rel(u.output.mem, top) < 1e-2      # dumps carry 6 decimals of ~1e-4 weights
+    g = gd_conv.GradientDescentConv(wf, kx=5, ky=5, padding=(2, 2, 2, 2), sliding=(1, 1),
+                                    n_kernels=2, learning_rate=0.0, weights_decay=0.0,
+                                    apply_gradient=False, gradient_moment=0.0)
+    g.err_output = Array(top_err.copy())
+    g.link_attrs(u, "input", "output", "weights", "bias")
+    g.initialize(device="numpy")
+    g.run()
+    assert _rel(g.err_input.mem, bot_err) < 1e-2
+
+
+@pytest.mark.parametrize("fname", ["pool.txt", "pool_grad.txt"])
+def test_max_pooling_matches_caffe(fname):
+    lines = [l.replace("\t\n", "\n") for l in _lines(fname)]
+    bottom = read_blob(lines, "bottom", (2, 32, 32, 2))
+    top = read_blob(lines, "top", (2, 16, 16, 2))
+    wf = DummyWorkflow()
+    u = pooling.MaxPooling(wf, kx=3, ky=3, sliding=(2, 2))
+    u.input = Array(bottom.copy())
+    u.initialize(device="numpy")
+    u.run()
+    assert _rel(u.output.mem, top) < 1e-6
+    if fname == "pool_grad.txt":
+        top_err = read_blob(lines, "top_diff", (2, 16, 16, 2))
+        bot_err = read_blob(lines, "bottom_diff", (2, 32, 32, 2))
+        g = gd_pooling.GDMaxPooling(wf, kx=3, ky=3, sliding=(2, 2))
+        g.err_output = Array(top_err.copy())
+        g.link_attrs(u, "input", "input_offset", "output")
+        g.initialize(device="numpy")
+        g.run()
+        # errors of ~1e-6 printed with 6 decimals + tie-breaking between equal maxima
+        assert _rel(g.err_input.mem, bot_err) < 0.03
+
+
+def test_lrn_matches_caffe():
+    lines = _lines("norm_gd.txt")
+    bottom = read_blob(lines, "bottom", (2, 16, 16, 2))
+    top = read_blob(lines, "top", (2, 16, 16, 2))
+    top_err = read_blob(lines, "top_diff", (2, 16, 16, 2))
+    bot_err = read_blob(lines, "bottom_diff", (2, 16, 16, 2))
+    wf = DummyWorkflow()
+    f = normalization.LRNormalizerForward(wf, k=1)
+    f.input = Array(bottom.copy())
+    f.initialize(device="numpy")
+    f.run()
+    assert _rel(f.output.mem, top) < 0.02          # the reference allows 2 %
+    b = normalization.LRNormalizerBackward(wf, k=1)
+    b.input, b.output = f.input, f.output
+    b.err_output = Array(top_err.copy())
+    b.initialize(device="numpy")
+    b.run()
+    assert _rel(b.err_input.mem, bot_err) < 0.02
