@@ -57,7 +57,8 @@ struct GemmParams {
   // A_GATHER_K only: consecutive 128-row tiles streamed through ONE pipeline per CTA, each with
   // its own TMEM columns (amortises prologue / epilogue latency for short-K convolutions)
   int mt;
-  int dbg;                     // experiments: 1 = producers skip the gather, 2 = skip the MMAs
+  int dbg;                     // experiments: 1 = producers skip the gather, 2 = skip the MMAs,
+                               // 4 = skip the TMA loads, 8 = skip the epilogue stores, 32 = empty kernel
 };
 
 // ---- gather: 8 consecutive "inner" indices of one "pixel" -> 16 bytes ------------------------
@@ -289,6 +290,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
+  if (p.dbg & 32) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt_cfg = (A_MODE == A_GATHER_K && p.mt > 1) ? p.mt : 1;
   const int m_tiles_total = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -334,6 +336,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
         const int k0 = (kb_begin + i) * BLOCK_K;
+        if (p.dbg & 4) { mbar_arrive(&full_bar[s]); continue; }
         mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
         if (A_MODE == A_TMA_K) {
           tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
@@ -492,7 +495,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (row < p.M) {
+      if (row < p.M && !(p.dbg & 8)) {
         const int nb = n0 + c0;
         const bool fast = (p.split_stride == 0) && !p.out_trans && p.out_bf16 && p.beta == 0.f &&
                           (nb + CH <= p.N) && ((p.ldo & 7) == 0);
