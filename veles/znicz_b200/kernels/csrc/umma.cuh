@@ -48,7 +48,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc),
+  // .ca: keep the line in L1 - an implicit-GEMM gather re-reads every input element once per
+  // filter tap (25x for 5x5), and the tile's halo (<= 20 KB) fits L1; with .cg all of those
+  // re-reads went to L2 and the conv kernels were L2-bandwidth bound
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc),
                "r"(src_bytes)
                : "memory");
 }
