@@ -57,6 +57,7 @@ struct GemmParams {
   // A_GATHER_K only: consecutive 128-row tiles streamed through ONE pipeline per CTA, each with
   // its own TMEM columns (amortises prologue / epilogue latency for short-K convolutions)
   int mt;
+  int tma_store;               // epilogue: stage the bf16 tile in smem, one TMA store per warp
   int dbg;                     // experiments: 1 = producers skip the gather, 2 = skip the MMAs,
                                // 4 = skip the TMA loads, 8 = skip the epilogue stores, 32 = empty kernel
 };
@@ -269,7 +270,7 @@ __host__ __device__ constexpr int min_ctas() {
 template <int BLOCK_N, int A_MODE, int B_MODE, int GKIND, int GVEC, int STAGES>
 __global__ void __launch_bounds__(192, (min_ctas<BLOCK_N, B_MODE, STAGES>()))
 gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   constexpr int B_BYTES = b_bytes<BLOCK_N, B_MODE>();
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr bool A_GATHER = (A_MODE == A_GATHER_K || A_MODE == A_GATHER_MN);
@@ -495,7 +496,23 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (row < p.M && !(p.dbg & 8)) {
+      if (p.tma_store) {
+        // bias + activation + bf16 pack into this warp's staging rows (the pipeline stages are
+        // idle by now); the whole 32 x BLOCK_N sub-tile leaves with one TMA store below
+        uint8_t* stg = tiles + warp * 8192 + lane * (BLOCK_N * 2) + c0 * 2;
+        const int nb = n0 + c0;
+#pragma unroll
+        for (int j8 = 0; j8 < CH; j8 += 8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t = __uint_as_float(r[j8 + j]);
+            if (p.bias && nb + j8 + j < p.N) t += __ldg(p.bias + nb + j8 + j);
+            v[j] = act_fwd5_fast(p.act, t) * p.alpha;
+          }
+          st8(reinterpret_cast<__nv_bfloat16*>(stg) + j8, v);
+        }
+      } else if (row < p.M && !(p.dbg & 8)) {
         const int nb = n0 + c0;
         const bool fast = (p.split_stride == 0) && !p.out_trans && p.out_bf16 && p.beta == 0.f &&
                           (nb + CH <= p.N) && ((p.ldo & 7) == 0);
@@ -520,6 +537,16 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       }
+    }
+    if (p.tma_store) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && !(p.dbg & 8)) {
+        // rows / columns beyond M / N are clipped by the tensor map
+        tma_store_2d(&tmap_c, tiles + warp * 8192, n0, m0 + tj * BLOCK_M + warp * 32);
+        tma_store_commit_and_wait_read();
+      }
+      __syncwarp();
     }
     }   // tiles of this CTA
     tc_fence_before();
@@ -564,8 +591,22 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// bf16 output tile map for the TMA-store epilogue: dims {N, M}, box {BN, 32}, no swizzle
+static int make_map_out(CUtensorMap* m, const void* ptr, long long N, long long M, long long ldo, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)(ldo * 2)};
+  cuuint32_t box[2] = {(cuuint32_t)bn, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 template <int BN, int AM, int BM, int GK, int GV, int NS>
-static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, dim3 grid,
                          cudaStream_t st) {
   constexpr int smem = NS * (A_BYTES + b_bytes<BN, BM>()) + 1024;
   static bool attr_set = false;
@@ -575,7 +616,17 @@ static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm_umma_k<BN, AM, BM, GK, GV, NS><<<grid, 192, smem, st>>>(ta, tb, p);
+  GemmParams p = p_in;
+  CUtensorMap tc = ta;
+  // TMA-store epilogue: plain bf16 row-major output (conv fprop / dgrad, FC forward / dgrad)
+  static int no_tma_store = -1;
+  if (no_tma_store < 0) { const char* e = getenv("ZNICZ_UMMA_NO_TMA_STORE"); no_tma_store = e ? atoi(e) : 0; }
+  p.tma_store = 0;
+  if (!no_tma_store && p.out_bf16 && p.split_stride == 0 && !p.out_trans && p.beta == 0.f &&
+      (p.ldo % 8) == 0 && ((uintptr_t)p.out & 15) == 0 && 4 * 32 * BN * 2 <= smem - 1024) {
+    if (make_map_out(&tc, p.out, p.N, p.M, p.ldo, BN) == 0) p.tma_store = 1;
+  }
+  gemm_umma_k<BN, AM, BM, GK, GV, NS><<<grid, 192, smem, st>>>(ta, tb, tc, p);
   return (int)cudaGetLastError();
 }
 
