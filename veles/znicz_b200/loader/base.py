@@ -367,17 +367,33 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
         import torch
         pd = self._pinned_
         slot = pd["slot"]
+        cur = torch.cuda.current_stream()
         for a, pair, views in pd["bufs"].values():
             pin = pair[slot]
             dst = a.devmem
             if dst.dtype != pin.dtype:
+                # big fp32 payload: H2D on a side stream into a per-slot device staging buffer
+                # (overlaps the previous step's kernels), then one cast kernel on the compute
+                # stream produces the bf16 minibatch
                 key = "_stage_%d_" % id(a)
-                tmp = self.__dict__.get(key)
-                if tmp is None:
-                    tmp = torch.empty(pin.shape, dtype=pin.dtype, device=dst.device)
-                    self.__dict__[key] = tmp
-                tmp.copy_(pin, non_blocking=True)
-                self.device.ext.cast_copy(tmp, dst)
+                st = self.__dict__.get(key)
+                if st is None:
+                    st = {"tmp": [torch.empty(pin.shape, dtype=pin.dtype, device=dst.device)
+                                  for _ in range(2)],
+                          "copied": [torch.cuda.Event(), torch.cuda.Event()],
+                          "consumed": [torch.cuda.Event(), torch.cuda.Event()],
+                          "stream": torch.cuda.Stream(device=dst.device)}
+                    for e in st["consumed"]:
+                        e.record(cur)
+                    self.__dict__[key] = st
+                cs = st["stream"]
+                cs.wait_event(st["consumed"][slot])      # the cast of 2 steps ago is done
+                with torch.cuda.stream(cs):
+                    st["tmp"][slot].copy_(pin, non_blocking=True)
+                    st["copied"][slot].record(cs)
+                cur.wait_event(st["copied"][slot])
+                self.device.ext.cast_copy(st["tmp"][slot], dst)
+                st["consumed"][slot].record(cur)
             else:
                 dst.copy_(pin, non_blocking=True)
             a.dev_written()
@@ -386,6 +402,8 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
         hn[1] = self.minibatch_class
         hn[2] = self.epoch_number
         self.header_dev_.copy_(pd["header"], non_blocking=True)
+        # the pinned slot may be refilled once every copy out of it has been issued and finished:
+        # the compute stream already waits for the side-stream copy, so one event covers both
         pd["events"][slot].record()
 
     # -- IDistributable: the master serves indices, the slaves read the data --------------
