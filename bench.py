@@ -238,6 +238,9 @@ def main():
                    "global_batch": batch * n, "per_gpu_batch": batch, "seq_len": None,
                    "image": {"cifar_caffe": "32x32x3", "mnist_conv": "28x28x1",
                              "alexnet": "227x227x3"}[args.model], "parallelism": "dp%d" % n,
+                   "dp_collective": ("fused peer-memory reduce+update kernel (no NCCL on the "
+                                     "step path)" if os.environ.get("ZNICZ_DP_MODE", "fused") ==
+                                     "fused" else "NCCL all-reduce baseline") if n > 1 else None,
                    "optimizer": "SGD momentum 0.9 + L2 5e-4 + factor_ortho 1e-3, "
                                 "arbitrary_step LR",
                    "cuda_graphs": not args.no_graphs,

@@ -248,8 +248,8 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
         acc.dev_written()
     if vel:
         vel.dev_written()
-    if dp is not None and dp.symm is None and dp.world_size > 1:
-        raise RuntimeError("data-parallel GD without symmetric buffers is not wired")
+    if dp is not None and dp.symm is None and dp.world_size > 1 and step is None:
+        raise RuntimeError("the NCCL baseline mode needs the fused step (engine.fused_step)")
 
 
 def fc_backward(unit):

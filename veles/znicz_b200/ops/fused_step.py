@@ -152,6 +152,14 @@ class FusedStep(object):
                 raise RuntimeError("FusedStep: table changed during graph capture")
             self._upload()
         dp = self.dp
+        if dp is not None and dp.world_size > 1 and dp.symm is None:
+            # NCCL *baseline* mode (ZNICZ_DP_MODE=nccl): one library all-reduce per gradient
+            # buffer, then the single-GPU update - what the fused peer-memory path is
+            # measured against
+            import torch.distributed as dist
+            for e in self.entries:
+                if e.touched:
+                    dist.all_reduce(e.keep[-1], op=dist.ReduceOp.SUM)
         for table, n, tiles, ortho in self.chunks:
             self.device.ext.multi_update(table, n, tiles, ortho, self.flag_ptrs, self.epoch_ptr,
                                          dp.rank if dp is not None else 0, self.gridsync,
