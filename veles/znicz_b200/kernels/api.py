@@ -159,6 +159,17 @@ def eff_act(unit):
     return fused_act(unit) or unit.ACT
 
 
+_WARNED = set()
+
+
+def _warn_once(unit, what, code):
+    key = (id(unit), what)
+    if key not in _WARNED:
+        _WARNED.add(key)
+        unit.warning("tcgen05 %s kernel declined this shape (code %d): using the SIMT kernel",
+                     what, code)
+
+
 FC_SMALL_MAX_OUT = 16
 
 
@@ -369,7 +380,12 @@ def conv_forward(unit):
             g = list(g)
             g[3] = cp
         r = ext.conv_fprop(x, w, w.shape[1], False, bias, out, g, eff_act(unit), 1)
-        if r != 0:
+        if r in (-3, -4) and not cp:
+            _warn_once(unit, "fprop", r)
+            w = unit.weights.dev
+            ext.conv_fprop(unit.input.dev, w, w.shape[1], bool(unit.weights_transposed), bias,
+                           out, _conv_geom(unit), eff_act(unit), 0)
+        elif r != 0:
             raise RuntimeError("%s: tcgen05 conv fprop refused (code %d)" % (unit, r))
     else:
         w = unit.weights.dev
@@ -401,13 +417,18 @@ def conv_backward(unit):
              getattr(fwd, "weights_lp_t_", None) is not None)
     if unit.need_err_input:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
+        r = -1
         if lp_ok:
             wd = fwd.weights_lp_t_
             r = ext.conv_dgrad(err, wd, wd.shape[1], False, ei, g, float(unit.err_input_alpha),
                                float(unit.err_input_beta), 1)
-            if r != 0:
+            if r not in (0, -3, -4):
                 raise RuntimeError("%s: tcgen05 conv dgrad refused (code %d)" % (unit, r))
-        else:
+            if r != 0:
+                _warn_once(unit, "dgrad", r)
+        if r != 0:
+            # fp32 / odd shapes the tensor-core kernel declines (alignment, gather table): our own
+            # SIMT implicit-GEMM kernel with the fp32 master weights
             w = unit.weights.dev
             ext.conv_dgrad(err, w, w.shape[1], bool(unit.weights_transposed), ei, g,
                            float(unit.err_input_alpha), float(unit.err_input_beta), 0)

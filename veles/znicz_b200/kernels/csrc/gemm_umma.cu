@@ -66,7 +66,7 @@ struct GemmParams {
 // All div/mod of the reduction index is hoisted into a per-CTA shared-memory table built once:
 // vec mode   : ktab[k / 8] = (ky << 24) | (kx << 16) | c0     (16-byte chunks never straddle a tap)
 // scalar mode: ktab[k]     = (ky << 24) | (kx << 16) | c
-constexpr int KTAB = 2048;
+constexpr int KTAB = 4096;
 
 struct PixCtx { const __nv_bfloat16* base; int y, x, valid; };
 
