@@ -206,6 +206,9 @@ def test_multi_update_matches_per_tensor_update(ext):
     specs.append(dict(rows=1, cols=32, nparts=128, flags=1 | 2, bias=True, conv=None, lanes=32))
     specs.append(dict(rows=64, cols=800, nparts=5, flags=1 | 2 | 8, bias=False,
                       conv=(25, 32, 32, 0, 0), lanes=1))
+    # >= 2^20 elements: the 4-elements-per-thread tile path (FC6-sized tensors)
+    specs.append(dict(rows=1030, cols=1048, nparts=2, flags=1 | 2 | 4, bias=False, conv=None,
+                      lanes=1))
     ref, new, descs = [], [], []
     for sp in specs:
         rows, cols = sp["rows"], sp["cols"]

@@ -530,6 +530,29 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             st8(q + j8, v);
           }
+        } else if (!p.out_bf16 && p.beta == 0.f && p.alpha == 1.f && !p.bias && p.act == 0) {
+          // raw fp32 result (split-K partials of the wgrad kernels, FC weight gradients):
+          //   transposed  -> for a fixed column the 32 lanes hold consecutive rows = one coalesced
+          //                  128-byte store per column
+          //   row-major   -> 16-byte stores along the thread's own row
+          float* base = reinterpret_cast<float*>(p.out) +
+                        (p.split_stride > 0 ? (long long)blockIdx.z * p.split_stride : 0LL);
+          if (p.out_trans) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (nb + j < p.N) base[(long long)(nb + j) * p.ldo + row] = __uint_as_float(r[j]);
+          } else if (nb + CH <= p.N && (p.ldo & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+            float4* q = reinterpret_cast<float4*>(base + (long long)row * p.ldo + nb);
+#pragma unroll
+            for (int j4 = 0; j4 < CH / 4; ++j4)
+              q[j4] = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                                  __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (nb + j < p.N) base[(long long)row * p.ldo + nb + j] = __uint_as_float(r[j]);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < CH; ++j) {

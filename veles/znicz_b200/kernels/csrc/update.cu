@@ -205,6 +205,7 @@ struct TensorDesc {
   int nparts, g_cpad, flags, is_bias, rows, cols, lanes, enabled;
   ShadowSpec sh;
   int tile_begin, n_tiles;
+  int ept;                    // elements per thread (lanes == 1 only): 4 for large tensors
   long long red_off;          // offset of this tensor in the cross-GPU reduction buffer
 };
 
@@ -289,14 +290,35 @@ __device__ __forceinline__ int multi_col_sums(const TensorDesc& d, int base) {
 // MODE 1: sum this rank's partials into its slot of the symmetric reduction buffer;
 // MODE 2 (after the cross-GPU flag barrier): sum the ranks' slots in fixed order and update.
 template <int MODE>
+__device__ __forceinline__ void multi_elem(const TensorDesc& d, long long i, bool valid, int lane,
+                                           const RedBufs& rb, long long poff);
+
+template <int MODE>
 __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, const RedBufs& rb,
                                            long long poff) {
   const int L = d.lanes;                         // power of two, <= 32
   const int tid = threadIdx.x;
+  if (d.ept > 1) {
+    // large tensors: 4 independent elements per thread (stride 256 keeps every access coalesced)
+    // so that each thread has 4x the loads in flight
+    const long long base = (long long)tile * (256 * 4) + tid;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + k * 256;
+      multi_elem<MODE>(d, i, i < d.size, 0, rb, poff);
+    }
+    return;
+  }
   const int lane = tid & (L - 1);
   const int ept = 256 / L;                       // elements per tile
   const long long i = (long long)tile * ept + tid / L;
-  const bool valid = i < d.size;
+  multi_elem<MODE>(d, i, i < d.size, lane, rb, poff);
+}
+
+template <int MODE>
+__device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long i, const bool valid,
+                                           const int lane, const RedBufs& rb, long long poff) {
+  const int L = d.ept > 1 ? 1 : d.lanes;
   const int is_bias = d.is_bias;
   float g = 0.f;
   if (MODE == 2) {
@@ -450,7 +472,8 @@ int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begi
   d.sh.lp_conv = (__nv_bfloat16*)f[27]; d.sh.taps = (int)f[28]; d.sh.C = (int)f[29];
   d.sh.c_pad = (int)f[30];
   if (d.lanes < 1) d.lanes = 1;
-  const int ept = 256 / d.lanes;
+  d.ept = (d.lanes == 1 && d.size >= (1LL << 20)) ? 4 : 1;
+  const int ept = d.ept > 1 ? 1024 : 256 / d.lanes;
   d.tile_begin = tile_begin;
   d.n_tiles = (int)((d.size + ept - 1) / ept);
   d.red_off = red_off;
