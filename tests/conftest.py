@@ -40,4 +40,7 @@ def _fresh_config(tmp_path):
     root.common.engine.compute_type = "fp32"
     prng.get(1).seed(1234)
     prng.get(2).seed(5678)
+    disable = {k: root.common.disable.get(k) for k in ("plotting", "snapshotting", "publishing")}
     yield
+    for k, v in disable.items():
+        setattr(root.common.disable, k, v)

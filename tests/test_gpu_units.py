@@ -104,7 +104,9 @@ def test_fc_odd_shapes_and_softmax(compute):
 @pytest.mark.parametrize("geom", [
     ((6, 16, 16, 32), 32, 5, 5, (2, 2, 2, 2), (1, 1)),
     ((5, 32, 32, 3), 32, 5, 5, (2, 2, 2, 2), (1, 1)),
-    ((3, 11, 9, 8), 24, 3, 2, (1, 0, 2, 1), (2, 1))])
+    ((3, 11, 9, 8), 24, 3, 2, (1, 0, 2, 1), (2, 1)),
+    ((6, 12, 12, 64), 87, 5, 5, (0, 0, 0, 0), (1, 1)),      # n_kernels % 8 != 0 (MNIST conv)
+    ((4, 14, 14, 3), 27, 3, 3, (1, 1, 1, 1), (1, 1))])
 def test_conv(fwd, bwd, geom, compute):
     shape, f, ky, kx, pad, sl = geom
     x = RS.uniform(-1, 1, shape).astype(numpy.float32)

@@ -90,7 +90,10 @@ def ensure_shadows(fwd):
     dev = fwd.device.torch_device
     fwd.weights_lp_ = torch.zeros((rows, ld), dtype=torch.bfloat16, device=dev)
     if is_conv:
-        fwd.weights_lp_t_ = torch.zeros((taps * rows, c_pad), dtype=torch.bfloat16, device=dev)
+        # dgrad operand [tap][f_pad][c_pad]: f padded to a multiple of 8 (zero rows) so that a
+        # channel-padded err_output can use the 16-byte gather when n_kernels % 8 != 0
+        fwd.weights_lp_t_ = torch.zeros((taps * _roundup(rows, 8), c_pad), dtype=torch.bfloat16,
+                                        device=dev)
 
 
 def refresh_weight_shadows(fwd):
@@ -415,13 +418,24 @@ def conv_backward(unit):
     fwd = unit.forward_unit
     lp_ok = (lp_enabled(unit) and _is_bf16(err) and _is_bf16(x) and fwd is not None and
              getattr(fwd, "weights_lp_t_", None) is not None)
+    f_pad = _roundup(f, 8)
+    err_mm, g_mm = err, g
+    if lp_ok and f_pad != f:
+        # n_kernels % 8 != 0 (e.g. the GA-tuned MNIST conv with 87 kernels): one pad kernel makes
+        # err_output [pixels][f_pad] so dgrad and wgrad stay on the tensor cores with 16-byte
+        # gathers / TMA instead of the element-wise gather
+        err_mm = _tmp(unit, "errpad", (pixels, f_pad), err.dtype)
+        ext.pad_channels(err, err_mm, f, f_pad)
+        _launch()
+        g_mm = list(g)
+        g_mm[6] = f_pad
     if unit.need_err_input:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
         r = -1
         if lp_ok:
             wd = fwd.weights_lp_t_
-            r = ext.conv_dgrad(err, wd, wd.shape[1], False, ei, g, float(unit.err_input_alpha),
-                               float(unit.err_input_beta), 1)
+            r = ext.conv_dgrad(err_mm, wd, wd.shape[1], False, ei, g_mm,
+                               float(unit.err_input_alpha), float(unit.err_input_beta), 1)
             if r not in (0, -3, -4):
                 raise RuntimeError("%s: tcgen05 conv dgrad refused (code %d)" % (unit, r))
             if r != 0:
@@ -436,31 +450,33 @@ def conv_backward(unit):
         _launch()
     if not need_w:
         return
-    use_umma = lp_ok and f % 8 == 0
+    use_umma = lp_ok
     g_cp = 0
+    f_rows = f                    # rows of one gradient partial
     if use_umma:
         g_cp = lp_cpad(fwd)
+        g = list(g_mm)
         if g_cp:
             xp = fwd.__dict__.get("tmp_xpad_")
             if xp is None:
                 raise RuntimeError("%s: padded input of the forward pass is missing" % unit)
             x = xp
-            g = list(g)
             g[3] = g_cp
             kw = unit.kx * unit.ky * g_cp
-        splits = int(ext.pick_splits(kw, f, pixels, _MAX_SPLITS))
+        f_rows = f_pad            # padded rows (zeros) sit at the end of every partial
+        splits = int(ext.pick_splits(kw, f_rows, pixels, _MAX_SPLITS))
     else:
         tiles = ((f + 63) // 64) * ((kw + 63) // 64)
         splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
-    gbuf = _grad_buffer(unit, "wgrad", (splits, f, kw))
+    gbuf = _grad_buffer(unit, "wgrad", (splits, f_rows, kw))
     if use_umma:
-        r = ext.conv_wgrad(err, x, gbuf, splits, g, False, 1)
+        r = ext.conv_wgrad(err_mm, x, gbuf, splits, g, False, 1)
         if r != 0:
             raise RuntimeError("%s: tcgen05 conv wgrad refused (code %d)" % (unit, r))
     else:
         ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0)
     _launch()
-    _update(unit, False, gbuf, splits, f * kw, f, unit._kernel_size, g_cpad=g_cp)
+    _update(unit, False, gbuf, splits, f_rows * kw, f, unit._kernel_size, g_cpad=g_cp)
     if need_b:
         _update(unit, True, parts, slices, f, 1, f)
 

@@ -35,7 +35,7 @@ struct ShadowSpec {
   __nv_bfloat16* lp;       // [rows][ld] bf16 copy of w (row-major as w), may be null
   int ld;
   int lp_cpad;             // > 0: lp rows are [tap][lp_cpad] channel-padded
-  __nv_bfloat16* lp_conv;  // conv dgrad operand [tap][f][c_pad], may be null
+  __nv_bfloat16* lp_conv;  // conv dgrad operand [tap][f_pad = roundup(rows, 8)][c_pad], may be null
   int taps, C, c_pad;
 };
 
@@ -141,7 +141,7 @@ __global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __r
       sh.lp[(size_t)r * sh.ld + lc] = __float2bfloat16_rn(wv);
       if (sh.lp_conv) {
         int tap = c / sh.C, ch = c % sh.C;      // w[f=r][tap][ch]
-        sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
+        sh.lp_conv[((size_t)tap * ((rows + 7) & ~7) + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
       }
     }
   }
@@ -177,7 +177,7 @@ __global__ void refresh_shadows_k(const float* __restrict__ w, long long size, i
     if (sh.lp) sh.lp[(size_t)r * sh.ld + lc] = __float2bfloat16_rn(wv);
     if (sh.lp_conv) {
       int tap = c / sh.C, ch = c % sh.C;
-      sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
+      sh.lp_conv[((size_t)tap * ((rows + 7) & ~7) + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
     }
   }
 }
@@ -391,7 +391,7 @@ __device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long 
     sh.lp[(size_t)r * sh.ld + lc] = __float2bfloat16_rn(wv);
     if (sh.lp_conv) {
       const int tap = c / sh.C, ch = c % sh.C;
-      sh.lp_conv[((size_t)tap * rows + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
+      sh.lp_conv[((size_t)tap * ((rows + 7) & ~7) + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
     }
   }
 }

@@ -200,8 +200,12 @@ def main(argv=None):
 
         def evaluate(values):
             genetics.apply_values(root, markers, values)
+            old = root.common.disable.snapshotting
             root.common.disable.snapshotting = True
-            launcher = run_once(args, module)
+            try:
+                launcher = run_once(args, module)
+            finally:
+                root.common.disable.snapshotting = old
             return _fitness(launcher.workflow)
         opt = genetics.GeneticsOptimizer(
             markers, evaluate, population_size=int(pop), generations=int(gen or 3),
