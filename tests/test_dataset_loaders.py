@@ -203,3 +203,40 @@ def test_preparation_imagenet_roundtrip(tmp_path):
     assert ld.has_mean_file and ld.mean.shape == (16, 16, 3)
     ld.run()
     assert ld.minibatch_data.shape == (4, 12, 12, 3) and numpy.isfinite(ld.minibatch_data.mem).all()
+
+
+def test_xmltodict_and_bbox_preparation(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from veles.znicz_b200.external import xmltodict
+    from veles.znicz_b200.utils import preparation_imagenet as prep
+    doc = ('<annotation v="1"><folder>n01</folder>'
+           '<object><name>cat</name><bndbox><xmin>2</xmin><ymin>3</ymin><xmax>12</xmax>'
+           '<ymax>13</ymax></bndbox></object>'
+           '<object><name>dog</name><bndbox><xmin>20</xmin><ymin>0</ymin><xmax>30</xmax>'
+           '<ymax>10</ymax></bndbox></object></annotation>')
+    tree = xmltodict.parse(doc)
+    assert tree["annotation"]["@v"] == "1" and tree["annotation"]["folder"] == "n01"
+    assert [o["name"] for o in tree["annotation"]["object"]] == ["cat", "dog"]
+    assert xmltodict.parse(xmltodict.unparse(tree, pretty=True)) == tree
+    single = xmltodict.parse("<a><b>1</b></a>", force_list=("b",))
+    assert single["a"]["b"] == ["1"]
+    # one sample per bounding box, labelled by the object name
+    d = tmp_path / "src" / "train" / "n01"
+    os.makedirs(d)
+    img = numpy.zeros((24, 32, 3), numpy.uint8)
+    img[3:13, 2:12] = 200          # the "cat" box is bright, the "dog" box stays dark
+    cv2.imwrite(str(d / "im0.png"), img)
+    cv2.imwrite(str(d / "im1.png"), img)          # no annotation → whole frame, dir label
+    ann = tmp_path / "ann" / "train" / "n01"
+    os.makedirs(ann)
+    (ann / "im0.xml").write_text(doc)
+    info = prep.prepare(str(tmp_path / "src"), str(tmp_path / "out"), size=8, workers=1,
+                        annotations=str(tmp_path / "ann"))
+    assert info["samples"] == 3 and info["labels"] == 3
+    data = numpy.memmap(info["loader_config"]["samples_filename"], dtype=numpy.uint8,
+                        mode="r", shape=(3, 8, 8, 3))
+    assert data[0].min() == 200 and data[1].max() == 0
+    import pickle
+    with open(info["loader_config"]["original_labels_filename"], "rb") as f:
+        labels = [l for l, _ in pickle.load(f)]
+    assert labels == ["cat", "dog", "n01"]

@@ -27,6 +27,14 @@ def _train_fc(tmp_path):
     return wf
 
 
+def _python_forward(wf, x):
+    f0, f1 = wf.forwards
+    h = 1.7159 * numpy.tanh(0.6666 * (x.reshape(len(x), -1).dot(f0.weights.mem.T) + f0.bias.mem))
+    s = h.dot(f1.weights.mem.T) + f1.bias.mem
+    e = numpy.exp(s - s.max(1, keepdims=True))
+    return e / e.sum(1, keepdims=True)
+
+
 def test_package_export_formats(tmp_path):
     wf = _train_fc(tmp_path)
 
@@ -97,10 +105,16 @@ def test_native_cpp_test_binary(tmp_path):
     wf.package_export(pkg, precision=16)
     from veles.znicz_b200.native import _build_impl
     _build_impl.build(verbose=False)
-    r = subprocess.run([_build_impl.TEST_BIN, pkg], stdout=subprocess.PIPE,
+    # functional check: python forward of a batch vs the C++ executors on the same package
+    x = numpy.random.RandomState(5).uniform(-1, 1, (7, 784)).astype(numpy.float32)
+    ref = _python_forward(wf, x)
+    numpy.save(str(tmp_path / "x.npy"), x)
+    numpy.save(str(tmp_path / "ref.npy"), ref.astype(numpy.float32))
+    r = subprocess.run([_build_impl.TEST_BIN, pkg, str(tmp_path / "x.npy"),
+                        str(tmp_path / "ref.npy")], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0, r.stdout
-    assert "0 failures" in r.stdout
+    assert "0 failures" in r.stdout and "functional cpu" in r.stdout
 
 
 def test_native_loads_reference_package():

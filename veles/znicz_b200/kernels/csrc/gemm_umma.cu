@@ -57,6 +57,7 @@ struct GemmParams {
   // A_GATHER_K only: consecutive 128-row tiles streamed through ONE pipeline per CTA, each with
   // its own TMEM columns (amortises prologue / epilogue latency for short-K convolutions)
   int mt;
+  int ktab_n;                  // entries of the gather lookup table (dynamic shared memory)
   int tma_store;               // epilogue: stage the bf16 tile in smem, one TMA store per warp
   int dbg;                     // experiments: 1 = producers skip the gather, 2 = skip the MMAs,
                                // 4 = skip the TMA loads, 8 = skip the epilogue stores, 32 = empty kernel
@@ -285,11 +286,15 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ int ktab[A_GATHER ? KTAB : 1];
 
   // 1024-byte aligned tile area (SWIZZLE_128B atoms are 1024 B)
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // behind the ring: the gather lookup table (only as many entries as this geometry needs - a
+  // fixed-size table cost the BLOCK_N = 64 conv kernels their second CTA per SM) and the tile's
+  // bias slice (the epilogue would otherwise wait on one L2 round trip per 8 columns)
+  int* const ktab = reinterpret_cast<int*>(tiles + (size_t)STAGES * STAGE_BYTES);
+  float* const s_bias = reinterpret_cast<float*>(ktab + ((p.ktab_n + 3) & ~3));
 
   if (p.dbg & 32) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -322,6 +327,10 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tmem_relinquish();
   }
   if (A_GATHER) build_ktab(ktab, p.g, GKIND, p.gK);
+  if (threadIdx.x < BLOCK_N) {
+    const int n = blockIdx.x * BLOCK_N + threadIdx.x;
+    s_bias[threadIdx.x] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -473,94 +482,110 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
     }
-    constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+    // The epilogue runs once per tile, so every instruction of it is an instruction-cache miss:
+    // the former 32-column unrolled version (4-5 K SASS instructions) cost ~10 us per tile on
+    // fetch stalls alone. This one is a rolled loop over 8-column chunks - TMEM loads double
+    // buffered (the next chunk is in flight while this one is stored) - with the output mode
+    // decided once per thread; the loop body is a few hundred instructions, fetched once.
+    enum { EPI_TMA = 0, EPI_BF16 = 1, EPI_RAW_T = 2, EPI_RAW = 3, EPI_SLOW = 4, EPI_NONE = 5 };
 #pragma unroll 1
     for (int tj = 0; tj < ntiles; ++tj) {
     const int row = m0 + tj * BLOCK_M + warp * 32 + lane;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
-      uint32_t r[32];
-      if (num_kb > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                               (uint32_t)(tj * BLOCK_N + c0);
-        if (CH == 32) {
-          tmem_ld_32x32(taddr, r);
-        } else {
-          uint32_t r16[16];
-          tmem_ld_32x16(taddr, r16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = r16[j];
+    const bool raw32 = !p.out_bf16 && p.beta == 0.f && p.alpha == 1.f && !p.bias && p.act == 0;
+    float* const rbase = reinterpret_cast<float*>(p.out) +
+                         (p.split_stride > 0 ? (long long)blockIdx.z * p.split_stride : 0LL);
+    int mode;
+    if (p.tma_store) mode = EPI_TMA;
+    else if (row >= p.M || (p.dbg & 8)) mode = EPI_NONE;
+    else if (p.split_stride == 0 && !p.out_trans && p.out_bf16 && p.beta == 0.f) mode = EPI_BF16;
+    else if (raw32 && p.out_trans) mode = EPI_RAW_T;
+    else if (raw32 && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(rbase) & 15) == 0)
+      mode = EPI_RAW;
+    else mode = EPI_SLOW;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tj * BLOCK_N);
+
+    auto emit = [&](const uint32_t (&r)[8], int c0) {
+      const int nb = n0 + c0;
+      if (mode == EPI_NONE) return;
+      if (mode == EPI_TMA || mode == EPI_BF16) {
+        float v[8];
+        {
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+          v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w;
+          v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
         }
-        tmem_ld_wait();
+        // activation selected once per chunk (not per element): the executed path stays short
+        switch (p.act) {
+          case ACT_LINEAR:
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(r[j]) + v[j]) * p.alpha;
+            break;
+          case ACT_STRICT_RELU:
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f) * p.alpha;
+            break;
+          case ACT_TANH:
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v[j] = 1.7159f * tanh_approx(0.6666f * (__uint_as_float(r[j]) + v[j])) * p.alpha;
+            break;
+          default:
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v[j] = act_fwd5_fast(p.act, __uint_as_float(r[j]) + v[j]) * p.alpha;
+        }
+        // bf16 pack: one 16-byte store per 8 outputs. TMA mode stages the 32 x BLOCK_N sub-tile
+        // of this warp in the (idle by now) pipeline buffers; it leaves with one TMA store below
+        __nv_bfloat16* q = (mode == EPI_TMA)
+            ? reinterpret_cast<__nv_bfloat16*>(tiles + warp * 8192 + lane * (BLOCK_N * 2)) + c0
+            : reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + nb;
+        if (mode == EPI_TMA || (nb + 8 <= p.N && (p.ldo & 7) == 0)) {
+          st8(q, v);
+        } else {                       // ragged last chunk / row pitch not a multiple of 16 bytes
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (nb + j < p.N) q[j] = __float2bfloat16_rn(v[j]);
+        }
+      } else if (mode == EPI_RAW_T) {
+        // raw fp32 (split-K partials / FC weight gradients), transposed: for a fixed column the
+        // 32 lanes hold consecutive rows = one coalesced 128-byte store per column
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (nb + j < p.N) rbase[(long long)(nb + j) * p.ldo + row] = __uint_as_float(r[j]);
+      } else if (mode == EPI_RAW && nb + 8 <= p.N) {
+        float4* q = reinterpret_cast<float4*>(rbase + (long long)row * p.ldo + nb);
+        q[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]),
+                           __uint_as_float(r[3]));
+        q[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]),
+                           __uint_as_float(r[7]));
+      } else if (raw32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (nb + j < p.N) rbase[(long long)row * p.ldo + nb + j] = __uint_as_float(r[j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+        for (int j = 0; j < 8; ++j)     // (static indices: r stays in registers)
+          if (nb + j < p.N) epi_store_slow(p, row, nb + j, __uint_as_float(r[j]), blockIdx.z);
       }
-      if (p.tma_store) {
-        // bias + activation + bf16 pack into this warp's staging rows (the pipeline stages are
-        // idle by now); the whole 32 x BLOCK_N sub-tile leaves with one TMA store below
-        uint8_t* stg = tiles + warp * 8192 + lane * (BLOCK_N * 2) + c0 * 2;
-        const int nb = n0 + c0;
+    };
+
+    // rb receives the TMEM load of the next chunk while the current one (ra) is converted and
+    // stored; a single copy of the emit code serves every chunk
+    uint32_t ra[8], rb[8];
 #pragma unroll
-        for (int j8 = 0; j8 < CH; j8 += 8) {
-          float v[8];
+    for (int j = 0; j < 8; ++j) rb[j] = 0u;
+    if (num_kb > 0) tmem_ld_32x8(trow, rb);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
+      if (n0 + c0 >= p.N && mode != EPI_TMA) break;     // chunk beyond the last column
+      if (num_kb > 0) tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t = __uint_as_float(r[j8 + j]);
-            if (p.bias && nb + j8 + j < p.N) t += __ldg(p.bias + nb + j8 + j);
-            v[j] = act_fwd5_fast(p.act, t) * p.alpha;
-          }
-          st8(reinterpret_cast<__nv_bfloat16*>(stg) + j8, v);
-        }
-      } else if (row < p.M && !(p.dbg & 8)) {
-        const int nb = n0 + c0;
-        const bool fast = (p.split_stride == 0) && !p.out_trans && p.out_bf16 && p.beta == 0.f &&
-                          (nb + CH <= p.N) && ((p.ldo & 7) == 0);
-        if (fast) {
-          // bias + activation + bf16 pack: one 16-byte store per 8 outputs
-          __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + nb;
-#pragma unroll
-          for (int j8 = 0; j8 < CH; j8 += 8) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float t = __uint_as_float(r[j8 + j]);
-              if (p.bias) t += __ldg(p.bias + nb + j8 + j);
-              v[j] = act_fwd5_fast(p.act, t) * p.alpha;
-            }
-            st8(q + j8, v);
-          }
-        } else if (!p.out_bf16 && p.beta == 0.f && p.alpha == 1.f && !p.bias && p.act == 0) {
-          // raw fp32 result (split-K partials of the wgrad kernels, FC weight gradients):
-          //   transposed  -> for a fixed column the 32 lanes hold consecutive rows = one coalesced
-          //                  128-byte store per column
-          //   row-major   -> 16-byte stores along the thread's own row
-          float* base = reinterpret_cast<float*>(p.out) +
-                        (p.split_stride > 0 ? (long long)blockIdx.z * p.split_stride : 0LL);
-          if (p.out_trans) {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (nb + j < p.N) base[(long long)(nb + j) * p.ldo + row] = __uint_as_float(r[j]);
-          } else if (nb + CH <= p.N && (p.ldo & 3) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
-            float4* q = reinterpret_cast<float4*>(base + (long long)row * p.ldo + nb);
-#pragma unroll
-            for (int j4 = 0; j4 < CH / 4; ++j4)
-              q[j4] = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
-                                  __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (nb + j < p.N) base[(long long)row * p.ldo + nb + j] = __uint_as_float(r[j]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            if (nb + j < p.N) epi_store_slow(p, row, nb + j, __uint_as_float(r[j]), blockIdx.z);
-          }
-        }
-      }
+      for (int j = 0; j < 8; ++j) ra[j] = rb[j];
+      if (num_kb > 0 && c0 + 8 < BLOCK_N) tmem_ld_32x8(trow + c0 + 8, rb);
+      emit(ra, c0);
     }
+    if (num_kb > 0) tmem_ld_wait();
     if (p.tma_store) {
       fence_proxy_async_smem();
       __syncwarp();
@@ -631,15 +656,23 @@ static int make_map_out(CUtensorMap* m, const void* ptr, long long N, long long 
 template <int BN, int AM, int BM, int GK, int GV, int NS>
 static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, dim3 grid,
                          cudaStream_t st) {
-  constexpr int smem = NS * (A_BYTES + b_bytes<BN, BM>()) + 1024;
+  constexpr int ring = NS * (A_BYTES + b_bytes<BN, BM>()) + 1024;
+  constexpr bool gather = (AM == A_GATHER_K || AM == A_GATHER_MN);
+  constexpr int smem_max = ring + (gather ? KTAB * 4 : 0) + BN * 4 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_umma_k<BN, AM, BM, GK, GV, NS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   GemmParams p = p_in;
+  p.ktab_n = 0;
+  if (gather) {       // must match build_ktab()
+    const int step = p.g.vec ? 8 : 1;
+    p.ktab_n = p.g.tpk > 0 ? p.g.ntaps : std::min(KTAB, (p.gK + step - 1) / step);
+  }
+  const int smem = ring + ((p.ktab_n + 3) & ~3) * 4 + BN * 4;
   CUtensorMap tc = ta;
   // TMA-store epilogue (smem staging + one tile store per warp) for plain bf16 row-major outputs.
   // Measured on B200 it is slower than the direct 16-byte stores for these narrow tiles
@@ -648,7 +681,7 @@ static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   if (no_tma_store < 0) { const char* e = getenv("ZNICZ_UMMA_TMA_STORE"); no_tma_store = (e && atoi(e)) ? 0 : 1; }
   p.tma_store = 0;
   if (!no_tma_store && p.out_bf16 && p.split_stride == 0 && !p.out_trans && p.beta == 0.f &&
-      (p.ldo % 8) == 0 && ((uintptr_t)p.out & 15) == 0 && 4 * 32 * BN * 2 <= smem - 1024) {
+      (p.ldo % 8) == 0 && ((uintptr_t)p.out & 15) == 0 && 4 * 32 * BN * 2 <= ring - 1024) {
     if (make_map_out(&tc, p.out, p.N, p.M, p.ldo, BN) == 0) p.tma_store = 1;
   }
   gemm_umma_k<BN, AM, BM, GK, GV, NS><<<grid, 192, smem, st>>>(ta, tb, tc, p);

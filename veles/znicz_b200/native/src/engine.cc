@@ -190,9 +190,11 @@ std::vector<float> Engine::run_cpu(const float* input, const Shape4& in) {
     nxt.assign((size_t)o.size(), 0.f);
     if (u.kind == "all2all") {
       const int K = (int)u.weights.shape[1], N = o.c;
+      // (pragmas are inert unless the build enables OpenMP: -DZNICZ_OPENMP=ON)
+#pragma omp parallel for collapse(2) schedule(static)
       for (int b = 0; b < s.n; ++b) {
-        const float* x = cur.data() + (size_t)b * K;
         for (int n = 0; n < N; ++n) {
+          const float* x = cur.data() + (size_t)b * K;
           const float* w = u.weights.data.data() + (size_t)n * K;
           double acc = u.include_bias ? u.bias.data[n] : 0.0;
           for (int k = 0; k < K; ++k) acc += (double)x[k] * w[k];
@@ -202,6 +204,7 @@ std::vector<float> Engine::run_cpu(const float* input, const Shape4& in) {
       if (u.softmax) softmax_rows(nxt.data(), s.n, N);
     } else if (u.kind == "conv") {
       const int K = u.kx * u.ky * s.c;
+#pragma omp parallel for collapse(3) schedule(static)
       for (int b = 0; b < s.n; ++b) for (int oy = 0; oy < o.h; ++oy) for (int ox = 0; ox < o.w; ++ox)
         for (int f = 0; f < o.c; ++f) {
           const float* w = u.weights.data.data() + (size_t)f * K;

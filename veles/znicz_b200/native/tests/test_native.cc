@@ -109,6 +109,39 @@ static void test_errors() {
   EXPECT_NEAR(j.at("b").at("c").num, -300.0, 0);
 }
 
+static std::string slurp(const char* path) {
+  std::FILE* f = std::fopen(path, "rb");
+  if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+  std::string data; char buf[65536]; size_t n;
+  while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
+  std::fclose(f);
+  return data;
+}
+
+// End-to-end check of an exported network (the body the reference's functional_mnist.cc never
+// got, /root/reference/libZnicz/tests/functional_mnist.cc): run the packaged workflow on a batch
+// saved by python and compare with python's own forward pass, on every available executor.
+static void test_functional(const char* pkg, const char* in_npy, const char* ref_npy) {
+  try {
+    znicz::Engine e(pkg);
+    znicz::NpyArray x = znicz::parse_npy(slurp(in_npy)), ref = znicz::parse_npy(slurp(ref_npy));
+    znicz::Shape4 in;
+    in.n = (int)x.shape.at(0);
+    if (x.shape.size() == 4) { in.h = (int)x.shape[1]; in.w = (int)x.shape[2]; in.c = (int)x.shape[3]; }
+    else { int64_t k = 1; for (size_t i = 1; i < x.shape.size(); ++i) k *= x.shape[i]; in.c = (int)k; }
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1 && !znicz::Engine::cuda_available()) break;
+      std::vector<float> y = pass ? e.run_cuda(x.data.data(), in) : e.run_cpu(x.data.data(), in);
+      EXPECT_TRUE(y.size() == ref.data.size());
+      double worst = 0;
+      for (size_t i = 0; i < y.size() && i < ref.data.size(); ++i)
+        worst = std::max(worst, std::fabs((double)y[i] - ref.data[i]));
+      std::printf("functional %s: %zu outputs, max |diff| %.3g\n", pass ? "cuda" : "cpu", y.size(), worst);
+      EXPECT_TRUE(worst < 2e-3);    // fp16-packed weights vs python fp32
+    }
+  } catch (const std::exception& ex) { ++g_fail; std::printf("FAIL functional: %s\n", ex.what()); }
+}
+
 int main(int argc, char** argv) {
   // expectations: s = W x + b = {29, 0, 9}
   const double lin[3] = {29, 0, 9};
@@ -125,6 +158,9 @@ int main(int argc, char** argv) {
   if (argc > 1) {   // extra: load a package produced by the python exporter
     try { znicz::Engine e(argv[1]); EXPECT_TRUE(e.num_units() > 0); std::printf("loaded %s: %zu units\n", argv[1], e.num_units()); }
     catch (const std::exception& ex) { ++g_fail; std::printf("FAIL load %s: %s\n", argv[1], ex.what()); }
+  }
+  if (argc > 3) {   // functional: package + input.npy + expected.npy (python forward of the same net)
+    test_functional(argv[1], argv[2], argv[3]);
   }
   std::printf("%d checks, %d failures, cuda=%d\n", g_checks, g_fail, (int)znicz::Engine::cuda_available());
   return g_fail ? 1 : 0;
