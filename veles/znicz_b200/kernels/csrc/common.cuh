@@ -5,7 +5,48 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <string.h>
+#include <stdlib.h>
+
 namespace zn {
+
+// ---- programmatic dependent launch -------------------------------------------------------------
+// Every kernel of the step is launched with the programmatic-stream-serialization attribute
+// (also inside captured CUDA graphs, where it becomes a programmatic edge): kernel N+1's CTAs are
+// scheduled as soon as all CTAs of kernel N have started, run their prologue (index math, smem
+// carve-up, barrier init, TMEM allocation) and block in pdl_wait() until kernel N has completed
+// and flushed. The ~25 launches of a training step otherwise pay one full drain + launch latency
+// each. ZNICZ_PDL=0 switches the attribute off (plain stream order).
+#ifndef ZN_PDL_EARLY_TRIGGER
+#define ZN_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if ZN_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ZNICZ_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- activation codes (must match ops/nn_units.py and ops/activation.py) ----
 enum Act : int {

@@ -10,6 +10,7 @@ namespace zn {
 template <typename T>
 __global__ void act_forward_k(const T* __restrict__ x, T* __restrict__ y, long long n, int act,
                               float factor) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) stf(y + i, act_fwd(act, ldf(x + i), factor, (int)(i & 1)));
@@ -19,6 +20,7 @@ template <typename T>
 __global__ void act_backward_k(const T* __restrict__ err_y, const T* __restrict__ x,
                                const T* __restrict__ y, T* __restrict__ err_x, long long n,
                                int act, float factor) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -34,6 +36,7 @@ __global__ void act_backward_k(const T* __restrict__ err_y, const T* __restrict_
 template <typename T>
 __global__ void err_act_colsum_k(T* __restrict__ err_y, const T* __restrict__ y, int rows, int cols,
                                  int act, float* __restrict__ partial /*[gridDim.y][cols]*/) {
+  pdl_entry();
   __shared__ float red[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -64,6 +67,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) err_act_colsum_vec_k(T* __restrict__ err_y, const T* __restrict__ y,
                                                          int rows, int cols, int act,
                                                          float* __restrict__ partial) {
+  pdl_entry();
   __shared__ float red[256][9];
   const int groups = cols >> 3;                 // <= 256
   const int lanes = 256 / groups;
@@ -102,6 +106,7 @@ template <typename T>
 __global__ void dropout_forward_k(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ mask,
                                   long long n, const int* __restrict__ rng, uint32_t threshold,
                                   float scale) {
+  pdl_entry();
   uint32_t seed = (uint32_t)rng[0], counter = (uint32_t)rng[1];
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -114,12 +119,14 @@ __global__ void dropout_forward_k(const T* __restrict__ x, T* __restrict__ y, T*
 
 template <typename T>
 __global__ void mul_k(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) stf(o + i, ldf(a + i) * ldf(b + i));
 }
 template <typename T>
 __global__ void add_k(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) stf(o + i, ldf(a + i) + ldf(b + i));
@@ -128,6 +135,7 @@ template <typename T>
 __global__ void mul_backward_k(const T* __restrict__ x, const T* __restrict__ y,
                                const T* __restrict__ e, T* __restrict__ ex, T* __restrict__ ey,
                                long long n) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -141,6 +149,7 @@ __global__ void mul_backward_k(const T* __restrict__ x, const T* __restrict__ y,
 template <typename T>
 __global__ void axpby_2d_k(const T* __restrict__ src, int src_ld, int soff, T* __restrict__ dst,
                            int dst_ld, int doff, int rows, int len, float alpha, float beta) {
+  pdl_entry();
   long long n = (long long)rows * len;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -157,6 +166,7 @@ __global__ void axpby_2d_k(const T* __restrict__ src, int src_ld, int soff, T* _
 template <typename T>
 __global__ void crop_nhwc_k(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C,
                             int oh, int ow, int top, int left, int backward) {
+  pdl_entry();
   if (!backward) {
     long long n = (long long)N * oh * ow * C;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,6 +195,7 @@ __global__ void crop_nhwc_k(const T* __restrict__ in, T* __restrict__ out, int N
 template <typename TS, typename TD>
 __global__ void gather_rows_k(const TS* __restrict__ src, const int* __restrict__ idx,
                               TD* __restrict__ dst, int count, int max_rows, long long row) {
+  pdl_entry();
   long long n = (long long)max_rows * row;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -197,6 +208,7 @@ __global__ void gather_rows_k(const TS* __restrict__ src, const int* __restrict_
 }
 __global__ void gather_labels_k(const int* __restrict__ src, const int* __restrict__ idx,
                                 int* __restrict__ dst, int count, int max_rows) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < max_rows) dst[i] = i < count ? src[idx[i]] : -1;
 }
@@ -207,6 +219,7 @@ __global__ void gather_minibatch_k(const TS* __restrict__ src, const int* __rest
                                    const int* __restrict__ hdr, TD* __restrict__ dst,
                                    int* __restrict__ labels_dst, int max_rows, int row8,
                                    TD* __restrict__ dst_pad, int C, int CP) {
+  pdl_entry();
   const int count = hdr[0];
   const int* idx = hdr + 4;
   const int total = max_rows * row8;
@@ -246,6 +259,7 @@ __global__ void gather_minibatch_k(const TS* __restrict__ src, const int* __rest
 // implicit-GEMM gather can use 16-byte chunks
 template <typename T>
 __global__ void pad_channels_k(const T* __restrict__ x, T* __restrict__ y, int pixels, int C, int CP) {
+  pdl_entry();
   const int total = pixels * CP;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int p = i / CP, c = i - p * CP;
@@ -257,6 +271,7 @@ __global__ void pad_channels_k(const T* __restrict__ x, T* __restrict__ y, int p
 
 template <typename T>
 __global__ void mask_mul_k(T* __restrict__ w, const T* __restrict__ mask, long long n) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) stf(w + i, ldf(w + i) * ldf(mask + i));
@@ -264,6 +279,7 @@ __global__ void mask_mul_k(T* __restrict__ w, const T* __restrict__ mask, long l
 
 template <typename TS, typename TD>
 __global__ void cast_k(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) stf(d + i, ldf(s + i));
@@ -273,6 +289,7 @@ __global__ void cast_k(const TS* __restrict__ s, TD* __restrict__ d, long long n
 template <typename T>
 __global__ void scatter_offsets_k(const T* __restrict__ in, const int* __restrict__ offs,
                                   T* __restrict__ out, long long n, int accumulate) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[offs[i]] = in[i];
@@ -290,11 +307,11 @@ static inline int grid_for(long long n, int block = 256) {
 
 void launch_act_forward(const void* x, void* y, long long n, int act, float factor, bool bf16,
                         cudaStream_t st) {
-  DISPATCH_T(bf16, act_forward_k<T><<<grid_for(n), 256, 0, st>>>((const T*)x, (T*)y, n, act, factor));
+  DISPATCH_T(bf16, launch_k(act_forward_k<T>, grid_for(n), 256, 0, st, (const T*)x, (T*)y, n, act, factor));
 }
 void launch_act_backward(const void* ey, const void* x, const void* y, void* ex, long long n, int act,
                          float factor, bool bf16, cudaStream_t st) {
-  DISPATCH_T(bf16, act_backward_k<T><<<grid_for(n), 256, 0, st>>>(
+  DISPATCH_T(bf16, launch_k(act_backward_k<T>, grid_for(n), 256, 0, st, 
       (const T*)ey, (const T*)x, (const T*)y, (T*)ex, n, act, factor));
 }
 int err_act_colsum_slices(int rows) { int s = (rows + 63) / 64; return s < 1 ? 1 : (s > 128 ? 128 : s); }
@@ -302,48 +319,48 @@ void launch_err_act_colsum(void* err_y, const void* y, int rows, int cols, int a
                            int slices, bool bf16, cudaStream_t st) {
   if (cols % 8 == 0 && cols <= 256 && (((uintptr_t)err_y) & 15) == 0 &&
       (y == nullptr || (((uintptr_t)y) & 15) == 0)) {
-    DISPATCH_T(bf16, err_act_colsum_vec_k<T><<<slices, 256, 0, st>>>((T*)err_y, (const T*)y, rows,
+    DISPATCH_T(bf16, launch_k(err_act_colsum_vec_k<T>, slices, 256, 0, st, (T*)err_y, (const T*)y, rows,
                                                                        cols, act, partial));
     return;
   }
   dim3 grid((cols + 31) / 32, slices), block(32, 8);
-  DISPATCH_T(bf16, err_act_colsum_k<T><<<grid, block, 0, st>>>((T*)err_y, (const T*)y, rows, cols, act,
+  DISPATCH_T(bf16, launch_k(err_act_colsum_k<T>, grid, block, 0, st, (T*)err_y, (const T*)y, rows, cols, act,
                                                               partial));
 }
 void launch_dropout_forward(const void* x, void* y, void* mask, long long n, const int* rng,
                             uint32_t threshold, float scale, bool bf16, cudaStream_t st) {
-  DISPATCH_T(bf16, dropout_forward_k<T><<<grid_for(n), 256, 0, st>>>(
+  DISPATCH_T(bf16, launch_k(dropout_forward_k<T>, grid_for(n), 256, 0, st, 
       (const T*)x, (T*)y, (T*)mask, n, rng, threshold, scale));
 }
 void launch_binary(const void* a, const void* b, void* o, long long n, int op, bool bf16,
                    cudaStream_t st) {
-  if (op == 0) { DISPATCH_T(bf16, mul_k<T><<<grid_for(n), 256, 0, st>>>((const T*)a, (const T*)b, (T*)o, n)); }
-  else { DISPATCH_T(bf16, add_k<T><<<grid_for(n), 256, 0, st>>>((const T*)a, (const T*)b, (T*)o, n)); }
+  if (op == 0) { DISPATCH_T(bf16, launch_k(mul_k<T>, grid_for(n), 256, 0, st, (const T*)a, (const T*)b, (T*)o, n)); }
+  else { DISPATCH_T(bf16, launch_k(add_k<T>, grid_for(n), 256, 0, st, (const T*)a, (const T*)b, (T*)o, n)); }
 }
 void launch_mul_backward(const void* x, const void* y, const void* e, void* ex, void* ey, long long n,
                          bool bf16, cudaStream_t st) {
-  DISPATCH_T(bf16, mul_backward_k<T><<<grid_for(n), 256, 0, st>>>(
+  DISPATCH_T(bf16, launch_k(mul_backward_k<T>, grid_for(n), 256, 0, st, 
       (const T*)x, (const T*)y, (const T*)e, (T*)ex, (T*)ey, n));
 }
 void launch_axpby_2d(const void* src, int src_ld, int soff, void* dst, int dst_ld, int doff, int rows,
                      int len, float alpha, float beta, bool bf16, cudaStream_t st) {
-  DISPATCH_T(bf16, axpby_2d_k<T><<<grid_for((long long)rows * len), 256, 0, st>>>(
+  DISPATCH_T(bf16, launch_k(axpby_2d_k<T>, grid_for((long long)rows * len), 256, 0, st, 
       (const T*)src, src_ld, soff, (T*)dst, dst_ld, doff, rows, len, alpha, beta));
 }
 void launch_crop_nhwc(const void* in, void* out, int N, int H, int W, int C, int oh, int ow, int top,
                       int left, int backward, bool bf16, cudaStream_t st) {
   long long n = backward ? (long long)N * H * W * C : (long long)N * oh * ow * C;
-  DISPATCH_T(bf16, crop_nhwc_k<T><<<grid_for(n), 256, 0, st>>>((const T*)in, (T*)out, N, H, W, C, oh, ow,
+  DISPATCH_T(bf16, launch_k(crop_nhwc_k<T>, grid_for(n), 256, 0, st, (const T*)in, (T*)out, N, H, W, C, oh, ow,
                                                               top, left, backward));
 }
 void launch_gather_rows(const void* src, bool src_bf16, const int* idx, void* dst, bool dst_bf16,
                         int count, int max_rows, long long row, cudaStream_t st) {
   long long n = (long long)max_rows * row;
   int g = grid_for(n);
-  if (!src_bf16 && !dst_bf16) gather_rows_k<float, float><<<g, 256, 0, st>>>((const float*)src, idx, (float*)dst, count, max_rows, row);
-  else if (!src_bf16 && dst_bf16) gather_rows_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
-  else if (src_bf16 && dst_bf16) gather_rows_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
-  else gather_rows_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (float*)dst, count, max_rows, row);
+  if (!src_bf16 && !dst_bf16) launch_k(gather_rows_k<float, float>, g, 256, 0, st, (const float*)src, idx, (float*)dst, count, max_rows, row);
+  else if (!src_bf16 && dst_bf16) launch_k(gather_rows_k<float, __nv_bfloat16>, g, 256, 0, st, (const float*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
+  else if (src_bf16 && dst_bf16) launch_k(gather_rows_k<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
+  else launch_k(gather_rows_k<__nv_bfloat16, float>, g, 256, 0, st, (const __nv_bfloat16*)src, idx, (float*)dst, count, max_rows, row);
 }
 void launch_gather_minibatch(const void* src, bool src_bf16, const int* labels_src, const int* hdr,
                              void* dst, bool dst_bf16, int* labels_dst, int max_rows, long long row,
@@ -351,31 +368,31 @@ void launch_gather_minibatch(const void* src, bool src_bf16, const int* labels_s
   int row8 = (int)(row / 8);
   int g = grid_for((long long)max_rows * row8);
   if (g * 256 < max_rows) g = (max_rows + 255) / 256;
-  if (!src_bf16 && dst_bf16) gather_minibatch_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8, (__nv_bfloat16*)dst_pad, C, CP);
-  else if (!src_bf16) gather_minibatch_k<float, float><<<g, 256, 0, st>>>((const float*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8, (float*)dst_pad, C, CP);
-  else if (dst_bf16) gather_minibatch_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8, (__nv_bfloat16*)dst_pad, C, CP);
-  else gather_minibatch_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8, (float*)dst_pad, C, CP);
+  if (!src_bf16 && dst_bf16) launch_k(gather_minibatch_k<float, __nv_bfloat16>, g, 256, 0, st, (const float*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8, (__nv_bfloat16*)dst_pad, C, CP);
+  else if (!src_bf16) launch_k(gather_minibatch_k<float, float>, g, 256, 0, st, (const float*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8, (float*)dst_pad, C, CP);
+  else if (dst_bf16) launch_k(gather_minibatch_k<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)src, labels_src, hdr, (__nv_bfloat16*)dst, labels_dst, max_rows, row8, (__nv_bfloat16*)dst_pad, C, CP);
+  else launch_k(gather_minibatch_k<__nv_bfloat16, float>, g, 256, 0, st, (const __nv_bfloat16*)src, labels_src, hdr, (float*)dst, labels_dst, max_rows, row8, (float*)dst_pad, C, CP);
 }
 void launch_gather_labels(const int* src, const int* idx, int* dst, int count, int max_rows,
                           cudaStream_t st) {
-  gather_labels_k<<<(max_rows + 255) / 256, 256, 0, st>>>(src, idx, dst, count, max_rows);
+  launch_k(gather_labels_k, (max_rows + 255) / 256, 256, 0, st, src, idx, dst, count, max_rows);
 }
 void launch_pad_channels(const void* x, void* y, int pixels, int C, int CP, bool bf16, cudaStream_t st) {
-  DISPATCH_T(bf16, pad_channels_k<T><<<grid_for((long long)pixels * CP), 256, 0, st>>>((const T*)x, (T*)y, pixels, C, CP));
+  DISPATCH_T(bf16, launch_k(pad_channels_k<T>, grid_for((long long)pixels * CP), 256, 0, st, (const T*)x, (T*)y, pixels, C, CP));
 }
 void launch_mask_mul(void* w, const void* mask, long long n, bool bf16, cudaStream_t st) {
-  DISPATCH_T(bf16, mask_mul_k<T><<<grid_for(n), 256, 0, st>>>((T*)w, (const T*)mask, n));
+  DISPATCH_T(bf16, launch_k(mask_mul_k<T>, grid_for(n), 256, 0, st, (T*)w, (const T*)mask, n));
 }
 void launch_cast(const void* s, bool s_bf16, void* d, bool d_bf16, long long n, cudaStream_t st) {
   int g = grid_for(n);
-  if (s_bf16 && !d_bf16) cast_k<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)s, (float*)d, n);
-  else if (!s_bf16 && d_bf16) cast_k<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)s, (__nv_bfloat16*)d, n);
-  else if (s_bf16) cast_k<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)s, (__nv_bfloat16*)d, n);
-  else cast_k<float, float><<<g, 256, 0, st>>>((const float*)s, (float*)d, n);
+  if (s_bf16 && !d_bf16) launch_k(cast_k<__nv_bfloat16, float>, g, 256, 0, st, (const __nv_bfloat16*)s, (float*)d, n);
+  else if (!s_bf16 && d_bf16) launch_k(cast_k<float, __nv_bfloat16>, g, 256, 0, st, (const float*)s, (__nv_bfloat16*)d, n);
+  else if (s_bf16) launch_k(cast_k<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)s, (__nv_bfloat16*)d, n);
+  else launch_k(cast_k<float, float>, g, 256, 0, st, (const float*)s, (float*)d, n);
 }
 void launch_scatter_offsets(const void* in, const int* offs, void* out, long long n, bool bf16,
                             cudaStream_t st) {
-  DISPATCH_T(bf16, scatter_offsets_k<T><<<grid_for(n), 256, 0, st>>>((const T*)in, offs, (T*)out, n, 0));
+  DISPATCH_T(bf16, launch_k(scatter_offsets_k<T>, grid_for(n), 256, 0, st, (const T*)in, offs, (T*)out, n, 0));
 }
 
 }  // namespace zn
@@ -394,6 +411,7 @@ __global__ void lstm_cell_fwd_k(const float* __restrict__ z, const float* __rest
                                 float* __restrict__ c, float* __restrict__ gates,
                                 T* __restrict__ h_out, long long ldh, T* __restrict__ h_next,
                                 long long ldn, int batch, int H) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * H) return;
   const int b = i / H, j = i - b * H;
@@ -420,6 +438,7 @@ __global__ void lstm_cell_bwd_k(const T* __restrict__ err_h, long long lde,
                                 const float* __restrict__ dc_next, const float* __restrict__ gates,
                                 const float* __restrict__ c, const float* __restrict__ c_prev,
                                 float* __restrict__ dc_prev, T* __restrict__ dz, int batch, int H) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * H) return;
   const int b = i / H, j = i - b * H;
@@ -444,7 +463,7 @@ void launch_lstm_cell_fwd(const float* z, const float* c_prev, float* c, float* 
                           long long ldh, void* h_next, long long ldn, int batch, int H, bool bf16,
                           cudaStream_t st) {
   const int g = (batch * H + 255) / 256;
-  DISPATCH_T(bf16, lstm_cell_fwd_k<T><<<g, 256, 0, st>>>(z, c_prev, c, gates, (T*)h_out, ldh,
+  DISPATCH_T(bf16, launch_k(lstm_cell_fwd_k<T>, g, 256, 0, st, z, c_prev, c, gates, (T*)h_out, ldh,
                                                          (T*)h_next, ldn, batch, H));
 }
 void launch_lstm_cell_bwd(const void* err_h, long long lde, const void* dh_rec, long long ldr,
@@ -452,7 +471,7 @@ void launch_lstm_cell_bwd(const void* err_h, long long lde, const void* dh_rec, 
                           const float* c_prev, float* dc_prev, void* dz, int batch, int H, bool bf16,
                           cudaStream_t st) {
   const int g = (batch * H + 255) / 256;
-  DISPATCH_T(bf16, lstm_cell_bwd_k<T><<<g, 256, 0, st>>>((const T*)err_h, lde, (const T*)dh_rec, ldr,
+  DISPATCH_T(bf16, launch_k(lstm_cell_bwd_k<T>, g, 256, 0, st, (const T*)err_h, lde, (const T*)dh_rec, ldr,
                                                          dc_next, gates, c, c_prev, dc_prev, (T*)dz,
                                                          batch, H));
 }

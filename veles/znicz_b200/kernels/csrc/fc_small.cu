@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(128)
 fc_small_forward_k(const T* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ bias, T* __restrict__ out_t, float* __restrict__ out_f,
                    int* __restrict__ max_idx, int n_in, int n_out, int act, int softmax) {
+  pdl_entry();
   __shared__ float red[4][FCS_MAX_OUT];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const T* xr = x + (size_t)row * n_in;
@@ -81,6 +82,7 @@ fc_small_backward_k(const T* __restrict__ err, const T* __restrict__ y, const T*
                     const float* __restrict__ w, T* __restrict__ err_in,
                     float* __restrict__ gw_parts, float* __restrict__ gb_parts, int batch, int n_in,
                     int n_out, int act, float alpha, float beta, int need_ei, int need_gw) {
+  pdl_entry();
   extern __shared__ float s_err[];       // [rows_here][FCS_MAX_OUT]
   const int bs = gridDim.y, part = blockIdx.y;
   const int per = (batch + bs - 1) / bs;
@@ -146,10 +148,10 @@ void launch_fc_small_forward(const void* x, bool bf16, const float* w, const flo
                              float* out_f, int* max_idx, int batch, int n_in, int n_out, int act,
                              int softmax, cudaStream_t st) {
   if (bf16)
-    fc_small_forward_k<__nv_bfloat16><<<batch, 128, 0, st>>>(
+    launch_k(fc_small_forward_k<__nv_bfloat16>, batch, 128, 0, st, 
         (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)out_t, out_f, max_idx, n_in, n_out, act, softmax);
   else
-    fc_small_forward_k<float><<<batch, 128, 0, st>>>((const float*)x, w, bias, (float*)out_t, out_f,
+    launch_k(fc_small_forward_k<float>, batch, 128, 0, st, (const float*)x, w, bias, (float*)out_t, out_f,
                                                      max_idx, n_in, n_out, act, softmax);
 }
 
@@ -161,11 +163,11 @@ void launch_fc_small_backward(void* err, const void* y, const void* x, bool bf16
   const size_t smem = (size_t)per * FCS_MAX_OUT * sizeof(float);
   const int need_ei = err_in != nullptr, need_gw = gw_parts != nullptr;
   if (bf16)
-    fc_small_backward_k<__nv_bfloat16><<<grid, 128, smem, st>>>(
+    launch_k(fc_small_backward_k<__nv_bfloat16>, grid, 128, smem, st, 
         (const __nv_bfloat16*)err, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x, w, (__nv_bfloat16*)err_in,
         gw_parts, gb_parts, batch, n_in, n_out, act, alpha, beta, need_ei, need_gw);
   else
-    fc_small_backward_k<float><<<grid, 128, smem, st>>>((const float*)err, (const float*)y, (const float*)x, w,
+    launch_k(fc_small_backward_k<float>, grid, 128, smem, st, (const float*)err, (const float*)y, (const float*)x, w,
                                                         (float*)err_in, gw_parts, gb_parts, batch, n_in,
                                                         n_out, act, alpha, beta, need_ei, need_gw);
 }

@@ -76,6 +76,7 @@ struct Epilogue {
 template <typename AL, typename BL>
 __global__ void __launch_bounds__(256) gemm_simt_k(AL A, BL B, Epilogue ep, int M, int N, int K,
                                                    int k_chunk) {
+  pdl_entry();
   __shared__ float As[16][65];
   __shared__ float Bs[16][65];
   int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -145,7 +146,7 @@ static void run(AL a, BL b, const Epilogue& ep, int M, int N, int K, int splits,
   int k_chunk = (K + splits - 1) / splits;
   k_chunk = ((k_chunk + 15) / 16) * 16;
   dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-  gemm_simt_k<AL, BL><<<grid, 256, 0, st>>>(a, b, ep, M, N, K, k_chunk);
+  launch_k(gemm_simt_k<AL, BL>, grid, 256, 0, st, a, b, ep, M, N, K, k_chunk);
 }
 
 // C[M,N] = act(alpha * opA(A) opB(B) + bias) (+ beta*C); a/b dtype selected independently

@@ -272,6 +272,7 @@ template <int BLOCK_N, int A_MODE, int B_MODE, int GKIND, int GVEC, int STAGES>
 __global__ void __launch_bounds__(192, (min_ctas<BLOCK_N, B_MODE, STAGES>()))
 gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  pdl_trigger();
   constexpr int B_BYTES = b_bytes<BLOCK_N, B_MODE>();
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr bool A_GATHER = (A_MODE == A_GATHER_K || A_MODE == A_GATHER_MN);
@@ -327,6 +328,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tmem_relinquish();
   }
   if (A_GATHER) build_ktab(ktab, p.g, GKIND, p.gK);
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global reads start here
   if (threadIdx.x < BLOCK_N) {
     const int n = blockIdx.x * BLOCK_N + threadIdx.x;
     s_bias[threadIdx.x] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
@@ -684,7 +686,7 @@ static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
       (p.ldo % 8) == 0 && ((uintptr_t)p.out & 15) == 0 && 4 * 32 * BN * 2 <= ring - 1024) {
     if (make_map_out(&tc, p.out, p.N, p.M, p.ldo, BN) == 0) p.tma_store = 1;
   }
-  gemm_umma_k<BN, AM, BM, GK, GV, NS><<<grid, 192, smem, st>>>(ta, tb, tc, p);
+  launch_k(gemm_umma_k<BN, AM, BM, GK, GV, NS>, grid, 192, smem, st, ta, tb, tc, p);
   return (int)cudaGetLastError();
 }
 

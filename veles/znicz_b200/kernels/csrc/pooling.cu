@@ -17,6 +17,7 @@ struct PoolGeom { int N, H, W, C, OH, OW, KY, KX, SY, SX; int act; };
 template <typename T>
 __global__ void pool_forward_k(const T* __restrict__ in, T* __restrict__ out, int* __restrict__ offs,
                                PoolGeom g, int mode, const int* __restrict__ rng) {
+  pdl_entry();
   long long total = (long long)g.N * g.OH * g.OW * g.C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -92,6 +93,7 @@ __global__ void pool_forward_k(const T* __restrict__ in, T* __restrict__ out, in
 template <typename T>
 __global__ void pool_backward_max_k(const T* __restrict__ err_out, const int* __restrict__ offs,
                                     T* __restrict__ err_in, PoolGeom g, const T* __restrict__ yact) {
+  pdl_entry();
   long long total = (long long)g.N * g.H * g.W * g.C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -114,6 +116,7 @@ __global__ void pool_backward_max_k(const T* __restrict__ err_out, const int* __
 template <typename T>
 __global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict__ err_in, PoolGeom g,
                                     const T* __restrict__ yact) {
+  pdl_entry();
   long long total = (long long)g.N * g.H * g.W * g.C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -140,6 +143,7 @@ __global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict
 template <typename T>
 __global__ void pool_forward_vec_k(const T* __restrict__ in, T* __restrict__ out, int* __restrict__ offs,
                                    PoolGeom g, int mode) {
+  pdl_entry();
   const int C8 = g.C >> 3;
   const int total = g.N * g.OH * g.OW * C8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,6 +192,7 @@ template <typename T>
 __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __restrict__ offs,
                                     T* __restrict__ err_in, PoolGeom g, int is_avg,
                                     const T* __restrict__ yact) {
+  pdl_entry();
   const int C8 = g.C >> 3;
   const int total = g.N * g.H * g.W * C8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,6 +239,7 @@ __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __
 template <typename T, int half>
 __global__ void lrn_vec_k(const T* __restrict__ x, const T* __restrict__ ey, T* __restrict__ out,
                           int pixels, int C, float alpha, float beta, float k, int backward) {
+  pdl_entry();
   const int C8 = C >> 3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pixels * C8) return;
@@ -298,13 +304,13 @@ void launch_pool_forward(const void* in, void* out, int* offs, int N, int H, int
   if (mode <= POOL_AVG && C % 8 == 0 && (long long)N * H * W * C < (1LL << 31) &&
       (((uintptr_t)in | (uintptr_t)out | (uintptr_t)offs) & 15) == 0) {
     int gridv = cdiv(total / 8, 256);
-    if (bf16) pool_forward_vec_k<__nv_bfloat16><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, offs, g, mode);
-    else pool_forward_vec_k<float><<<gridv, 256, 0, st>>>((const float*)in, (float*)out, offs, g, mode);
+    if (bf16) launch_k(pool_forward_vec_k<__nv_bfloat16>, gridv, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, offs, g, mode);
+    else launch_k(pool_forward_vec_k<float>, gridv, 256, 0, st, (const float*)in, (float*)out, offs, g, mode);
     return;
   }
   int grid = cdiv(total, 256);
-  if (bf16) pool_forward_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, offs, g, mode, rng);
-  else pool_forward_k<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, offs, g, mode, rng);
+  if (bf16) launch_k(pool_forward_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, offs, g, mode, rng);
+  else launch_k(pool_forward_k<float>, grid, 256, 0, st, (const float*)in, (float*)out, offs, g, mode, rng);
 }
 void launch_pool_backward(const void* err_out, const int* offs, void* err_in, int N, int H, int W, int C,
                           int OH, int OW, int KY, int KX, int SY, int SX, int is_avg, bool bf16,
@@ -314,17 +320,17 @@ void launch_pool_backward(const void* err_out, const int* offs, void* err_in, in
   if (C % 8 == 0 && total < (1LL << 31) &&
       (((uintptr_t)err_out | (uintptr_t)err_in | (uintptr_t)offs | (uintptr_t)yact) & 15) == 0) {
     int gridv = cdiv(total / 8, 256);
-    if (bf16) pool_backward_vec_k<__nv_bfloat16><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, is_avg, (const __nv_bfloat16*)yact);
-    else pool_backward_vec_k<float><<<gridv, 256, 0, st>>>((const float*)err_out, offs, (float*)err_in, g, is_avg, (const float*)yact);
+    if (bf16) launch_k(pool_backward_vec_k<__nv_bfloat16>, gridv, 256, 0, st, (const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, is_avg, (const __nv_bfloat16*)yact);
+    else launch_k(pool_backward_vec_k<float>, gridv, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, is_avg, (const float*)yact);
     return;
   }
   int grid = cdiv(total, 256);
   if (is_avg) {
-    if (bf16) pool_backward_avg_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)err_out, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
-    else pool_backward_avg_k<float><<<grid, 256, 0, st>>>((const float*)err_out, (float*)err_in, g, (const float*)yact);
+    if (bf16) launch_k(pool_backward_avg_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)err_out, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
+    else launch_k(pool_backward_avg_k<float>, grid, 256, 0, st, (const float*)err_out, (float*)err_in, g, (const float*)yact);
   } else {
-    if (bf16) pool_backward_max_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
-    else pool_backward_max_k<float><<<grid, 256, 0, st>>>((const float*)err_out, offs, (float*)err_in, g, (const float*)yact);
+    if (bf16) launch_k(pool_backward_max_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
+    else launch_k(pool_backward_max_k<float>, grid, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, (const float*)yact);
   }
 }
 
@@ -333,6 +339,7 @@ void launch_pool_backward(const void* err_out, const int* offs, void* err_in, in
 template <typename T>
 __global__ void lrn_forward_k(const T* __restrict__ x, T* __restrict__ y, long long pixels, int C,
                               int half, float alpha, float beta, float k) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pixels * C) return;
   int c = (int)(i % C);
@@ -347,6 +354,7 @@ __global__ void lrn_forward_k(const T* __restrict__ x, T* __restrict__ y, long l
 template <typename T>
 __global__ void lrn_backward_k(const T* __restrict__ ey, const T* __restrict__ x, T* __restrict__ eh,
                                long long pixels, int C, int half, float alpha, float beta, float k) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pixels * C) return;
   int c = (int)(i % C);
@@ -373,17 +381,17 @@ void launch_lrn_forward(const void* x, void* y, long long pixels, int C, int n, 
       (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
     int gridv = cdiv(pixels * C / 8, 256);
     if (n / 2 == 1) {
-      if (bf16) lrn_vec_k<__nv_bfloat16, 1><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, (int)pixels, C, alpha, beta, k, 0);
-      else lrn_vec_k<float, 1><<<gridv, 256, 0, st>>>((const float*)x, nullptr, (float*)y, (int)pixels, C, alpha, beta, k, 0);
+      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 1>, gridv, 256, 0, st, (const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, (int)pixels, C, alpha, beta, k, 0);
+      else launch_k(lrn_vec_k<float, 1>, gridv, 256, 0, st, (const float*)x, nullptr, (float*)y, (int)pixels, C, alpha, beta, k, 0);
     } else {
-      if (bf16) lrn_vec_k<__nv_bfloat16, 2><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, (int)pixels, C, alpha, beta, k, 0);
-      else lrn_vec_k<float, 2><<<gridv, 256, 0, st>>>((const float*)x, nullptr, (float*)y, (int)pixels, C, alpha, beta, k, 0);
+      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 2>, gridv, 256, 0, st, (const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)y, (int)pixels, C, alpha, beta, k, 0);
+      else launch_k(lrn_vec_k<float, 2>, gridv, 256, 0, st, (const float*)x, nullptr, (float*)y, (int)pixels, C, alpha, beta, k, 0);
     }
     return;
   }
   int grid = cdiv(pixels * C, 256);
-  if (bf16) lrn_forward_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, pixels, C, n / 2, alpha, beta, k);
-  else lrn_forward_k<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, pixels, C, n / 2, alpha, beta, k);
+  if (bf16) launch_k(lrn_forward_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, pixels, C, n / 2, alpha, beta, k);
+  else launch_k(lrn_forward_k<float>, grid, 256, 0, st, (const float*)x, (float*)y, pixels, C, n / 2, alpha, beta, k);
 }
 void launch_lrn_backward(const void* ey, const void* x, void* eh, long long pixels, int C, int n,
                          float alpha, float beta, float k, bool bf16, cudaStream_t st) {
@@ -391,17 +399,17 @@ void launch_lrn_backward(const void* ey, const void* x, void* eh, long long pixe
       (((uintptr_t)x | (uintptr_t)ey | (uintptr_t)eh) & 15) == 0) {
     int gridv = cdiv(pixels * C / 8, 256);
     if (n / 2 == 1) {
-      if (bf16) lrn_vec_k<__nv_bfloat16, 1><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
-      else lrn_vec_k<float, 1><<<gridv, 256, 0, st>>>((const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
+      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 1>, gridv, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
+      else launch_k(lrn_vec_k<float, 1>, gridv, 256, 0, st, (const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
     } else {
-      if (bf16) lrn_vec_k<__nv_bfloat16, 2><<<gridv, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
-      else lrn_vec_k<float, 2><<<gridv, 256, 0, st>>>((const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
+      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 2>, gridv, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
+      else launch_k(lrn_vec_k<float, 2>, gridv, 256, 0, st, (const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
     }
     return;
   }
   int grid = cdiv(pixels * C, 256);
-  if (bf16) lrn_backward_k<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)ey, (const __nv_bfloat16*)x, (__nv_bfloat16*)eh, pixels, C, n / 2, alpha, beta, k);
-  else lrn_backward_k<float><<<grid, 256, 0, st>>>((const float*)ey, (const float*)x, (float*)eh, pixels, C, n / 2, alpha, beta, k);
+  if (bf16) launch_k(lrn_backward_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)ey, (const __nv_bfloat16*)x, (__nv_bfloat16*)eh, pixels, C, n / 2, alpha, beta, k);
+  else launch_k(lrn_backward_k<float>, grid, 256, 0, st, (const float*)ey, (const float*)x, (float*)eh, pixels, C, n / 2, alpha, beta, k);
 }
 
 }  // namespace zn

@@ -12,6 +12,7 @@ namespace zn {
 template <typename T>
 __global__ void softmax_rows_k(const T* __restrict__ in, float* __restrict__ out,
                                int* __restrict__ max_idx, int rows, int cols) {
+  pdl_entry();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const T* r = in + (size_t)warp * cols;
@@ -38,6 +39,7 @@ __global__ void evaluate_softmax_k(const float* __restrict__ y, const int* __res
                                    const float* __restrict__ bp, int rows, int cols,
                                    int* __restrict__ n_err, int* __restrict__ confusion,
                                    float* __restrict__ max_err_sum) {
+  pdl_entry();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   int batch = (int)bp[0]; float mult = bp[1];
@@ -69,6 +71,7 @@ __global__ void evaluate_mse_k(const TY* __restrict__ y, const TY* __restrict__ 
                                TE* __restrict__ err, const float* __restrict__ bp, int rows, int cols,
                                const float* __restrict__ denorm_mul, int root,
                                float* __restrict__ metrics, float* __restrict__ mse) {
+  pdl_entry();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   int batch = (int)bp[0]; float mult = bp[1];
@@ -102,6 +105,7 @@ template <typename TY>
 __global__ void mse_find_closest_k(const TY* __restrict__ y, const float* __restrict__ class_targets,
                                    const int* __restrict__ labels, const float* __restrict__ bp,
                                    int rows, int cols, int n_targets, int* __restrict__ n_err) {
+  pdl_entry();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows || warp >= (int)bp[0]) return;
   const TY* r = y + (size_t)warp * cols;
@@ -122,34 +126,34 @@ __global__ void mse_find_closest_k(const TY* __restrict__ y, const float* __rest
 void launch_softmax_rows(const void* in, bool in_bf16, float* out, int* max_idx, int rows, int cols,
                          cudaStream_t st) {
   int grid = cdiv((long long)rows * 32, 128);
-  if (in_bf16) softmax_rows_k<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)in, out, max_idx, rows, cols);
-  else softmax_rows_k<float><<<grid, 128, 0, st>>>((const float*)in, out, max_idx, rows, cols);
+  if (in_bf16) launch_k(softmax_rows_k<__nv_bfloat16>, grid, 128, 0, st, (const __nv_bfloat16*)in, out, max_idx, rows, cols);
+  else launch_k(softmax_rows_k<float>, grid, 128, 0, st, (const float*)in, out, max_idx, rows, cols);
 }
 void launch_evaluate_softmax(const float* y, const int* max_idx, const int* labels, void* err,
                              bool err_bf16, const float* bp, int rows, int cols, int* n_err,
                              int* confusion, float* max_err_sum, cudaStream_t st) {
   int grid = cdiv((long long)rows * 32, 128);
-  if (err_bf16) evaluate_softmax_k<__nv_bfloat16><<<grid, 128, 0, st>>>(y, max_idx, labels, (__nv_bfloat16*)err, bp, rows, cols, n_err, confusion, max_err_sum);
-  else evaluate_softmax_k<float><<<grid, 128, 0, st>>>(y, max_idx, labels, (float*)err, bp, rows, cols, n_err, confusion, max_err_sum);
+  if (err_bf16) launch_k(evaluate_softmax_k<__nv_bfloat16>, grid, 128, 0, st, y, max_idx, labels, (__nv_bfloat16*)err, bp, rows, cols, n_err, confusion, max_err_sum);
+  else launch_k(evaluate_softmax_k<float>, grid, 128, 0, st, y, max_idx, labels, (float*)err, bp, rows, cols, n_err, confusion, max_err_sum);
 }
 void launch_evaluate_mse(const void* y, const void* target, bool y_bf16, void* err, bool err_bf16,
                          const float* bp, int rows, int cols, const float* denorm_mul, int root,
                          float* metrics, float* mse, cudaStream_t st) {
   int grid = cdiv((long long)rows * 32, 128);
   if (y_bf16) {
-    if (err_bf16) evaluate_mse_k<__nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)target, (__nv_bfloat16*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
-    else evaluate_mse_k<__nv_bfloat16, float><<<grid, 128, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)target, (float*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
+    if (err_bf16) launch_k(evaluate_mse_k<__nv_bfloat16, __nv_bfloat16>, grid, 128, 0, st, (const __nv_bfloat16*)y, (const __nv_bfloat16*)target, (__nv_bfloat16*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
+    else launch_k(evaluate_mse_k<__nv_bfloat16, float>, grid, 128, 0, st, (const __nv_bfloat16*)y, (const __nv_bfloat16*)target, (float*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
   } else {
-    if (err_bf16) evaluate_mse_k<float, __nv_bfloat16><<<grid, 128, 0, st>>>((const float*)y, (const float*)target, (__nv_bfloat16*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
-    else evaluate_mse_k<float, float><<<grid, 128, 0, st>>>((const float*)y, (const float*)target, (float*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
+    if (err_bf16) launch_k(evaluate_mse_k<float, __nv_bfloat16>, grid, 128, 0, st, (const float*)y, (const float*)target, (__nv_bfloat16*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
+    else launch_k(evaluate_mse_k<float, float>, grid, 128, 0, st, (const float*)y, (const float*)target, (float*)err, bp, rows, cols, denorm_mul, root, metrics, mse);
   }
 }
 void launch_mse_find_closest(const void* y, bool y_bf16, const float* class_targets, const int* labels,
                              const float* bp, int rows, int cols, int n_targets, int* n_err,
                              cudaStream_t st) {
   int grid = cdiv((long long)rows * 32, 128);
-  if (y_bf16) mse_find_closest_k<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)y, class_targets, labels, bp, rows, cols, n_targets, n_err);
-  else mse_find_closest_k<float><<<grid, 128, 0, st>>>((const float*)y, class_targets, labels, bp, rows, cols, n_targets, n_err);
+  if (y_bf16) launch_k(mse_find_closest_k<__nv_bfloat16>, grid, 128, 0, st, (const __nv_bfloat16*)y, class_targets, labels, bp, rows, cols, n_targets, n_err);
+  else launch_k(mse_find_closest_k<float>, grid, 128, 0, st, (const float*)y, class_targets, labels, bp, rows, cols, n_targets, n_err);
 }
 
 }  // namespace zn

@@ -11,6 +11,7 @@ namespace zn {
 __global__ void som_winners_k(const float* __restrict__ x, const float* __restrict__ w,
                               int* __restrict__ argmins, int* __restrict__ winners, int neurons,
                               int len, int count_winners) {
+  pdl_entry();
   const int s = blockIdx.x;
   const float* xs = x + (size_t)s * len;
   float best = 3.0e38f; int bi = 0x7fffffff;
@@ -46,6 +47,7 @@ __global__ void som_winners_k(const float* __restrict__ x, const float* __restri
 __global__ void som_update_k(const float* __restrict__ x, float* __restrict__ w,
                              const float* __restrict__ coords, const int* __restrict__ argmins,
                              int batch, int neurons, int len, float sigma, float gmult) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= neurons * len) return;
   const int n = i / len, k = i - n * len;
@@ -64,12 +66,12 @@ __global__ void som_update_k(const float* __restrict__ x, float* __restrict__ w,
 void launch_som_winners(const float* x, const float* w, int* argmins, int* winners, int batch,
                         int neurons, int len, int count_winners, cudaStream_t st) {
   int threads = neurons >= 256 ? 256 : ((neurons + 31) / 32) * 32;
-  som_winners_k<<<batch, threads, 0, st>>>(x, w, argmins, winners, neurons, len, count_winners);
+  launch_k(som_winners_k, batch, threads, 0, st, x, w, argmins, winners, neurons, len, count_winners);
 }
 void launch_som_update(const float* x, float* w, const float* coords, const int* argmins, int batch,
                        int neurons, int len, float sigma, float gmult, cudaStream_t st) {
   int total = neurons * len;
-  som_update_k<<<(total + 255) / 256, 256, 0, st>>>(x, w, coords, argmins, batch, neurons, len, sigma, gmult);
+  launch_k(som_update_k, (total + 255) / 256, 256, 0, st, x, w, coords, argmins, batch, neurons, len, sigma, gmult);
 }
 
 }  // namespace zn

@@ -76,6 +76,7 @@ __global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __r
                                const float* __restrict__ hyper, const float* __restrict__ col_sums,
                                int flags, int is_bias, long long size, int rows, int cols,
                                ShadowSpec sh, PeerSync ps) {
+  pdl_entry();
   __shared__ uint32_t s_epoch;
   uint32_t epoch = 0;
   if (MULTI) {
@@ -154,6 +155,7 @@ __global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __r
 // column sums of W (pre-update) for the orthogonality regulariser: out[col] = sum_row w[row, col]
 __global__ void col_sums_k(const float* __restrict__ w, float* __restrict__ out, int rows, int cols,
                            int transposed) {
+  pdl_entry();
   // logical matrix [rows=Y][cols=H]; when transposed the storage is [H][Y]
   int col = blockIdx.x * blockDim.y + threadIdx.y;
   if (col >= cols) return;
@@ -167,6 +169,7 @@ __global__ void col_sums_k(const float* __restrict__ w, float* __restrict__ out,
 // shadow refresh without an update step (initialisation, rollback, weights from a snapshot)
 __global__ void refresh_shadows_k(const float* __restrict__ w, long long size, int rows, int cols,
                                   ShadowSpec sh) {
+  pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < size; i += stride) {
@@ -399,18 +402,22 @@ __device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long 
 __global__ void __launch_bounds__(256, 4)
 multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int has_ortho,
                PeerSync ps, GridSync gsync, RedBufs rb) {
+  pdl_trigger();
   __shared__ uint32_t s_epoch;
   __shared__ TensorDesc s_table[MU_MAX_TENSORS];     // the whole table: no dependent global loads
   const bool multi = ps.nranks > 1;
   uint32_t epoch = 0;
-  if (multi) {
-    if (threadIdx.x == 0) s_epoch = ps.epoch[blockIdx.x] + 1;
-  }
   {
+    // the descriptor table is written by the host when the step is built, never by a kernel:
+    // staging it may overlap the tail of the preceding (last wgrad) kernel
     const int words = n * (int)(sizeof(TensorDesc) / 4);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(table);
     uint32_t* dst = reinterpret_cast<uint32_t*>(s_table);
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  pdl_wait();
+  if (multi) {
+    if (threadIdx.x == 0) s_epoch = ps.epoch[blockIdx.x] + 1;
   }
   __syncthreads();
   if (multi) epoch = s_epoch;
@@ -496,7 +503,7 @@ void launch_multi_update(const void* table, int n, int total_tiles, int has_orth
   RedBufs rb{};
   rb.nranks = ps.nranks; rb.rank = rank; rb.half = red_half; rb.chunks = chunks;
   if (red_ptrs) for (int r = 0; r < nranks; ++r) rb.ptr[r] = red_ptrs[r];
-  multi_update_k<<<blocks, 256, 0, st>>>((const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs, rb);
+  launch_k(multi_update_k, blocks, 256, 0, st, (const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs, rb);
 }
 
 int fused_update_blocks(long long size) {
@@ -522,22 +529,22 @@ void launch_fused_update(float* w, const float* const* grad_ptrs, int nranks, in
   if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
   if (blocks <= 0) blocks = fused_update_blocks(size);
   if (peer_flags && nranks > 1)
-    fused_update_k<true><<<blocks, 256, 0, st>>>(w, gs, grad_out, acc, vel, hyper, col_sums, flags,
+    launch_k(fused_update_k<true>, blocks, 256, 0, st, w, gs, grad_out, acc, vel, hyper, col_sums, flags,
                                                   is_bias, size, rows, cols, sh, ps);
   else
-    fused_update_k<false><<<blocks, 256, 0, st>>>(w, gs, grad_out, acc, vel, hyper, col_sums, flags,
+    launch_k(fused_update_k<false>, blocks, 256, 0, st, w, gs, grad_out, acc, vel, hyper, col_sums, flags,
                                                    is_bias, size, rows, cols, sh, ps);
 }
 void launch_col_sums(const float* w, float* out, int rows, int cols, int transposed, cudaStream_t st) {
   dim3 block(32, 8);
-  col_sums_k<<<(cols + 7) / 8, block, 0, st>>>(w, out, rows, cols, transposed);
+  launch_k(col_sums_k, (cols + 7) / 8, block, 0, st, w, out, rows, cols, transposed);
 }
 void launch_refresh_shadows(const float* w, long long size, int rows, int cols, __nv_bfloat16* lp, int ld,
                             __nv_bfloat16* lp_conv, int taps, int C, int c_pad, int lp_cpad,
                             cudaStream_t st) {
   ShadowSpec sh{lp, ld, lp_cpad, lp_conv, taps, C, c_pad};
   long long b = (size + 255) / 256; if (b > 592) b = 592; if (b < 1) b = 1;
-  refresh_shadows_k<<<(int)b, 256, 0, st>>>(w, size, rows, cols, sh);
+  launch_k(refresh_shadows_k, (int)b, 256, 0, st, w, size, rows, cols, sh);
 }
 
 }  // namespace zn
