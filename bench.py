@@ -150,6 +150,7 @@ def run_arm(args, streaming):
     e0.record()
     wf.run(iterations=args.steps)
     e1.record()
+    t_enq = time.perf_counter()       # host finished enqueueing (the device may still be busy)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     if world > 1:
@@ -169,6 +170,9 @@ def run_arm(args, streaming):
         "n_err": int(reader.last[0]) if reader and reader.last is not None else None,
     }
     if os.environ.get("ZNICZ_BENCH_STATS") and int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("host enqueue %.4f ms/step, device %.4f ms/step, drain after enqueue "
+                         "%.3f ms\n" % ((t_enq - t0) * 1e3 / args.steps, ms_dev / args.steps,
+                                        (t1 - t_enq) * 1e3))
         rows = sorted(((u.total_run_time, u._run_calls, u.name) for u in wf.units), reverse=True)
         for t_, c_, n_ in rows[:25]:
             sys.stderr.write("  %-28s calls %6d  host %9.3f ms  (%.1f us/call)\n" % (

@@ -147,10 +147,14 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
         return
     splits = int(ext.pick_splits(kw, f, n * oh * ow, 16)) if engine == 1 else 4
     parts = torch.full((splits, f, kw), float("nan"), device=dev)
-    r = ext.conv_wgrad(eo, x, parts, splits, g, False, engine)
-    assert r == 0
+    bparts = torch.full((splits, f), float("nan"), device=dev) if engine == 1 else None
+    r = ext.conv_wgrad(eo, x, parts, splits, g, False, engine, bparts)
+    assert r in (0, 1)
     torch.cuda.synchronize()
     assert _rel(parts.sum(0), wr.grad) < 5e-3
+    if r == 1:      # bias gradient delivered as the extra "ones" row of the product
+        ref_b = eo.float().reshape(-1, f).sum(0)
+        assert _rel(bparts.sum(0), ref_b) < 5e-3
 
 
 def test_fused_update_matches_reference_formula(ext):
@@ -360,11 +364,20 @@ def test_pooling_fused_activation(ext, dtype, mode, c):
     err = torch.randn(n, oh, ow, c, device=dev).to(dtype)
     ei_f = torch.empty_like(x)
     ei_p = torch.empty_like(x)
-    ext.pool_backward(err, offs_f, ei_f, oh, ow, k, k, s, s, mode == 2, out_f, 3)
+    ext.pool_backward(err, offs_f, ei_f, oh, ow, k, k, s, s, mode == 2, out_f, 3, None, 0)
     masked = (err.float() * (out_f.float() > 0)).to(dtype)
-    ext.pool_backward(masked, offs_p, ei_p, oh, ow, k, k, s, s, mode == 2, None, 0)
+    ext.pool_backward(masked, offs_p, ei_p, oh, ow, k, k, s, s, mode == 2, None, 0, None, 0)
     torch.cuda.synchronize()
     assert _rel(ei_f.float(), ei_p.float()) < (1e-6 if dtype == torch.float32 else 1e-2)
+    # producer-side derivative: err_input *= f'(pooling input) (tanh: f' = 1.14381894 - 0.388484177 y^2)
+    ei_d = torch.empty_like(x)
+    ext.pool_backward(err, offs_p, ei_d, oh, ow, k, k, s, s, mode == 2, None, 0, x, 1)
+    torch.cuda.synchronize()
+    ref = ei_p.float() * 0 + 0      # plain backward of the unmasked error, then the derivative
+    ext.pool_backward(err, offs_p, ei_p, oh, ow, k, k, s, s, mode == 2, None, 0, None, 0)
+    torch.cuda.synchronize()
+    ref = ei_p.float() * (1.14381894 - 0.388484177 * x.float() ** 2)
+    assert _rel(ei_d.float(), ref) < (1e-6 if dtype == torch.float32 else 1e-2)
 
 
 @pytest.mark.parametrize("src_dt,dst_dt", [(torch.float32, torch.bfloat16),

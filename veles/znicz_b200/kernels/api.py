@@ -407,17 +407,23 @@ def conv_backward(unit):
     kw = unit._kernel_size
     need_w = unit.need_gradient_weights and unit.weights
     need_b = need_w and unit.include_bias and unit.bias
-    if eff_act(unit) != ACT_LINEAR or need_b:
-        parts = None
-        if need_b:
-            slices, parts = _bias_partials(unit, pixels, f)
-        y = unit.output.dev if eff_act(unit) != ACT_LINEAR else None
-        ext.err_act_colsum(err, y, pixels, f, eff_act(unit), parts)
-        unit.err_output.dev_written()
-        _launch()
     fwd = unit.forward_unit
     lp_ok = (lp_enabled(unit) and _is_bf16(err) and _is_bf16(x) and fwd is not None and
              getattr(fwd, "weights_lp_t_", None) is not None)
+    act = eff_act(unit)
+    if unit.__dict__.get("deriv_upstream_"):
+        act = ACT_LINEAR       # the consumer's backward kernel already applied f'(y) (fusion.py)
+    # bias gradient: with nothing to multiply into err_output, the tcgen05 wgrad kernel delivers the
+    # column sums as an extra product row (no separate pass over err_output at all)
+    bias_row = bool(need_b and act == ACT_LINEAR and lp_ok)
+    parts = slices = None
+    if act != ACT_LINEAR or (need_b and not bias_row):
+        if need_b:
+            slices, parts = _bias_partials(unit, pixels, f)
+        y = unit.output.dev if act != ACT_LINEAR else None
+        ext.err_act_colsum(err, y, pixels, f, act, parts)
+        unit.err_output.dev_written()
+        _launch()
     f_pad = _roundup(f, 8)
     err_mm, g_mm = err, g
     if lp_ok and f_pad != f:
@@ -469,16 +475,29 @@ def conv_backward(unit):
         tiles = ((f + 63) // 64) * ((kw + 63) // 64)
         splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
     gbuf = _grad_buffer(unit, "wgrad", (splits, f_rows, kw))
+    brow = None
     if use_umma:
-        r = ext.conv_wgrad(err_mm, x, gbuf, splits, g, False, 1)
-        if r != 0:
+        if bias_row:
+            brow = _grad_buffer(unit, "bias_row", (splits, f_rows))
+        r = ext.conv_wgrad(err_mm, x, gbuf, splits, g, False, 1, brow)
+        if r not in (0, 1):
             raise RuntimeError("%s: tcgen05 conv wgrad refused (code %d)" % (unit, r))
+        if r == 0:
+            brow = None
     else:
-        ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0)
+        ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0, None)
     _launch()
+    if bias_row and brow is None:
+        # geometry without a spare product row (kernel size a multiple of 128): classic column sums
+        slices, parts = _bias_partials(unit, pixels, f)
+        ext.err_act_colsum(err, None, pixels, f, ACT_LINEAR, parts)
+        _launch()
     _update(unit, False, gbuf, splits, f_rows * kw, f, unit._kernel_size, g_cpad=g_cp)
     if need_b:
-        _update(unit, True, parts, slices, f, 1, f)
+        if brow is not None:
+            _update(unit, True, brow, splits, f_rows, 1, f)
+        else:
+            _update(unit, True, parts, slices, f, 1, f)
 
 
 # ------------------------------------------------------------------------------------------
@@ -514,9 +533,12 @@ def pooling_backward(unit):
     ei = unit.err_input.dev_out
     act = fused_act(unit)
     y = unit.output.dev if act else None
+    in_act = int(unit.__dict__.get("in_deriv_act_", 0) or 0)      # see workflow/fusion.py
+    xin = unit.input.dev if in_act else None
     ext.pool_backward(err.view(ei.shape[0], oy, ox, ei.shape[3]), offs, ei, oy, ox, unit.ky,
                       unit.kx, unit.sliding[1], unit.sliding[0], is_avg,
-                      y.view(ei.shape[0], oy, ox, ei.shape[3]) if act else None, act)
+                      y.view(ei.shape[0], oy, ox, ei.shape[3]) if act else None, act,
+                      xin, in_act)
     _launch()
 
 
@@ -706,7 +728,7 @@ def deconv_backward(unit):
     tiles = ((f + 63) // 64) * ((kw + 63) // 64)
     splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
     gbuf = _grad_buffer(unit, "wgrad", (splits, f, kw))
-    ext.conv_wgrad(unit.input.dev, err, gbuf, splits, g, bool(unit.weights_transposed), 0)
+    ext.conv_wgrad(unit.input.dev, err, gbuf, splits, g, bool(unit.weights_transposed), 0, None)
     _launch()
     _update(unit, False, gbuf, splits, f * kw, f, kw)
 

@@ -24,7 +24,7 @@ void launch_pad_channels(const void*, void*, int, int, int, bool, cudaStream_t);
 void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
 void launch_scatter_offsets(const void*, const int*, void*, long long, bool, cudaStream_t);
 void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int, const int*, bool, int, cudaStream_t);
-void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, const void*, int, cudaStream_t);
+void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, const void*, int, const void*, int, cudaStream_t);
 void launch_lrn_forward(const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
 void launch_lrn_backward(const void*, const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
 void launch_softmax_rows(const void*, bool, float*, int*, int, int, cudaStream_t);
@@ -52,7 +52,7 @@ void launch_som_update(const float*, float*, const float*, const int*, int, int,
 int launch_gemm_umma(const void*, long long, int, const void*, long long, int, void*, int, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
 int launch_conv_fprop_umma(const void*, const void*, long long, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_dgrad_umma(const void*, const void*, long long, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, float, float, cudaStream_t);
-int launch_conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int launch_conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
 }  // namespace zn
 
 // The SIMT conv launchers take a struct by value; redeclare with the real layout.
@@ -222,8 +222,15 @@ void pool_forward(Tensor in, c10::optional<Tensor> out, c10::optional<Tensor> of
 }
 void pool_backward(Tensor err_out, c10::optional<Tensor> offs, Tensor err_in, int64_t OH, int64_t OW,
                    int64_t KY, int64_t KX, int64_t SY, int64_t SX, bool is_avg, c10::optional<Tensor> yact,
-                   int64_t act) {
+                   int64_t act, c10::optional<Tensor> xin, int64_t in_act) {
   chk(err_out, "err_out"); same_dt(err_out, err_in);
+  const void* xp = nullptr;
+  if (in_act != 0) {      // err_input *= f'(pooling input): the producer's activation derivative
+    TORCH_CHECK(in_act >= 1 && in_act <= 4 && xin.has_value() && xin->defined(), "input derivative needs the input");
+    same_dt(err_in, *xin);
+    TORCH_CHECK(xin->numel() == err_in.numel());
+    xp = xin->data_ptr();
+  }
   const void* yp = nullptr;
   if (act != 0) {
     TORCH_CHECK(act >= 1 && act <= 4 && yact.has_value() && yact->defined(), "fused activation needs the output");
@@ -235,7 +242,7 @@ void pool_backward(Tensor err_out, c10::optional<Tensor> offs, Tensor err_in, in
   TORCH_CHECK(is_avg || fp, "offsets required");
   zn::launch_pool_backward(err_out.data_ptr(), fp, err_in.data_ptr(), (int)err_in.size(0), (int)err_in.size(1),
                            (int)err_in.size(2), (int)err_in.size(3), (int)OH, (int)OW, (int)KY, (int)KX,
-                           (int)SY, (int)SX, is_avg ? 1 : 0, is_bf16(err_out), yp, (int)act, cur());
+                           (int)SY, (int)SX, is_avg ? 1 : 0, is_bf16(err_out), yp, (int)act, xp, (int)in_act, cur());
   kcheck();
 }
 void lrn_forward(Tensor x, Tensor y, int64_t n, double alpha, double beta, double k) {
@@ -534,15 +541,20 @@ int64_t conv_dgrad(Tensor err_out, Tensor w, int64_t ldw, bool w_trans, Tensor e
   return 0;
 }
 int64_t conv_wgrad(Tensor err_out, Tensor x, Tensor partials, int64_t splits, std::vector<int64_t> g,
-                   bool out_trans, int64_t engine) {
+                   bool out_trans, int64_t engine, c10::optional<Tensor> bias_parts) {
   TORCH_CHECK(g.size() == 13 && partials.scalar_type() == torch::kFloat32);
   int gi[13]; for (int i = 0; i < 13; ++i) gi[i] = (int)g[i];
   if (engine == 1) {
     TORCH_CHECK(is_bf16(err_out) && is_bf16(x) && !out_trans);
+    float* bp = nullptr;
+    if (bias_parts.has_value() && bias_parts->defined()) {
+      TORCH_CHECK(bias_parts->scalar_type() == torch::kFloat32 && bias_parts->numel() >= splits * gi[6]);
+      bp = bias_parts->data_ptr<float>();
+    }
     int r = zn::launch_conv_wgrad_umma(err_out.data_ptr(), x.data_ptr(), partials.data_ptr<float>(),
                                        (int)splits, gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], gi[7],
-                                       gi[8], gi[9], gi[10], gi[11], gi[12], cur());
-    if (r == 0) kcheck();
+                                       gi[8], gi[9], gi[10], gi[11], gi[12], bp, cur());
+    if (r == 0 || r == 1) kcheck();
     return r;
   }
   zn::launch_conv_wgrad_simt_raw(err_out.data_ptr(), is_bf16(err_out), x.data_ptr(), is_bf16(x),

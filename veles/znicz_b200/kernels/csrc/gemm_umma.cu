@@ -42,6 +42,10 @@ struct ConvGeomU {
   // tap mode (GVEC == 2): a 64-wide block of the reduction index covers ``tpk`` whole taps
   // (inner = 64 / tpk channels each) or a 64-channel slice of one tap (tpk == 1, inner % 64 == 0)
   int tpk, ntaps, inner;
+  // wgrad only: 16 bytes holding bf16 {1, 0, 0, 0, 0, 0, 0, 0}. The gathered im2col operand gets a
+  // "ones" row at reduction-weight index Kw (first padding row of the last M tile), so that
+  // row Kw of the product is sum_pixels err[pixel][f] = the bias gradient - for free.
+  const __nv_bfloat16* ones;
 };
 
 struct GemmParams {
@@ -50,6 +54,7 @@ struct GemmParams {
   // epilogue
   void* out; int out_bf16; long long ldo; int out_trans;
   const float* bias; int act; float alpha, beta;
+  float* bias_out;             // wgrad: row M of the product -> bias_out[blockIdx.z][N] (see ones)
   long long split_stride;      // > 0: fp32 partial [blockIdx.z][...]
   // gather source
   const __nv_bfloat16* gsrc; ConvGeomU g; int gather_kind;
@@ -201,12 +206,14 @@ __device__ __forceinline__ void gather_taps_async(uint32_t row_base, int sw, con
       ok = ok && (unsigned)ty < (unsigned)g.OH && (unsigned)tx < (unsigned)g.OW;
       off = (ty * g.OW + tx) * g.F;
     }
-    const __nv_bfloat16* ptr = c.base + (ok ? off + c0 : 0);
+    const bool one = KIND == G_IM2COL && g.ones != nullptr && c.valid && tap == g.ntaps && c0 == 0;
+    const __nv_bfloat16* ptr = one ? g.ones : c.base + (ok ? off + c0 : 0);
     const uint32_t nbytes = ok ? 16u : 0u;
 #pragma unroll
     for (int q = 0; q < CPT; ++q) {
       const int c8 = j * CPT + q;
-      cp_async_16(row_base + (uint32_t)((c8 ^ sw) << 4), ptr + q * 8, nbytes);
+      cp_async_16(row_base + (uint32_t)((c8 ^ sw) << 4), one ? ptr : ptr + q * 8,
+                  (one && q == 0) ? 16u : nbytes);
     }
   }
 }
@@ -489,7 +496,8 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // fetch stalls alone. This one is a rolled loop over 8-column chunks - TMEM loads double
     // buffered (the next chunk is in flight while this one is stored) - with the output mode
     // decided once per thread; the loop body is a few hundred instructions, fetched once.
-    enum { EPI_TMA = 0, EPI_BF16 = 1, EPI_RAW_T = 2, EPI_RAW = 3, EPI_SLOW = 4, EPI_NONE = 5 };
+    enum { EPI_TMA = 0, EPI_BF16 = 1, EPI_RAW_T = 2, EPI_RAW = 3, EPI_SLOW = 4, EPI_NONE = 5,
+           EPI_BIASROW = 6 };
 #pragma unroll 1
     for (int tj = 0; tj < ntiles; ++tj) {
     const int row = m0 + tj * BLOCK_M + warp * 32 + lane;
@@ -498,7 +506,8 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                          (p.split_stride > 0 ? (long long)blockIdx.z * p.split_stride : 0LL);
     int mode;
     if (p.tma_store) mode = EPI_TMA;
-    else if (row >= p.M || (p.dbg & 8)) mode = EPI_NONE;
+    else if (row >= p.M || (p.dbg & 8))
+      mode = (p.bias_out && row == p.M && !(p.dbg & 8)) ? EPI_BIASROW : EPI_NONE;
     else if (p.split_stride == 0 && !p.out_trans && p.out_bf16 && p.beta == 0.f) mode = EPI_BF16;
     else if (raw32 && p.out_trans) mode = EPI_RAW_T;
     else if (raw32 && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(rbase) & 15) == 0)
@@ -509,6 +518,12 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     auto emit = [&](const uint32_t (&r)[8], int c0) {
       const int nb = n0 + c0;
       if (mode == EPI_NONE) return;
+      if (mode == EPI_BIASROW) {       // product row M = column sums of err (see ConvGeomU::ones)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (nb + j < p.N) p.bias_out[(long long)blockIdx.z * p.N + nb + j] = __uint_as_float(r[j]);
+        return;
+      }
       if (mode == EPI_TMA || mode == EPI_BF16) {
         float v[8];
         {
@@ -871,9 +886,13 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
 
 // partials[z][f][kidx] = sum_{pix in split z} err_out[pix, f] * im2col(x)[pix, kidx]
 // (computed as D[kidx, f] with the im2col operand on the 128-wide M side, stored transposed)
+__device__ __align__(16) unsigned short zn_ones_bf16[8] = {0x3F80, 0, 0, 0, 0, 0, 0, 0};
+
+// Returns 0, or 1 when ``bias_parts`` [splits][F] was filled with the per-split column sums of
+// err_out as well (tap-mode gather and Kw % 128 != 0, i.e. the last M tile has a spare row).
 int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, int splits, int N, int H,
                            int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX, int PT,
-                           int PL, cudaStream_t st) {
+                           int PL, float* bias_parts, cudaStream_t st) {
   if ((F % 8) || ((uintptr_t)err_out & 15) || ((uintptr_t)x & 15)) return -3;
   int Kw = KY * KX * C, P = N * OH * OW;
   if ((C % 8 == 0 ? (Kw + 7) / 8 : Kw) > KTAB || KY > 255 || KX > 255) return -4;
@@ -892,7 +911,17 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
   p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.beta = 0.f; p.split_stride = (long long)F * Kw;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
-  if (set_tap_mode(p.g, C, false)) return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 2>(bn, ta, tb, p, splits, st);
+  if (set_tap_mode(p.g, C, false)) {
+    bool row = bias_parts != nullptr && (Kw % BLOCK_M) != 0;
+    if (row) {
+      static void* ones = nullptr;
+      if (!ones && cudaGetSymbolAddress(&ones, zn_ones_bf16) != cudaSuccess) ones = nullptr;
+      row = ones != nullptr;
+      if (row) { p.g.ones = (const __nv_bfloat16*)ones; p.bias_out = bias_parts; }
+    }
+    r = launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 2>(bn, ta, tb, p, splits, st);
+    return (r == 0 && row) ? 1 : r;
+  }
   if (C % 8 == 0) return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 1>(bn, ta, tb, p, splits, st);
   return launch_bn<A_GATHER_MN, B_TMA_MN, G_IM2COL, 0>(bn, ta, tb, p, splits, st);
 }

@@ -12,7 +12,10 @@ enum PoolMode { POOL_MAX = 0, POOL_MAXABS = 1, POOL_AVG = 2, POOL_STOCH = 3, POO
 
 // act: activation fused behind the pooling (0 = none; forward applies f, backward multiplies the
 // incoming error by f'(y) with y = the pooled+activated output)
-struct PoolGeom { int N, H, W, C, OH, OW, KY, KX, SY, SX; int act; };
+struct PoolGeom { int N, H, W, C, OH, OW, KY, KX, SY, SX; int act; int in_act; };
+// in_act (backward only): derivative of the PRODUCER's activation, applied to err_input through the
+// pooling input x (= the producer's output y): err_input *= f'(x). Saves the conv / FC layer below a
+// separate err_output *= f'(y) pass (/root/reference/gd_conv.py:645-750 runs one per layer).
 
 template <typename T>
 __global__ void pool_forward_k(const T* __restrict__ in, T* __restrict__ out, int* __restrict__ offs,
@@ -92,7 +95,8 @@ __global__ void pool_forward_k(const T* __restrict__ in, T* __restrict__ out, in
 // err_in[n,y,x,c] = sum over windows covering (y,x) of err_out[window] * [offs[window]==self]
 template <typename T>
 __global__ void pool_backward_max_k(const T* __restrict__ err_out, const int* __restrict__ offs,
-                                    T* __restrict__ err_in, PoolGeom g, const T* __restrict__ yact) {
+                                    T* __restrict__ err_in, PoolGeom g, const T* __restrict__ yact,
+                                    const T* __restrict__ xin) {
   pdl_entry();
   long long total = (long long)g.N * g.H * g.W * g.C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,12 +114,13 @@ __global__ void pool_backward_max_k(const T* __restrict__ err_out, const int* __
       if (offs[o] == (int)i)
         s += ldf(err_out + o) * (g.act ? act_deriv(g.act, 0.f, ldf(yact + o)) : 1.f);
     }
+  if (g.in_act) s *= act_deriv(g.in_act, 0.f, ldf(xin + i));
   stf(err_in + i, s);
 }
 
 template <typename T>
 __global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict__ err_in, PoolGeom g,
-                                    const T* __restrict__ yact) {
+                                    const T* __restrict__ yact, const T* __restrict__ xin) {
   pdl_entry();
   long long total = (long long)g.N * g.H * g.W * g.C;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,6 +139,7 @@ __global__ void pool_backward_avg_k(const T* __restrict__ err_out, T* __restrict
       s += ldf(err_out + o) * (g.act ? act_deriv(g.act, 0.f, ldf(yact + o)) : 1.f) / (float)(hy * hx);
     }
   }
+  if (g.in_act) s *= act_deriv(g.in_act, 0.f, ldf(xin + i));
   stf(err_in + i, s);
 }
 
@@ -191,7 +197,7 @@ __global__ void pool_forward_vec_k(const T* __restrict__ in, T* __restrict__ out
 template <typename T>
 __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __restrict__ offs,
                                     T* __restrict__ err_in, PoolGeom g, int is_avg,
-                                    const T* __restrict__ yact) {
+                                    const T* __restrict__ yact, const T* __restrict__ xin) {
   pdl_entry();
   const int C8 = g.C >> 3;
   const int total = g.N * g.H * g.W * C8;
@@ -231,6 +237,12 @@ __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __
         for (int j = 0; j < 8; ++j) if (of[j] == self + j) s[j] += e[j];
       }
     }
+  }
+  if (g.in_act) {
+    float xv[8];
+    ld8(xin + (size_t)i * 8, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] *= act_deriv(g.in_act, 0.f, xv[j]);
   }
   st8(err_in + (size_t)i * 8, s);
 }
@@ -314,23 +326,24 @@ void launch_pool_forward(const void* in, void* out, int* offs, int N, int H, int
 }
 void launch_pool_backward(const void* err_out, const int* offs, void* err_in, int N, int H, int W, int C,
                           int OH, int OW, int KY, int KX, int SY, int SX, int is_avg, bool bf16,
-                          const void* yact, int act, cudaStream_t st) {
-  PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX, yact ? act : 0};
+                          const void* yact, int act, const void* xin, int in_act, cudaStream_t st) {
+  PoolGeom g{N, H, W, C, OH, OW, KY, KX, SY, SX, yact ? act : 0, xin ? in_act : 0};
   long long total = (long long)N * H * W * C;
+  typedef __nv_bfloat16 bf;
   if (C % 8 == 0 && total < (1LL << 31) &&
-      (((uintptr_t)err_out | (uintptr_t)err_in | (uintptr_t)offs | (uintptr_t)yact) & 15) == 0) {
+      (((uintptr_t)err_out | (uintptr_t)err_in | (uintptr_t)offs | (uintptr_t)yact | (uintptr_t)xin) & 15) == 0) {
     int gridv = cdiv(total / 8, 256);
-    if (bf16) launch_k(pool_backward_vec_k<__nv_bfloat16>, gridv, 256, 0, st, (const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, is_avg, (const __nv_bfloat16*)yact);
-    else launch_k(pool_backward_vec_k<float>, gridv, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, is_avg, (const float*)yact);
+    if (bf16) launch_k(pool_backward_vec_k<bf>, gridv, 256, 0, st, (const bf*)err_out, offs, (bf*)err_in, g, is_avg, (const bf*)yact, (const bf*)xin);
+    else launch_k(pool_backward_vec_k<float>, gridv, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, is_avg, (const float*)yact, (const float*)xin);
     return;
   }
   int grid = cdiv(total, 256);
   if (is_avg) {
-    if (bf16) launch_k(pool_backward_avg_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)err_out, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
-    else launch_k(pool_backward_avg_k<float>, grid, 256, 0, st, (const float*)err_out, (float*)err_in, g, (const float*)yact);
+    if (bf16) launch_k(pool_backward_avg_k<bf>, grid, 256, 0, st, (const bf*)err_out, (bf*)err_in, g, (const bf*)yact, (const bf*)xin);
+    else launch_k(pool_backward_avg_k<float>, grid, 256, 0, st, (const float*)err_out, (float*)err_in, g, (const float*)yact, (const float*)xin);
   } else {
-    if (bf16) launch_k(pool_backward_max_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)err_out, offs, (__nv_bfloat16*)err_in, g, (const __nv_bfloat16*)yact);
-    else launch_k(pool_backward_max_k<float>, grid, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, (const float*)yact);
+    if (bf16) launch_k(pool_backward_max_k<bf>, grid, 256, 0, st, (const bf*)err_out, offs, (bf*)err_in, g, (const bf*)yact, (const bf*)xin);
+    else launch_k(pool_backward_max_k<float>, grid, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, (const float*)yact, (const float*)xin);
   }
 }
 

@@ -14,7 +14,13 @@ pure HBM round trips, so before the units are initialised this pass folds every
             activation's GD unit aliases ``err_input`` to ``err_output``.
 
 All four functions have derivatives expressible through the output y alone, so aliasing
-input and output loses nothing. The unit graph, the layer DSL, snapshots and
+input and output loses nothing.
+
+A second pass (:func:`fuse_backward_derivatives`) moves the ``err_output *= f'(y)`` multiply of a
+convolutional layer into the backward kernel of the pooling layer above it (which writes that
+very ``err_output`` and has y as its own input), and lets the tcgen05 weight-gradient kernel
+deliver the bias gradient as an extra product row: the conv layer's separate pass over
+``err_output`` (one launch per layer per step in the reference, gd_conv.py:645-750) disappears. The unit graph, the layer DSL, snapshots and
 ``package_export`` are unchanged — only launches disappear. ``root.common.engine.
 fuse_activations = False`` switches the pass off.
 """
@@ -39,6 +45,8 @@ def _producer_ok(p):
 
 def clear(workflow):
     for u in list(workflow.forwards) + [g for g in workflow.gds if g is not None]:
+        u.__dict__.pop("in_deriv_act_", None)
+        u.__dict__.pop("deriv_upstream_", None)
         if "fused_act_" in u.__dict__:
             u.__dict__["fused_act_"] = 0
         if getattr(u, "fused_into_", None) is not None:
@@ -73,5 +81,43 @@ def fuse_activations(workflow, device):
             ga.fused_into_ = gp
         p.__dict__["fused_act_"] = a.CODE
         a.fused_into_ = p
+        n += 1
+    return n
+
+
+def fuse_backward_derivatives(workflow, device):
+    """conv (activation f, own or fused) → [fused activation unit] → pooling: the pooling GD
+    multiplies its err_input by f'(its input); the conv GD skips its derivative pass.
+    Must run after :func:`fuse_activations`. Returns the number of conv layers relieved."""
+    if device is None or not device.is_cuda or \
+            not root.common.engine.get("fuse_activations", True):
+        return 0
+    from ..ops.gd_conv import GradientDescentConv
+    from ..ops.gd_pooling import GDPooling
+    fwds = list(workflow.forwards)
+    gds = [g for g in workflow.gds if g is not None]
+    gd_of = {id(g.forward_unit): g for g in gds if getattr(g, "forward_unit", None) is not None}
+    n = 0
+    for i, p in enumerate(fwds):
+        if not isinstance(p, Conv) or getattr(p, "force_numpy", False):
+            continue
+        gp = gd_of.get(id(p))
+        if not isinstance(gp, GradientDescentConv) or getattr(gp, "force_numpy", False):
+            continue
+        act = int(gp.__dict__.get("fused_act_", 0) or 0) or int(getattr(gp, "ACT", 0) or 0)
+        if act not in FUSABLE_CODES:
+            continue
+        j = i + 1
+        while j < len(fwds) and getattr(fwds[j], "fused_into_", None) is p:
+            j += 1                       # activation units folded into the conv
+        if j >= len(fwds):
+            continue
+        c = fwds[j]
+        gc = gd_of.get(id(c))
+        if not isinstance(gc, GDPooling) or getattr(gc, "force_numpy", False) or \
+                getattr(c, "force_numpy", False) or not gc.need_err_input:
+            continue
+        gc.__dict__["in_deriv_act_"] = act
+        gp.__dict__["deriv_upstream_"] = True
         n += 1
     return n

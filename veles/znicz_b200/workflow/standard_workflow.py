@@ -579,6 +579,7 @@ class StandardWorkflow(StandardWorkflowBase):
             device = get_device(device)
         from . import fusion
         self.fused_activations_ = fusion.fuse_activations(self, device)
+        self.fused_derivatives_ = fusion.fuse_backward_derivatives(self, device)
         res = super().initialize(device=device, **kwargs)
         dev = self.device
         if dev is not None and not dev.is_cuda:
