@@ -97,7 +97,7 @@ def build_workflow(streaming, compute, graphs, n_train, model="cifar_caffe"):
     from veles.znicz_b200.core.config import root
     root.common.engine.compute_type = compute
     root.common.disable.snapshotting = True
-    batch = MODELS[model][0]
+    batch = _batch_of(model)
     common = dict(
         use_graphs=graphs,
         decision_config={"max_epochs": 1000000000, "fail_iterations": 1000000},
@@ -123,6 +123,12 @@ def build_workflow(streaming, compute, graphs, n_train, model="cifar_caffe"):
                        "on_device": not streaming, "shuffle_limit": 2000000000}, **common)
 
 
+def _batch_of(model):
+    # ZNICZ_BENCH_BATCH: diagnostic only (host- vs device-bound check); the reported config
+    # carries whatever batch actually ran
+    return int(os.environ.get("ZNICZ_BENCH_BATCH", MODELS[model][0]))
+
+
 def run_arm(args, streaming):
     import torch
     import torch.distributed as dist
@@ -138,6 +144,8 @@ def run_arm(args, streaming):
         wf.step_hooks_.append(reader)
     wf.run(iterations=args.warmup)
     torch.cuda.synchronize()
+    if os.environ.get("ZNICZ_BENCH_STATS"):
+        wf.real_loader.__dict__["prof_"] = [0.0, 0.0, 0.0, 0]
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -173,6 +181,10 @@ def run_arm(args, streaming):
         sys.stderr.write("host enqueue %.4f ms/step, device %.4f ms/step, drain after enqueue "
                          "%.3f ms\n" % ((t_enq - t0) * 1e3 / args.steps, ms_dev / args.steps,
                                         (t1 - t_enq) * 1e3))
+        pr = wf.real_loader.__dict__.get("prof_")
+        if pr and pr[3]:
+            sys.stderr.write("loader per step: slot wait %.1f us, host assembly %.1f us, "
+                             "H2D enqueue %.1f us\n" % tuple(1e6 * v / pr[3] for v in pr[:3]))
         rows = sorted(((u.total_run_time, u._run_calls, u.name) for u in wf.units), reverse=True)
         for t_, c_, n_ in rows[:25]:
             sys.stderr.write("  %-28s calls %6d  host %9.3f ms  (%.1f us/call)\n" % (
@@ -226,7 +238,7 @@ def main():
     if rank != 0:
         return 0
     n = max(world, 1)
-    batch = MODELS[args.model][0]
+    batch = _batch_of(args.model)
     images = args.steps * batch * n
     value = images / (main_res["ms_dev"] / 1e3)
     out = {

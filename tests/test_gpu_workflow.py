@@ -191,3 +191,37 @@ def test_imagenet_models_step_on_gpu(family):
         assert numpy.isfinite(out).all() and abs(float(out[0].sum()) - 1.0) < 1e-2
     finally:
         root.common.engine.compute_type = "fp32"
+
+
+@pytest.mark.parametrize("compute", ["fp32", "bf16"])
+@pytest.mark.parametrize("on_device", [False, True])
+def test_loader_minibatch_on_device_matches_host(compute, on_device):
+    """Streaming (packed pinned slot filled by the native gather, one H2D per step) and
+    device-resident (index upload + gather kernel) loaders must both deliver
+    original_data[indices] / labels[indices] on the device, padded tail zero / -1."""
+    from veles.znicz_b200.core.workflow import DummyWorkflow
+    from veles.znicz_b200.loader.synthetic import SyntheticImageLoader
+    root.common.engine.compute_type = compute
+    try:
+        wf = DummyWorkflow()
+        ld = SyntheticImageLoader(wf, minibatch_size=32, shape=(8, 8, 3), n_classes=5,
+                                  n_train=80, n_valid=40, n_test=0, on_device=on_device)
+        ld.initialize(device="cuda")
+        if not on_device:
+            assert ld._packed_ is not None and ld.h2d_bytes_per_step < 2 * 32 * 192 * 4
+        for _ in range(7):              # 40 = 32 + 8 (short minibatch), then train 32 + 32 + 16
+            ld.run()
+            n = int(ld.minibatch_size)
+            idx = ld.minibatch_indices.mem[:n].copy()
+            ref = ld.original_data.mem[idx]
+            ld.minibatch_data.map_read()
+            got = ld.minibatch_data.mem
+            tol = 0 if compute == "fp32" else 1e-2
+            assert numpy.abs(got[:n] - ref).max() <= tol * max(1.0, numpy.abs(ref).max())
+            assert not got[n:].any()
+            ld.minibatch_labels.map_read()
+            lab = ld.minibatch_labels.mem
+            numpy.testing.assert_array_equal(lab[:n], ld._mapped_original_labels.mem[idx])
+            assert (lab[n:] == -1).all()
+    finally:
+        root.common.engine.compute_type = "fp32"

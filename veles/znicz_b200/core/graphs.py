@@ -51,9 +51,22 @@ def _launch_counters():
 
 
 class GraphSegment(object):
-    def __init__(self, name, units, key_fn=None, warmup=2, enabled=True):
+    def __init__(self, name, units, key_fn=None, warmup=2, enabled=True, prelude=None):
         self.name = name
         self.units = list(units)
+        # device-only callables run at the head of the segment (captured with it), e.g. the
+        # loader's minibatch gather kernel: one eager launch and one graph boundary less per step
+        self.prelude = list(prelude or [])
+        # Train-step fusion: ``tail`` is a later segment (the backward chain) that may be run
+        # together with this one as ONE graph when ``fuse_fn()`` says nothing on the host can
+        # intervene between the two this iteration (steady-state TRAIN minibatch, not the last of
+        # its epoch): one graph launch per training step instead of two.
+        self.tail = None
+        self.fuse_fn = None
+        self.head = None             # set on the tail by fuse_with()
+        self.iteration = 0           # executions of this segment (stamps the tail's skip mark)
+        self._skip_iter = -1
+        self.fused_replays = 0
         self.key_fn = key_fn or (lambda: 0)
         self.warmup = warmup
         self.enabled = enabled
@@ -75,17 +88,36 @@ class GraphSegment(object):
             self.execute()
         # other members were executed as part of the segment this iteration
 
-    def _eager(self):
-        for u in self.units:
+    def fuse_with(self, tail, fuse_fn):
+        self.tail, self.fuse_fn = tail, fuse_fn
+        tail.head = self
+
+    def _eager(self, units=None):
+        for fn in self.prelude:
+            fn()
+        for u in (units or self.units):
             u._backend_run_()
         self.eager_runs += 1
 
     def execute(self):
         global _active_recorder
         import torch
-        for u in self.units:
-            u.cuda_prepare()
+        if self.head is not None and self._skip_iter == self.head.iteration:
+            self._skip_iter = -1     # already executed this iteration by the head segment
+            return
+        self.iteration += 1
+        units = self.units
         key = self.key_fn()
+        tail = self.tail
+        if tail is not None and tail.enabled and self.enabled and self.fuse_fn() and \
+                self._runs.get(key, 0) >= self.warmup and tail._runs.get(key, 0) >= tail.warmup:
+            # both halves are past their eager warm-up: run them as one graph
+            units = self.units + tail.units
+            key = ("fused", key)
+            tail._skip_iter = self.iteration
+            self.fused_replays += 1
+        for u in units:
+            u.cuda_prepare()
         cap = self._graphs.get(key)
         if cap is not None:
             for a in cap.reads:
@@ -99,7 +131,8 @@ class GraphSegment(object):
             return
         n = self._runs.get(key, 0)
         self._runs[key] = n + 1
-        if not self.enabled or n < self.warmup:
+        fused = units is not self.units
+        if not fused and (not self.enabled or n < self.warmup):
             self._eager()
             return
         # capture
@@ -112,7 +145,9 @@ class GraphSegment(object):
         try:
             # make every input current *before* capture (H2D copies are not captured)
             with torch.cuda.graph(g):
-                for u in self.units:
+                for fn in self.prelude:
+                    fn()
+                for u in units:
                     u._backend_run_()
         finally:
             _active_recorder = None

@@ -90,7 +90,7 @@ def build(force=False, verbose=True):
     abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
     ext_obj = os.path.join(BUILD, "ext.o")
     objs.append(ext_obj)
-    jobs.append(["g++", "-O2", "-std=c++17", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=%d" % abi,
+    jobs.append(["g++", "-O3", "-std=c++17", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=%d" % abi,
                  "-DTORCH_EXTENSION_NAME=_znicz_b200_C", "-DTORCH_API_INCLUDE_EXTENSION_H",
                  "-w"] + inc + ["-c", os.path.join(CSRC, "ext.cpp"), "-o", ext_obj])
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

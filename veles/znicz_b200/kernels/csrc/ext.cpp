@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <vector>
+#include <cstring>
+#include <ATen/Parallel.h>
 
 namespace zn {
 struct ConvGeom { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
@@ -578,6 +580,54 @@ void som_update(Tensor x, Tensor w, Tensor coords, Tensor argmins, double sigma,
   kcheck();
 }
 
+// ---------------------------------------------------------------------------- host-side loader
+// Streaming loaders (dataset in host memory): assemble the minibatch straight into the pinned
+// staging buffer the H2D copy reads - rows gathered by index on the intra-op thread pool and,
+// when the device-side minibatch is bf16, converted on the fly (round-to-nearest-even), so only
+// half the bytes cross PCIe and no cast kernel runs. Replaces numpy.take + a device cast
+// (/root/reference/loader: fill_minibatch is a python loop over samples there).
+static inline uint16_t f32_to_bf16_rne(uint32_t u) {      // branch-free: vectorises
+  const uint32_t rounded = (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+  const uint32_t is_nan = ((u & 0x7fffffffu) > 0x7f800000u) ? 0xffffffffu : 0u;
+  return (uint16_t)((rounded & ~is_nan) | (((u >> 16) | 0x40u) & is_nan));
+}
+// one row; cloned per ISA and dispatched once at load time (the build has no -march flag)
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
+void convert_row_bf16(const uint32_t* __restrict__ iu, uint16_t* __restrict__ o16, int64_t row) {
+#pragma GCC ivdep
+  for (int64_t j = 0; j < row; ++j) o16[j] = f32_to_bf16_rne(iu[j]);
+}
+void host_gather_rows(Tensor src, Tensor idx, Tensor dst, int64_t n) {
+  TORCH_CHECK(!src.is_cuda() && !idx.is_cuda() && !dst.is_cuda(), "host tensors expected");
+  TORCH_CHECK(src.is_contiguous() && dst.is_contiguous() && idx.is_contiguous());
+  TORCH_CHECK(src.scalar_type() == torch::kFloat32 && idx.scalar_type() == torch::kInt32);
+  const bool to_bf16 = dst.scalar_type() == torch::kBFloat16;
+  TORCH_CHECK(to_bf16 || dst.scalar_type() == torch::kFloat32, "dst must be fp32 or bf16");
+  const int64_t rows = src.size(0), row = src.numel() / std::max<int64_t>(rows, 1);
+  const int64_t cap = dst.size(0);
+  TORCH_CHECK(n <= cap && n <= idx.numel() && dst.numel() == cap * row, "shape mismatch");
+  const float* sp = src.data_ptr<float>();
+  const int* ip = idx.data_ptr<int>();
+  uint8_t* dp = reinterpret_cast<uint8_t*>(dst.data_ptr());
+  const size_t esz = to_bf16 ? 2 : 4;
+  // at most 8 workers: the fork/join of a wide pool (128 hardware threads on the benchmark host)
+  // costs more than the 0.6-1.2 MB copy itself
+  const int64_t grain = std::max<int64_t>(1, (cap + 7) / 8);
+  at::parallel_for(0, cap, grain, [&](int64_t b, int64_t e) {
+    for (int64_t r = b; r < e; ++r) {
+      uint8_t* out = dp + (size_t)r * row * esz;
+      if (r >= n) { memset(out, 0, (size_t)row * esz); continue; }
+      int64_t k = ip[r];
+      k = k < 0 ? 0 : (k >= rows ? rows - 1 : k);
+      const float* in = sp + (size_t)k * row;
+      if (!to_bf16) { memcpy(out, in, (size_t)row * 4); continue; }
+      convert_row_bf16(reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint16_t*>(out), row);
+    }
+  });
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("som_winners", &som_winners); m.def("som_update", &som_update);
   m.doc() = "znicz_b200 sm_100a kernels";
@@ -587,6 +637,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
   m.def("gather_minibatch", &gather_minibatch);
+  m.def("host_gather_rows", &host_gather_rows);
   m.def("mask_mul", &mask_mul); m.def("pad_channels", &pad_channels); m.def("cast_copy", &cast_copy); m.def("scatter_offsets", &scatter_offsets);
   m.def("pool_forward", &pool_forward); m.def("pool_backward", &pool_backward);
   m.def("lrn_forward", &lrn_forward); m.def("lrn_backward", &lrn_backward);

@@ -183,7 +183,7 @@ __device__ __forceinline__ void gather_taps(uint4 (&nv)[8], const int* ttab, con
 // zero-filled by the copy itself. No registers are staged and the thread never waits for global
 // memory: the stage's full-barrier gets this thread's arrival when its copies have landed, so
 // up to STAGES k-blocks of gathers are in flight per thread.
-template <int KIND, int TPK>
+template <int KIND, int TPK, bool ONES = false>
 __device__ __forceinline__ void gather_taps_async(uint32_t row_base, int sw, const int* ttab,
                                                   const ConvGeomU& g, const PixCtx& c, int k0) {
   constexpr int CPT = 8 / TPK;
@@ -206,7 +206,9 @@ __device__ __forceinline__ void gather_taps_async(uint32_t row_base, int sw, con
       ok = ok && (unsigned)ty < (unsigned)g.OH && (unsigned)tx < (unsigned)g.OW;
       off = (ty * g.OW + tx) * g.F;
     }
-    const bool one = KIND == G_IM2COL && g.ones != nullptr && c.valid && tap == g.ntaps && c0 == 0;
+    // ONES: this 64-wide block holds reduction-weight index Kw (see ConvGeomU::ones) - only the
+    // wgrad kernel instantiates it, and only for the one block of the last M tile that needs it
+    const bool one = ONES && c.valid && tap == g.ntaps && c0 == 0;
     const __nv_bfloat16* ptr = one ? g.ones : c.base + (ok ? off + c0 : 0);
     const uint32_t nbytes = ok ? 16u : 0u;
 #pragma unroll
@@ -217,14 +219,14 @@ __device__ __forceinline__ void gather_taps_async(uint32_t row_base, int sw, con
     }
   }
 }
-template <int KIND>
+template <int KIND, bool ONES = false>
 __device__ __forceinline__ void gather_row_async(uint32_t row_base, int sw, const int* ktab,
                                                  const ConvGeomU& g, const PixCtx& c, int k0) {
   switch (g.tpk) {
-    case 1: gather_taps_async<KIND, 1>(row_base, sw, ktab, g, c, k0); break;
-    case 2: gather_taps_async<KIND, 2>(row_base, sw, ktab, g, c, k0); break;
-    case 4: gather_taps_async<KIND, 4>(row_base, sw, ktab, g, c, k0); break;
-    default: gather_taps_async<KIND, 8>(row_base, sw, ktab, g, c, k0); break;
+    case 1: gather_taps_async<KIND, 1, ONES>(row_base, sw, ktab, g, c, k0); break;
+    case 2: gather_taps_async<KIND, 2, ONES>(row_base, sw, ktab, g, c, k0); break;
+    case 4: gather_taps_async<KIND, 4, ONES>(row_base, sw, ktab, g, c, k0); break;
+    default: gather_taps_async<KIND, 8, ONES>(row_base, sw, ktab, g, c, k0); break;
   }
 }
 
@@ -449,6 +451,9 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // A_GATHER_MN (conv wgrad): tile = [64 reduction rows (pixels)][128 m (kidx)];
         // thread -> reduction row kr = t % 64, 64-wide m block = t / 64 (8 chunks of 8 kidx)
         const int kr = t & 63, mblk = t >> 6;
+        // only the 64-wide m block that contains index Kw carries the bias "ones" row
+        const int kk0 = m0 + mblk * 64;
+        const bool has_one = p.g.ones != nullptr && kk0 <= p.gK && p.gK < kk0 + 64;
         if (GVEC == 2) {
 #pragma unroll 1
           for (int i = 0; i < num_kb; ++i) {
@@ -458,7 +463,8 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const PixCtx ctx = decode_out_pixel(p.gsrc, p.g, pix, p.K);
             const uint32_t row_base =
                 smem_u32(tiles + (size_t)s * STAGE_BYTES) + mblk * 8192 + kr * 128;
-            gather_row_async<G_IM2COL>(row_base, kr & 7, ktab, p.g, ctx, m0 + mblk * 64);
+            if (has_one) gather_row_async<G_IM2COL, true>(row_base, kr & 7, ktab, p.g, ctx, kk0);
+            else gather_row_async<G_IM2COL, false>(row_base, kr & 7, ktab, p.g, ctx, kk0);
             cp_async_mbar_arrive_noinc(&full_bar[s]);
           }
         } else {

@@ -209,9 +209,10 @@ __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __
   const int oy_lo = (y - g.KY + 1 <= 0) ? 0 : (y - g.KY + g.SY) / g.SY;
   const int ox_lo = (x - g.KX + 1 <= 0) ? 0 : (x - g.KX + g.SX) / g.SX;
   const int self = i * 8;     // flat element index of channel 0 of this group
-  float s[8];
+  float s[8], xv[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; xv[j] = 0.f; }
+  if (g.in_act) ld8(xin + (size_t)i * 8, xv);     // issued first: overlaps the window loads
   for (int oy = oy_lo; oy <= oy_hi; ++oy) {
     const int hy = min(oy * g.SY + g.KY, g.H) - oy * g.SY;
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
@@ -239,8 +240,6 @@ __global__ void pool_backward_vec_k(const T* __restrict__ err_out, const int* __
     }
   }
   if (g.in_act) {
-    float xv[8];
-    ld8(xin + (size_t)i * 8, xv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] *= act_deriv(g.in_act, 0.f, xv[j]);
   }

@@ -294,8 +294,14 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
     def run(self):
         if self.global_offset == 0 or self.global_offset >= self.total_samples:
             self.shuffle()  # epoch start: reshuffle the train part
+        prof = self.__dict__.get("prof_")      # ZNICZ_BENCH_STATS: where the host time goes
+        if prof is not None:
+            import time
+            t0 = time.perf_counter()
         if self.on_cuda:
             self._cuda_begin_step()
+        if prof is not None:
+            t1 = time.perf_counter()
         cls, start, count = self._advance()
         self.minibatch_class = cls
         self.minibatch_size = count
@@ -306,8 +312,16 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
             self.fill_minibatch()
         self.map_minibatch_labels()
         self._update_flags()
+        if prof is not None:
+            t2 = time.perf_counter()
         if self.on_cuda:
             self._cuda_serve()
+        if prof is not None:
+            t3 = time.perf_counter()
+            prof[0] += t1 - t0     # wait for the pinned slot (= how far the device lags)
+            prof[1] += t2 - t1     # bookkeeping + minibatch assembly on the host
+            prof[2] += t3 - t2     # H2D enqueue (+ gather launch)
+            prof[3] += 1
 
     def _update_flags(self):
         last_mb = self.global_offset == self.class_end_offsets[self.minibatch_class]

@@ -121,6 +121,8 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         self.original_data.reset(data)
 
     def fill_minibatch(self):
+        if self.__dict__.get("_packed_") is not None:
+            return self._fill_packed()
         n = self.minibatch_size
         idx = self.minibatch_indices.mem[:n]
         self.minibatch_data.map_invalidate()
@@ -159,9 +161,90 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
             self.h2d_bytes_per_step = n * 4
             row = self.original_data.size // self.original_data.shape[0]
             self._fused_gather_ = (row % 8 == 0)
+        else:
+            self._setup_packed()
+
+    # -- streaming from host memory: one packed pinned buffer, one H2D copy per step ----------
+    def _setup_packed(self):
+        """Header, labels and the minibatch share ONE device buffer fed by ONE asynchronous copy
+        from a pinned slot; the slot is filled by the native gather (rows by index on the
+        intra-op thread pool, converted to the device dtype on the fly), so a bf16 model moves
+        half the bytes and needs no cast kernel. The Arrays' device tensors become views."""
+        import torch
+        self.__dict__["_packed_"] = None
+        ext = getattr(self.device, "ext", None)
+        md, ml = self.minibatch_data, self.minibatch_labels
+        od = self.original_data.mem
+        if ext is None or not hasattr(ext, "host_gather_rows") or type(self).fill_minibatch \
+                is not FullBatchLoader.fill_minibatch or od.dtype != numpy.float32 or \
+                not od.flags["C_CONTIGUOUS"] or md.devmem is None or \
+                md.devmem.dtype not in (torch.float32, torch.bfloat16) or \
+                self.minibatch_indices.mem.dtype != numpy.int32:
+            return
+        labels = bool(self.has_labels and ml and ml.devmem is not None and
+                      ml.devmem.dtype == torch.int32)
+        if self.has_labels and not labels:
+            return
+        mb = self.max_minibatch_size
+        dt = md.devmem.dtype
+        esz = 2 if dt == torch.bfloat16 else 4
+        off_data = (16 + (4 * mb if labels else 0) + 255) // 256 * 256
+        total = off_data + md.size * esz
+        devp = torch.zeros(total, dtype=torch.uint8, device=self.device.torch_device)
+        pins = [torch.zeros(total, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+        def views(buf):
+            hdr = buf[:16].view(torch.int32)
+            lab = buf[16:16 + 4 * mb].view(torch.int32) if labels else None
+            data = buf[off_data:].view(dt).view(tuple(md.shape))
+            return hdr, lab, data
+        hdr_d, lab_d, data_d = views(devp)
+        md._devmem_ = data_d
+        if labels:
+            ml._devmem_ = lab_d.view(tuple(ml.shape))
+        self.header_dev_ = hdr_d
+        slots = []
+        for p in pins:
+            hdr, lab, data = views(p)
+            slots.append({"pin": p, "hdr": hdr.numpy(), "lab": lab.numpy() if labels else None,
+                          "data": data})
+        self._pinned_["bufs"] = {}
+        self.__dict__["_packed_"] = {
+            "dev": devp, "slots": slots, "labels": labels,
+            "src": torch.from_numpy(od),
+            "idx": torch.from_numpy(self.minibatch_indices.mem)}
+        self.h2d_bytes_per_step = total
+
+    def _fill_packed(self):
+        pk = self._packed_
+        sl = pk["slots"][self._pinned_["slot"]]
+        n = int(self.minibatch_size)
+        self.device.ext.host_gather_rows(pk["src"], pk["idx"], sl["data"], n)
+        if pk["labels"]:
+            lab = sl["lab"]
+            numpy.take(self._mapped_original_labels.mem, self.minibatch_indices.mem[:n],
+                       out=lab[:n], mode="clip")
+            lab[n:] = -1
+
+    def _serve_packed(self):
+        pk = self._packed_
+        pd = self._pinned_
+        slot = pd["slot"]
+        sl = pk["slots"][slot]
+        hn = sl["hdr"]
+        hn[0] = self.minibatch_size
+        hn[1] = self.minibatch_class
+        hn[2] = self.epoch_number
+        pk["dev"].copy_(sl["pin"], non_blocking=True)
+        pd["events"][slot].record()
+        self.minibatch_data.dev_written()
+        if pk["labels"]:
+            self.minibatch_labels.dev_written()
 
     def _cuda_serve(self):
         if not self.on_device:
+            if self.__dict__.get("_packed_") is not None:
+                return self._serve_packed()
             return super()._cuda_serve()
         pd = self._pinned_
         slot = pd["slot"]
@@ -173,8 +256,23 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         hn[4:4 + self.max_minibatch_size] = self.minibatch_indices.mem
         self._hdr_idx_dev_.copy_(pd["hdr_idx"][slot], non_blocking=True)
         pd["events"][slot].record()
+        if self.__dict__.get("gather_in_graph_"):
+            return          # the forward graph segment starts with the gather (graph_prelude)
+        self._device_gather()
+
+    def graph_prelude(self):
+        """Called by the workflow when it builds its forward CUDA-graph segment: hands the
+        device-side minibatch gather over to the segment (it only reads the header + index
+        buffer this loader uploads each step, so it can be captured)."""
+        if not (self.on_cuda and self.on_device and self.__dict__.get("_fused_gather_")):
+            return None
+        self.__dict__["gather_in_graph_"] = True
+        return self._device_gather
+
+    def _device_gather(self):
         ext = self.device.ext
         labels = self.has_labels
+        n = int(self.minibatch_size)
         if self._fused_gather_:
             # a first conv layer with C % 8 != 0 asks for a channel-padded copy
             # (``pad_request_`` on the Array, kernels/api.py::conv_forward): produce it here

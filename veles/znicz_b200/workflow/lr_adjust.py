@@ -149,15 +149,25 @@ class LearningRateAdjust(Unit):
                 self.base_lr[i] = gd.learning_rate
                 self.base_lr_bias[i] = gd.learning_rate_bias
             self.already_get_base_lr = True
+        # layers that share a base rate share the schedule value: evaluate each distinct
+        # (policy, base) once per minibatch instead of once per layer (this unit runs on the
+        # host between two graph launches every step)
+        memo = {}
+        wname, bname = self.lr_policy_name, self.bias_lr_policy_name
         for i, gd in enumerate(self._gd_units):
-            lr = self.adjust_learning_rate((i, "w"), self.base_lr[i],
-                                           self.lr_policy_name, self.lr_parameters)
-            if lr is not None:
+            if wname is not None:
+                base = self.base_lr[i]
+                lr = memo.get((0, base))
+                if lr is None:
+                    lr = memo[(0, base)] = self.adjust_learning_rate(
+                        ("w", base), base, wname, self.lr_parameters)
                 gd.learning_rate = lr
-            lrb = self.adjust_learning_rate((i, "b"), self.base_lr_bias[i],
-                                            self.bias_lr_policy_name,
-                                            self.bias_lr_parameters)
-            if lrb is not None:
+            if bname is not None:
+                base = self.base_lr_bias[i]
+                lrb = memo.get((1, base))
+                if lrb is None:
+                    lrb = memo[(1, base)] = self.adjust_learning_rate(
+                        ("b", base), base, bname, self.bias_lr_parameters)
                 gd.learning_rate_bias = lrb
         self._minibatches_count += 1
 

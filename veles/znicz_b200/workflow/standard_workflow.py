@@ -607,12 +607,28 @@ class StandardWorkflow(StandardWorkflowBase):
         self.segments_ = []
         fwd_units = [u for u in self.forwards] + [self.evaluator]
         if all(getattr(u, "on_cuda", False) for u in fwd_units):
+            ld = getattr(self, "real_loader", None) or self.loader
+            hook = getattr(ld, "graph_prelude", None)
+            pre = hook() if callable(hook) else None
             self.segments_.append(GraphSegment(
-                "forward", fwd_units, key_fn=self._segment_key))
+                "forward", fwd_units, key_fn=self._segment_key, prelude=[pre] if pre else None))
         gd_units = [u for u in reversed(self.gds) if u is not None]
         if gd_units and all(getattr(u, "on_cuda", False) for u in gd_units):
             self.segments_.append(GraphSegment("backward", gd_units,
                                                key_fn=self._segment_key))
+            if len(self.segments_) == 2 and root.common.engine.get("fuse_train_step", True):
+                self.segments_[0].fuse_with(self.segments_[1], self._train_step_fusable)
+
+    def _train_step_fusable(self):
+        """Forward and backward may run as ONE graph on a steady-state TRAIN minibatch: nothing
+        that executes on the host between them (decision, snapshotter, rollback, plotters) acts
+        before the last minibatch of the epoch, and the GD gates are open."""
+        ld, dec = self.loader, self.decision
+        if ld.minibatch_class != 2 or bool(ld.last_minibatch) or bool(dec.complete) or \
+                bool(getattr(dec, "gd_skip", False)):
+            return False
+        g0 = self.segments_[1].units[0]
+        return not bool(g0.gate_skip) and not bool(g0.gate_block)
 
     def _segment_key(self):
         return int(self.loader.minibatch_class == 2)
