@@ -131,6 +131,12 @@ def _batch_of(model):
 
 def run_arm(args, streaming):
     import torch
+    if os.environ.get("ZNICZ_LOADER_PULL") == "0":          # diagnostic
+        from veles.znicz_b200.core.config import root
+        root.common.engine.loader_pull = False
+    if os.environ.get("ZNICZ_LOADER_PREFETCH") == "0":      # diagnostic
+        from veles.znicz_b200.core.config import root
+        root.common.engine.loader_prefetch = False
     import torch.distributed as dist
     from veles.znicz_b200.kernels import api
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,6 +191,9 @@ def run_arm(args, streaming):
         if pr and pr[3]:
             sys.stderr.write("loader per step: slot wait %.1f us, host assembly %.1f us, "
                              "H2D enqueue %.1f us\n" % tuple(1e6 * v / pr[3] for v in pr[:3]))
+        pk = wf.real_loader.__dict__.get("_packed_")
+        if pk:
+            sys.stderr.write("loader prefetch hits: %d\n" % pk.get("hits", 0))
         rows = sorted(((u.total_run_time, u._run_calls, u.name) for u in wf.units), reverse=True)
         for t_, c_, n_ in rows[:25]:
             sys.stderr.write("  %-28s calls %6d  host %9.3f ms  (%.1f us/call)\n" % (

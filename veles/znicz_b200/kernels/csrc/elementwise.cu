@@ -362,6 +362,35 @@ void launch_gather_rows(const void* src, bool src_bf16, const int* idx, void* ds
   else if (src_bf16 && dst_bf16) launch_k(gather_rows_k<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, count, max_rows, row);
   else launch_k(gather_rows_k<__nv_bfloat16, float>, g, 256, 0, st, (const __nv_bfloat16*)src, idx, (float*)dst, count, max_rows, row);
 }
+// Host -> device "pull": the SMs read a pinned (mapped) host buffer directly over PCIe and write
+// device memory. Used instead of cudaMemcpyAsync for the per-step loader uploads: on this platform
+// every switch between the copy engine and compute work in one stream costs ~100 us (measured,
+// profiles/host_vs_device_r1.md), a kernel reading host memory costs one PCIe round trip.
+// ld.global.cv: never serve a slot the host has rewritten since from a cached line.
+__global__ void pull_from_host_k(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16,
+                                 const unsigned char* __restrict__ src_b, unsigned char* __restrict__ dst_b,
+                                 int tail) {
+  pdl_entry();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+    dst[i] = __ldcv(src + i);
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_b[threadIdx.x] = __ldcv(src_b + threadIdx.x);
+}
+void launch_pull_from_host(const void* src_dev_alias, void* dst, long long nbytes, cudaStream_t st) {
+  const long long n16 = nbytes / 16;
+  const int tail = (int)(nbytes - n16 * 16);
+  long long blocks = (n16 + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) blocks = 1;
+  launch_k(pull_from_host_k, (int)blocks, 256, 0, st, (const uint4*)src_dev_alias, (uint4*)dst, n16,
+           (const unsigned char*)src_dev_alias + n16 * 16, (unsigned char*)dst + n16 * 16, tail);
+}
+
+void launch_pull_from_host_bytes(const void* src, void* dst, int nbytes, cudaStream_t st) {
+  launch_k(pull_from_host_k, 1, 256, 0, st, (const uint4*)nullptr, (uint4*)nullptr, 0LL,
+           (const unsigned char*)src, (unsigned char*)dst, nbytes);
+}
+
 void launch_gather_minibatch(const void* src, bool src_bf16, const int* labels_src, const int* hdr,
                              void* dst, bool dst_bf16, int* labels_dst, int max_rows, long long row,
                              void* dst_pad, int C, int CP, cudaStream_t st) {

@@ -5,7 +5,7 @@
 #include <cuda_bf16.h>
 #include <vector>
 #include <cstring>
-#include <ATen/Parallel.h>
+#include "host_loader.h"
 
 namespace zn {
 struct ConvGeom { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
@@ -26,6 +26,8 @@ void launch_pad_channels(const void*, void*, int, int, int, bool, cudaStream_t);
 void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
 void launch_scatter_offsets(const void*, const int*, void*, long long, bool, cudaStream_t);
 void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int, const int*, bool, int, cudaStream_t);
+void launch_pull_from_host(const void*, void*, long long, cudaStream_t);
+void launch_pull_from_host_bytes(const void*, void*, int, cudaStream_t);
 void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, const void*, int, const void*, int, cudaStream_t);
 void launch_lrn_forward(const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
 void launch_lrn_backward(const void*, const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
@@ -183,6 +185,38 @@ void gather_minibatch(Tensor src, c10::optional<Tensor> labels_src, Tensor hdr, 
   int* ld = (labels_dst.has_value() && labels_dst->defined()) ? labels_dst->data_ptr<int>() : nullptr;
   zn::launch_gather_minibatch(src.data_ptr(), is_bf16(src), ls, hdr.data_ptr<int>(), dst.data_ptr(),
                               is_bf16(dst), ld, (int)dst.size(0), row, pad, (int)C, 8, cur());
+  kcheck();
+}
+// dst (device) <- src (pinned host tensor), by a kernel that reads the host memory (see
+// launch_pull_from_host). Both 16-byte aligned; sizes in bytes must match.
+void pull_from_host(Tensor src, Tensor dst) {
+  TORCH_CHECK(!src.is_cuda() && src.is_pinned() && src.is_contiguous(), "src must be pinned host memory");
+  TORCH_CHECK(dst.is_cuda() && dst.is_contiguous(), "dst must be a device tensor");
+  const long long nbytes = (long long)src.numel() * src.element_size();
+  TORCH_CHECK(nbytes == (long long)dst.numel() * dst.element_size(), "size mismatch");
+  void* alias = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&alias, src.data_ptr(), 0);
+  TORCH_CHECK(e == cudaSuccess, "cudaHostGetDevicePointer: ", cudaGetErrorString(e));
+  TORCH_CHECK(((uintptr_t)alias & 15) == 0 && ((uintptr_t)dst.data_ptr() & 15) == 0, "16-byte alignment");
+  zn::launch_pull_from_host(alias, dst.data_ptr(), nbytes, cur());
+  kcheck();
+}
+// dst (pinned host tensor) <- src (device): the same kernel storing straight into mapped host
+// memory (per-step result read-back without a copy-engine operation in the stream).
+void push_to_host(Tensor src, Tensor dst) {
+  TORCH_CHECK(!dst.is_cuda() && dst.is_pinned() && dst.is_contiguous(), "dst must be pinned host memory");
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous(), "src must be a device tensor");
+  const long long nbytes = (long long)src.numel() * src.element_size();
+  TORCH_CHECK(nbytes == (long long)dst.numel() * dst.element_size(), "size mismatch");
+  void* alias = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&alias, dst.data_ptr(), 0);
+  TORCH_CHECK(e == cudaSuccess, "cudaHostGetDevicePointer: ", cudaGetErrorString(e));
+  if ((((uintptr_t)alias | (uintptr_t)src.data_ptr()) & 15) == 0) {
+    zn::launch_pull_from_host(src.data_ptr(), alias, nbytes, cur());
+  } else {      // unaligned (tiny) payloads: byte tail path only
+    TORCH_CHECK(nbytes <= 256, "unaligned push_to_host is limited to 256 bytes");
+    zn::launch_pull_from_host_bytes(src.data_ptr(), alias, (int)nbytes, cur());
+  }
   kcheck();
 }
 void pad_channels(Tensor x, Tensor y, int64_t C, int64_t CP) {
@@ -581,52 +615,32 @@ void som_update(Tensor x, Tensor w, Tensor coords, Tensor argmins, double sigma,
 }
 
 // ---------------------------------------------------------------------------- host-side loader
-// Streaming loaders (dataset in host memory): assemble the minibatch straight into the pinned
-// staging buffer the H2D copy reads - rows gathered by index on the intra-op thread pool and,
-// when the device-side minibatch is bf16, converted on the fly (round-to-nearest-even), so only
-// half the bytes cross PCIe and no cast kernel runs. Replaces numpy.take + a device cast
-// (/root/reference/loader: fill_minibatch is a python loop over samples there).
-static inline uint16_t f32_to_bf16_rne(uint32_t u) {      // branch-free: vectorises
-  const uint32_t rounded = (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
-  const uint32_t is_nan = ((u & 0x7fffffffu) > 0x7f800000u) ? 0xffffffffu : 0u;
-  return (uint16_t)((rounded & ~is_nan) | (((u >> 16) | 0x40u) & is_nan));
-}
-// one row; cloned per ISA and dispatched once at load time (the build has no -march flag)
-#if defined(__x86_64__) && defined(__GNUC__)
-__attribute__((target_clones("avx512f", "avx2", "default")))
-#endif
-void convert_row_bf16(const uint32_t* __restrict__ iu, uint16_t* __restrict__ o16, int64_t row) {
-#pragma GCC ivdep
-  for (int64_t j = 0; j < row; ++j) o16[j] = f32_to_bf16_rne(iu[j]);
-}
-void host_gather_rows(Tensor src, Tensor idx, Tensor dst, int64_t n) {
+// (host_loader.h) Streaming loaders: the minibatch is assembled straight into the pinned staging
+// slot the H2D copy reads - converted to bf16 on the fly when the device-side minibatch is bf16,
+// so only half the bytes cross PCIe and no cast kernel runs - synchronously or one step ahead on
+// the prefetch pool.
+static znhost::GatherJob make_gather_job(const Tensor& src, const Tensor& idx, const Tensor& dst, int64_t n) {
   TORCH_CHECK(!src.is_cuda() && !idx.is_cuda() && !dst.is_cuda(), "host tensors expected");
   TORCH_CHECK(src.is_contiguous() && dst.is_contiguous() && idx.is_contiguous());
   TORCH_CHECK(src.scalar_type() == torch::kFloat32 && idx.scalar_type() == torch::kInt32);
   const bool to_bf16 = dst.scalar_type() == torch::kBFloat16;
   TORCH_CHECK(to_bf16 || dst.scalar_type() == torch::kFloat32, "dst must be fp32 or bf16");
-  const int64_t rows = src.size(0), row = src.numel() / std::max<int64_t>(rows, 1);
-  const int64_t cap = dst.size(0);
-  TORCH_CHECK(n <= cap && n <= idx.numel() && dst.numel() == cap * row, "shape mismatch");
-  const float* sp = src.data_ptr<float>();
-  const int* ip = idx.data_ptr<int>();
-  uint8_t* dp = reinterpret_cast<uint8_t*>(dst.data_ptr());
-  const size_t esz = to_bf16 ? 2 : 4;
-  // at most 8 workers: the fork/join of a wide pool (128 hardware threads on the benchmark host)
-  // costs more than the 0.6-1.2 MB copy itself
-  const int64_t grain = std::max<int64_t>(1, (cap + 7) / 8);
-  at::parallel_for(0, cap, grain, [&](int64_t b, int64_t e) {
-    for (int64_t r = b; r < e; ++r) {
-      uint8_t* out = dp + (size_t)r * row * esz;
-      if (r >= n) { memset(out, 0, (size_t)row * esz); continue; }
-      int64_t k = ip[r];
-      k = k < 0 ? 0 : (k >= rows ? rows - 1 : k);
-      const float* in = sp + (size_t)k * row;
-      if (!to_bf16) { memcpy(out, in, (size_t)row * 4); continue; }
-      convert_row_bf16(reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint16_t*>(out), row);
-    }
-  });
+  znhost::GatherJob j;
+  j.rows = src.size(0); j.row = src.numel() / std::max<int64_t>(j.rows, 1);
+  j.cap = dst.size(0); j.n = n;
+  TORCH_CHECK(n >= 0 && n <= j.cap && n <= idx.numel() && dst.numel() == j.cap * j.row, "shape mismatch");
+  j.src = src.data_ptr<float>(); j.idx = idx.data_ptr<int>(); j.dst = dst.data_ptr(); j.to_bf16 = to_bf16;
+  return j;
 }
+void host_gather_rows(Tensor src, Tensor idx, Tensor dst, int64_t n) {
+  znhost::GatherJob j = make_gather_job(src, idx, dst, n);
+  znhost::gather_range(j, 0, j.cap);
+}
+// The caller keeps src / dst alive until host_prefetch_wait(ticket) returned.
+int64_t host_prefetch_submit(Tensor src, Tensor idx, Tensor dst, int64_t n) {
+  return (int64_t)znhost::HostPrefetcher::get().submit(make_gather_job(src, idx, dst, n));
+}
+void host_prefetch_wait(int64_t ticket) { znhost::HostPrefetcher::get().wait((uint64_t)ticket); }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("som_winners", &som_winners); m.def("som_update", &som_update);
@@ -637,7 +651,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
   m.def("gather_minibatch", &gather_minibatch);
+  m.def("pull_from_host", &pull_from_host); m.def("push_to_host", &push_to_host);
   m.def("host_gather_rows", &host_gather_rows);
+  m.def("host_prefetch_submit", &host_prefetch_submit);
+  m.def("host_prefetch_wait", &host_prefetch_wait, py::call_guard<py::gil_scoped_release>());
   m.def("mask_mul", &mask_mul); m.def("pad_channels", &pad_channels); m.def("cast_copy", &cast_copy); m.def("scatter_offsets", &scatter_offsets);
   m.def("pool_forward", &pool_forward); m.def("pool_backward", &pool_backward);
   m.def("lrn_forward", &lrn_forward); m.def("lrn_backward", &lrn_backward);

@@ -73,6 +73,7 @@ struct GemmParams {
 // vec mode   : ktab[k / 8] = (ky << 24) | (kx << 16) | c0     (16-byte chunks never straddle a tap)
 // scalar mode: ktab[k]     = (ky << 24) | (kx << 16) | c
 constexpr int KTAB = 4096;
+constexpr int MT_MAX = 4;      // tiles streamed through one CTA (TMEM columns: BLOCK_N * mt <= 512)
 
 struct PixCtx { const __nv_bfloat16* base; int y, x, valid; };
 
@@ -294,7 +295,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[MT_MAX];    // one per streamed tile
   __shared__ uint32_t tmem_base_smem;
 
   // 1024-byte aligned tile area (SWIZZLE_128B atoms are 1024 B)
@@ -325,7 +326,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&full_bar[s], (A_GATHER ? 128u : 0u) + 1u);
       mbar_init(&empty_bar[s], 1u);
     }
-    mbar_init(&tmem_full_bar, 1u);
+    for (int j = 0; j < MT_MAX; ++j) mbar_init(&tmem_full_bar[j], 1u);
     fence_barrier_init();
   }
   if (warp == 4 && lane == 0) {
@@ -396,16 +397,23 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (!(p.dbg & 2)) mma_f16(d_tmem, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
+        if (i == num_kb - 1) mma_commit(&tmem_full_bar[gi / num_kb]);   // this tile's accumulator
       }
-      mma_commit(&tmem_full_bar);           // accumulator complete
     }
   } else {
-    // ===================== gather producers (warps 0-3) =====================
-    if (A_GATHER) {
+    // ============ gather producers, then epilogue (warps 0-3), software-pipelined ============
+    // Round tt issues the gathers of tile tt and then drains the accumulator of tile tt - 1:
+    // with several tiles streamed through one CTA (GemmParams::mt) the epilogue of a tile
+    // overlaps the MMAs of the next one (up to STAGES k-blocks of operands are already in flight),
+    // and the prologue (barriers, TMEM, lookup table) is paid once.
+#pragma unroll 1
+    for (int tt = 0; tt <= ntiles; ++tt) {
+    if (A_GATHER && tt < ntiles) {
       const int t = threadIdx.x;            // 0..127
       if (A_MODE == A_GATHER_K) {
         // tile row r = t is GEMM row m0 + t (a pixel); chunks run over the reduction index
-        for (int tj = 0; tj < ntiles; ++tj) {
+        {
+        const int tj = tt;
         const int m = m0 + tj * BLOCK_M + t;
         const int gbase = tj * num_kb;           // position of this tile in the stage sequence
         const PixCtx ctx = (GKIND == G_IM2COL) ? decode_out_pixel(p.gsrc, p.g, m, p.M)
@@ -492,9 +500,11 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
-    // ===================== epilogue (warps 0-3) =====================
+    // ===================== epilogue of tile tt - 1 =====================
+    if (tt == 0) continue;
+    const int tj = tt - 1;
     if (num_kb > 0) {
-      mbar_wait(&tmem_full_bar, 0);
+      mbar_wait(&tmem_full_bar[tj], 0);
       tc_fence_after();
     }
     // The epilogue runs once per tile, so every instruction of it is an instruction-cache miss:
@@ -504,8 +514,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // decided once per thread; the loop body is a few hundred instructions, fetched once.
     enum { EPI_TMA = 0, EPI_BF16 = 1, EPI_RAW_T = 2, EPI_RAW = 3, EPI_SLOW = 4, EPI_NONE = 5,
            EPI_BIASROW = 6 };
-#pragma unroll 1
-    for (int tj = 0; tj < ntiles; ++tj) {
+    {
     const int row = m0 + tj * BLOCK_M + warp * 32 + lane;
     const bool raw32 = !p.out_bf16 && p.beta == 0.f && p.alpha == 1.f && !p.bias && p.act == 0;
     float* const rbase = reinterpret_cast<float*>(p.out) +
@@ -619,7 +628,8 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       __syncwarp();
     }
-    }   // tiles of this CTA
+    }
+    }   // rounds (tiles of this CTA)
     tc_fence_before();
   }
   __syncthreads();
@@ -704,7 +714,8 @@ static int launch_stages(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   if (no_tma_store < 0) { const char* e = getenv("ZNICZ_UMMA_TMA_STORE"); no_tma_store = (e && atoi(e)) ? 0 : 1; }
   p.tma_store = 0;
   if (!no_tma_store && p.out_bf16 && p.split_stride == 0 && !p.out_trans && p.beta == 0.f &&
-      (p.ldo % 8) == 0 && ((uintptr_t)p.out & 15) == 0 && 4 * 32 * BN * 2 <= ring - 1024) {
+      (p.ldo % 8) == 0 && ((uintptr_t)p.out & 15) == 0 && 4 * 32 * BN * 2 <= ring - 1024 &&
+      p.mt <= 1) {      // (streamed tiles: the ring is busy with the next tile during the epilogue)
     if (make_map_out(&tc, p.out, p.N, p.M, p.ldo, BN) == 0) p.tma_store = 1;
   }
   launch_k(gemm_umma_k<BN, AM, BM, GK, GV, NS>, grid, 192, smem, st, ta, tb, tc, p);

@@ -19,10 +19,19 @@ from __future__ import annotations
 
 import numpy
 
+from ..core.config import root
+
 from ..core.accelerated_units import host_dtype
 from ..core.memory import Array
 from .base import (Loader, LoaderMSEMixin, LoaderWithValidationRatio, TEST, VALID,
                    TRAIN, LoaderError)
+
+
+def _pull_ok(ext):
+    """Per-step uploads go through a kernel that reads the pinned buffer (ext.pull_from_host)
+    rather than cudaMemcpyAsync; ``root.common.engine.loader_pull = False`` restores the copies."""
+    return ext is not None and hasattr(ext, "pull_from_host") and \
+        bool(root.common.engine.get("loader_pull", True))
 
 
 class FullBatchLoader(Loader, LoaderWithValidationRatio):
@@ -191,7 +200,8 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         off_data = (16 + (4 * mb if labels else 0) + 255) // 256 * 256
         total = off_data + md.size * esz
         devp = torch.zeros(total, dtype=torch.uint8, device=self.device.torch_device)
-        pins = [torch.zeros(total, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        depth = 4       # pinned slots: the prefetcher fills slot i+1 while the copy out of slot i
+        pins = [torch.zeros(total, dtype=torch.uint8).pin_memory() for _ in range(depth)]
 
         def views(buf):
             hdr = buf[:16].view(torch.int32)
@@ -207,39 +217,83 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         for p in pins:
             hdr, lab, data = views(p)
             slots.append({"pin": p, "hdr": hdr.numpy(), "lab": lab.numpy() if labels else None,
-                          "data": data})
+                          "data": data, "event": torch.cuda.Event(), "used": False})
         self._pinned_["bufs"] = {}
         self.__dict__["_packed_"] = {
-            "dev": devp, "slots": slots, "labels": labels,
+            "dev": devp, "slots": slots, "labels": labels, "i": 0, "pending": None,
             "src": torch.from_numpy(od),
-            "idx": torch.from_numpy(self.minibatch_indices.mem)}
+            "idx": torch.from_numpy(self.minibatch_indices.mem),
+            "prefetch": hasattr(ext, "host_prefetch_submit") and
+            root.common.engine.get("loader_prefetch", True),
+            "pull": _pull_ok(ext)}
         self.h2d_bytes_per_step = total
 
     def _fill_packed(self):
+        """Minibatch → pinned slot: already there when the prefetcher guessed this minibatch
+        (same index list), otherwise gathered now."""
         pk = self._packed_
-        sl = pk["slots"][self._pinned_["slot"]]
+        ext = self.device.ext
         n = int(self.minibatch_size)
-        self.device.ext.host_gather_rows(pk["src"], pk["idx"], sl["data"], n)
+        idx = self.minibatch_indices.mem
+        pend, pk["pending"] = pk["pending"], None
+        hit = False
+        if pend is not None:
+            ext.host_prefetch_wait(pend["ticket"])
+            hit = pend["slot"] == pk["i"] and pend["n"] == n and \
+                numpy.array_equal(pend["idx"], idx[:n])
+        sl = pk["slots"][pk["i"]]
+        if not hit:
+            if sl["used"]:
+                sl["event"].synchronize()      # the copy out of this slot must be done
+            ext.host_gather_rows(pk["src"], pk["idx"], sl["data"], n)
+        pk["hits"] = pk.get("hits", 0) + int(hit)
         if pk["labels"]:
             lab = sl["lab"]
-            numpy.take(self._mapped_original_labels.mem, self.minibatch_indices.mem[:n],
-                       out=lab[:n], mode="clip")
+            numpy.take(self._mapped_original_labels.mem, idx[:n], out=lab[:n], mode="clip")
             lab[n:] = -1
 
     def _serve_packed(self):
         pk = self._packed_
-        pd = self._pinned_
-        slot = pd["slot"]
-        sl = pk["slots"][slot]
+        sl = pk["slots"][pk["i"]]
         hn = sl["hdr"]
         hn[0] = self.minibatch_size
         hn[1] = self.minibatch_class
         hn[2] = self.epoch_number
-        pk["dev"].copy_(sl["pin"], non_blocking=True)
-        pd["events"][slot].record()
+        if pk["pull"]:
+            self.device.ext.pull_from_host(sl["pin"], pk["dev"])    # SMs read the pinned slot
+        else:
+            pk["dev"].copy_(sl["pin"], non_blocking=True)
+        sl["event"].record()
+        sl["used"] = True
         self.minibatch_data.dev_written()
         if pk["labels"]:
             self.minibatch_labels.dev_written()
+        pk["i"] = (pk["i"] + 1) % len(pk["slots"])
+        if pk["prefetch"]:
+            self._prefetch_next()
+
+    def _prefetch_next(self):
+        """Start assembling the following minibatch (same epoch only: its indices are already
+        fixed in ``shuffled_indices``) into the next pinned slot on the native worker pool."""
+        pk = self._packed_
+        start = self.global_offset
+        if start <= 0 or start >= self.total_samples:
+            return                              # epoch wrap: the train part is reshuffled first
+        cls = self.class_index_by_offset(start)
+        n = int(min(self.max_minibatch_size, self.class_end_offsets[cls] - start))
+        sl = pk["slots"][pk["i"]]
+        if n <= 0:
+            return
+        if sl["used"] and not sl["event"].query():
+            # the copy out of this slot (issued depth - 1 steps ago) has not finished: the device
+            # is that far behind, so the host has time to spare - wait for it rather than give
+            # up the prefetch (bounds the run-ahead to depth - 1 steps)
+            sl["event"].synchronize()
+        idx = numpy.ascontiguousarray(self.shuffled_indices.mem[start:start + n], numpy.int32)
+        import torch
+        ticket = self.device.ext.host_prefetch_submit(pk["src"], torch.from_numpy(idx),
+                                                      sl["data"], n)
+        pk["pending"] = {"ticket": ticket, "slot": pk["i"], "n": n, "idx": idx}
 
     def _cuda_serve(self):
         if not self.on_device:
@@ -254,7 +308,11 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         hn[1] = self.minibatch_class
         hn[2] = self.epoch_number
         hn[4:4 + self.max_minibatch_size] = self.minibatch_indices.mem
-        self._hdr_idx_dev_.copy_(pd["hdr_idx"][slot], non_blocking=True)
+        if _pull_ok(self.device.ext):
+            # no copy-engine operation in the step's stream (profiles/host_vs_device_r1.md)
+            self.device.ext.pull_from_host(pd["hdr_idx"][slot], self._hdr_idx_dev_)
+        else:
+            self._hdr_idx_dev_.copy_(pd["hdr_idx"][slot], non_blocking=True)
         pd["events"][slot].record()
         if self.__dict__.get("gather_in_graph_"):
             return          # the forward graph segment starts with the gather (graph_prelude)

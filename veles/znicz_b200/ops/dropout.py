@@ -101,13 +101,11 @@ class DropoutForward(Forward, Dropout, TriviallyDistributable):
     def cuda_prepare(self):
         import torch
         if self.rng_dev_ is None:
-            self.rng_dev_ = torch.zeros(2, dtype=torch.int32,
-                                        device=self.device.torch_device)
-            self.rng_host_ = torch.zeros(2, dtype=torch.int32).pin_memory()
+            from ..core.memory import ScalarUploader
+            self.rng_up_ = ScalarUploader(self.device, 2, torch.int32)
+            self.rng_dev_ = self.rng_up_.dev
         if self.active:
-            self.rng_host_[0] = self.seed & 0x7FFFFFFF
-            self.rng_host_[1] = self.rng_counter & 0x7FFFFFFF
-            self.rng_dev_.copy_(self.rng_host_, non_blocking=True)
+            self.rng_up_.upload((self.seed & 0x7FFFFFFF, self.rng_counter & 0x7FFFFFFF))
             self.rng_counter += 1
 
     def cuda_run(self):

@@ -30,7 +30,11 @@ class StepResultReader(object):
         if self.pending[s]:
             self.events[s].synchronize()
             self.last = self.slots[s].clone()
-        self.slots[s].copy_(ev.n_err.devmem, non_blocking=True)
+        ext = getattr(getattr(ev, "device", None), "ext", None)
+        if ext is not None and hasattr(ext, "push_to_host"):
+            ext.push_to_host(ev.n_err.devmem, self.slots[s])   # a kernel stores into pinned memory
+        else:
+            self.slots[s].copy_(ev.n_err.devmem, non_blocking=True)
         self.events[s].record()
         self.pending[s] = True
         self.i += 1
