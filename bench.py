@@ -131,6 +131,9 @@ def _batch_of(model):
 
 def run_arm(args, streaming):
     import torch
+    if os.environ.get("ZNICZ_OVERLAP_WGRAD") == "0":        # diagnostic
+        from veles.znicz_b200.core.config import root
+        root.common.engine.overlap_wgrad = False
     if os.environ.get("ZNICZ_LOADER_PULL") == "0":          # diagnostic
         from veles.znicz_b200.core.config import root
         root.common.engine.loader_pull = False

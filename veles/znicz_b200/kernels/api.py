@@ -13,9 +13,12 @@ a shape raises — there is no silent fallback to PyTorch.
 """
 from __future__ import annotations
 
+import contextlib
+
 import numpy
 import torch
 
+from ..core.config import root
 from ..ops.nn_units import ACT_LINEAR
 
 _MAX_SPLITS = 64
@@ -182,6 +185,28 @@ def _fc_small_ok(unit, n_out):
             unit.weights.dev.dtype == torch.float32)
 
 
+# -- weight-gradient overlap ---------------------------------------------------------------------
+# dgrad and wgrad of a layer both only *read* err_output, and nothing consumes the weight gradient
+# before the optimizer step: the wgrad kernels run on the device's side stream (a parallel branch
+# of the captured graph) while the main stream carries the err_input chain down the network. The
+# small-grid kernels of small nets (50-200 CTAs) then share the 148 SMs instead of queueing.
+def _fork_side(unit):
+    dev = unit.device
+    if not root.common.engine.get("overlap_wgrad", True) or getattr(dev, "side_stream", None) is None:
+        return None
+    side = dev.side_stream
+    side.wait_stream(torch.cuda.current_stream())
+    dev.__dict__["side_pending_"] = True
+    return side
+
+
+def join_side(dev):
+    """Main stream waits for the outstanding side-stream work (before gradients are consumed)."""
+    if dev.__dict__.get("side_pending_"):
+        torch.cuda.current_stream().wait_stream(dev.side_stream)
+        dev.__dict__["side_pending_"] = False
+
+
 def _bias_partials(unit, rows, cols):
     ext = _ext(unit)
     slices = ext.colsum_slices(rows)
@@ -209,6 +234,8 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
         acc, vel = unit.accumulated_gradient_weights, unit.gradient_weights_with_moment
     flags = unit.update_flags(for_bias=is_bias)
     step = unit.step_
+    if step is None:
+        join_side(unit.device)       # per-tensor update launches right here: gradients must be in
     colsums = None
     if not is_bias and unit.factor_ortho:
         colsums = unit.col_sums.dev_out
@@ -435,6 +462,8 @@ def conv_backward(unit):
         _launch()
         g_mm = list(g)
         g_mm[6] = f_pad
+    # fork here: everything wgrad needs exists; it runs beside the dgrad launched next
+    side = _fork_side(unit) if (need_w and unit.need_err_input) else None
     if unit.need_err_input:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
         r = -1
@@ -476,22 +505,24 @@ def conv_backward(unit):
         splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
     gbuf = _grad_buffer(unit, "wgrad", (splits, f_rows, kw))
     brow = None
-    if use_umma:
-        if bias_row:
-            brow = _grad_buffer(unit, "bias_row", (splits, f_rows))
-        r = ext.conv_wgrad(err_mm, x, gbuf, splits, g, False, 1, brow)
-        if r not in (0, 1):
-            raise RuntimeError("%s: tcgen05 conv wgrad refused (code %d)" % (unit, r))
-        if r == 0:
-            brow = None
-    else:
-        ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0, None)
-    _launch()
-    if bias_row and brow is None:
-        # geometry without a spare product row (kernel size a multiple of 128): classic column sums
-        slices, parts = _bias_partials(unit, pixels, f)
-        ext.err_act_colsum(err, None, pixels, f, ACT_LINEAR, parts)
+    if bias_row and use_umma:
+        brow = _grad_buffer(unit, "bias_row", (splits, f_rows))
+    with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        if use_umma:
+            r = ext.conv_wgrad(err_mm, x, gbuf, splits, g, False, 1, brow)
+            if r not in (0, 1):
+                raise RuntimeError("%s: tcgen05 conv wgrad refused (code %d)" % (unit, r))
+            if r == 0:
+                brow = None
+        else:
+            ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0, None)
         _launch()
+        if bias_row and brow is None:
+            # geometry without a spare product row (kernel size a multiple of 128): classic
+            # column sums
+            slices, parts = _bias_partials(unit, pixels, f)
+            ext.err_act_colsum(err, None, pixels, f, ACT_LINEAR, parts)
+            _launch()
     _update(unit, False, gbuf, splits, f_rows * kw, f, unit._kernel_size, g_cpad=g_cp)
     if need_b:
         if brow is not None:

@@ -151,6 +151,7 @@ class FusedStep(object):
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("FusedStep: table changed during graph capture")
             self._upload()
+        api.join_side(self.device)      # wgrad kernels of the side-stream branch
         dp = self.dp
         if dp is not None and dp.world_size > 1 and dp.symm is None:
             # NCCL *baseline* mode (ZNICZ_DP_MODE=nccl): one library all-reduce per gradient
