@@ -337,6 +337,8 @@ def fc_backward(unit):
     lp_ok = (lp_enabled(unit) and _is_bf16(err) and _is_bf16(x) and
              unit.forward_unit is not None and
              getattr(unit.forward_unit, "weights_lp_", None) is not None)
+    # the weight-gradient GEMM runs beside the err_input GEMM (see _fork_side)
+    side = _fork_side(unit) if (need_w and unit.need_err_input) else None
     # 2. err_input = alpha * err . W + beta * err_input
     if unit.need_err_input:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
@@ -361,14 +363,16 @@ def fc_backward(unit):
         return
     # 3. gradW[out][in] = err^T . x  (reduction over the batch)
     gbuf = _grad_buffer(unit, "wgrad", (1,) + tuple(unit.weights.shape))
-    if lp_ok and n_out % 8 == 0 and n_in % 8 == 0:
-        r = ext.gemm(err, n_out, True, x, n_in, False, gbuf, n_in, False,
-                     n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 1)
-        if r != 0:
-            raise RuntimeError("%s: tcgen05 FC wgrad refused (code %d)" % (unit, r))
-    else:
-        ext.gemm(err, n_out, True, x, n_in, False, gbuf, n_out if unit.weights_transposed else n_in,
-                 bool(unit.weights_transposed), n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 0)
+    with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        if lp_ok and n_out % 8 == 0 and n_in % 8 == 0:
+            r = ext.gemm(err, n_out, True, x, n_in, False, gbuf, n_in, False,
+                         n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 1)
+            if r != 0:
+                raise RuntimeError("%s: tcgen05 FC wgrad refused (code %d)" % (unit, r))
+        else:
+            ext.gemm(err, n_out, True, x, n_in, False, gbuf,
+                     n_out if unit.weights_transposed else n_in,
+                     bool(unit.weights_transposed), n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 0)
     _launch()
     rows, cols = (n_out, n_in)
     _update(unit, False, gbuf, 1, 0, rows, cols)

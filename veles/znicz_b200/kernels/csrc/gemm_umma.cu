@@ -747,6 +747,16 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     if (deep < 0) { const char* e = getenv("ZNICZ_UMMA_DEEP"); deep = e ? atoi(e) : 0; }
     if (deep && ctas <= 160 && kb >= 8) return launch_stages<BN, AM, BM, GK, GV, 8>(ta, tb, p, grid, st);
   }
+  // Short reductions (K <= 4 k-blocks, e.g. a 5x5 first layer on 8 padded channels) in grids of
+  // several waves: a 3-stage ring already holds almost the whole K and is small enough for a
+  // third CTA per SM (ncu: these kernels are latency-bound at 15 % warp occupancy).
+  if constexpr (AM == A_GATHER_K && GV == 2 && BN <= 64) {
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    static int s3 = -1;
+    if (s3 < 0) { const char* e = getenv("ZNICZ_UMMA_S3"); s3 = e ? atoi(e) : 1; }
+    if (s3 && p.k_blocks_per_split <= 4 && ctas > 2 * 148)
+      return launch_stages<BN, AM, BM, GK, GV, 3>(ta, tb, p, grid, st);
+  }
   return launch_stages<BN, AM, BM, GK, GV, STAGES_DEFAULT>(ta, tb, p, grid, st);
 }
 
