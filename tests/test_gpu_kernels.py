@@ -213,6 +213,12 @@ def test_multi_update_matches_per_tensor_update(ext):
     # >= 2^20 elements: the 4-elements-per-thread tile path (FC6-sized tensors)
     specs.append(dict(rows=1030, cols=1048, nparts=2, flags=1 | 2 | 4, bias=False, conv=None,
                       lanes=1))
+    # float4 path with per-element shadows (conv-shaped 1.33 M weights, bf16 [tap][F][C] shadow)
+    specs.append(dict(rows=384, cols=3456, nparts=3, flags=1 | 2 | 8, bias=False,
+                      conv=(9, 384, 384, 0, 0), lanes=1))
+    # float4 chunks that straddle rows (cols % 4 != 0)
+    specs.append(dict(rows=1031, cols=1049, nparts=1, flags=1 | 2, bias=False, conv=None,
+                      lanes=1))
     ref, new, descs = [], [], []
     for sp in specs:
         rows, cols = sp["rows"], sp["cols"]
@@ -256,7 +262,7 @@ def test_multi_update_matches_per_tensor_update(ext):
         new.append(b)
         sp["g"] = g
     packed, tiles, red = ext.multi_update_table(descs, 0)
-    assert red == sum(d[15] for d in descs)
+    assert red == sum((d[15] + 3) // 4 * 4 for d in descs)     # 16-byte aligned slots
     table = packed.cuda()
     sync = torch.zeros(2, dtype=torch.int32, device=dev)
     for _ in range(1):
@@ -297,7 +303,8 @@ def test_fc_small_forward(ext, dtype, n_out, act, softmax):
     out = torch.full((batch, n_out), float("nan"), device=dev,
                      dtype=torch.float32 if softmax else dtype)
     mi = torch.full((batch,), -1, device=dev, dtype=torch.int32)
-    ext.fc_small_forward(x, w, b, out, mi if softmax else None, batch, n_in, n_out, act, softmax)
+    ext.fc_small_forward(x, w, b, out, mi if softmax else None, batch, n_in, n_out, act, softmax,
+                         [])
     torch.cuda.synchronize()
     z = x.float() @ w.t() + b
     if softmax:
@@ -407,3 +414,35 @@ def test_gather_minibatch_with_channel_padding(ext, src_dt, dst_dt):
     ext.gather_minibatch(data, labels, hdr, dst2, ldst, None, 0)
     torch.cuda.synchronize()
     assert torch.equal(dst2, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fc_small_forward_fused_evaluator(ext, dtype):
+    """softmax FC + evaluator in one launch == fc_small_forward followed by evaluate_softmax."""
+    torch.manual_seed(11)
+    dev = "cuda"
+    batch, valid, n_in, n_out = 50, 43, 256, 10
+    x = torch.randn(batch, n_in, device=dev).to(dtype)
+    w = torch.randn(n_out, n_in, device=dev) * 0.1
+    b = torch.randn(n_out, device=dev)
+    labels = torch.randint(0, n_out, (batch,), device=dev, dtype=torch.int32)
+    labels[5] = -1                                        # ignored sample
+    bp = torch.tensor([float(valid), 1.0 / valid], device=dev)
+
+    def fresh():
+        return dict(out=torch.empty(batch, n_out, device=dev),
+                    mi=torch.zeros(batch, dtype=torch.int32, device=dev),
+                    err=torch.full((batch, n_out), float("nan"), device=dev).to(dtype),
+                    n_err=torch.zeros(2, dtype=torch.int32, device=dev),
+                    conf=torch.zeros(n_out, n_out, dtype=torch.int32, device=dev),
+                    mx=torch.zeros(1, device=dev))
+    a, f = fresh(), fresh()
+    ext.fc_small_forward(x, w, b, a["out"], a["mi"], batch, n_in, n_out, 0, True, [])
+    ext.evaluate_softmax(a["out"], a["mi"], labels, a["err"], bp, a["n_err"], a["conf"], a["mx"])
+    ext.fc_small_forward(x, w, b, f["out"], f["mi"], batch, n_in, n_out, 0, True,
+                         [labels, f["err"], bp, f["n_err"], f["mx"], f["conf"]])
+    torch.cuda.synchronize()
+    assert torch.equal(a["out"], f["out"]) and torch.equal(a["mi"], f["mi"])
+    assert torch.equal(a["n_err"], f["n_err"]) and torch.equal(a["conf"], f["conf"])
+    assert torch.allclose(a["err"].float(), f["err"].float(), atol=1e-6 if dtype == torch.float32 else 1e-3)
+    assert abs(float(a["mx"]) - float(f["mx"])) < 1e-3

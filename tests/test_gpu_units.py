@@ -70,7 +70,10 @@ def _compare(fwd_cls, gd_cls, x, fkw=None, gkw=None, links=("weights", "bias"), 
             res[name] = float(numpy.sqrt((d * d).sum()) /
                               max(1e-12, numpy.sqrt((a.mem.astype(numpy.float64) ** 2).sum())))
         assert numpy.isfinite(b.mem).all(), name
-        assert res[name] < tol, (name, res, compute)
+        # (bias gradients of tiny layers are sums over a few hundred gated pixels: a ReLU gate
+        # that flips under bf16 rounding moves them more than the weights)
+        lim = tol * (1.5 if (name == "bias" and compute != "fp32") else 1.0)
+        assert res[name] < lim, (name, res, compute)
     root.common.engine.compute_type = "fp32"
     return res
 
@@ -106,7 +109,9 @@ def test_fc_odd_shapes_and_softmax(compute):
     ((5, 32, 32, 3), 32, 5, 5, (2, 2, 2, 2), (1, 1)),
     ((3, 11, 9, 8), 24, 3, 2, (1, 0, 2, 1), (2, 1)),
     ((6, 12, 12, 64), 87, 5, 5, (0, 0, 0, 0), (1, 1)),      # n_kernels % 8 != 0 (MNIST conv)
-    ((4, 14, 14, 3), 27, 3, 3, (1, 1, 1, 1), (1, 1))])
+    ((4, 14, 14, 3), 27, 3, 3, (1, 1, 1, 1), (1, 1)),
+    ((2, 13, 13, 96), 64, 3, 3, (1, 1, 1, 1), (1, 1)),      # 96 -> 128 channel padding (tap mode)
+    ((3, 9, 9, 24), 16, 5, 5, (2, 2, 2, 2), (1, 1))])       # 24 -> 32
 def test_conv(fwd, bwd, geom, compute):
     shape, f, ky, kx, pad, sl = geom
     x = RS.uniform(-1, 1, shape).astype(numpy.float32)

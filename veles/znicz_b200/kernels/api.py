@@ -72,17 +72,33 @@ def _shadow_spec(unit):
     if hasattr(unit, "kx") and hasattr(unit, "n_kernels"):
         c = unit._n_channels
         taps = unit.kx * unit.ky
-        c_pad = _roundup(c, 8)
-        if c % 8:
-            ld = taps * c_pad
+        c_pad = _roundup(c, 8)              # dgrad shadow [tap][f][c_pad]
+        cp = _fprop_cpad(c)
+        if cp:
+            ld = taps * cp                  # fprop shadow [f][tap][cp]
         return rows, cols, ld, True, taps, c, c_pad
     return rows, cols, ld, False, 0, 0, 0
 
 
+def _fprop_cpad(c):
+    """Channel count the tap-mode gather wants for a conv input with ``c`` channels (0 = as is).
+
+    A 64-wide reduction block must cover whole filter taps (8 / 16 / 32 / 64 channels per tap) or
+    a 64-channel slice of one tap (c % 64 == 0). Other counts - the first layer's 3, AlexNet
+    conv2's 96 - would fall back to the per-chunk table gather, 2-3x slower per k-block, so the
+    input is channel-padded once per forward instead (96 -> 128: +33 % MMA work, -60 % time)."""
+    if c <= 64:
+        for v in (8, 16, 32, 64):
+            if c <= v:
+                return 0 if v == c else v
+    r = _roundup(c, 64)
+    return 0 if r == c else r
+
+
 def lp_cpad(unit):
     """Channel padding of the fprop weight shadow / padded input (0 = none)."""
-    if hasattr(unit, "kx") and hasattr(unit, "n_kernels") and unit._n_channels % 8:
-        return _roundup(unit._n_channels, 8)
+    if hasattr(unit, "kx") and hasattr(unit, "n_kernels"):
+        return _fprop_cpad(unit._n_channels)
     return 0
 
 
@@ -129,9 +145,23 @@ def fc_forward(unit, softmax=False):
     act = ACT_LINEAR if softmax else eff_act(unit)
     if _fc_small_ok(unit, n_out) and act <= 4:
         # few outputs: one launch does GEMV x n_out + bias + activation (+ softmax + arg-max)
+        ev_args = []
+        ev = unit.__dict__.get("fused_eval_") if softmax else None
+        if ev is not None and getattr(ev, "on_cuda", False) and not ev.testing and \
+                ev.output is unit.output and ev.labels and ev.err_output:
+            # softmax evaluator folded into this launch (workflow/fusion.py::fuse_evaluator)
+            ev.cuda_prepare()
+            ev_args = [ev.labels.dev, ev.err_output.dev_out, ev.batch_dev_, ev.n_err.dev,
+                       ev.max_err_output_sum.dev]
+            if ev.confusion_matrix:
+                ev_args.append(ev.confusion_matrix.dev)
+                ev.confusion_matrix.dev_written()
+            ev.n_err.dev_written()
+            ev.max_err_output_sum.dev_written()
+            ev.__dict__["fused_done_"] = True
         ext.fc_small_forward(x, unit.weights.dev, bias, unit.output.dev_out,
                              unit.max_idx.dev_out if softmax else None, batch, n_in, n_out,
-                             act, bool(softmax))
+                             act, bool(softmax), ev_args)
         _launch()
         return
     if use_lp:
@@ -365,8 +395,12 @@ def fc_backward(unit):
     gbuf = _grad_buffer(unit, "wgrad", (1,) + tuple(unit.weights.shape))
     with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
         if lp_ok and n_out % 8 == 0 and n_in % 8 == 0:
-            r = ext.gemm(err, n_out, True, x, n_in, False, gbuf, n_in, False,
-                         n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 1)
+            # computed as (x^T . err) with a transposed store: for a fixed output column the 32
+            # lanes of a warp then write 32 consecutive floats of gradW[out][in] (one 128-byte
+            # store); the direct form wrote 16-byte pieces 36 KB apart and ran FC6's 151 MB
+            # gradient at ~200 GB/s
+            r = ext.gemm(x, n_in, True, err, n_out, False, gbuf, n_in, True,
+                         n_in, n_out, batch, None, 0, 1.0, 0.0, 1, 0, 1)
             if r != 0:
                 raise RuntimeError("%s: tcgen05 FC wgrad refused (code %d)" % (unit, r))
         else:
@@ -668,6 +702,8 @@ def zero_filler(unit):
 # evaluators
 # ------------------------------------------------------------------------------------------
 def evaluate_softmax(unit):
+    if unit.__dict__.pop("fused_done_", False):
+        return          # the few-output FC kernel already did this step's evaluation
     ext = _ext(unit)
     y = unit.output.dev
     if y.dtype != torch.float32:

@@ -41,7 +41,7 @@ void launch_col_sums(const float*, float*, int, int, int, cudaStream_t);
 void launch_lstm_cell_fwd(const float*, const float*, float*, float*, void*, long long, void*, long long, int, int, bool, cudaStream_t);
 void launch_lstm_cell_bwd(const void*, long long, const void*, long long, const float*, const float*, const float*, const float*, float*, void*, int, int, bool, cudaStream_t);
 int fc_small_max_out();
-void launch_fc_small_forward(const void*, bool, const float*, const float*, void*, float*, int*, int, int, int, int, int, cudaStream_t);
+void launch_fc_small_forward(const void*, bool, const float*, const float*, void*, float*, int*, int, int, int, int, int, const int*, void*, int, const float*, int*, int*, float*, cudaStream_t);
 void launch_fc_small_backward(void*, const void*, const void*, bool, const float*, void*, float*, float*, int, int, int, int, float, float, int, cudaStream_t);
 size_t multi_update_desc_size();
 int multi_update_max_tensors();
@@ -381,7 +381,9 @@ std::tuple<Tensor, int64_t, int64_t> multi_update_table(std::vector<std::vector<
     TORCH_CHECK(descs[i].size() == 31, "descriptor must have 31 fields");
     std::vector<long long> f(descs[i].begin(), descs[i].end());
     tiles += zn::multi_update_pack(f.data(), 31, out.data_ptr<uint8_t>() + i * ds, tiles, red);
-    red += f[15];        // size: one fp32 slot per element in the cross-GPU reduction buffer
+    // one fp32 slot per element in the cross-GPU reduction buffer; every tensor starts on a
+    // 16-byte boundary (the 4-elements-per-thread tile path uses float4 accesses)
+    red += (f[15] + 3) / 4 * 4;
   }
   return std::make_tuple(out, (int64_t)tiles, (int64_t)red);
 }
@@ -458,8 +460,11 @@ void lstm_cell_bwd(c10::optional<Tensor> err_h, int64_t e_off, int64_t lde, c10:
 
 // FC layers with n_out <= fc_small_max_out(): see csrc/fc_small.cu
 int64_t fc_small_max_out() { return zn::fc_small_max_out(); }
+// ev = [labels(int32), err_output, batch_dev(float[2]), n_err(int32[2]), max_err_sum(float[1]),
+//       confusion(int32, optional)] - the fused softmax evaluator (see fc_small.cu::EvalArgs)
 void fc_small_forward(Tensor x, Tensor w, c10::optional<Tensor> bias, Tensor out, c10::optional<Tensor> max_idx,
-                      int64_t batch, int64_t n_in, int64_t n_out, int64_t act, bool softmax) {
+                      int64_t batch, int64_t n_in, int64_t n_out, int64_t act, bool softmax,
+                      std::vector<Tensor> ev) {
   chk(x, "x"); chk(out, "out");
   TORCH_CHECK(w.scalar_type() == torch::kFloat32 && w.is_cuda() && w.is_contiguous(), "weights must be fp32");
   TORCH_CHECK(n_out <= zn::fc_small_max_out() && w.numel() == n_out * n_in);
@@ -476,8 +481,26 @@ void fc_small_forward(Tensor x, Tensor w, c10::optional<Tensor> bias, Tensor out
   void* out_t = (out_f32 && xb) ? nullptr : out.data_ptr();
   float* out_f = (out_f32 && xb) ? out.data_ptr<float>() : nullptr;
   if (!xb) { out_t = out.data_ptr(); out_f = nullptr; }
+  const int* ev_labels = nullptr; void* ev_err = nullptr; int ev_bf16 = 0; const float* ev_bp = nullptr;
+  int* ev_n_err = nullptr; int* ev_conf = nullptr; float* ev_max = nullptr;
+  if (!ev.empty()) {
+    TORCH_CHECK(softmax && mi && ev.size() >= 5, "fused evaluator needs the softmax + arg-max path");
+    TORCH_CHECK(ev[0].scalar_type() == torch::kInt32 && ev[0].numel() >= batch, "labels");
+    chk(ev[1], "err_output");
+    TORCH_CHECK(ev[1].numel() >= batch * n_out, "err_output size");
+    TORCH_CHECK(ev[2].scalar_type() == torch::kFloat32 && ev[2].numel() >= 2, "batch scalars");
+    TORCH_CHECK(ev[3].scalar_type() == torch::kInt32 && ev[3].numel() >= 2, "n_err");
+    TORCH_CHECK(ev[4].scalar_type() == torch::kFloat32 && ev[4].numel() >= 1, "max_err_sum");
+    ev_labels = ev[0].data_ptr<int>(); ev_err = ev[1].data_ptr(); ev_bf16 = is_bf16(ev[1]) ? 1 : 0;
+    ev_bp = ev[2].data_ptr<float>(); ev_n_err = ev[3].data_ptr<int>(); ev_max = ev[4].data_ptr<float>();
+    if (ev.size() > 5) {
+      TORCH_CHECK(ev[5].scalar_type() == torch::kInt32 && ev[5].numel() >= n_out * n_out, "confusion");
+      ev_conf = ev[5].data_ptr<int>();
+    }
+  }
   zn::launch_fc_small_forward(x.data_ptr(), xb, w.data_ptr<float>(), fptr_or_null(bias), out_t, out_f, mi,
-                              (int)batch, (int)n_in, (int)n_out, (int)act, softmax ? 1 : 0, cur());
+                              (int)batch, (int)n_in, (int)n_out, (int)act, softmax ? 1 : 0, ev_labels,
+                              ev_err, ev_bf16, ev_bp, ev_n_err, ev_conf, ev_max, cur());
   kcheck();
 }
 void fc_small_backward(Tensor err, c10::optional<Tensor> y, Tensor x, Tensor w, c10::optional<Tensor> err_in,

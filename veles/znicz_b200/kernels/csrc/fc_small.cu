@@ -18,11 +18,20 @@ namespace zn {
 
 constexpr int FCS_MAX_OUT = 16;
 
+// Optional fused softmax evaluator (workflow/fusion.py::fuse_evaluator): the loss gradient
+// err = (p - onehot) * mult, the error counters, the confusion matrix and max |err| row sum are
+// produced by the warp that already holds the row's probabilities - the stand-alone
+// evaluate_softmax launch (softmax_eval.cu, /root/reference/cuda/evaluator.jcu:21) disappears.
+struct EvalArgs {
+  const int* labels; void* err; int err_bf16; const float* bp;   // bp[0] = batch size, bp[1] = mult
+  int* n_err; int* confusion; float* max_err_sum;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 fc_small_forward_k(const T* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ bias, T* __restrict__ out_t, float* __restrict__ out_f,
-                   int* __restrict__ max_idx, int n_in, int n_out, int act, int softmax) {
+                   int* __restrict__ max_idx, int n_in, int n_out, int act, int softmax, EvalArgs ev) {
   pdl_entry();
   __shared__ float red[4][FCS_MAX_OUT];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -68,6 +77,25 @@ fc_small_forward_k(const T* __restrict__ x, const float* __restrict__ w,
     const float s = warp_sum(e);
     v = e / s;
     if (lane == 0 && max_idx) max_idx[row] = mi;
+    if (ev.labels) {
+      const int batch = (int)ev.bp[0];
+      const float mult = ev.bp[1];
+      const int label = row < batch ? ev.labels[row] : -1;
+      float d = 0.f;
+      if (label >= 0 && lane < n_out) d = (v - (lane == label ? 1.f : 0.f)) * mult;
+      if (lane < n_out) {
+        if (ev.err_bf16) reinterpret_cast<__nv_bfloat16*>(ev.err)[(size_t)row * n_out + lane] = __float2bfloat16_rn(d);
+        else reinterpret_cast<float*>(ev.err)[(size_t)row * n_out + lane] = d;
+      }
+      // |err| of the value as stored (the stand-alone kernel sums what it wrote in fp32)
+      const float asum = warp_sum(fabsf(d));
+      if (lane == 0 && label >= 0) {
+        if (mi != label) atomicAdd(ev.n_err, 1);
+        atomicAdd(ev.n_err + 1, 1);
+        if (ev.confusion) atomicAdd(ev.confusion + (size_t)mi * n_out + label, 1);
+        atomicMax(reinterpret_cast<int*>(ev.max_err_sum), __float_as_int(asum));   // asum >= 0
+      }
+    }
   }
   if (lane < n_out) {
     if (out_f) out_f[(size_t)row * n_out + lane] = v;
@@ -146,13 +174,16 @@ int fc_small_max_out() { return FCS_MAX_OUT; }
 
 void launch_fc_small_forward(const void* x, bool bf16, const float* w, const float* bias, void* out_t,
                              float* out_f, int* max_idx, int batch, int n_in, int n_out, int act,
-                             int softmax, cudaStream_t st) {
+                             int softmax, const int* ev_labels, void* ev_err, int ev_err_bf16,
+                             const float* ev_bp, int* ev_n_err, int* ev_confusion, float* ev_max_err,
+                             cudaStream_t st) {
+  EvalArgs ev{ev_labels, ev_err, ev_err_bf16, ev_bp, ev_n_err, ev_confusion, ev_max_err};
   if (bf16)
     launch_k(fc_small_forward_k<__nv_bfloat16>, batch, 128, 0, st, 
-        (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)out_t, out_f, max_idx, n_in, n_out, act, softmax);
+        (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)out_t, out_f, max_idx, n_in, n_out, act, softmax, ev);
   else
     launch_k(fc_small_forward_k<float>, batch, 128, 0, st, (const float*)x, w, bias, (float*)out_t, out_f,
-                                                     max_idx, n_in, n_out, act, softmax);
+                                                     max_idx, n_in, n_out, act, softmax, ev);
 }
 
 void launch_fc_small_backward(void* err, const void* y, const void* x, bool bf16, const float* w,

@@ -121,3 +121,22 @@ def fuse_backward_derivatives(workflow, device):
         gp.__dict__["deriv_upstream_"] = True
         n += 1
     return n
+
+
+def fuse_evaluator(workflow, device):
+    """softmax layer served by the few-output FC kernel → EvaluatorSoftmax: the evaluator's work
+    rides in the FC launch (kernels/api.py::fc_forward checks the remaining run-time conditions
+    and falls back to the stand-alone kernel when they do not hold). Returns 1 if armed."""
+    for f in workflow.forwards:
+        f.__dict__.pop("fused_eval_", None)
+    if device is None or not device.is_cuda or \
+            not root.common.engine.get("fuse_activations", True) or not workflow.forwards:
+        return 0
+    from .evaluator import EvaluatorSoftmax
+    last = workflow.forwards[-1]
+    ev = getattr(workflow, "evaluator", None)
+    if not isinstance(last, All2AllSoftmax) or type(ev) is not EvaluatorSoftmax or \
+            getattr(last, "force_numpy", False) or getattr(ev, "force_numpy", False):
+        return 0
+    last.__dict__["fused_eval_"] = ev
+    return 1

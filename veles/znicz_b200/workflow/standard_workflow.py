@@ -580,6 +580,7 @@ class StandardWorkflow(StandardWorkflowBase):
         from . import fusion
         self.fused_activations_ = fusion.fuse_activations(self, device)
         self.fused_derivatives_ = fusion.fuse_backward_derivatives(self, device)
+        self.fused_evaluator_ = fusion.fuse_evaluator(self, device)
         res = super().initialize(device=device, **kwargs)
         dev = self.device
         if dev is not None and not dev.is_cuda:
