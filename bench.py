@@ -90,6 +90,7 @@ MODELS = {
                          "conv64-5/relu/avgpool/softmax10)"),
     "mnist_conv": (6, "mnist_conv_config (conv64-5/mp2/conv87-5/mp2/fc791-softplus/softmax10)"),
     "alexnet": (128, "AlexNet 227x227x3 (5 conv, 2-group zero_filter, LRN, 3 FC, dropout)"),
+    "lstm": (128, "lstm_seq 128 features x 32 steps -> LSTM 256 -> softmax10"),
 }
 
 
@@ -115,6 +116,12 @@ def build_workflow(streaming, compute, graphs, n_train, model="cifar_caffe"):
             loader_config={"minibatch_size": batch, "n_train": min(n_train, 60000),
                            "n_valid": 0, "n_test": 0, "normalization_type": "linear",
                            "on_device": not streaming, "shuffle_limit": 2000000000}, **common)
+    if model == "lstm":
+        from veles.znicz_b200.models import lstm_seq
+        return lstm_seq.build(
+            loader_config={"minibatch_size": batch, "n_train": min(n_train, 16384), "n_valid": 0,
+                           "n_test": 0, "on_device": not streaming,
+                           "shuffle_limit": 2000000000}, **common)
     from veles.znicz_b200.models import alexnet
     return alexnet.build(
         loader_name="synthetic_imagenet", layers=alexnet.alexnet_layers(1000),
@@ -253,33 +260,38 @@ def main():
     batch = _batch_of(args.model)
     images = args.steps * batch * n
     value = images / (main_res["ms_dev"] / 1e3)
+    unit_name = "sequences" if args.model == "lstm" else "images"
     out = {
         "metric": {"cifar_caffe": "CIFAR-10 caffe-conv", "mnist_conv": "MNIST conv",
-                   "alexnet": "AlexNet"}[args.model] +
-                  " training images/sec (whole job, device-timed, max over ranks)",
-        "value": round(value, 1), "unit": "images/s", "n_gpus": n, "steps": args.steps,
+                   "alexnet": "AlexNet", "lstm": "LSTM sequence"}[args.model] +
+                  " training %s/sec (whole job, device-timed, max over ranks)" % unit_name,
+        "value": round(value, 1), "unit": unit_name + "/s", "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(main_res["ms_dev"] / args.steps, 5),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "impl": "znicz_b200" if args.impl == "b200" else "baseline(in-repo, reference-equivalent)",
         "config": {"model": MODELS[args.model][1],
-                   "global_batch": batch * n, "per_gpu_batch": batch, "seq_len": None,
+                   "global_batch": batch * n, "per_gpu_batch": batch,
+                   "seq_len": 32 if args.model == "lstm" else None,
                    "image": {"cifar_caffe": "32x32x3", "mnist_conv": "28x28x1",
-                             "alexnet": "227x227x3"}[args.model], "parallelism": "dp%d" % n,
+                             "alexnet": "227x227x3", "lstm": None}[args.model],
+                   "parallelism": "dp%d" % n,
                    "dp_collective": ("fused peer-memory reduce+update kernel (no NCCL on the "
                                      "step path)" if os.environ.get("ZNICZ_DP_MODE", "fused") ==
                                      "fused" else "NCCL all-reduce baseline") if n > 1 else None,
-                   "optimizer": "SGD momentum 0.9 + L2 5e-4 + factor_ortho 1e-3, "
-                                "arbitrary_step LR",
+                   "optimizer": ("SGD momentum 0.9 + L2 5e-4 + factor_ortho 1e-3, "
+                                 "arbitrary_step LR") if args.model == "cifar_caffe" else
+                                "SGD momentum + L2 as in the model's layer config",
                    "cuda_graphs": not args.no_graphs,
-                   "l2": "inputs larger than L2: the whole fp32 dataset (614 MB for 50000x32x32x3) "
-                         "is resident in HBM, random minibatch rows gathered each step"},
+                   "l2": "inputs larger than L2: the whole fp32 dataset (614 MB for 50000x32x32x3 "
+                         "in the CIFAR config) is resident in HBM, random minibatch rows gathered "
+                         "each step"},
         "clocks": {k: main_res["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
         "gpu_launches": main_res["launches"],
     }
     if e2e_res is not None:
         out["e2e"] = {
-            "value": round(images / (e2e_res["ms_wall"] / 1e3), 1), "unit": "images/s",
+            "value": round(images / (e2e_res["ms_wall"] / 1e3), 1), "unit": unit_name + "/s",
             "h2d_bytes_per_step": int(e2e_res["h2d"]), "d2h_bytes_per_step": int(e2e_res["d2h"]),
             "ms_per_step": round(e2e_res["ms_wall"] / args.steps, 5),
             "timing": "wall clock around the public-API loop, cuda synchronize on both sides",

@@ -115,3 +115,23 @@ def test_lstm_seq_in_standard_workflow():
     assert type(wf.gds[0]).__name__ == "GDLSTMSequence"
     wf.run()
     assert wf.decision.best_n_err_pt[1] < 20.0, wf.decision.best_n_err_pt
+
+
+def test_lstm_seq_model_builds_and_trains():
+    """models/lstm_seq.py (north-star config 5) on the numpy backend."""
+    from veles.znicz_b200.models import lstm_seq
+    root.common.disable.snapshotting = True
+    try:
+        wf = lstm_seq.build(seq_len=6, features=8, hidden=12, n_classes=3,
+                            loader_config={"minibatch_size": 16, "n_train": 96, "n_valid": 32,
+                                           "noise": 0.2},
+                            decision_config={"max_epochs": 3, "fail_iterations": 10})
+        wf.initialize(device="numpy")
+        assert [type(f).__name__ for f in wf.forwards] == ["LSTMSequence", "All2AllSoftmax"]
+        w0 = wf.forwards[0].weights.mem.copy()
+        wf.run()
+        assert bool(wf.decision.complete)
+        assert numpy.isfinite(wf.forwards[0].weights.mem).all()
+        assert numpy.abs(wf.forwards[0].weights.mem - w0).max() > 0
+    finally:
+        root.common.disable.snapshotting = False
