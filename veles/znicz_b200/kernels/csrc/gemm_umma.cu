@@ -513,7 +513,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // buffered (the next chunk is in flight while this one is stored) - with the output mode
     // decided once per thread; the loop body is a few hundred instructions, fetched once.
     enum { EPI_TMA = 0, EPI_BF16 = 1, EPI_RAW_T = 2, EPI_RAW = 3, EPI_SLOW = 4, EPI_NONE = 5,
-           EPI_BIASROW = 6 };
+           EPI_BIASROW = 6, EPI_F32 = 7 };
     {
     const int row = m0 + tj * BLOCK_M + warp * 32 + lane;
     const bool raw32 = !p.out_bf16 && p.beta == 0.f && p.alpha == 1.f && !p.bias && p.act == 0;
@@ -524,6 +524,9 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     else if (row >= p.M || (p.dbg & 8))
       mode = (p.bias_out && row == p.M && !(p.dbg & 8)) ? EPI_BIASROW : EPI_NONE;
     else if (p.split_stride == 0 && !p.out_trans && p.out_bf16 && p.beta == 0.f) mode = EPI_BF16;
+    else if (p.split_stride == 0 && !p.out_trans && !p.out_bf16 && p.beta == 0.f && !raw32)
+      mode = EPI_F32;        // fp32 row-major with bias / activation (LSTM gate pre-activations,
+                             // softmax logits): same inline path as bf16, fp32 stores
     else if (raw32 && p.out_trans) mode = EPI_RAW_T;
     else if (raw32 && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(rbase) & 15) == 0)
       mode = EPI_RAW;
@@ -539,7 +542,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (nb + j < p.N) p.bias_out[(long long)blockIdx.z * p.N + nb + j] = __uint_as_float(r[j]);
         return;
       }
-      if (mode == EPI_TMA || mode == EPI_BF16) {
+      if (mode == EPI_TMA || mode == EPI_BF16 || mode == EPI_F32) {
         float v[8];
         {
           const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0);
@@ -569,6 +572,18 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         // bf16 pack: one 16-byte store per 8 outputs. TMA mode stages the 32 x BLOCK_N sub-tile
         // of this warp in the (idle by now) pipeline buffers; it leaves with one TMA store below
+        if (mode == EPI_F32) {
+          float* qf = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + nb;
+          if (nb + 8 <= p.N && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+            reinterpret_cast<float4*>(qf)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(qf)[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (nb + j < p.N) qf[j] = v[j];
+          }
+          return;
+        }
         __nv_bfloat16* q = (mode == EPI_TMA)
             ? reinterpret_cast<__nv_bfloat16*>(tiles + warp * 8192 + lane * (BLOCK_N * 2)) + c0
             : reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + nb;
