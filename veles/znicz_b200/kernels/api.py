@@ -838,9 +838,9 @@ def lstm_seq_forward(unit):
     bias = unit.bias.dev if unit.include_bias and unit.bias else None
     # [x_t] part of every step's operand in one strided copy; h_{-1} = 0
     xh_flat = xh.view((t + 1) * b, i + h)
-    for s in range(t):
-        ext.axpby_2d(x.view(b, t * i), s * i, xh[s], 0, i, 1.0, 0.0)
-        _launch()
+    # x [B][T][I] -> the [x_t] part of xh[t][b][0:I] for every step, one launch
+    ext.swap01_2d(x, i, 0, xh, i + h, 0, b, t, i)
+    _launch()
     ext.axpby_2d(xh[0], i, xh[0], i, h, 0.0, 0.0)
     _launch()
     z = _tmp(unit, "z", (b, 4 * h), torch.float32)
@@ -852,9 +852,8 @@ def lstm_seq_forward(unit):
         _launch()
     # the unit's output: the whole sequence [B, T, H] or the last step [B, H]
     if seq:
-        for s in range(t):
-            ext.axpby_2d(hidden[s], 0, out.view(b, t * h), s * h, h, 1.0, 0.0)
-            _launch()
+        ext.swap01_2d(hidden, h, 0, out, h, 0, t, b, h)      # [T][B][H] -> [B][T][H]
+        _launch()
     else:
         ext.axpby_2d(hidden[t - 1], 0, out, 0, h, 1.0, 0.0)
         _launch()

@@ -162,6 +162,23 @@ __global__ void axpby_2d_k(const T* __restrict__ src, int src_ld, int soff, T* _
   }
 }
 
+// dst[(j * A + i), doff + c] = src[(i * Bn + j), soff + c]  (i < A, j < Bn, c < len): swaps the two
+// leading axes of a [A][Bn][len] block while re-basing the rows - [batch][time] <-> [time][batch]
+// for the whole sequence in ONE launch (the LSTM sequence unit issued one strided copy per step)
+template <typename T>
+__global__ void swap01_2d_k(const T* __restrict__ src, int src_ld, int soff, T* __restrict__ dst,
+                            int dst_ld, int doff, int A, int Bn, int len) {
+  pdl_entry();
+  const long long n = (long long)A * Bn * len;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const int c = (int)(q % len);
+    const long long r = q / len;              // destination row = j * A + i
+    const int i = (int)(r % A), j = (int)(r / A);
+    dst[(size_t)r * dst_ld + doff + c] = src[((size_t)i * Bn + j) * src_ld + soff + c];
+  }
+}
+
 // NHWC crop: out[n, y, x, c] = in[n, y + top, x + left, c]; backward pastes into zeros.
 template <typename T>
 __global__ void crop_nhwc_k(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C,
@@ -346,6 +363,11 @@ void launch_axpby_2d(const void* src, int src_ld, int soff, void* dst, int dst_l
                      int len, float alpha, float beta, bool bf16, cudaStream_t st) {
   DISPATCH_T(bf16, launch_k(axpby_2d_k<T>, grid_for((long long)rows * len), 256, 0, st, 
       (const T*)src, src_ld, soff, (T*)dst, dst_ld, doff, rows, len, alpha, beta));
+}
+void launch_swap01_2d(const void* src, int src_ld, int soff, void* dst, int dst_ld, int doff, int A,
+                      int Bn, int len, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, launch_k(swap01_2d_k<T>, grid_for((long long)A * Bn * len), 256, 0, st,
+      (const T*)src, src_ld, soff, (T*)dst, dst_ld, doff, A, Bn, len));
 }
 void launch_crop_nhwc(const void* in, void* out, int N, int H, int W, int C, int oh, int ow, int top,
                       int left, int backward, bool bf16, cudaStream_t st) {

@@ -27,6 +27,7 @@ void launch_cast(const void*, bool, void*, bool, long long, cudaStream_t);
 void launch_scatter_offsets(const void*, const int*, void*, long long, bool, cudaStream_t);
 void launch_pool_forward(const void*, void*, int*, int, int, int, int, int, int, int, int, int, int, int, const int*, bool, int, cudaStream_t);
 void launch_pull_from_host(const void*, void*, long long, cudaStream_t);
+void launch_swap01_2d(const void*, int, int, void*, int, int, int, int, int, bool, cudaStream_t);
 void launch_pull_from_host_bytes(const void*, void*, int, cudaStream_t);
 void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, const void*, int, const void*, int, cudaStream_t);
 void launch_lrn_forward(const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
@@ -146,6 +147,16 @@ void axpby_2d(Tensor src, int64_t soff, Tensor dst, int64_t doff, int64_t len, d
   zn::launch_axpby_2d(src.data_ptr(), (int)(src.numel() / rows), (int)soff, dst.data_ptr(),
                       (int)(dst.numel() / rows), (int)doff, rows, (int)len, (float)alpha, (float)beta,
                       is_bf16(src), cur());
+  kcheck();
+}
+// dst[(j * A + i)][doff + c] = src[(i * Bn + j)][soff + c]; row pitches given explicitly
+void swap01_2d(Tensor src, int64_t src_ld, int64_t soff, Tensor dst, int64_t dst_ld, int64_t doff,
+               int64_t A, int64_t Bn, int64_t len) {
+  chk(src, "src"); same_dt(src, dst);
+  TORCH_CHECK(soff + len <= src_ld && doff + len <= dst_ld && src.numel() >= A * Bn * src_ld - (src_ld - soff - len)
+              && dst.numel() >= A * Bn * dst_ld - (dst_ld - doff - len), "swap01_2d: out of range");
+  zn::launch_swap01_2d(src.data_ptr(), (int)src_ld, (int)soff, dst.data_ptr(), (int)dst_ld, (int)doff,
+                       (int)A, (int)Bn, (int)len, is_bf16(src), cur());
   kcheck();
 }
 void crop_nhwc(Tensor in, Tensor out, int64_t top, int64_t left, bool backward) {
@@ -674,6 +685,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
   m.def("gather_minibatch", &gather_minibatch);
+  m.def("swap01_2d", &swap01_2d);
   m.def("pull_from_host", &pull_from_host); m.def("push_to_host", &push_to_host);
   m.def("host_gather_rows", &host_gather_rows);
   m.def("host_prefetch_submit", &host_prefetch_submit);
