@@ -446,3 +446,21 @@ def test_fc_small_forward_fused_evaluator(ext, dtype):
     assert torch.equal(a["n_err"], f["n_err"]) and torch.equal(a["conf"], f["conf"])
     assert torch.allclose(a["err"].float(), f["err"].float(), atol=1e-6 if dtype == torch.float32 else 1e-3)
     assert abs(float(a["mx"]) - float(f["mx"])) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c", [32, 5])
+def test_lrn_backward_with_producer_derivative(ext, dtype, c):
+    """LRN backward with the producer's strict-ReLU derivative folded in == LRN backward
+    followed by a separate err *= (x > 0)."""
+    torch.manual_seed(c)
+    dev = "cuda"
+    x = torch.relu(torch.randn(3, 7, 7, c, device=dev)).to(dtype)
+    ey = torch.randn(3, 7, 7, c, device=dev).to(dtype)
+    plain = torch.empty_like(x)
+    fused = torch.empty_like(x)
+    ext.lrn_backward(ey, x, plain, 3, 5e-5, 0.75, 1.0, 0)
+    ext.lrn_backward(ey, x, fused, 3, 5e-5, 0.75, 1.0, 3)
+    torch.cuda.synchronize()
+    ref = plain.float() * (x.float() > 0)
+    assert _rel(fused.float(), ref) < (1e-6 if dtype == torch.float32 else 1e-2)

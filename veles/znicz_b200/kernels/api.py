@@ -625,7 +625,8 @@ def lrn_forward(unit):
 
 def lrn_backward(unit):
     _ext(unit).lrn_backward(unit.err_output.dev, unit.input.dev, unit.err_input.dev_out,
-                            unit.n, unit.alpha, unit.beta, unit.k)
+                            unit.n, unit.alpha, unit.beta, unit.k,
+                            int(unit.__dict__.get("in_deriv_act_", 0) or 0))
     _launch()
 
 

@@ -31,7 +31,7 @@ void launch_swap01_2d(const void*, int, int, void*, int, int, int, int, int, boo
 void launch_pull_from_host_bytes(const void*, void*, int, cudaStream_t);
 void launch_pool_backward(const void*, const int*, void*, int, int, int, int, int, int, int, int, int, int, int, bool, const void*, int, const void*, int, cudaStream_t);
 void launch_lrn_forward(const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
-void launch_lrn_backward(const void*, const void*, void*, long long, int, int, float, float, float, bool, cudaStream_t);
+void launch_lrn_backward(const void*, const void*, void*, long long, int, int, float, float, float, bool, int, cudaStream_t);
 void launch_softmax_rows(const void*, bool, float*, int*, int, int, cudaStream_t);
 void launch_evaluate_softmax(const float*, const int*, const int*, void*, bool, const float*, int, int, int*, int*, float*, cudaStream_t);
 void launch_evaluate_mse(const void*, const void*, bool, void*, bool, const float*, int, int, const float*, int, float*, float*, cudaStream_t);
@@ -299,11 +299,13 @@ void lrn_forward(Tensor x, Tensor y, int64_t n, double alpha, double beta, doubl
                          (float)k, is_bf16(x), cur());
   kcheck();
 }
-void lrn_backward(Tensor ey, Tensor x, Tensor eh, int64_t n, double alpha, double beta, double k) {
+void lrn_backward(Tensor ey, Tensor x, Tensor eh, int64_t n, double alpha, double beta, double k,
+                  int64_t in_act) {
   chk(x, "x"); same_dt(x, ey); same_dt(x, eh);
+  TORCH_CHECK(in_act >= 0 && in_act <= 4, "producer derivative: tanh / softplus / relu / sigmoid only");
   int C = (int)x.size(-1);
   zn::launch_lrn_backward(ey.data_ptr(), x.data_ptr(), eh.data_ptr(), x.numel() / C, C, (int)n,
-                          (float)alpha, (float)beta, (float)k, is_bf16(x), cur());
+                          (float)alpha, (float)beta, (float)k, is_bf16(x), (int)in_act, cur());
   kcheck();
 }
 void softmax_rows(Tensor in, Tensor out, Tensor max_idx) {

@@ -276,6 +276,10 @@ __global__ void lrn_vec_k(const T* __restrict__ x, const T* __restrict__ ey, T* 
     }
   }
   // s[q] for local positions q in [8 - half, 16 + half): window clipped to [0, C) == zeros outside
+  // backward: bit 0 = backward pass, bits 8.. = activation code of the PRODUCER whose derivative
+  // is folded in (err_input *= f'(x), x = this unit's input = the producer's output; see PoolGeom)
+  const int in_act = backward >> 8;
+  backward &= 1;
   float res[8];
   if (!backward) {
 #pragma unroll
@@ -302,6 +306,7 @@ __global__ void lrn_vec_k(const T* __restrict__ x, const T* __restrict__ ey, T* 
         acc += ev[q] * xv[q] * __powf(s, -beta - 1.f);
       }
       res[j] = ev[8 + j] * __powf(si, -beta) - 2.f * alpha * beta * xv[8 + j] * acc;
+      if (in_act) res[j] *= act_deriv(in_act, 0.f, xv[8 + j]);
     }
   }
   st8(out + (size_t)i * 8, res);
@@ -556,7 +561,8 @@ __global__ void lrn_forward_k(const T* __restrict__ x, T* __restrict__ y, long l
 // eh_i = ey_i s_i^-b - 2ab x_i sum_{j in win(i)} ey_j x_j s_j^(-b-1)
 template <typename T>
 __global__ void lrn_backward_k(const T* __restrict__ ey, const T* __restrict__ x, T* __restrict__ eh,
-                               long long pixels, int C, int half, float alpha, float beta, float k) {
+                               long long pixels, int C, int half, float alpha, float beta, float k,
+                               int in_act) {
   pdl_entry();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pixels * C) return;
@@ -575,7 +581,9 @@ __global__ void lrn_backward_k(const T* __restrict__ ey, const T* __restrict__ x
     if (j == c) si = s;
     acc += ldf(pe + j) * ldf(px + j) * __powf(s, -beta - 1.f);
   }
-  stf(eh + i, ldf(pe + c) * __powf(si, -beta) - 2.f * alpha * beta * xi * acc);
+  float r = ldf(pe + c) * __powf(si, -beta) - 2.f * alpha * beta * xi * acc;
+  if (in_act) r *= act_deriv(in_act, 0.f, xi);
+  stf(eh + i, r);
 }
 
 void launch_lrn_forward(const void* x, void* y, long long pixels, int C, int n, float alpha, float beta,
@@ -597,22 +605,23 @@ void launch_lrn_forward(const void* x, void* y, long long pixels, int C, int n, 
   else launch_k(lrn_forward_k<float>, grid, 256, 0, st, (const float*)x, (float*)y, pixels, C, n / 2, alpha, beta, k);
 }
 void launch_lrn_backward(const void* ey, const void* x, void* eh, long long pixels, int C, int n,
-                         float alpha, float beta, float k, bool bf16, cudaStream_t st) {
+                         float alpha, float beta, float k, bool bf16, int in_act, cudaStream_t st) {
+  const int bw = 1 | (in_act << 8);
   if (C % 8 == 0 && (n / 2 == 1 || n / 2 == 2) && pixels * C < (1LL << 31) &&
       (((uintptr_t)x | (uintptr_t)ey | (uintptr_t)eh) & 15) == 0) {
     int gridv = cdiv(pixels * C / 8, 256);
     if (n / 2 == 1) {
-      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 1>, gridv, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
-      else launch_k(lrn_vec_k<float, 1>, gridv, 256, 0, st, (const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
+      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 1>, gridv, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, bw);
+      else launch_k(lrn_vec_k<float, 1>, gridv, 256, 0, st, (const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, bw);
     } else {
-      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 2>, gridv, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, 1);
-      else launch_k(lrn_vec_k<float, 2>, gridv, 256, 0, st, (const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, 1);
+      if (bf16) launch_k(lrn_vec_k<__nv_bfloat16, 2>, gridv, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ey, (__nv_bfloat16*)eh, (int)pixels, C, alpha, beta, k, bw);
+      else launch_k(lrn_vec_k<float, 2>, gridv, 256, 0, st, (const float*)x, (const float*)ey, (float*)eh, (int)pixels, C, alpha, beta, k, bw);
     }
     return;
   }
   int grid = cdiv(pixels * C, 256);
-  if (bf16) launch_k(lrn_backward_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)ey, (const __nv_bfloat16*)x, (__nv_bfloat16*)eh, pixels, C, n / 2, alpha, beta, k);
-  else launch_k(lrn_backward_k<float>, grid, 256, 0, st, (const float*)ey, (const float*)x, (float*)eh, pixels, C, n / 2, alpha, beta, k);
+  if (bf16) launch_k(lrn_backward_k<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)ey, (const __nv_bfloat16*)x, (__nv_bfloat16*)eh, pixels, C, n / 2, alpha, beta, k, in_act);
+  else launch_k(lrn_backward_k<float>, grid, 256, 0, st, (const float*)ey, (const float*)x, (float*)eh, pixels, C, n / 2, alpha, beta, k, in_act);
 }
 
 }  // namespace zn

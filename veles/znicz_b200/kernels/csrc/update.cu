@@ -308,8 +308,14 @@ __device__ __forceinline__ void multi_elem4(const TensorDesc& d, const long long
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 g4 = z4;
   if (MODE == 2) {
-    for (int r = 0; r < rb.nranks; ++r)      // fixed rank order
-      g4 = f4add(g4, *reinterpret_cast<const float4*>(rb.ptr[r] + poff + d.red_off + i0));
+    // all peer loads in flight at once (a run-time loop issues them one NVLink round trip after
+    // the other), then a fixed-order sum: replicas stay bit-identical
+    float4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      v[r] = (r < rb.nranks) ? *reinterpret_cast<const float4*>(rb.ptr[r] + poff + d.red_off + i0) : z4;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) g4 = f4add(g4, v[r]);
   } else {
     const float* base = d.grad[0] + i0;
     const long long st = d.part_stride;
@@ -438,7 +444,12 @@ __device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long 
   float g = 0.f;
   if (MODE == 2) {
     if (valid && lane == 0) {
-      for (int r = 0; r < rb.nranks; ++r) g += rb.ptr[r][poff + d.red_off + i];   // fixed rank order
+      // every peer load in flight at once, then a fixed-order sum (bit-identical replicas)
+      float v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = (r < rb.nranks) ? rb.ptr[r][poff + d.red_off + i] : 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) g += v[r];
     }
   } else if (valid) {
     long long gi = i;

@@ -86,14 +86,15 @@ def fuse_activations(workflow, device):
 
 
 def fuse_backward_derivatives(workflow, device):
-    """conv (activation f, own or fused) → [fused activation unit] → pooling: the pooling GD
-    multiplies its err_input by f'(its input); the conv GD skips its derivative pass.
+    """conv (activation f, own or fused) → [fused activation unit] → pooling or LRN: that layer's
+    GD multiplies its err_input by f'(its input); the conv GD skips its derivative pass.
     Must run after :func:`fuse_activations`. Returns the number of conv layers relieved."""
     if device is None or not device.is_cuda or \
             not root.common.engine.get("fuse_activations", True):
         return 0
     from ..ops.gd_conv import GradientDescentConv
     from ..ops.gd_pooling import GDPooling
+    from ..ops.normalization import LRNormalizerBackward
     fwds = list(workflow.forwards)
     gds = [g for g in workflow.gds if g is not None]
     gd_of = {id(g.forward_unit): g for g in gds if getattr(g, "forward_unit", None) is not None}
@@ -114,7 +115,8 @@ def fuse_backward_derivatives(workflow, device):
             continue
         c = fwds[j]
         gc = gd_of.get(id(c))
-        if not isinstance(gc, GDPooling) or getattr(gc, "force_numpy", False) or \
+        if not isinstance(gc, (GDPooling, LRNormalizerBackward)) or \
+                getattr(gc, "force_numpy", False) or \
                 getattr(c, "force_numpy", False) or not gc.need_err_input:
             continue
         gc.__dict__["in_deriv_act_"] = act
