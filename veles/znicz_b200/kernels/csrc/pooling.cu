@@ -481,13 +481,20 @@ pool_backward_win_k(const T* __restrict__ err_out, const int* __restrict__ offs,
   st8(err_in + (size_t)i * 8, s);
 }
 
-static bool pool_win_enabled() {
-  static int on = -1;
-  // Measured on B200 (CIFAR step, same box, alternating runs): 456 K images/s with these kernels vs
-  // 477 K with the generic ones - hoisting every load costs more in registers / occupancy than
-  // the serialised round trips it removes. Opt-in (ZNICZ_POOL_WIN=1) for experiments.
-  if (on < 0) { const char* e = getenv("ZNICZ_POOL_WIN"); on = (e && atoi(e) != 0) ? 1 : 0; }
-  return on != 0;
+// Per-kernel ncu timing on B200 (CIFAR layers, bf16): the fixed-window FORWARD kernel is faster
+// than the generic one (3.7-4.2 us vs 5.2-5.9 us, pool1 7.1 vs 7.7 us) and is the default; the
+// fixed-window BACKWARD kernel is slower (pool1 27 us vs 17.5 us: 4 positions x (err + offsets +
+// output) held in registers costs more occupancy than the serialised round trips it removes)
+// and stays opt-in (ZNICZ_POOL_WIN_BWD=1). ZNICZ_POOL_WIN=0 disables both.
+static bool pool_win_enabled(bool backward) {
+  static int fwd = -1, bwd = -1;
+  if (fwd < 0) {
+    const char* e = getenv("ZNICZ_POOL_WIN");
+    fwd = (e && atoi(e) == 0) ? 0 : 1;
+    const char* b = getenv("ZNICZ_POOL_WIN_BWD");
+    bwd = (fwd && b && atoi(b) != 0) ? 1 : 0;
+  }
+  return backward ? bwd != 0 : fwd != 0;
 }
 
 void launch_pool_forward(const void* in, void* out, int* offs, int N, int H, int W, int C, int OH, int OW,
@@ -499,10 +506,10 @@ void launch_pool_forward(const void* in, void* out, int* offs, int N, int H, int
       (((uintptr_t)in | (uintptr_t)out | (uintptr_t)offs) & 15) == 0) {
     int gridv = cdiv(total / 8, 256);
     typedef __nv_bfloat16 bf;
-    if (pool_win_enabled() && KY == 3 && KX == 3 && SY == 2 && SX == 2) {
+    if (pool_win_enabled(false) && KY == 3 && KX == 3 && SY == 2 && SX == 2) {
       if (bf16) launch_k(pool_forward_win_k<bf, 3, 3, 2, 2>, gridv, 256, 0, st, (const bf*)in, (bf*)out, offs, g, mode);
       else launch_k(pool_forward_win_k<float, 3, 3, 2, 2>, gridv, 256, 0, st, (const float*)in, (float*)out, offs, g, mode);
-    } else if (pool_win_enabled() && KY == 2 && KX == 2 && SY == 2 && SX == 2) {
+    } else if (pool_win_enabled(false) && KY == 2 && KX == 2 && SY == 2 && SX == 2) {
       if (bf16) launch_k(pool_forward_win_k<bf, 2, 2, 2, 2>, gridv, 256, 0, st, (const bf*)in, (bf*)out, offs, g, mode);
       else launch_k(pool_forward_win_k<float, 2, 2, 2, 2>, gridv, 256, 0, st, (const float*)in, (float*)out, offs, g, mode);
     } else if (bf16) launch_k(pool_forward_vec_k<__nv_bfloat16>, gridv, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, offs, g, mode);
@@ -522,10 +529,10 @@ void launch_pool_backward(const void* err_out, const int* offs, void* err_in, in
   if (C % 8 == 0 && total < (1LL << 31) &&
       (((uintptr_t)err_out | (uintptr_t)err_in | (uintptr_t)offs | (uintptr_t)yact | (uintptr_t)xin) & 15) == 0) {
     int gridv = cdiv(total / 8, 256);
-    if (pool_win_enabled() && KY == 3 && KX == 3 && SY == 2 && SX == 2) {
+    if (pool_win_enabled(true) && KY == 3 && KX == 3 && SY == 2 && SX == 2) {
       if (bf16) launch_k(pool_backward_win_k<bf, 3, 3, 2, 2>, gridv, 256, 0, st, (const bf*)err_out, offs, (bf*)err_in, g, is_avg, (const bf*)yact, (const bf*)xin);
       else launch_k(pool_backward_win_k<float, 3, 3, 2, 2>, gridv, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, is_avg, (const float*)yact, (const float*)xin);
-    } else if (pool_win_enabled() && KY == 2 && KX == 2 && SY == 2 && SX == 2) {
+    } else if (pool_win_enabled(true) && KY == 2 && KX == 2 && SY == 2 && SX == 2) {
       if (bf16) launch_k(pool_backward_win_k<bf, 2, 2, 2, 2>, gridv, 256, 0, st, (const bf*)err_out, offs, (bf*)err_in, g, is_avg, (const bf*)yact, (const bf*)xin);
       else launch_k(pool_backward_win_k<float, 2, 2, 2, 2>, gridv, 256, 0, st, (const float*)err_out, offs, (float*)err_in, g, is_avg, (const float*)yact, (const float*)xin);
     } else if (bf16) launch_k(pool_backward_vec_k<bf>, gridv, 256, 0, st, (const bf*)err_out, offs, (bf*)err_in, g, is_avg, (const bf*)yact, (const bf*)xin);

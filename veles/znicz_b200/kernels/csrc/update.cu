@@ -436,11 +436,13 @@ __device__ __forceinline__ void multi_tile(const TensorDesc& d, int tile, const 
   multi_elem<MODE>(d, i, i < d.size, lane, rb, poff);
 }
 
+// gradient of element i: sum of the split-K partials (this rank) or of the ranks' slots; the
+// result is valid on lane 0 of the element's lane group. Loads only - no stores - so the caller
+// may issue it for the next tile before the current tile's update has been written.
 template <int MODE>
-__device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long i, const bool valid,
-                                           const int lane, const RedBufs& rb, long long poff) {
+__device__ __forceinline__ float multi_grad(const TensorDesc& d, const long long i, const bool valid,
+                                            const int lane, const RedBufs& rb, long long poff) {
   const int L = d.ept > 1 ? 1 : d.lanes;
-  const int is_bias = d.is_bias;
   float g = 0.f;
   if (MODE == 2) {
     if (valid && lane == 0) {
@@ -479,6 +481,14 @@ __device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long 
   }
   if (MODE != 2)
     for (int o = L >> 1; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  return g;
+}
+
+template <int MODE>
+__device__ __forceinline__ void multi_apply(const TensorDesc& d, const long long i, const bool valid,
+                                            const int lane, const float g, const RedBufs& rb,
+                                            long long poff) {
+  const int is_bias = d.is_bias;
   if (!valid || lane != 0) return;
   if (MODE == 1) { rb.ptr[rb.rank][poff + d.red_off + i] = g; return; }
 
@@ -520,6 +530,12 @@ __device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long 
       sh.lp_conv[((size_t)tap * ((rows + 7) & ~7) + r) * sh.c_pad + ch] = __float2bfloat16_rn(wv);
     }
   }
+}
+
+template <int MODE>
+__device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long i, const bool valid,
+                                           const int lane, const RedBufs& rb, long long poff) {
+  multi_apply<MODE>(d, i, valid, lane, multi_grad<MODE>(d, i, valid, lane, rb, poff), rb, poff);
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -567,14 +583,54 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
     peer_barrier(ps, 2 * epoch - 1);
   }
   if (has_ortho) grid_barrier(gsync);    // col_sums of all tensors complete before any update
-  {
+  if (!multi) {
+    // single GPU: software-pipelined tile loop - the partial sums of the CTA's next tile are
+    // loaded (multi_grad: loads only) while the current tile is being updated; small tensors
+    // (one element per lane group) only, the float4 / 4-element tiles keep their own path
+    int t = 0;
+    int tile = blockIdx.x;
+    float g_next = 0.f;
+    bool have_next = false;
+    auto locate = [&](int tl) {
+      while (t + 1 < n && tl >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;   // uniform
+      return t;
+    };
+    auto elem_of = [&](const TensorDesc& d, int tl, long long& i, int& lane) {
+      const int L = d.lanes;
+      lane = threadIdx.x & (L - 1);
+      i = (long long)(tl - d.tile_begin) * (256 / L) + threadIdx.x / L;
+    };
+    while (tile < total_tiles) {
+      const int tc = locate(tile);
+      const TensorDesc& d = s_table[tc];
+      const int nxt = tile + gridDim.x;
+      if (!d.enabled) { tile = nxt; have_next = false; continue; }
+      if (d.ept > 1) { multi_tile<0>(d, tile - d.tile_begin, rb, poff); tile = nxt; have_next = false; continue; }
+      long long i; int lane;
+      elem_of(d, tile, i, lane);
+      const bool valid = i < d.size;
+      const float g = have_next ? g_next : multi_grad<0>(d, i, valid, lane, rb, poff);
+      have_next = false;
+      if (nxt < total_tiles) {
+        const int tn = locate(nxt);           // t advances monotonically; d stays a valid reference
+        const TensorDesc& dn = s_table[tn];
+        if (dn.enabled && dn.ept <= 1) {
+          long long in_; int ln;
+          elem_of(dn, nxt, in_, ln);
+          g_next = multi_grad<0>(dn, in_, in_ < dn.size, ln, rb, poff);
+          have_next = true;
+        }
+      }
+      multi_apply<0>(d, i, valid, lane, g, rb, poff);
+      tile = nxt;
+    }
+  } else {
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;   // uniform
       const TensorDesc& d = s_table[t];
       if (!d.enabled) continue;
-      if (multi) multi_tile<2>(d, tile - d.tile_begin, rb, poff);
-      else multi_tile<0>(d, tile - d.tile_begin, rb, poff);
+      multi_tile<2>(d, tile - d.tile_begin, rb, poff);
     }
   }
   if (multi) {
