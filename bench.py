@@ -141,6 +141,9 @@ def run_arm(args, streaming):
     if os.environ.get("ZNICZ_OVERLAP_WGRAD") == "0":        # diagnostic
         from veles.znicz_b200.core.config import root
         root.common.engine.overlap_wgrad = False
+    if os.environ.get("ZNICZ_LOADER_EARLY") == "0":         # diagnostic
+        from veles.znicz_b200.core.config import root
+        root.common.engine.loader_early_pull = False
     if os.environ.get("ZNICZ_LOADER_PULL") == "0":          # diagnostic
         from veles.znicz_b200.core.config import root
         root.common.engine.loader_pull = False

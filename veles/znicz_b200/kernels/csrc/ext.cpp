@@ -230,6 +230,15 @@ void push_to_host(Tensor src, Tensor dst) {
   }
   kcheck();
 }
+// device -> device byte copy by the same SM kernel (no copy-engine operation in the stream)
+void device_copy(Tensor src, Tensor dst) {
+  TORCH_CHECK(src.is_cuda() && dst.is_cuda() && src.is_contiguous() && dst.is_contiguous());
+  const long long nbytes = (long long)src.numel() * src.element_size();
+  TORCH_CHECK(nbytes == (long long)dst.numel() * dst.element_size(), "size mismatch");
+  TORCH_CHECK((((uintptr_t)src.data_ptr() | (uintptr_t)dst.data_ptr()) & 15) == 0, "16-byte alignment");
+  zn::launch_pull_from_host(src.data_ptr(), dst.data_ptr(), nbytes, cur());
+  kcheck();
+}
 void pad_channels(Tensor x, Tensor y, int64_t C, int64_t CP) {
   chk(x, "x"); same_dt(x, y);
   zn::launch_pad_channels(x.data_ptr(), y.data_ptr(), (int)(x.numel() / C), (int)C, (int)CP, is_bf16(x), cur());
@@ -687,7 +696,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
   m.def("gather_minibatch", &gather_minibatch);
-  m.def("swap01_2d", &swap01_2d);
+  m.def("swap01_2d", &swap01_2d); m.def("device_copy", &device_copy);
   m.def("pull_from_host", &pull_from_host); m.def("push_to_host", &push_to_host);
   m.def("host_gather_rows", &host_gather_rows);
   m.def("host_prefetch_submit", &host_prefetch_submit);

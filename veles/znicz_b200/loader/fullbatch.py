@@ -227,6 +227,20 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
             root.common.engine.get("loader_prefetch", True),
             "pull": _pull_ok(ext)}
         self.h2d_bytes_per_step = total
+        # Early pull: the host runs 1-3 steps ahead of the device, so the PCIe pull of the next
+        # minibatch is issued on the copy stream into a small ring of device staging buffers and
+        # executes while earlier steps still compute; the step's own stream only carries a
+        # device-to-device copy (615 KB: 2-3 us instead of the 18 us PCIe-bound pull).
+        pk = self._packed_
+        pk["early"] = bool(pk["pull"] and hasattr(ext, "device_copy") and
+                           getattr(self.device, "copy_stream", None) is not None and
+                           root.common.engine.get("loader_early_pull", True))
+        if pk["early"]:
+            pk["stage"] = [torch.zeros_like(devp) for _ in range(3)]
+            pk["stage_evt"] = [torch.cuda.Event() for _ in range(3)]
+            pk["stage_used"] = [False] * 3
+            pk["pull_evt"] = [torch.cuda.Event() for _ in range(3)]
+            pk["s"] = 0
 
     def _fill_packed(self):
         """Minibatch → pinned slot: already there when the prefetcher guessed this minibatch
@@ -259,11 +273,29 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         hn[0] = self.minibatch_size
         hn[1] = self.minibatch_class
         hn[2] = self.epoch_number
-        if pk["pull"]:
+        if pk.get("early"):
+            import torch
+            ext = self.device.ext
+            k = pk["s"]
+            pk["s"] = (k + 1) % len(pk["stage"])
+            side = self.device.copy_stream      # (not the wgrad side stream: that one is captured)
+            if pk["stage_used"][k]:
+                side.wait_event(pk["stage_evt"][k])      # its previous contents were copied out
+            with torch.cuda.stream(side):
+                ext.pull_from_host(sl["pin"], pk["stage"][k])
+                pk["pull_evt"][k].record()
+                sl["event"].record()                      # pinned slot free once the pull is done
+            main = torch.cuda.current_stream()
+            main.wait_event(pk["pull_evt"][k])
+            ext.device_copy(pk["stage"][k], pk["dev"])
+            pk["stage_evt"][k].record()
+            pk["stage_used"][k] = True
+        elif pk["pull"]:
             self.device.ext.pull_from_host(sl["pin"], pk["dev"])    # SMs read the pinned slot
+            sl["event"].record()
         else:
             pk["dev"].copy_(sl["pin"], non_blocking=True)
-        sl["event"].record()
+            sl["event"].record()
         sl["used"] = True
         self.minibatch_data.dev_written()
         if pk["labels"]:
