@@ -327,6 +327,16 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
                                                       sl["data"], n)
         pk["pending"] = {"ticket": ticket, "slot": pk["i"], "n": n, "idx": idx}
 
+    def stop(self):
+        """Do not leave a prefetch job writing into a pinned slot behind."""
+        pk = self.__dict__.get("_packed_")
+        if pk and pk.get("pending") is not None:
+            pend, pk["pending"] = pk["pending"], None
+            self.device.ext.host_prefetch_wait(pend["ticket"])
+        parent = super()
+        if hasattr(parent, "stop"):
+            parent.stop()
+
     def _cuda_serve(self):
         if not self.on_device:
             if self.__dict__.get("_packed_") is not None:
