@@ -464,3 +464,39 @@ def test_lrn_backward_with_producer_derivative(ext, dtype, c):
     torch.cuda.synchronize()
     ref = plain.float() * (x.float() > 0)
     assert _rel(fused.float(), ref) < (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 512), (100, 72, 384), (257, 1000, 4096)])
+@pytest.mark.parametrize("out_dt", [torch.bfloat16, torch.float32])
+def test_gemm_fp8_e4m3(ext, M, N, K, out_dt):
+    """tcgen05 kind::f8f6f4 GEMM on per-tensor-scaled e4m3 operands: exact (up to fp32
+    accumulation order) against the same quantised operands multiplied in fp32, and within
+    fp8 tolerance of the unquantised product."""
+    torch.manual_seed(M + N)
+    dev = "cuda"
+    a = torch.randn(M, K, device=dev)
+    b = torch.randn(N, K, device=dev) / K ** 0.5
+    bias = torch.randn(N, device=dev)
+    qa = torch.empty(M, K, device=dev, dtype=torch.uint8)
+    qb = torch.empty(N, K, device=dev, dtype=torch.uint8)
+    amax = torch.zeros(2, device=dev)
+    ext.fp8_absmax(a, amax[0:1])
+    ext.fp8_absmax(b, amax[1:2])
+    ext.fp8_quantize(a, qa, amax[0:1])
+    ext.fp8_quantize(b, qb, amax[1:2])
+    torch.cuda.synchronize()
+    assert abs(float(amax[0]) - float(a.abs().max())) < 1e-6
+    sa, sb = 448.0 / float(amax[0]), 448.0 / float(amax[1])
+    # our quantiser == torch's e4m3 cast of the scaled tensor
+    ref_qa = (a * sa).to(torch.float8_e4m3fn)
+    assert torch.equal(qa.view(torch.float8_e4m3fn).float(), ref_qa.float())
+    out = torch.full((M, N), float("nan"), device=dev, dtype=out_dt)
+    r = ext.gemm_fp8(qa, qb, out, bias, 3, 1.0 / (sa * sb))
+    assert r == 0
+    torch.cuda.synchronize()
+    fa = qa.view(torch.float8_e4m3fn).float()
+    fb = qb.view(torch.float8_e4m3fn).float()
+    ref_q = torch.relu(fa @ fb.t() / (sa * sb) + bias)
+    assert _rel(out.float(), ref_q) < (1e-2 if out_dt == torch.bfloat16 else 1e-5)
+    ref = torch.relu(a @ b.t() + bias)
+    assert _rel(out.float(), ref) < 6e-2

@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(256) gemm_simt_k(AL A, BL B, Epilogue ep, int 
         reinterpret_cast<float*>(ep.out)[(long long)blockIdx.z * ep.split_stride + o] = v;
         continue;
       }
+      v *= ep.alpha;                       // act(alpha * acc + bias), same as the tcgen05 epilogue
       if (ep.bias) v += ep.bias[n];
       v = act_fwd5(ep.act, v);
-      v *= ep.alpha;
       if (ep.out_bf16) {
         __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ep.out) + o;
         if (ep.beta != 0.f) v += ep.beta * __bfloat162float(*p);

@@ -260,8 +260,9 @@ __device__ __noinline__ void epi_store_slow(const GemmParams& p, int row, int n,
     reinterpret_cast<float*>(p.out)[(long long)z * p.split_stride + o] = v;
     return;
   }
+  v *= p.alpha;
   if (p.bias) v += p.bias[n];
-  v = act_fwd5(p.act, v) * p.alpha;
+  v = act_fwd5(p.act, v);
   if (p.out_bf16) {
     __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
     if (p.beta != 0.f) v += p.beta * __bfloat162float(*q);
@@ -278,7 +279,9 @@ __host__ __device__ constexpr int min_ctas() {
   return (2 * (STAGES * (A_BYTES + b_bytes<BLOCK_N, B_MODE>()) + 2048) <= 227 * 1024) ? 2 : 1;
 }
 
-template <int BLOCK_N, int A_MODE, int B_MODE, int GKIND, int GVEC, int STAGES>
+// FP8: operands are e4m3 bytes (TMA / TMA, both K-major): the byte geometry of a stage is the
+// same (128-byte swizzled rows), a k-block is 128 elements and every MMA consumes 32 of them.
+template <int BLOCK_N, int A_MODE, int B_MODE, int GKIND, int GVEC, int STAGES, bool FP8 = false>
 __global__ void __launch_bounds__(192, (min_ctas<BLOCK_N, B_MODE, STAGES>()))
 gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
@@ -289,7 +292,10 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr bool A_MN = (A_MODE == A_TMA_MN || A_MODE == A_GATHER_MN);
   constexpr bool B_MN = (B_MODE == B_TMA_MN);
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-  constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr uint32_t IDESC = FP8 ? make_idesc_e4m3(BLOCK_M, BLOCK_N)
+                                 : make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr int KBLK = FP8 ? 2 * BLOCK_K : BLOCK_K;      // elements per k-block (128 bytes per row)
+  static_assert(!FP8 || (A_MODE == A_TMA_K && B_MODE == B_TMA_K), "fp8: TMA K-major operands only");
   constexpr uint32_t TX_BYTES = (A_GATHER ? 0 : A_BYTES) + B_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -316,7 +322,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int m0 = mtile0 * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
   uint32_t tmem_cols = TMEM_COLS;                                 // power of two >= 32
   while (tmem_cols < (uint32_t)(BLOCK_N * mt_cfg)) tmem_cols <<= 1;
-  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int total_kb = (p.K + KBLK - 1) / KBLK;
   const int kb_begin = blockIdx.z * p.k_blocks_per_split;
   const int kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
   const int num_kb = max(0, kb_end - kb_begin);
@@ -357,7 +363,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
-        const int k0 = (kb_begin + i) * BLOCK_K;
+        const int k0 = (kb_begin + i) * KBLK;
         if (p.dbg & 4) { mbar_arrive(&full_bar[s]); continue; }
         mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
         if (A_MODE == A_TMA_K) {
@@ -394,7 +400,10 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                    : make_smem_desc(sa + k * 32, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
                                    : make_smem_desc(sb + k * 32, 16, 1024);
-          if (!(p.dbg & 2)) mma_f16(d_tmem, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          if (!(p.dbg & 2)) {
+            if (FP8) mma_f8(d_tmem, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+            else mma_f16(d_tmem, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          }
         }
         mma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs retire
         if (i == num_kb - 1) mma_commit(&tmem_full_bar[gi / num_kb]);   // this tile's accumulator
@@ -552,23 +561,25 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         // activation selected once per chunk (not per element): the executed path stays short
         switch (p.act) {
+          // out = act(alpha * acc + bias): alpha is the operand de-scaling of the fp8 path and the
+          // err_input_alpha of dgrad (no bias, linear); every other caller passes alpha = 1
           case ACT_LINEAR:
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(r[j]) + v[j]) * p.alpha;
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, v[j]);
             break;
           case ACT_STRICT_RELU:
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + v[j], 0.f) * p.alpha;
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[j]), p.alpha, v[j]), 0.f);
             break;
           case ACT_TANH:
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              v[j] = 1.7159f * tanh_approx(0.6666f * (__uint_as_float(r[j]) + v[j])) * p.alpha;
+              v[j] = 1.7159f * tanh_approx(0.6666f * fmaf(__uint_as_float(r[j]), p.alpha, v[j]));
             break;
           default:
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              v[j] = act_fwd5_fast(p.act, __uint_as_float(r[j]) + v[j]) * p.alpha;
+              v[j] = act_fwd5_fast(p.act, fmaf(__uint_as_float(r[j]), p.alpha, v[j]));
         }
         // bf16 pack: one 16-byte store per 8 outputs. TMA mode stages the 32 x BLOCK_N sub-tile
         // of this warp in the (idle by now) pipeline buffers; it leaves with one TMA store below
@@ -839,6 +850,61 @@ int launch_gemm_umma(const void* a, long long lda, int a_mn, const void* b, long
   if (!a_mn && b_mn) return launch_bn<A_TMA_K, B_TMA_MN, 0, 0>(bn, ta, tb, p, splits, st);
   if (a_mn && !b_mn) return launch_bn<A_TMA_MN, B_TMA_K, 0, 0>(bn, ta, tb, p, splits, st);
   return launch_bn<A_TMA_MN, B_TMA_MN, 0, 0>(bn, ta, tb, p, splits, st);
+}
+
+// ---- fp8 (e4m3 x e4m3 -> fp32 accumulate) GEMM: out = act(alpha * a . b^T + bias) -------------
+static int make_map_u8(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld,
+                       int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld};
+  cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+template <int BN>
+static int launch_fp8_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+                         cudaStream_t st) {
+  constexpr int ring = STAGES_DEFAULT * (A_BYTES + b_bytes<BN, B_TMA_K>()) + 1024;
+  constexpr int smem = ring + BN * 4 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_umma_k<BN, A_TMA_K, B_TMA_K, 0, 0, STAGES_DEFAULT, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  launch_k(gemm_umma_k<BN, A_TMA_K, B_TMA_K, 0, 0, STAGES_DEFAULT, true>, grid, 192, smem, st, ta, tb, ta, p);
+  return (int)cudaGetLastError();
+}
+// a [M][lda] e4m3, b [N][ldb] e4m3 (both K-major, ld % 16 == 0); alpha carries 1/(scale_a*scale_b)
+int launch_gemm_fp8(const void* a, long long lda, const void* b, long long ldb, void* out, int out_bf16,
+                    long long ldo, int M, int N, int K, const float* bias, int act, float alpha,
+                    cudaStream_t st) {
+  if ((lda % 16) || (ldb % 16) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return -3;
+  CUtensorMap ta, tb;
+  const int bn = pick_bn(N);
+  int r = make_map_u8(&ta, a, K, M, lda, BLOCK_M);
+  if (r) return r;
+  r = make_map_u8(&tb, b, K, N, ldb, bn);
+  if (r) return r;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.k_blocks_per_split = (K + 2 * BLOCK_K - 1) / (2 * BLOCK_K);
+  p.out = out; p.out_bf16 = out_bf16; p.ldo = ldo; p.out_trans = 0;
+  p.bias = bias; p.act = act; p.alpha = alpha; p.beta = 0.f; p.split_stride = 0;
+  p.gather_kind = G_NONE; p.mt = 1;
+  dim3 grid((N + bn - 1) / bn, (M + BLOCK_M - 1) / BLOCK_M, 1);
+  switch (bn) {
+    case 16: return launch_fp8_bn<16>(ta, tb, p, grid, st);
+    case 32: return launch_fp8_bn<32>(ta, tb, p, grid, st);
+    case 64: return launch_fp8_bn<64>(ta, tb, p, grid, st);
+    default: return launch_fp8_bn<128>(ta, tb, p, grid, st);
+  }
 }
 
 static ConvGeomU geom(int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX,
