@@ -47,7 +47,7 @@ for name, n, h, w, c, f in SHAPES:
     splits = int(ext.pick_splits(kw, f, n * h * w, 64))
     parts = torch.empty(splits, f, kw, device=dev)
     t_f = timeit(lambda: ext.conv_fprop(x, wl, kw, False, bias, out, g, 3, 1))
-    t_d = timeit(lambda: ext.conv_dgrad(eo, wd, wd.shape[1], False, ei, g, 1.0, 0.0, 1)) if c >= 32 else 0
+    t_d = timeit(lambda: ext.conv_dgrad(eo, wd, wd.shape[1], False, ei, g, 1.0, 0.0, 1, None, 0)) if c >= 32 else 0
     t_w = timeit(lambda: ext.conv_wgrad(eo, x, parts, splits, g, False, 1, None))
     print("%s fprop %.1f us  dgrad %.1f us  wgrad %.1f us (splits %d)  dbg=%s deep=%s mt=%s" % (
         name, t_f, t_d, t_w, splits, os.environ.get("ZNICZ_UMMA_DBG", "0"),

@@ -56,7 +56,7 @@ def test_fusion_passes_on_cifar_caffe():
 
 def test_derivative_fusion_on_alexnet():
     """conv1 / conv2 / conv5 feed max-pooling layers (their derivative moves there); conv3 / conv4
-    feed the next convolution and keep their own err_output pass."""
+    feed the next convolution, whose dgrad epilogue applies it."""
     from veles.znicz_b200.models import alexnet
     root.common.disable.snapshotting = True
     try:
@@ -71,7 +71,8 @@ def test_derivative_fusion_on_alexnet():
                   if g is not None and g.__dict__.get("in_deriv_act_")]
         relieved = [g.forward_unit.name for g in wf.gds
                     if g is not None and g.__dict__.get("deriv_upstream_")]
-        assert n == len(marked) == len(relieved) == 3
-        assert all(m in ("GDMaxPooling", "LRNormalizerBackward") for m in marked)
+        assert n == len(marked) == len(relieved) == 5
+        assert sum(m in ("GDMaxPooling", "LRNormalizerBackward") for m in marked) == 3
+        assert sum("Conv" in m for m in marked) == 2        # conv4 / conv5 dgrad epilogues
     finally:
         root.common.disable.snapshotting = False

@@ -136,9 +136,17 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
         cp = (c + 7) // 8 * 8
         wd = torch.zeros(ky * kx * f, cp, device=dev, dtype=torch.bfloat16)
         wd.view(ky * kx, f, cp)[:, :, :c] = wq.view(f, ky * kx, c).permute(1, 0, 2).bfloat16()
-        r = ext.conv_dgrad(eo, wd, cp, False, ei, g, 1.0, 0.0, 1)
+        r = ext.conv_dgrad(eo, wd, cp, False, ei, g, 1.0, 0.0, 1, None, 0)
+        if r == 0 and c % 8 == 0:
+            # the same dgrad with the producer's strict-ReLU derivative folded into the epilogue
+            ei2 = torch.empty_like(ei)
+            xin = torch.randn(n, h, w_, c, device=dev).bfloat16()
+            r2 = ext.conv_dgrad(eo, wd, cp, False, ei2, g, 1.0, 0.0, 1, xin, 3)
+            assert r2 == 0
+            torch.cuda.synchronize()
+            assert torch.equal(ei2, (ei.float() * (xin.float() > 0)).bfloat16())
     else:
-        r = ext.conv_dgrad(eo, wq.contiguous(), kw, False, ei, g, 1.0, 0.0, 0)
+        r = ext.conv_dgrad(eo, wq.contiguous(), kw, False, ei, g, 1.0, 0.0, 0, None, 0)
     assert r == 0
     torch.cuda.synchronize()
     assert _rel(ei, xr.grad) < 2e-2

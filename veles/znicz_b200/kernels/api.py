@@ -505,10 +505,22 @@ def conv_backward(unit):
     if unit.need_err_input:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
         r = -1
+        # derivative of the producer layer's activation, folded into this dgrad's epilogue
+        # (workflow/fusion.py::fuse_backward_derivatives)
+        in_act = int(unit.__dict__.get("in_deriv_act_", 0) or 0)
+        folded = False
         if lp_ok:
             wd = fwd.weights_lp_t_
+            fold = bool(in_act and _is_bf16(ei) and not unit.err_input_beta)
             r = ext.conv_dgrad(err_mm, wd, wd.shape[1], False, ei, g_mm,
-                               float(unit.err_input_alpha), float(unit.err_input_beta), 1)
+                               float(unit.err_input_alpha), float(unit.err_input_beta), 1,
+                               x if fold else None, in_act if fold else 0)
+            if r == -5:      # the fold was declined (alignment): plain tensor-core dgrad
+                r = ext.conv_dgrad(err_mm, wd, wd.shape[1], False, ei, g_mm,
+                                   float(unit.err_input_alpha), float(unit.err_input_beta), 1,
+                                   None, 0)
+                fold = False
+            folded = fold and r == 0
             if r not in (0, -3, -4):
                 raise RuntimeError("%s: tcgen05 conv dgrad refused (code %d)" % (unit, r))
             if r != 0:
@@ -518,9 +530,14 @@ def conv_backward(unit):
             # SIMT implicit-GEMM kernel with the fp32 master weights
             w = unit.weights.dev
             ext.conv_dgrad(err, w, w.shape[1], bool(unit.weights_transposed), ei, g,
-                           float(unit.err_input_alpha), float(unit.err_input_beta), 0)
+                           float(unit.err_input_alpha), float(unit.err_input_beta), 0, None, 0)
         unit.err_input.dev_written()
         _launch()
+        if in_act and not folded:
+            # the tensor-core kernel declined: apply the promised derivative in a separate pass
+            ext.err_act_colsum(ei, unit.input.dev, ei.numel() // ei.shape[-1], ei.shape[-1],
+                               in_act, None)
+            _launch()
     if not need_w:
         return
     use_umma = lp_ok
@@ -768,7 +785,7 @@ def deconv_forward(unit):
     g = _deconv_geom(unit)
     w = unit.weights.dev
     alpha = 1.0 if unit.hits else float(unit.scale)
-    ext.conv_dgrad(x, w, w.shape[1], bool(unit.weights_transposed), out, g, alpha, 0.0, 0)
+    ext.conv_dgrad(x, w, w.shape[1], bool(unit.weights_transposed), out, g, alpha, 0.0, 0, None, 0)
     _launch()
     if unit.hits:
         ext.mask_mul(out, _rhits(unit, out))

@@ -59,7 +59,7 @@ void launch_som_winners(const float*, const float*, int*, int*, int, int, int, i
 void launch_som_update(const float*, float*, const float*, const int*, int, int, int, float, float, cudaStream_t);
 int launch_gemm_umma(const void*, long long, int, const void*, long long, int, void*, int, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
 int launch_conv_fprop_umma(const void*, const void*, long long, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int launch_conv_dgrad_umma(const void*, const void*, long long, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int launch_conv_dgrad_umma(const void*, const void*, long long, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, float, float, const void*, int, cudaStream_t);
 int launch_conv_wgrad_umma(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
 }  // namespace zn
 
@@ -631,16 +631,24 @@ int64_t conv_fprop(Tensor x, Tensor w, int64_t ldw, bool w_trans, c10::optional<
   kcheck();
   return 0;
 }
+// dmul / dact (engine 1 only): err_in *= f'(dmul), dmul = the layer's input (the producer's output)
 int64_t conv_dgrad(Tensor err_out, Tensor w, int64_t ldw, bool w_trans, Tensor err_in,
-                   std::vector<int64_t> g, double alpha, double beta, int64_t engine) {
+                   std::vector<int64_t> g, double alpha, double beta, int64_t engine,
+                   c10::optional<Tensor> dmul, int64_t dact) {
   TORCH_CHECK(g.size() == 13);
   int gi[13]; for (int i = 0; i < 13; ++i) gi[i] = (int)g[i];
+  const void* dm = nullptr;
+  if (dmul.has_value() && dmul->defined() && dact != 0) {
+    TORCH_CHECK(engine == 1 && dact >= 1 && dact <= 4 && is_bf16(*dmul) && dmul->is_cuda() &&
+                dmul->is_contiguous() && dmul->numel() == err_in.numel(), "dgrad derivative operand");
+    dm = dmul->data_ptr();
+  }
   if (engine == 1) {
     TORCH_CHECK(is_bf16(err_out) && is_bf16(w));
     int r = zn::launch_conv_dgrad_umma(err_out.data_ptr(), w.data_ptr(), ldw, err_in.data_ptr(),
                                        is_bf16(err_in) ? 1 : 0, gi[0], gi[1], gi[2], gi[3], gi[4], gi[5],
                                        gi[6], gi[7], gi[8], gi[9], gi[10], gi[11], gi[12], (float)alpha,
-                                       (float)beta, cur());
+                                       (float)beta, dm, (int)dact, cur());
     if (r == 0) kcheck();
     return r;
   }

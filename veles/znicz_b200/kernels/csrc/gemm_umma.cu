@@ -55,6 +55,8 @@ struct GemmParams {
   void* out; int out_bf16; long long ldo; int out_trans;
   const float* bias; int act; float alpha, beta;
   float* bias_out;             // wgrad: row M of the product -> bias_out[blockIdx.z][N] (see ones)
+  const __nv_bfloat16* dmul;   // dgrad: out *= f'(dmul[row][col]) - the producer layer's activation
+  int dact;                    //        derivative (dmul = this layer's input, same layout as out)
   long long split_stride;      // > 0: fp32 partial [blockIdx.z][...]
   // gather source
   const __nv_bfloat16* gsrc; ConvGeomU g; int gather_kind;
@@ -583,6 +585,20 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         // bf16 pack: one 16-byte store per 8 outputs. TMA mode stages the 32 x BLOCK_N sub-tile
         // of this warp in the (idle by now) pipeline buffers; it leaves with one TMA store below
+        if (p.dmul != nullptr && mode == EPI_BF16) {
+          // err_input *= f'(x): x has the layout of the output (row pitch ldo)
+          const __nv_bfloat16* dx = p.dmul + (long long)row * p.ldo + nb;
+          if (nb + 8 <= p.N && (p.ldo & 7) == 0) {
+            float xv[8];
+            ld8(dx, xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= act_deriv(p.dact, 0.f, xv[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (nb + j < p.N) v[j] *= act_deriv(p.dact, 0.f, __bfloat162float(dx[j]));
+          }
+        }
         if (mode == EPI_F32) {
           float* qf = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + nb;
           if (nb + 8 <= p.N && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
@@ -968,7 +984,10 @@ int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const
 // wd_lp stored [KY*KX*F][ldc] bf16 (ldc % 8 == 0, zero padded columns)
 int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc, void* err_in,
                            int ei_bf16, int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX,
-                           int SY, int SX, int PT, int PL, float alpha, float beta, cudaStream_t st) {
+                           int SY, int SX, int PT, int PL, float alpha, float beta, const void* dmul,
+                           int dact, cudaStream_t st) {
+  // the folded derivative needs the inline bf16 epilogue mode (row-major bf16 output, no beta)
+  if (dmul && (!ei_bf16 || beta != 0.f || ((uintptr_t)dmul & 15))) return -5;
   if ((ldc % 8) || ((uintptr_t)wd_lp & 15) || ((uintptr_t)err_out & 15)) return -3;
   int Kd = KY * KX * F;
   if ((F % 8 == 0 ? (Kd + 7) / 8 : Kd) > KTAB || KY > 255 || KX > 255) return -4;
@@ -986,6 +1005,7 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
   p.gsrc = (const __nv_bfloat16*)err_out;
   p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, F % 8 == 0);
   p.gather_kind = G_DGRAD; p.gK = Kd;
+  p.dmul = (const __nv_bfloat16*)dmul; p.dact = dmul ? dact : 0;
   p.mt = pick_mt(p.M, p.N, bn);
   if (set_tap_mode(p.g, F, true)) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 2>(bn, ta, tb, p, 1, st);
   if (F % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 1>(bn, ta, tb, p, 1, st);

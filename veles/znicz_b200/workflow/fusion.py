@@ -86,8 +86,9 @@ def fuse_activations(workflow, device):
 
 
 def fuse_backward_derivatives(workflow, device):
-    """conv (activation f, own or fused) → [fused activation unit] → pooling or LRN: that layer's
-    GD multiplies its err_input by f'(its input); the conv GD skips its derivative pass.
+    """conv (activation f, own or fused) → [fused activation unit] → pooling, LRN or another conv:
+    that layer's GD multiplies its err_input by f'(its input) in the kernel it runs anyway (pooling /
+    LRN backward, the dgrad epilogue); the conv GD skips its derivative pass.
     Must run after :func:`fuse_activations`. Returns the number of conv layers relieved."""
     if device is None or not device.is_cuda or \
             not root.common.engine.get("fuse_activations", True):
@@ -108,14 +109,18 @@ def fuse_backward_derivatives(workflow, device):
         act = int(gp.__dict__.get("fused_act_", 0) or 0) or int(getattr(gp, "ACT", 0) or 0)
         if act not in FUSABLE_CODES:
             continue
+        from ..ops.weights_zerofilling import ZeroFiller
         j = i + 1
-        while j < len(fwds) and getattr(fwds[j], "fused_into_", None) is p:
-            j += 1                       # activation units folded into the conv
+        while j < len(fwds) and (getattr(fwds[j], "fused_into_", None) is p or
+                                 isinstance(fwds[j], ZeroFiller)):
+            j += 1      # activation units folded into the conv; weight-mask units carry no data
         if j >= len(fwds):
             continue
         c = fwds[j]
         gc = gd_of.get(id(c))
-        if not isinstance(gc, (GDPooling, LRNormalizerBackward)) or \
+        conv_ok = isinstance(gc, GradientDescentConv) and not gc.err_input_beta and \
+            not getattr(c, "weights_transposed", False)      # dgrad epilogue folds it (bf16 path)
+        if not (isinstance(gc, (GDPooling, LRNormalizerBackward)) or conv_ok) or \
                 getattr(gc, "force_numpy", False) or \
                 getattr(c, "force_numpy", False) or not gc.need_err_input:
             continue
