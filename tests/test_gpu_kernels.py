@@ -31,12 +31,16 @@ def test_gemm_nt_bias_act(ext, engine, M, N, K):
     bias = torch.randn(N, device=dev)
     ref = torch.relu(a.float() @ b.float().t() + bias)
     for out_dt in (torch.bfloat16, torch.float32):
-        out = torch.full((M, N), float("nan"), device=dev, dtype=out_dt)
+        # out-of-bounds guard of the reference's unit tests (tests/unit/test_gd.py:137-141): the
+        # buffer is twice as large and NaN-filled; whatever lies behind the result must stay NaN
+        big = torch.full((2 * M, N), float("nan"), device=dev, dtype=out_dt)
+        out = big[:M]
         r = ext.gemm(a, K, False, b, K, True, out, N, False, M, N, K, bias, 3, 1.0, 0.0, 1, 0,
                      engine)
         assert r == 0
         torch.cuda.synchronize()
         assert _rel(out, ref) < (2e-2 if out_dt == torch.bfloat16 else 2e-3), (engine, out_dt)
+        assert torch.isnan(big[M:]).all(), (engine, out_dt)
 
 
 @pytest.mark.parametrize("engine", [0, 1])
@@ -119,7 +123,8 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
     eo = torch.randn_like(ref).bfloat16()
     ref.backward(eo.float())
     # fprop
-    out = torch.full((n, oh, ow, f), float("nan"), device=dev, dtype=torch.bfloat16)
+    big_out = torch.full((2 * n, oh, ow, f), float("nan"), device=dev, dtype=torch.bfloat16)
+    out = big_out[:n]                      # out-of-bounds guard: the second half must stay NaN
     if engine == 1:
         ld = (kw + 7) // 8 * 8
         wlp = torch.zeros(f, ld, device=dev, dtype=torch.bfloat16)
@@ -130,6 +135,7 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
     assert r == 0
     torch.cuda.synchronize()
     assert _rel(out, ref.detach()) < 2e-2
+    assert torch.isnan(big_out[n:]).all()
     # dgrad
     ei = torch.full((n, h, w_, c), float("nan"), device=dev, dtype=torch.bfloat16)
     if engine == 1:
