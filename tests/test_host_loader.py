@@ -52,3 +52,30 @@ def test_prefetch_pool_matches_synchronous_gather(ext, dtype):
         ext.host_prefetch_wait(ticket)
         ext.host_gather_rows(src, idx_copy, b, n)
         assert torch.equal(a, b)
+
+
+def test_peek_next_indices_predicts_the_next_minibatch():
+    """The prefetcher assembles minibatch N+1 from ``peek_next_indices()``: it must name exactly
+    the indices the next run() serves, across class boundaries, and decline at epoch wraps."""
+    from veles.znicz_b200.core.workflow import DummyWorkflow
+    from veles.znicz_b200.loader.synthetic import SyntheticImageLoader
+    wf = DummyWorkflow()
+    ld = SyntheticImageLoader(wf, minibatch_size=32, shape=(4, 4, 3), n_classes=5,
+                              n_train=80, n_valid=40, n_test=10)
+    ld.initialize(device="numpy")
+    ld.run()
+    hits = wraps = 0
+    for _ in range(40):
+        peek = ld.peek_next_indices()
+        expected = None
+        if peek is not None:
+            start, n = peek
+            expected = ld.shuffled_indices.mem[start:start + n].copy()
+        ld.run()
+        got = ld.minibatch_indices.mem[:int(ld.minibatch_size)]
+        if expected is None:
+            wraps += 1
+        else:
+            hits += 1
+            numpy.testing.assert_array_equal(got, expected)
+    assert hits > 25 and wraps >= 5          # 130 samples / 32: 6 minibatches per epoch

@@ -304,18 +304,26 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         if pk["prefetch"]:
             self._prefetch_next()
 
+    def peek_next_indices(self):
+        """(start, count) of the slice of ``shuffled_indices`` the *next* ``run()`` will serve, or
+        None when that run starts a new epoch (the train part is reshuffled first, so its indices
+        are not known yet). Pure function of the loader state after a ``run()``."""
+        start = self.global_offset
+        if start <= 0 or start >= self.total_samples:
+            return None
+        cls = self.class_index_by_offset(start)
+        n = int(min(self.max_minibatch_size, self.class_end_offsets[cls] - start))
+        return (start, n) if n > 0 else None
+
     def _prefetch_next(self):
         """Start assembling the following minibatch (same epoch only: its indices are already
         fixed in ``shuffled_indices``) into the next pinned slot on the native worker pool."""
         pk = self._packed_
-        start = self.global_offset
-        if start <= 0 or start >= self.total_samples:
+        peek = self.peek_next_indices()
+        if peek is None:
             return                              # epoch wrap: the train part is reshuffled first
-        cls = self.class_index_by_offset(start)
-        n = int(min(self.max_minibatch_size, self.class_end_offsets[cls] - start))
+        start, n = peek
         sl = pk["slots"][pk["i"]]
-        if n <= 0:
-            return
         if sl["used"] and not sl["event"].query():
             # the copy out of this slot (issued depth - 1 steps ago) has not finished: the device
             # is that far behind, so the host has time to spare - wait for it rather than give
