@@ -933,9 +933,11 @@ static ConvGeomU geom(int N, int H, int W, int C, int OH, int OW, int F, int KY,
 static int pick_mt(int M, int N, int bn) {
   const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const long long n_tiles = (N + bn - 1) / bn;
-  // Measured on B200 (CIFAR conv1 fprop, 800 tiles, K = 200): streaming 4 tiles through one CTA
-  // is *slower* (36 us) than 800 independent CTAs (32.7 us) - CTA-level parallelism beats
-  // prologue amortisation - so the mode stays opt-in (ZNICZ_UMMA_MT=2|4) for experiments.
+  // Measured on B200 (CIFAR step): with the epilogue of tile t overlapping the MMAs of tile t + 1
+  // (the "rounds" loop of the kernel) streaming 2 or 4 tiles per CTA is neutral (444.9 K / 445.3 K
+  // vs 442.7-447 K images/s); before that overlap existed it was slower (conv1 fprop 36 us vs
+  // 32.7 us). Independent CTAs already hide each other's prologues, so the mode stays opt-in
+  // (ZNICZ_UMMA_MT=2|4); a persistent scheduler with TMEM double buffering is the round-2 form.
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("ZNICZ_UMMA_MT"); forced = e ? atoi(e) : 1; }
   int mt = 1;
