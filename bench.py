@@ -131,6 +131,7 @@ def build_workflow(streaming, compute, graphs, n_train, model="cifar_caffe"):
 
 
 GRAPH_CAPTURE_STEPS = 6
+ALIGN_STEPS = 3          # untimed, after the pre-timing barrier of a multi-rank run
 
 
 def _batch_of(model):
@@ -173,14 +174,23 @@ def run_arm(args, streaming):
     torch.cuda.synchronize()
     if os.environ.get("ZNICZ_BENCH_STATS"):
         wf.real_loader.__dict__["prof_"] = [0.0, 0.0, 0.0, 0]
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
+    # Everything host-side that can skew the ranks against each other happens BEFORE the final
+    # barrier: nvmlInit() enumerates all GPUs under a driver lock (tens of ms, serialised over 8
+    # processes) and a late rank makes every peer spin inside the step's cross-GPU flag barrier,
+    # on the device, inside the timed events (round-1 driver run: 0.28 efficiency at 8 GPUs).
     sampler = ClockSampler(dev.index)
-    sampler.start()
-    launches0 = api.counters["launches"]
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        # untimed aligned steps: the step's own cross-GPU barrier lines the devices up, and the
+        # hosts get their launch queues ahead of the devices again after the barrier's drain
+        wf.run(iterations=ALIGN_STEPS)
+    if streaming:
+        torch.cuda.synchronize()      # e2e is wall-clock timed: synchronised on both sides
+    launches0 = api.counters["launches"]
     t0 = time.perf_counter()
     e0.record()
     wf.run(iterations=args.steps)
@@ -295,6 +305,7 @@ def main():
                                 "SGD momentum + L2 as in the model's layer config",
                    "cuda_graphs": not args.no_graphs,
                    "untimed_graph_capture_steps": GRAPH_CAPTURE_STEPS,
+                   "untimed_align_steps_after_barrier": ALIGN_STEPS if n > 1 else 0,
                    "l2": "inputs larger than L2: the whole fp32 dataset (614 MB for 50000x32x32x3 "
                          "in the CIFAR config) is resident in HBM, random minibatch rows gathered "
                          "each step"},

@@ -72,3 +72,30 @@ def test_two_gpu_fused_reduce_update(tmp_path, compute, mode, dp_mode):
     assert res[0]["step_launches"] == (30 if mode == "eager" else 4)
     assert res[0]["epoch_n_err"] == res[1]["epoch_n_err"]
     assert res[0]["best_valid_err_pt"] < 85.0        # better than chance (90 %) after 30 steps
+
+
+def test_loader_shard_is_idempotent_and_reshardable():
+    """shard() used to shard the already-sharded state again on resume."""
+    import pickle
+    import numpy
+    from veles.znicz_b200.core.workflow import Workflow
+    from veles.znicz_b200.loader.synthetic import SyntheticImageLoader
+    wf = Workflow(None)
+    ld = SyntheticImageLoader(wf, minibatch_size=10, n_train=80, n_valid=40, n_test=0,
+                              shape=(4,), n_classes=3)
+    ld.initialize(device=None)
+    full = list(ld.class_lengths)
+    ld.shard(1, 4)
+    first = numpy.array(ld.shuffled_indices.mem, copy=True)
+    assert list(ld.class_lengths) == [n // 4 for n in full]
+    ld.shard(1, 4)                                  # second initialize(): no-op
+    assert list(ld.class_lengths) == [n // 4 for n in full]
+    assert (ld.shuffled_indices.mem == first).all()
+    state = pickle.loads(pickle.dumps({k: getattr(ld, k) for k in
+                                       ("unsharded_indices", "unsharded_class_lengths")}))
+    assert list(state["unsharded_class_lengths"]) == full
+    ld.shard(0, 2)                                  # resumed on 2 ranks: half, not 1/8
+    assert list(ld.class_lengths) == [n // 2 for n in full]
+    ld.shard(0, 1)                                  # resumed single-process: everything
+    assert list(ld.class_lengths) == full
+    assert sorted(ld.shuffled_indices.mem.tolist()) == sorted(state["unsharded_indices"].tolist())

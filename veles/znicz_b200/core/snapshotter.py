@@ -66,6 +66,10 @@ class SnapshotterBase(Unit, metaclass=SnapshotterRegistry):
         """Returns True when a snapshot was actually taken."""
         if root.common.disable.get("snapshotting", False) or self.is_slave:
             return False
+        if self._dp_rank() != 0:
+            # data parallel: replicas are bit-identical, `improved` is all-reduced - only rank 0
+            # writes (N ranks opening the same path with "wb" corrupt each other's pickle)
+            return False
         self._skipped_counter += 1
         if bool(self.skip):
             return False
@@ -83,6 +87,14 @@ class SnapshotterBase(Unit, metaclass=SnapshotterRegistry):
     def init_unpickled(self):
         super().init_unpickled()
         self._taken_once_ = False
+
+    def _dp_rank(self):
+        dp = getattr(self.workflow, "dp_", None)
+        if dp is not None:
+            return int(dp.rank)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            return int(os.environ.get("RANK", "0"))
+        return 0
 
     @property
     def _taken_once(self):
@@ -116,8 +128,11 @@ class SnapshotterToFile(SnapshotterBase):
         path = os.path.join(self.directory, rel)
         t0 = time.time()
         wf = self.workflow
-        with opener(path, "wb") as fout:
+        # write-then-rename: a reader (or a crash) never sees a half-written snapshot
+        tmp = "%s.tmp.%d" % (path, os.getpid())
+        with opener(tmp, "wb") as fout:
             pickle.dump(wf, fout, protocol=pickle.HIGHEST_PROTOCOL)
+        os.replace(tmp, path)
         self.destination = path
         self.info("Snapshotted to %s in %.2f sec (%d bytes)", path,
                   time.time() - t0, os.path.getsize(path))

@@ -251,13 +251,24 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
         """Data-parallel sharding: rank r keeps every world-th sample of each class
         (equal shard sizes, remainder dropped) — the synchronous equivalent of the master
         handing different minibatches to different slaves."""
-        if world <= 1:
+        # Idempotent and re-shardable: the unsharded index set is kept (and pickled with the
+        # snapshot), every call derives the shard from it. A snapshot taken on 8 ranks resumes
+        # on 8, 4 or 1 rank(s) over the whole dataset instead of 1/N^2 (or 1/N) of it.
+        cur = (getattr(self, "dp_rank", 0), getattr(self, "dp_world", 1))
+        if cur == (rank, max(world, 1)) and (world <= 1 or
+                                             getattr(self, "unsharded_indices", None) is not None):
             return
-        self.shuffled_indices.map_read()
-        full = self.shuffled_indices.mem
+        if getattr(self, "unsharded_indices", None) is None:
+            if world <= 1:
+                return
+            self.shuffled_indices.map_read()
+            self.unsharded_indices = numpy.array(self.shuffled_indices.mem, copy=True)
+            self.unsharded_class_lengths = list(self.class_lengths)
+        full = self.unsharded_indices
+        world = max(world, 1)
         parts, start = [], 0
         for i in range(3):
-            n = self.class_lengths[i]
+            n = self.unsharded_class_lengths[i]
             keep = (n // world)
             parts.append(full[start:start + keep * world][rank::world][:keep])
             start += n

@@ -20,6 +20,8 @@ update into the fused cross-GPU reduce+update kernel.
 """
 from __future__ import annotations
 
+import os
+
 from collections import namedtuple
 
 from ..core.avatar import Avatar
@@ -583,6 +585,11 @@ class StandardWorkflow(StandardWorkflowBase):
         self.fused_evaluator_ = fusion.fuse_evaluator(self, device)
         res = super().initialize(device=device, **kwargs)
         dev = self.device
+        if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+            # a data-parallel snapshot resumed in a single process: back to the whole dataset
+            ld = getattr(self, "real_loader", None) or self.loader
+            if getattr(ld, "dp_world", 1) > 1:
+                ld.shard(0, 1)
         if dev is not None and not dev.is_cuda:
             # CPU multi-process runs (gloo): same sharding / metric reduction, gradients are
             # all-reduced on the host inside the numpy GD step
