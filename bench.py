@@ -236,6 +236,122 @@ def run_arm(args, streaming):
     return res
 
 
+def _reference_timed(args, rank, world, streaming):
+    """K training minibatches of the unmodified reference sample on its stock cuda_run path
+    (see baseline/run_reference.py). Device-timed with driver-API events on the (legacy
+    default) stream every reference kernel and cuBLAS call uses; wall clock for e2e."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import run_reference as rr
+    wf, dev = rr.launch("cuda", force_numpy_loader=streaming, pinned=streaming)
+    import cuda4py
+    read_back = {"n": 0}
+    if streaming:
+        def hook(_wf):
+            wf.evaluator.n_err.map_read()        # the step's result, device -> host
+            read_back["n"] = int(wf.evaluator.n_err.mem[0])
+        wf.step_hooks_.append(hook)
+    # the reference serves VALID (10000 samples = 100 forward-only minibatches) before TRAIN:
+    # walk through them untimed, then W warm-up training steps
+    valid_steps = wf.loader.class_lengths[1] // wf.loader.max_minibatch_size
+    wf.run(iterations=valid_steps)
+    assert wf.loader.minibatch_class == 1 and bool(wf.loader.last_minibatch)
+    wf.run(iterations=args.warmup)
+    assert wf.loader.minibatch_class == 2
+    dev.sync()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    e0, e1 = cuda4py.Event(), cuda4py.Event()
+    l0, g0 = cuda4py.dry_stats["launches"], cuda4py.dry_stats["gemms"]
+    h0, d0 = dev.h2d_bytes, dev.d2h_bytes
+    t0 = time.perf_counter()
+    e0.record()
+    n = wf.run(iterations=args.steps)
+    e1.record()
+    dev.sync()
+    t1 = time.perf_counter()
+    assert n == args.steps and wf.loader.minibatch_class == 2, "timed region left TRAIN"
+    ms_dev = e0.elapsed_ms(e1)
+    clocks = sampler.stop()
+    res = {"ms_dev": ms_dev, "ms_wall": (t1 - t0) * 1e3, "clocks": clocks,
+           "launches": cuda4py.dry_stats["launches"] - l0, "gemms": cuda4py.dry_stats["gemms"] - g0,
+           "h2d": (dev.h2d_bytes - h0) / args.steps, "d2h": (dev.d2h_bytes - d0) / args.steps,
+           "n_err": read_back["n"], "batch": wf.loader.max_minibatch_size}
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([res["ms_dev"], res["ms_wall"]], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["ms_dev"], res["ms_wall"] = float(t[0]), float(t[1])
+        dist.barrier()
+    del wf
+    return res
+
+
+def run_reference_arm(args, rank, world):
+    """``--impl reference``: the UNMODIFIED reference (baseline/_ref) on its own stock GPU path;
+    the product package is never imported in this process."""
+    try:
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            import torch.distributed as dist
+            dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+        main_res = _reference_timed(args, rank, world, streaming=False)
+        e2e_res = None if args.skip_e2e else _reference_timed(args, rank, world, streaming=True)
+    except Exception as exc:        # never a fake number: say why the arm could not run
+        if rank == 0:
+            import traceback
+            sys.stderr.write(traceback.format_exc())
+            print(json.dumps({"impl": "reference",
+                              "unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:300])}))
+        return 0
+    if rank != 0:
+        return 0
+    n = max(world, 1)
+    batch = main_res["batch"]
+    images = args.steps * batch * n
+    out = {
+        "impl": "reference",
+        "metric": "CIFAR-10 caffe-conv training images/sec (whole job, device-timed, max over ranks)",
+        "value": round(images / (main_res["ms_dev"] / 1e3), 1), "unit": "images/s", "n_gpus": n,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(main_res["ms_dev"] / args.steps, 5),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"model": MODELS["cifar_caffe"][1], "global_batch": batch * n,
+                   "per_gpu_batch": batch, "image": "32x32x3",
+                   "parallelism": "dp1" if n == 1 else
+                   "%d independent replicas, no parameter exchange (upper bound of the "
+                   "reference's asynchronous master/slave scheme, whose ZeroMQ/Twisted "
+                   "transport lives in the absent Veles core)" % n,
+                   "code": "unmodified Samsung/veles.znicz (baseline/_ref, sha256 manifest): "
+                           "samples/CIFAR10/cifar.py + cifar_caffe_config.py, stock cuda_run "
+                           "path (NVRTC build of its cuda/*.cu + cuBLAS SGEMM, precision_type "
+                           "float)",
+                   "core": "baseline/veles_core: stand-in for the absent Veles core / cuda4py / "
+                           "zope.interface (unit graph, Array map/unmap, NVRTC, driver-API "
+                           "launches); none of veles.znicz_b200 is imported",
+                   "untimed": "100 validation minibatches + W warm-up training steps",
+                   "l2": "614 MB fp32 dataset resident in HBM, random rows gathered each step"},
+        "clocks": {k: main_res["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+        "gpu_launches": main_res["launches"] + main_res["gemms"],
+        "kernel_launches": main_res["launches"], "cublas_gemms": main_res["gemms"],
+    }
+    if e2e_res is not None:
+        out["e2e"] = {
+            "value": round(images / (e2e_res["ms_wall"] / 1e3), 1), "unit": "images/s",
+            "h2d_bytes_per_step": int(e2e_res["h2d"]), "d2h_bytes_per_step": int(e2e_res["d2h"]),
+            "ms_per_step": round(e2e_res["ms_wall"] / args.steps, 5),
+            "timing": "wall clock around workflow.run(), device synchronised on both sides; "
+                      "loader force_numpy=True: every minibatch is assembled on the host in "
+                      "page-locked memory and uploaded, n_err read back every step",
+            "last_n_err": e2e_res["n_err"]}
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,14 +368,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if rank == 0:
-            print(json.dumps({
-                "impl": "reference",
-                "unavailable": "Samsung/veles.znicz is a plugin of the Veles core (package "
-                               "`veles`, plus cuda4py/opencl4py/zope.interface) which is not in "
-                               "/root/reference nor in the offline wheelhouse; pip reports "
-                               "'neither setup.py nor pyproject.toml found'"}))
-        return 0
+        return run_reference_arm(args, rank, world)
     if args.impl == "baseline":
         # reference-equivalent decomposition inside this repo: fp32, exact SIMT GEMM/conv
         # kernels, one python-driven launch per reference kernel (no CUDA graphs, per-tensor
