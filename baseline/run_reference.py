@@ -47,12 +47,13 @@ def write_synthetic_cifar(root_dir, n_train=50000, n_valid=10000, seed=1):
     rs = numpy.random.RandomState(seed)
     protos = rs.randint(0, 256, (10, 3072)).astype(numpy.float32)
 
+    protos = protos.astype(numpy.uint8) // 2
+
     def batch(path, n):
         labels = rs.randint(0, 10, n)
-        data = numpy.clip(0.5 * protos[labels] + 0.5 * rs.randint(0, 256, (n, 3072)), 0, 255)
+        data = protos[labels] + rs.randint(0, 128, (n, 3072), dtype=numpy.uint8)
         with open(path, "wb") as f:
-            pickle.dump({"data": data.astype(numpy.uint8), "labels": labels.tolist()}, f,
-                        protocol=2)
+            pickle.dump({"data": data, "labels": labels.tolist()}, f, protocol=2)
     assert n_train % 10000 == 0 and n_valid == 10000
     for i in range(1, 6):
         batch(os.path.join(d, "data_batch_%d" % i), 10000)
@@ -81,7 +82,8 @@ def launch(backend="cuda", data_dir=None, force_numpy_loader=False, layers=None,
     from veles.dummy import DummyLauncher
     import veles.znicz  # noqa: F401  (adds its cuda/ dir to root.common.engine.source_dirs)
 
-    data_dir = data_dir or tempfile.mkdtemp(prefix="ref_cifar_")
+    data_dir = data_dir or os.environ.get("ZNICZ_REF_DATA_DIR") or \
+        tempfile.mkdtemp(prefix="ref_cifar_")
     root.common.dirs.datasets = data_dir
     if not os.path.isdir(os.path.join(data_dir, "cifar-10-batches-py")):
         write_synthetic_cifar(data_dir)

@@ -100,7 +100,10 @@ class CUBLAS(object):
                 ctypes.byref(a), _ptr(A), strideA, _ptr(B), strideB, ctypes.byref(b), _ptr(C),
                 strideC)
         if st != 0:
-            raise RuntimeError("cuBLAS gemm failed: status %d" % st)
+            raise RuntimeError("cuBLAS gemm failed: status %d (transA %s transB %s m %s n %s k %s "
+                               "lda %s ldb %s ldc %s A %s B %s C %s)" % (
+                                   st, transA, transB, rowsCountA, columnCountB, commonSideLength,
+                                   strideA, strideB, strideC, _ptr(A), _ptr(B), _ptr(C)))
 
     def sgemm(self, transA, transB, rowsCountA, columnCountB, commonSideLength, alpha, A, B,
               beta, C, strideA=0, strideB=0, strideC=0):

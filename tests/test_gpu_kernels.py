@@ -280,7 +280,7 @@ def test_multi_update_matches_per_tensor_update(ext):
     table = packed.cuda()
     sync = torch.zeros(2, dtype=torch.int32, device=dev)
     for _ in range(1):
-        ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync, [], 0, 1)
+        ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync, [], 0, 1, [], 0, 0, 0, 0)
     torch.cuda.synchronize()
     assert int(sync[0]) == 0 and int(sync[1]) == 1      # one grid barrier generation
     for a, b, sp in zip(ref, new, specs):
@@ -298,7 +298,7 @@ def test_multi_update_matches_per_tensor_update(ext):
     assert tiles2 == tiles
     table.copy_(packed)
     w_before = new[0]["w"].clone()
-    ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync, [], 0, 1)
+    ext.multi_update(table, len(descs), tiles, True, [], 0, 0, sync, [], 0, 1, [], 0, 0, 0, 0)
     torch.cuda.synchronize()
     assert torch.equal(new[0]["w"], w_before)
     assert int(sync[1]) == 2

@@ -50,7 +50,7 @@ void launch_fc_small_backward(void*, const void*, const void*, bool, const float
 size_t multi_update_desc_size();
 int multi_update_max_tensors();
 int multi_update_pack(const long long*, int, void*, int, long long);
-void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, float* const*, long long, int, cudaStream_t);
+void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, float* const*, long long, int, float* const*, float*, float*, int, int, cudaStream_t);
 void launch_refresh_shadows(const float*, long long, int, int, __nv_bfloat16*, int, __nv_bfloat16*, int, int, int, int, cudaStream_t);
 void launch_gemm_simt(const void*, bool, long long, int, const void*, bool, long long, int, void*, bool, long long, int, int, int, int, const float*, int, float, float, int, long long, cudaStream_t);
 struct ConvGeomS { int N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL; };
@@ -441,7 +441,9 @@ std::tuple<Tensor, int64_t, int64_t> multi_update_table(std::vector<std::vector<
 }
 void multi_update(Tensor table, int64_t n, int64_t total_tiles, bool has_ortho,
                   std::vector<int64_t> peer_flags, int64_t epoch_ptr, int64_t rank, Tensor gridsync,
-                  std::vector<int64_t> red_ptrs, int64_t red_half, int64_t chunks) {
+                  std::vector<int64_t> red_ptrs, int64_t red_half, int64_t chunks,
+                  std::vector<int64_t> sum_ptrs, int64_t mc_red, int64_t mc_sum, int64_t algo,
+                  int64_t max_blocks) {
   TORCH_CHECK(table.is_cuda() && table.scalar_type() == torch::kUInt8);
   TORCH_CHECK(gridsync.is_cuda() && gridsync.scalar_type() == torch::kInt32 && gridsync.numel() >= 2);
   uint32_t* fl[8];
@@ -453,9 +455,19 @@ void multi_update(Tensor table, int64_t n, int64_t total_tiles, bool has_ortho,
     TORCH_CHECK((int)red_ptrs.size() == nranks, "data-parallel multi_update needs the reduction buffers");
     for (int i = 0; i < nranks; ++i) rp[i] = reinterpret_cast<float*>(red_ptrs[i]);
   }
+  float* sp[8] = {nullptr};
+  TORCH_CHECK(algo >= 0 && algo <= 2, "multi_update: unknown algo");
+  if (nranks > 1 && algo == 1) {
+    TORCH_CHECK((int)sum_ptrs.size() == nranks, "two-shot multi_update needs the sum buffers");
+    for (int i = 0; i < nranks; ++i) sp[i] = reinterpret_cast<float*>(sum_ptrs[i]);
+    TORCH_CHECK((mc_red == 0) == (mc_sum == 0), "two-shot: both multicast mappings or none");
+  }
+  if (nranks > 1 && algo == 2) TORCH_CHECK(mc_red != 0, "one-shot NVLS needs the multicast mapping");
   zn::launch_multi_update(table.data_ptr(), (int)n, (int)total_tiles, has_ortho ? 1 : 0, nranks,
                           nranks > 1 ? fl : nullptr, reinterpret_cast<uint32_t*>(epoch_ptr), (int)rank,
-                          reinterpret_cast<unsigned*>(gridsync.data_ptr<int32_t>()), nranks > 1 ? rp : nullptr, (long long)red_half, (int)chunks, cur());
+                          reinterpret_cast<unsigned*>(gridsync.data_ptr<int32_t>()), nranks > 1 ? rp : nullptr, (long long)red_half, (int)chunks,
+                          (nranks > 1 && algo == 1) ? sp : nullptr, reinterpret_cast<float*>(mc_red),
+                          reinterpret_cast<float*>(mc_sum), (int)algo, (int)max_blocks, cur());
   kcheck();
 }
 void col_sums(Tensor w, Tensor out, int64_t rows, int64_t cols, bool transposed) {

@@ -54,6 +54,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A peer that never arrives (crashed rank, protocol bug) must not hang the box: trap after
+// ZN_PEER_TIMEOUT_NS of wall time (the host then sees a launch failure on every rank).
+#ifndef ZN_PEER_TIMEOUT_NS
+#define ZN_PEER_TIMEOUT_NS 20000000000ULL
+#endif
+
 // Block-level barrier across ranks: thread t < nranks signals rank t and waits for rank t.
 __device__ __forceinline__ void peer_barrier(const PeerSync& ps, uint32_t value) {
   __syncthreads();
@@ -61,12 +72,34 @@ __device__ __forceinline__ void peer_barrier(const PeerSync& ps, uint32_t value)
     int peer = threadIdx.x;
     st_release_sys(ps.flags[peer] + (size_t)blockIdx.x * 8 + ps.rank, value);
     const uint32_t* mine = ps.flags[ps.rank] + (size_t)blockIdx.x * 8 + peer;
-    long long spins = 0;
-    while ((int)(ld_acquire_sys(mine) - value) < 0) {
-      if (++spins > (1LL << 31)) { __trap(); }
+    if ((int)(ld_acquire_sys(mine) - value) < 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned spins = 0;
+      while ((int)(ld_acquire_sys(mine) - value) < 0) {
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > ZN_PEER_TIMEOUT_NS) { __trap(); }
+      }
     }
   }
   __syncthreads();
+}
+
+// ---- NVLS: loads / stores on the MULTICAST mapping of a symmetric buffer. A multimem load with
+// .add is reduced inside the NVSwitch over every rank's copy; a multimem store lands in every
+// rank's copy (one write on this GPU's link instead of N - 1).
+__device__ __forceinline__ float4 mm_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ float mm_ld_reduce_f1(const float* mc) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st_f4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // hyper layout: see GradientDescentBase.HYPER_FIELDS
@@ -216,7 +249,25 @@ struct TensorDesc {
 struct GridSync { unsigned* count; unsigned* gen; };
 // half > 0: the reduction buffer is double buffered (slot parity alternates every step), which
 // makes the trailing cross-GPU barrier unnecessary; chunks = launches per step
-struct RedBufs { float* ptr[8]; int nranks, rank; long long half; int chunks; };
+// algo: how phase B gets the cross-rank sum of an element
+//   ALGO_ONESHOT_PEER  every rank loads all N slots over NVLink ((N - 1) * P floats in per rank)
+//   ALGO_TWOSHOT       tile owners reduce their 1/N of the tiles and broadcast the sums into every
+//                      rank's ``sum`` buffer (reduce-scatter + all-gather: ~2 * P floats per rank,
+//                      one more flag barrier); with mc_red / mc_sum the reduce is ONE
+//                      multimem.ld_reduce per float4 (in-switch, NVLS) and the broadcast ONE
+//                      multimem.st, otherwise N peer loads and N peer stores per float4.
+//                      The owner computes each sum once => replicas stay bit-identical whatever
+//                      order the switch adds in.
+//   ALGO_ONESHOT_NVLS  every rank multimem.ld_reduce-s every element itself (single barrier;
+//                      bit-identical replicas only if the switch reduction is order-stable)
+enum { ALGO_ONESHOT_PEER = 0, ALGO_TWOSHOT = 1, ALGO_ONESHOT_NVLS = 2 };
+struct RedBufs {
+  float* ptr[8]; int nranks, rank; long long half; int chunks;
+  float* sum[8];            // two-shot: reduced gradients, sum[rank] is the local copy
+  float* mc_red;            // multicast address of the slot buffer (null: no NVLS)
+  float* mc_sum;            // multicast address of the sum buffer
+  int algo;
+};
 constexpr int MU_MAX_TENSORS = 48;
 constexpr int MU_MAX_PEER_BLOCKS = 592;     // size of the cross-GPU flag / epoch arrays
 
@@ -307,7 +358,11 @@ __device__ __forceinline__ void multi_elem4(const TensorDesc& d, const long long
                                             const long long poff) {
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 g4 = z4;
-  if (MODE == 2) {
+  if (MODE == 2 && rb.algo == ALGO_TWOSHOT) {
+    g4 = *reinterpret_cast<const float4*>(rb.sum[rb.rank] + poff + d.red_off + i0);
+  } else if (MODE == 2 && rb.algo == ALGO_ONESHOT_NVLS) {
+    g4 = mm_ld_reduce_f4(rb.mc_red + poff + d.red_off + i0);
+  } else if (MODE == 2) {
     // all peer loads in flight at once (a run-time loop issues them one NVLink round trip after
     // the other), then a fixed-order sum: replicas stay bit-identical
     float4 v[8];
@@ -444,7 +499,11 @@ __device__ __forceinline__ float multi_grad(const TensorDesc& d, const long long
                                             const int lane, const RedBufs& rb, long long poff) {
   const int L = d.ept > 1 ? 1 : d.lanes;
   float g = 0.f;
-  if (MODE == 2) {
+  if (MODE == 2 && rb.algo == ALGO_TWOSHOT) {
+    if (valid && lane == 0) g = rb.sum[rb.rank][poff + d.red_off + i];
+  } else if (MODE == 2 && rb.algo == ALGO_ONESHOT_NVLS) {
+    if (valid && lane == 0) g = mm_ld_reduce_f1(rb.mc_red + poff + d.red_off + i);
+  } else if (MODE == 2) {
     if (valid && lane == 0) {
       // every peer load in flight at once, then a fixed-order sum (bit-identical replicas)
       float v[8];
@@ -538,6 +597,37 @@ __device__ __forceinline__ void multi_elem(const TensorDesc& d, const long long 
   multi_apply<MODE>(d, i, valid, lane, multi_grad<MODE>(d, i, valid, lane, rb, poff), rb, poff);
 }
 
+// Two-shot, owner side: reduce one tile's slots over the ranks and broadcast the sums.
+// The tile's slot range is float4-aligned and padded to a multiple of 4 (multi_update_table).
+__device__ __forceinline__ void multi_reduce_bcast(const TensorDesc& d, int tile_local, const RedBufs& rb,
+                                                   long long poff) {
+  const long long n_tile = d.ept > 1 ? 1024 : 256 / d.lanes;
+  const long long e0 = (long long)tile_local * n_tile;
+  long long n = d.size - e0;
+  if (n > n_tile) n = n_tile;
+  n = (n + 3) & ~3LL;
+  const long long o = poff + d.red_off + e0;
+  for (long long c = (long long)threadIdx.x * 4; c < n; c += 256 * 4) {
+    float4 g;
+    if (rb.mc_red != nullptr) {
+      g = mm_ld_reduce_f4(rb.mc_red + o + c);
+      mm_st_f4(rb.mc_sum + o + c, g);
+    } else {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        v[r] = (r < rb.nranks) ? *reinterpret_cast<const float4*>(rb.ptr[r] + o + c) : z4;
+      g = z4;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) g = f4add(g, v[r]);       // fixed rank order
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < rb.nranks) *reinterpret_cast<float4*>(rb.sum[r] + o + c) = g;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 4)
 multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int has_ortho,
                PeerSync ps, GridSync gsync, RedBufs rb) {
@@ -581,6 +671,21 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
     // every rank maps tile -> block identically, so block b only needs block b of each peer:
     // publish (release, after the CTA barrier inside peer_barrier) and wait
     peer_barrier(ps, 2 * epoch - 1);
+    if (rb.algo == ALGO_TWOSHOT) {
+      // reduce-scatter + all-gather over tile owners. Tile t belongs to block t % grid on every
+      // rank, so the owner's block index equals the reader's: the per-block flag barrier below
+      // is all the synchronisation the broadcast needs.
+      int t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        while (t + 1 < n && tile >= s_table[t].tile_begin + s_table[t].n_tiles) ++t;
+        const TensorDesc& d = s_table[t];
+        if (!d.enabled) continue;
+        if ((int)(((unsigned)(tile / (int)gridDim.x) + (unsigned)tile) % (unsigned)rb.nranks) != rb.rank) continue;
+        multi_reduce_bcast(d, tile - d.tile_begin, rb, poff);
+      }
+      __threadfence_system();              // my broadcast stores before my flag
+      peer_barrier(ps, 2 * epoch);         // every owner's sums have landed in my sum buffer
+    }
   }
   if (has_ortho) grid_barrier(gsync);    // col_sums of all tensors complete before any update
   if (!multi) {
@@ -637,7 +742,7 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
     // single-buffered slots: wait until nobody still reads mine. Double-buffered slots need no
     // trailing barrier: a rank can be at most one step ahead (the phase barrier of step k + 1
     // is passed only after every peer finished reading step k), and step k + 1 uses the other half.
-    if (rb.half <= 0) peer_barrier(ps, 2 * epoch);
+    if (rb.half <= 0 && rb.algo != ALGO_TWOSHOT) peer_barrier(ps, 2 * epoch);
     if (threadIdx.x == 0) ps.epoch[blockIdx.x] = epoch;
   }
 }
@@ -676,7 +781,9 @@ int multi_update_pack(const long long* f, int n_fields, void* out, int tile_begi
 
 void launch_multi_update(const void* table, int n, int total_tiles, int has_ortho, int nranks,
                          uint32_t* const* peer_flags, uint32_t* epoch, int rank, unsigned* gridsync,
-                         float* const* red_ptrs, long long red_half, int chunks, cudaStream_t st) {
+                         float* const* red_ptrs, long long red_half, int chunks,
+                         float* const* sum_ptrs, float* mc_red, float* mc_sum, int algo, int max_blocks,
+                         cudaStream_t st) {
   PeerSync ps{};
   ps.rank = rank; ps.nranks = (peer_flags && nranks > 1) ? nranks : 1; ps.epoch = epoch;
   if (peer_flags) for (int r = 0; r < nranks; ++r) ps.flags[r] = peer_flags[r];
@@ -688,6 +795,10 @@ void launch_multi_update(const void* table, int n, int total_tiles, int has_orth
   RedBufs rb{};
   rb.nranks = ps.nranks; rb.rank = rank; rb.half = red_half; rb.chunks = chunks;
   if (red_ptrs) for (int r = 0; r < nranks; ++r) rb.ptr[r] = red_ptrs[r];
+  if (sum_ptrs) for (int r = 0; r < nranks; ++r) rb.sum[r] = sum_ptrs[r];
+  rb.mc_red = mc_red; rb.mc_sum = mc_sum;
+  rb.algo = ps.nranks > 1 ? algo : ALGO_ONESHOT_PEER;
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;   // (fake-peer tests share one GPU)
   launch_k(multi_update_k, blocks, 256, 0, st, (const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs, rb);
 }
 

@@ -47,8 +47,11 @@ class FusedStep(object):
         self.gridsync = torch.zeros(2, dtype=torch.int32, device=device.torch_device)
         self.flag_ptrs, self.epoch_ptr = [], 0
         self.launches = 0
-        if dp is not None and dp.symm is not None:
-            self.flag_ptrs, self.epoch_ptr = dp.symm.sync_state("fused_step")
+        self.sync = []            # per chunk: (flag ptrs per rank, local epoch ptr)
+        self.sum_ptrs, self.mc_red, self.mc_sum = [], 0, 0
+        self.algo = 0
+        self.algo_name = "single"
+        self.max_blocks = 0       # > 0 only in fake-peer tests (several "ranks" share one GPU)
 
     # -- wiring ------------------------------------------------------------------------------
     @classmethod
@@ -130,15 +133,52 @@ class FusedStep(object):
             self.chunks.append((old, len(part), int(tiles), ortho))
         self.tables = [c[0] for c in self.chunks]
         self.table = self.tables[0] if self.tables else None
-        if self.dp is not None and self.dp.symm is not None and red > self.red_numel:
+        symm = self.dp.symm if self.dp is not None else None
+        if symm is not None:
+            # every chunk (launch) of a step has its own flag / epoch arrays: the chunks' grids
+            # differ in size, a shared per-block epoch would advance unevenly
+            while len(self.sync) < len(self.chunks):
+                self.sync.append(symm.sync_state("fused_step_%d" % len(self.sync)))
+        if symm is not None and red > self.red_numel:
             # one fp32 slot per parameter in symmetric memory: ranks publish their locally
             # reduced gradients here, peers read them over NVLink (collective allocation:
             # all ranks build identical tables in the same step)
             # double buffered: step parity selects the half, so no trailing barrier is needed
-            self.red_ptrs = self.dp.symm.reduction_buffer("fused_step_red", 2 * int(red))
+            self.red_ptrs, self.mc_red = symm.reduction_buffer(
+                "fused_step_red", 2 * int(red), with_multicast=True)
             self.red_numel = int(red)
+            self._pick_algo(symm, int(red))
         self.enabled = [bool(e.touched) for e in self.entries]
         self.dirty = False
+
+    def _pick_algo(self, symm, numel):
+        """ZNICZ_DP_ALGO: auto | oneshot (N peer loads per element) | twoshot (owner reduce +
+        broadcast, NVLS multimem when the platform has multicast) | twoshot_peer (same without
+        multimem) | nvls1 (every rank multimem.ld_reduce-s everything, one barrier)."""
+        import os
+        name = os.environ.get("ZNICZ_DP_ALGO", "auto")
+        have_mc = bool(self.mc_red)
+        if name == "auto":
+            # NVLS two-shot moves ~2 P floats per rank instead of (N - 1) P and costs one more
+            # flag barrier; without multicast the peer-store form pays off for large models only
+            name = "twoshot" if have_mc else ("twoshot_peer" if numel >= (1 << 22) else "oneshot")
+        if name == "twoshot" and not have_mc:
+            name = "twoshot_peer"
+        if name == "nvls1" and not have_mc:
+            raise RuntimeError("ZNICZ_DP_ALGO=nvls1 needs multicast support")
+        self.algo_name = name
+        self.algo = {"oneshot": 0, "twoshot": 1, "twoshot_peer": 1, "nvls1": 2}[name]
+        self.sum_ptrs, self.mc_sum = [], 0
+        if self.algo == 1:
+            self.sum_ptrs, self.mc_sum = symm.reduction_buffer(
+                "fused_step_sum", 2 * numel, with_multicast=True)
+            if name == "twoshot_peer" or not self.mc_sum:
+                self.mc_sum = 0
+        mc_red = self.mc_red if name in ("twoshot", "nvls1") else 0
+        if name == "twoshot" and not self.mc_sum:
+            mc_red = 0
+            self.algo_name = "twoshot_peer"
+        self.mc_red_used = mc_red
 
     # -- the launch ------------------------------------------------------------------------------
     def flush(self):
@@ -161,11 +201,13 @@ class FusedStep(object):
             for e in self.entries:
                 if e.touched:
                     dist.all_reduce(e.keep[-1], op=dist.ReduceOp.SUM)
-        for table, n, tiles, ortho in self.chunks:
-            self.device.ext.multi_update(table, n, tiles, ortho, self.flag_ptrs, self.epoch_ptr,
+        for ci, (table, n, tiles, ortho) in enumerate(self.chunks):
+            flags, epoch = self.sync[ci] if self.sync else (self.flag_ptrs, self.epoch_ptr)
+            self.device.ext.multi_update(table, n, tiles, ortho, flags, epoch,
                                          dp.rank if dp is not None else 0, self.gridsync,
-                                         self.red_ptrs, self.red_numel if self.red_ptrs else 0,
-                                         len(self.chunks))
+                                         self.red_ptrs, self.red_numel if self.red_ptrs else 0, 1,
+                                         self.sum_ptrs, getattr(self, "mc_red_used", 0),
+                                         self.mc_sum, self.algo, self.max_blocks)
             api._launch()
         self.launches += 1
         for e in self.entries:

@@ -63,8 +63,10 @@ class SymmetricGradients(object):
         dist.barrier()
         return b.tensor.view(*shape)
 
-    def reduction_buffer(self, key, numel):
-        """fp32 buffer of ``numel`` elements in symmetric memory → per-rank base pointers."""
+    def reduction_buffer(self, key, numel, with_multicast=False):
+        """fp32 buffer of ``numel`` elements in symmetric memory → per-rank base pointers
+        (and, with ``with_multicast``, the NVLS multicast address of the same memory: 0 when
+        the platform has no multicast support)."""
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("symmetric buffers must be created before graph capture")
         t, h = self._alloc(numel, torch.float32)
@@ -73,7 +75,15 @@ class SymmetricGradients(object):
         self.bytes += numel * 4
         torch.cuda.synchronize()
         dist.barrier()
-        return [int(p) for p in h.buffer_ptrs]
+        ptrs = [int(p) for p in h.buffer_ptrs]
+        if not with_multicast:
+            return ptrs
+        mc = 0
+        try:
+            mc = int(h.multicast_ptr or 0)
+        except Exception:        # pragma: no cover - older torch / no NVSwitch
+            mc = 0
+        return ptrs, mc
 
     def sync_state(self, key):
         """(flag ptrs per rank, local epoch ptr) for a kernel that synchronises across
