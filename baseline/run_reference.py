@@ -70,7 +70,7 @@ def _load_module(name, path):
 
 
 def launch(backend="cuda", data_dir=None, force_numpy_loader=False, layers=None,
-           minibatch_size=None, pinned=False, log_level=None):
+           minibatch_size=None, pinned=False, log_level=None, loader_name=None):
     """The launcher's job: execute the config, let the sample build its workflow via
     ``run(load, main)``, initialise it on the device. Returns the workflow (not yet run)."""
     setup_path()
@@ -85,7 +85,7 @@ def launch(backend="cuda", data_dir=None, force_numpy_loader=False, layers=None,
     data_dir = data_dir or os.environ.get("ZNICZ_REF_DATA_DIR") or \
         tempfile.mkdtemp(prefix="ref_cifar_")
     root.common.dirs.datasets = data_dir
-    if not os.path.isdir(os.path.join(data_dir, "cifar-10-batches-py")):
+    if loader_name is None and not os.path.isdir(os.path.join(data_dir, "cifar-10-batches-py")):
         write_synthetic_cifar(data_dir)
     root.common.engine.backend = backend
     root.common.disable.snapshotting = True
@@ -101,6 +101,8 @@ def launch(backend="cuda", data_dir=None, force_numpy_loader=False, layers=None,
         root.cifar.loader.minibatch_size = minibatch_size
     if layers is not None:
         root.cifar.layers = layers
+    if loader_name is not None:          # tests: a tiny registered loader instead of the pickles
+        root.cifar.loader_name = loader_name
     cifar = _load_module("cifar_sample", os.path.join(sample_dir, "cifar.py"))
 
     state = {}

@@ -16,18 +16,23 @@ def _load():
     global _lib
     if _lib is not None:
         return _lib
-    names = ["libcublas.so.12", "libcublas.so"]
+    # libcublas and libcublasLt must come from the SAME directory: with LD_LIBRARY_PATH pointing
+    # at the toolkit, the wheel's libcublas.so.12 (12.8) otherwise binds to the toolkit's
+    # libcublasLt.so.12 (12.9) and SGEMM fails with CUBLAS_STATUS_INVALID_VALUE for valid
+    # arguments ("non-default emulation strategy ..." in the cublasLt log). Load Lt first, by path.
+    dirs = []
     try:
         import nvidia.cublas.lib as _nl          # the wheel torch depends on
-        d = os.path.dirname(_nl.__file__)
-        names = [os.path.join(d, "libcublas.so.12")] + names
+        dirs.append(os.path.dirname(_nl.__file__) if getattr(_nl, "__file__", None)
+                    else list(_nl.__path__)[0])
     except Exception:
         pass
-    names.append("/usr/local/cuda/lib64/libcublas.so.12")
+    dirs += ["/usr/local/cuda/lib64", ""]
     err = None
-    for n in names:
+    for d in dirs:
         try:
-            _lib = ctypes.CDLL(n, mode=ctypes.RTLD_GLOBAL)
+            ctypes.CDLL(os.path.join(d, "libcublasLt.so.12"), mode=ctypes.RTLD_GLOBAL)
+            _lib = ctypes.CDLL(os.path.join(d, "libcublas.so.12"), mode=ctypes.RTLD_GLOBAL)
             break
         except OSError as e:
             err = e

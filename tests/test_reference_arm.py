@@ -128,32 +128,49 @@ def test_cuda4py_standin_primitives():
 
 @pytest.mark.gpu
 def test_reference_cuda_backend_matches_its_numpy_backend(tmp_path):
-    """Same seeds, same synthetic pickles: 2 validation + 3 training minibatches of the
-    reference on its numpy back end and on its CUDA back end (through the stand-in core)."""
-    body = (TINY % BASE) + (
-        "wf, dev = rr.launch(sys.argv[1], data_dir=%r, layers=tiny, minibatch_size=5000)\n"
-        "wf.run(iterations=5)\n"
-        "out = {}\n"
-        "for i, f in enumerate(wf.forwards):\n"
-        "    if getattr(f, 'weights', None):\n"
-        "        f.weights.map_read(); f.bias.map_read()\n"
-        "        out['w%%d' %% i] = f.weights.mem.ravel()[:64].tolist(); out['b%%d' %% i] = f.bias.mem.ravel()[:8].tolist()\n"
-        "wf.evaluator.n_err.map_read(); out['n_err'] = wf.evaluator.n_err.mem.tolist(); out['cls'] = wf.loader.minibatch_class\n"
-        "print(json.dumps(out))\n") % str(tmp_path)
+    """Same seeds, same data: 2 validation + 4 training minibatches of the reference
+    StandardWorkflow (conv / max-pool / strict-relu / LRN / avg-pool / softmax, momentum + L2 +
+    ortho) on its numpy back end and on its CUDA back end through the stand-in core - the
+    oracle style of the reference's own unit tests (GPU == numpy)."""
+    body = (TINY % BASE) + """
+rr.setup_path()
+from veles.loader import FullBatchLoader
+class TinyLoader(FullBatchLoader):
+    MAPPING = "tiny_loader"
+    def load_data(self):
+        rs = numpy.random.RandomState(3)
+        self.class_lengths[:] = [0, 20, 40]
+        labels = rs.randint(0, 10, 60)
+        protos = rs.rand(10, 16, 16, 3)
+        self.original_data.reset((protos[labels] + 0.3 * rs.rand(60, 16, 16, 3)).astype(self.dtype))
+        self.original_labels = labels.tolist()
+wf, dev = rr.launch(sys.argv[1], layers=tiny, minibatch_size=10, loader_name="tiny_loader")
+wf.run(iterations=6)
+out = {}
+for i, f in enumerate(wf.forwards):
+    if getattr(f, 'weights', None):
+        f.weights.map_read(); f.bias.map_read()
+        out['w%d' % i] = f.weights.mem.ravel()[:64].tolist(); out['b%d' % i] = f.bias.mem.ravel()[:8].tolist()
+wf.forwards[-1].output.map_read(); out['y'] = wf.forwards[-1].output.mem.ravel()[:50].tolist()
+wf.gds[0].gradient_weights.map_read(); out['gw0'] = wf.gds[0].gradient_weights.mem.ravel()[:64].tolist()
+wf.evaluator.n_err.map_read(); out['n_err'] = [int(v) for v in wf.decision.epoch_n_err]; out['cls'] = wf.loader.minibatch_class
+print(json.dumps(out))
+"""
+    tiny_pool = body.replace('"kx": 8, "ky": 8, "sliding": (8, 8)', '"kx": 4, "ky": 4, "sliding": (4, 4)')
     script = tmp_path / "tiny_ref.py"
-    script.write_text(body)
+    script.write_text(tiny_pool)
     res = {}
     for be in ("numpy", "cuda"):
         e = dict(os.environ)
         e.pop("PYTHONPATH", None)
         r = subprocess.run([sys.executable, "-W", "ignore", str(script), be], capture_output=True,
-                           text=True, timeout=1500, env=e, cwd=str(tmp_path))
+                           text=True, timeout=600, env=e, cwd=str(tmp_path))
         assert r.returncode == 0, r.stderr[-4000:]
         res[be] = json.loads(r.stdout.strip().splitlines()[-1])
     import numpy
     assert res["numpy"]["cls"] == 2 and res["cuda"]["cls"] == 2
     assert res["numpy"]["n_err"] == res["cuda"]["n_err"]
     for k, v in res["numpy"].items():
-        if k[0] in "wb":
+        if k[0] in "wbyg":
             a, b = numpy.array(v), numpy.array(res["cuda"][k])
-            assert numpy.abs(a - b).max() <= 2e-4 * max(numpy.abs(a).max(), 1e-3) + 1e-6, k
+            assert numpy.abs(a - b).max() <= 1e-3 * max(numpy.abs(a).max(), 1e-4) + 1e-7, (k, a[:4], b[:4])
