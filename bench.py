@@ -213,6 +213,8 @@ def run_arm(args, streaming):
         "h2d": getattr(wf.real_loader, "h2d_bytes_per_step", 0),
         "d2h": reader.bytes_per_step if reader else 0,
         "n_err": int(reader.last[0]) if reader and reader.last is not None else None,
+        "dp_algo": getattr(getattr(wf, "fused_step_", None), "algo_name", None),
+        "dp_gradients": getattr(getattr(wf, "dp_", None), "gradient_mode", None),
     }
     if os.environ.get("ZNICZ_BENCH_STATS") and int(os.environ.get("RANK", "0")) == 0:
         sys.stderr.write("host enqueue %.4f ms/step, device %.4f ms/step, drain after enqueue "
@@ -407,8 +409,10 @@ def main():
                              "alexnet": "227x227x3", "lstm": None}[args.model],
                    "parallelism": "dp%d" % n,
                    "dp_collective": ("fused peer-memory reduce+update kernel (no NCCL on the "
-                                     "step path)" if os.environ.get("ZNICZ_DP_MODE", "fused") ==
+                                     "step path), algo=%s" % main_res.get("dp_algo")
+                                     if os.environ.get("ZNICZ_DP_MODE", "fused") ==
                                      "fused" else "NCCL all-reduce baseline") if n > 1 else None,
+                   "dp_gradients": main_res.get("dp_gradients") if n > 1 else None,
                    "optimizer": ("SGD momentum 0.9 + L2 5e-4 + factor_ortho 1e-3, "
                                  "arbitrary_step LR") if args.model == "cifar_caffe" else
                                 "SGD momentum + L2 as in the model's layer config",

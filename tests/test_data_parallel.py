@@ -99,3 +99,63 @@ def test_loader_shard_is_idempotent_and_reshardable():
     ld.shard(0, 1)                                  # resumed single-process: everything
     assert list(ld.class_lengths) == full
     assert sorted(ld.shuffled_indices.mem.tolist()) == sorted(state["unsharded_indices"].tolist())
+
+
+def _run_equiv(tmp_path, world, tag, env_extra):
+    env = dict(os.environ, PYTHONPATH=REPO)
+    env.update(env_extra)
+    worker = os.path.join(REPO, "tests", "dp_equiv_worker.py")
+    if world == 1:
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        cmd = [sys.executable, worker, str(tmp_path), tag]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1", "--master-port",
+               str(_free_port()), worker, str(tmp_path), tag]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (tag, r.stderr[-3000:])
+    return [json.load(open(tmp_path / ("%s_rank%d.json" % (tag, i)))) for i in range(world)]
+
+
+def _gpu_worlds():
+    try:
+        import torch
+        n = torch.cuda.device_count()
+    except Exception:
+        n = 0
+    return [w for w in (2, 4, 8) if w <= n]
+
+
+@pytest.mark.gpu
+def test_data_parallel_equals_single_process_at_global_batch(tmp_path):
+    """SURVEY §4 (what the reference never tested): N ranks x batch b with the fused
+    cross-GPU reduce + update  ==  the NCCL all-reduce path  ==  ONE process at batch N * b,
+    after 6 fp32 steps, for every algorithm of the collective; replicas bit-identical.
+    Needs >= 2 visible GPUs: skips LOUDLY otherwise."""
+    import numpy
+    worlds = _gpu_worlds()
+    if not worlds:
+        pytest.skip("MULTI-GPU TEST NOT RUN: fewer than 2 GPUs visible - the cross-GPU fused "
+                    "reduce+update has no coverage in this session")
+    _run_equiv(tmp_path, 1, "single", {})
+    ref = numpy.load(tmp_path / "single_weights.npy")
+    scale = float(numpy.abs(ref).max())
+    for world in worlds:
+        algos = ["auto", "oneshot", "twoshot_peer", "twoshot", "nvls1", "nccl"] if world == worlds[0] \
+            else ["auto", "nvls1"]
+        for algo in algos:
+            tag = "w%d_%s" % (world, algo)
+            env = {"ZNICZ_DP_MODE": "nccl"} if algo == "nccl" else \
+                {"ZNICZ_DP_MODE": "fused", "ZNICZ_DP_ALGO": algo}
+            try:
+                res = _run_equiv(tmp_path, world, tag, env)
+            except AssertionError as e:
+                if algo == "nvls1" and "multicast" in str(e):
+                    continue            # platform without NVLS: nothing to test for this mode
+                raise
+            assert all(r["finite"] for r in res), tag
+            assert len({r["sha"] for r in res}) == 1, "replicas diverged: %s" % tag
+            got = numpy.load(tmp_path / ("%s_weights.npy" % tag))
+            err = float(numpy.abs(got - ref).max()) / scale
+            assert err < 5e-5, (tag, err)

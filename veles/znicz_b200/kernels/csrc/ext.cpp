@@ -48,6 +48,8 @@ int fc_small_max_out();
 void launch_fc_small_forward(const void*, bool, const float*, const float*, void*, float*, int*, int, int, int, int, int, const int*, void*, int, const float*, int*, int*, float*, cudaStream_t);
 void launch_fc_small_backward(void*, const void*, const void*, bool, const float*, void*, float*, float*, int, int, int, int, float, float, int, cudaStream_t);
 size_t multi_update_desc_size();
+void set_dp_gradient_scale(float);
+float get_dp_gradient_scale();
 int multi_update_max_tensors();
 int multi_update_pack(const long long*, int, void*, int, long long);
 void launch_multi_update(const void*, int, int, int, int, uint32_t* const*, uint32_t*, int, unsigned*, float* const*, long long, int, float* const*, float*, float*, int, int, cudaStream_t);
@@ -759,6 +761,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("evaluate_mse", &evaluate_mse); m.def("mse_find_closest", &mse_find_closest);
   m.def("fused_update", &fused_update); m.def("update_blocks", &update_blocks);
   m.def("multi_update_table", &multi_update_table);
+  m.def("set_dp_gradient_scale", [](double s) { zn::set_dp_gradient_scale((float)s); });
+  m.def("get_dp_gradient_scale", []() { return (double)zn::get_dp_gradient_scale(); });
   m.def("multi_update_max_tensors", []() { return (int64_t)zn::multi_update_max_tensors(); }); m.def("multi_update", &multi_update);
   m.def("col_sums", &col_sums); m.def("refresh_shadows", &refresh_shadows);
   m.def("lstm_cell_fwd", &lstm_cell_fwd); m.def("lstm_cell_bwd", &lstm_cell_bwd);

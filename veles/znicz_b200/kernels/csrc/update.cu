@@ -29,6 +29,7 @@ struct GradSources {
   int nparts;            // split-K partials per rank
   long long part_stride; // elements between partials
   int g_cpad;            // > 0: gradient rows are [tap][g_cpad] channel-padded (first conv layer)
+  float gscale;          // multiplies the cross-rank sum (1 / world_size: data-parallel mean)
 };
 
 struct ShadowSpec {
@@ -149,6 +150,7 @@ __global__ void fused_update_k(float* __restrict__ w, GradSources gs, float* __r
       for (; p < gs.nparts; ++p) g0 += base[(long long)p * gs.part_stride];
       g += (g0 + g1) + (g2 + g3);
     }
+    g *= gs.gscale;
     if (grad_out) grad_out[i] = g;
     float wv = w[i];
     float sgn = wv > 0.f ? 1.f : (wv < 0.f ? -1.f : 0.f);
@@ -267,6 +269,8 @@ struct RedBufs {
   float* mc_red;            // multicast address of the slot buffer (null: no NVLS)
   float* mc_sum;            // multicast address of the sum buffer
   int algo;
+  float gscale;             // multiplies the cross-rank gradient sum (1 / world: mean over the
+                            // global batch, so N ranks x batch b == one process at batch N * b)
 };
 constexpr int MU_MAX_TENSORS = 48;
 constexpr int MU_MAX_PEER_BLOCKS = 592;     // size of the cross-GPU flag / epoch arrays
@@ -387,6 +391,7 @@ __device__ __forceinline__ void multi_elem4(const TensorDesc& d, const long long
     g4 = f4add(f4add(f4add(a[0], a[1]), f4add(a[2], a[3])), f4add(f4add(a[4], a[5]), f4add(a[6], a[7])));
   }
   if (MODE == 1) { *reinterpret_cast<float4*>(rb.ptr[rb.rank] + poff + d.red_off + i0) = g4; return; }
+  g4.x *= rb.gscale; g4.y *= rb.gscale; g4.z *= rb.gscale; g4.w *= rb.gscale;
 
   const int is_bias = d.is_bias;
   const float* hyper = d.hyper;
@@ -540,7 +545,7 @@ __device__ __forceinline__ float multi_grad(const TensorDesc& d, const long long
   }
   if (MODE != 2)
     for (int o = L >> 1; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-  return g;
+  return MODE == 1 ? g : g * rb.gscale;
 }
 
 template <int MODE>
@@ -747,6 +752,12 @@ multi_update_k(const TensorDesc* __restrict__ table, int n, int total_tiles, int
   }
 }
 
+// Data-parallel gradient scale (set once by parallel/data_parallel.py): the step kernels multiply
+// the cross-rank gradient sum by it. 1 = plain sum.
+static float g_dp_gscale = 1.f;
+void set_dp_gradient_scale(float s) { g_dp_gscale = s; }
+float get_dp_gradient_scale() { return g_dp_gscale; }
+
 size_t multi_update_desc_size() { return sizeof(TensorDesc); }
 int multi_update_max_tensors() { return MU_MAX_TENSORS; }
 
@@ -798,6 +809,7 @@ void launch_multi_update(const void* table, int n, int total_tiles, int has_orth
   if (sum_ptrs) for (int r = 0; r < nranks; ++r) rb.sum[r] = sum_ptrs[r];
   rb.mc_red = mc_red; rb.mc_sum = mc_sum;
   rb.algo = ps.nranks > 1 ? algo : ALGO_ONESHOT_PEER;
+  rb.gscale = g_dp_gscale;
   if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;   // (fake-peer tests share one GPU)
   launch_k(multi_update_k, blocks, 256, 0, st, (const TensorDesc*)table, n, total_tiles, has_ortho, ps, gs, rb);
 }
@@ -819,6 +831,7 @@ void launch_fused_update(float* w, const float* const* grad_ptrs, int nranks, in
   GradSources gs{};
   for (int r = 0; r < nranks; ++r) gs.ptr[r] = grad_ptrs[r];
   gs.nranks = nranks; gs.nparts = nparts; gs.part_stride = part_stride; gs.g_cpad = g_cpad;
+  gs.gscale = g_dp_gscale;
   ShadowSpec sh{lp, ld, lp_cpad, lp_conv, taps, C, c_pad};
   PeerSync ps{};
   ps.rank = rank; ps.nranks = nranks; ps.epoch = epoch;

@@ -25,6 +25,17 @@ class DataParallel(object):
         self.mode = mode or os.environ.get("ZNICZ_DP_MODE", "fused")
         self.symm = None
         self._step = 0
+        # Gradient semantics: "mean" (default) divides the cross-rank gradient sum by the world
+        # size, so N ranks at per-GPU batch b take exactly the step of ONE process at batch N*b
+        # with the same hyper-parameters (every evaluator already divides by its local batch);
+        # "sum" keeps the plain sum (step N times larger - the reference's asynchronous
+        # master applied every slave's gradient in full, /root/reference/nn_units.py:679-691).
+        from ..core.config import root
+        self.gradient_mode = os.environ.get(
+            "ZNICZ_DP_GRADIENTS", root.common.engine.get("dp_gradients", "mean"))
+        if self.gradient_mode not in ("mean", "sum"):
+            raise ValueError("dp_gradients must be 'mean' or 'sum'")
+        self.gradient_scale = 1.0 / world_size if self.gradient_mode == "mean" else 1.0
 
     @classmethod
     def from_env(cls, device):
@@ -55,6 +66,8 @@ class DataParallel(object):
                 u.dp_ = self
         self.broadcast_parameters(
             [u for u in workflow.forwards if isinstance(u, Forward)])
+        if self.device is not None and self.device.is_cuda:
+            self.device.ext.set_dp_gradient_scale(self.gradient_scale)
         if self.device is not None and self.device.is_cuda and self.mode == "fused":
             from .symmetric import SymmetricGradients
             gds = [g for g in workflow.gds if g is not None and g.weights]
@@ -133,4 +146,6 @@ class DataParallel(object):
         import torch.distributed as dist
         t = torch.from_numpy(arr)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if self.gradient_scale != 1.0:
+            arr *= arr.dtype.type(self.gradient_scale)
         return arr
