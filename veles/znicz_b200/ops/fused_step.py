@@ -159,9 +159,16 @@ class FusedStep(object):
         name = os.environ.get("ZNICZ_DP_ALGO", "auto")
         have_mc = bool(self.mc_red)
         if name == "auto":
-            # NVLS two-shot moves ~2 P floats per rank instead of (N - 1) P and costs one more
-            # flag barrier; without multicast the peer-store form pays off for large models only
-            name = "twoshot" if have_mc else ("twoshot_peer" if numel >= (1 << 22) else "oneshot")
+            # Small models are latency bound: ONE flag barrier per step, every rank reduces every
+            # element itself (one multimem.ld_reduce per float4 with NVLS, N peer loads without).
+            # Measured at 2 GPUs on the CIFAR net (0.58 MB of parameters, driver's 20-step run):
+            # nvls1 0.2172 / oneshot 0.2165 / twoshot 0.2336 ms per step (1 GPU: 0.2042).
+            # Large models are bandwidth bound: two-shot moves ~2 P floats per rank instead of
+            # (N - 1) P and pays one more barrier.
+            if numel >= (1 << 22):
+                name = "twoshot" if have_mc else "twoshot_peer"
+            else:
+                name = "nvls1" if have_mc else "oneshot"
         if name == "twoshot" and not have_mc:
             name = "twoshot_peer"
         if name == "nvls1" and not have_mc:
