@@ -296,6 +296,13 @@ def run_reference_arm(args, rank, world):
     """``--impl reference``: the UNMODIFIED reference (baseline/_ref) on its own stock GPU path;
     the product package is never imported in this process."""
     try:
+        if not os.environ.get("CUDA4PY_DRY"):
+            # fail fast (and before any rendezvous) on a box without a GPU
+            from cuda.bindings import driver as _drv
+            err, = _drv.cuInit(0)
+            n_dev = _drv.cuDeviceGetCount()[1] if int(err) == 0 else 0
+            if int(err) != 0 or n_dev < 1:
+                raise RuntimeError("no CUDA device visible (cuInit: %s)" % getattr(err, "name", err))
         if world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             import torch.distributed as dist

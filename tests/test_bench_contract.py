@@ -17,6 +17,15 @@ def _run(args, env=None):
 
 
 def test_reference_arm_reports_unavailable_and_exits_zero():
+    """On a box without a GPU (this tier) the reference arm says why in ONE JSON line, exit 0;
+    on a GPU box it reports the measured number (tests/test_reference_arm.py covers the rest)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("GPU present: the arm would run the real benchmark")
+    except ImportError:
+        pass
     r = _run(["--impl", "reference", "--gpus", "1", "--steps", "5", "--warmup", "3"])
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]

@@ -273,6 +273,8 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
             ext.col_sums(w.dev, colsums, rows, cols, bool(unit.weights_transposed))
             _launch()
     fwd = unit.forward_unit
+    if getattr(fwd, "weights_lp_", None) is None and unit.__dict__.get("shadow_owner_"):
+        fwd = unit.__dict__["shadow_owner_"]    # GDDeconv: the tied Conv owns the bf16 shadows
     lp = lp_conv = None
     ld = taps = c = c_pad = cpad_lp = 0
     if not is_bias and fwd is not None and getattr(fwd, "weights_lp_", None) is not None:
@@ -778,14 +780,59 @@ def _rhits(unit, like):
     return t
 
 
+def _deconv_owner(unit):
+    """The Conv unit that owns the (tied) weights of a Deconv / GDDeconv: its bf16 operand
+    shadows (``weights_lp_`` [F][ld] and ``weights_lp_t_`` [tap][F_pad][C_pad]) are exactly what
+    the tcgen05 kernels need with the roles swapped (deconv forward = conv dgrad, GDDeconv
+    err_input = conv fprop, GDDeconv wgrad = conv wgrad with image and error exchanged)."""
+    o = unit.__dict__.get("shadow_owner_", False)
+    if o is not False:
+        return o
+    o = None
+    cand = [getattr(unit, "forward_unit", None)]
+    wf = unit.workflow
+    if wf is not None:
+        cand += list(getattr(wf, "units", []))
+    for u in cand:
+        if u is None or u is unit or not hasattr(u, "weights_lp_t_"):
+            continue
+        if getattr(u, "weights", None) is unit.weights and getattr(u, "on_cuda", False):
+            o = u
+            break
+    unit.__dict__["shadow_owner_"] = o
+    return o
+
+
+def _deconv_lp(unit, *tensors):
+    """Owner conv with valid shadows when this deconv call can run on the tensor cores."""
+    o = _deconv_owner(unit)
+    if o is None or not lp_enabled(o) or not all(_is_bf16(t) for t in tensors):
+        return None
+    if unit.n_kernels % 8 or unit.weights_transposed:
+        return None
+    ensure_shadows(o)         # (filled by the owner's initialize() and by every update kernel)
+    return o
+
+
 def deconv_forward(unit):
     ext = _ext(unit)
     x = unit.input.dev                       # [N, oy, ox, F] plays the role of err_out
     out = unit.output.dev_out                # [N, sy, sx, C] plays the role of err_in
     g = _deconv_geom(unit)
-    w = unit.weights.dev
     alpha = 1.0 if unit.hits else float(unit.scale)
-    ext.conv_dgrad(x, w, w.shape[1], bool(unit.weights_transposed), out, g, alpha, 0.0, 0, None, 0)
+    o = _deconv_lp(unit, x, out)
+    r = -1
+    if o is not None:
+        wd = o.weights_lp_t_
+        r = int(ext.conv_dgrad(x, wd, wd.shape[1], False, out, g, alpha, 0.0, 1, None, 0))
+        if r not in (0, -3, -4):
+            raise RuntimeError("%s: tcgen05 deconv (dgrad kernel) refused (code %d)" % (unit, r))
+        if r != 0:
+            _warn_once(unit, "deconv", r)
+    if r != 0:
+        w = unit.weights.dev
+        ext.conv_dgrad(x, w, w.shape[1], bool(unit.weights_transposed), out, g, alpha, 0.0, 0,
+                       None, 0)
     _launch()
     if unit.hits:
         ext.mask_mul(out, _rhits(unit, out))
@@ -803,17 +850,55 @@ def deconv_backward(unit):
     unit.err_output.dev_written()
     _launch()
     g = _deconv_geom(unit)
-    w = unit.weights.dev
     f, kw = unit.n_kernels, unit._kernel_size
-    if unit.need_err_input:
-        ei = unit.err_input.dev_out
-        if unit.err_input_beta or unit.err_input_alpha != 1.0:
-            raise NotImplementedError("GDDeconv: err_input alpha/beta on the device path")
-        ext.conv_fprop(err, w, w.shape[1], bool(unit.weights_transposed), None, ei, g, 0, 0)
+    xin = unit.input.dev                     # [N, oy, ox, F]: the "error" operand of the wgrad
+    o = _deconv_lp(unit, err, xin)
+    # first-layer geometry: the owner's fprop shadow is channel-padded [F][tap][cp]; the image
+    # operand (= the scaled err_output here) is padded the same way, once, for fprop and wgrad
+    cp = lp_cpad(o) if o is not None else 0
+    img, g_lp = err, list(g)
+    if cp:
+        img = _tmp(unit, "errpad", tuple(err.shape[:3]) + (cp,), err.dtype)
+        ext.pad_channels(err, img, unit._n_channels, cp)
         _launch()
+        g_lp[3] = cp
+    if unit.need_err_input:
+        alpha, beta = float(unit.err_input_alpha), float(unit.err_input_beta)
+        plain = alpha == 1.0 and beta == 0.0
+        ei = unit.err_input.dev_out if beta == 0.0 else unit.err_input.dev
+        dst = ei if plain else _tmp(unit, "ei", tuple(ei.shape), ei.dtype)
+        r = -1
+        if o is not None and _is_bf16(ei):
+            w = o.weights_lp_
+            r = int(ext.conv_fprop(img, w, w.shape[1], False, None, dst, g_lp, 0, 1))
+            if r not in (0, -3, -4):
+                raise RuntimeError("%s: tcgen05 GDDeconv err_input refused (code %d)" % (unit, r))
+            if r != 0:
+                _warn_once(unit, "gd_deconv err_input", r)
+        if r != 0:
+            w = unit.weights.dev
+            ext.conv_fprop(err, w, w.shape[1], bool(unit.weights_transposed), None, dst, g, 0, 0)
+        _launch()
+        if not plain:
+            # err_input = alpha * (im2col(err_output) . W^T) + beta * err_input
+            # (/root/reference/gd_deconv.py:340-349)
+            n = ei.shape[0]
+            ext.axpby_2d(dst.view(n, -1), 0, ei.view(n, -1), 0, ei.numel() // n, alpha, beta)
+            _launch()
+        unit.err_input.dev_written()
     if not (unit.need_gradient_weights and unit.weights):
         return
     pixels = unit.input.size // f
+    if o is not None:
+        kw_lp = unit.kx * unit.ky * cp if cp else kw
+        splits = int(ext.pick_splits(kw_lp, f, pixels, _MAX_SPLITS))
+        gbuf = _grad_buffer(unit, "wgrad", (splits, f, kw_lp))
+        r = int(ext.conv_wgrad(xin, img, gbuf, splits, g_lp, False, 1, None))
+        if r not in (0, 1):
+            raise RuntimeError("%s: tcgen05 GDDeconv wgrad refused (code %d)" % (unit, r))
+        _launch()
+        _update(unit, False, gbuf, splits, f * kw_lp, f, kw, g_cpad=cp)
+        return
     tiles = ((f + 63) // 64) * ((kw + 63) // 64)
     splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
     gbuf = _grad_buffer(unit, "wgrad", (splits, f, kw))

@@ -696,6 +696,46 @@ int64_t conv_wgrad(Tensor err_out, Tensor x, Tensor partials, int64_t splits, st
   return 0;
 }
 
+namespace zn {
+void launch_som_split(const float*, __nv_bfloat16*, int, int, int, long long, long long, int, float*, cudaStream_t);
+void launch_som_argmin(const float*, const float*, int*, int*, int, int, cudaStream_t);
+void launch_som_gravity_split(const float*, const int*, __nv_bfloat16*, float*, int, int, int, float, cudaStream_t);
+void launch_som_apply(float*, const float*, const float*, int, int, float, cudaStream_t);
+}
+// fp32 [rows][len] -> bf16 hi/lo parts (see som.cu); stack_rows: parts stacked along the rows of
+// dst ([3 * rows_pad][ld]) instead of concatenated along its columns ([rows][3 * kp])
+void som_split(Tensor src, Tensor dst, int64_t rows, int64_t len, int64_t kp, int64_t ld,
+               int64_t part_stride, int64_t pattern, c10::optional<Tensor> norm_out) {
+  TORCH_CHECK(src.scalar_type() == torch::kFloat32 && is_bf16(dst) && src.is_cuda() && dst.is_cuda());
+  TORCH_CHECK(src.numel() >= rows * len && dst.numel() >= 2 * part_stride + (rows - 1) * ld + kp);
+  zn::launch_som_split(src.data_ptr<float>(), reinterpret_cast<__nv_bfloat16*>(dst.data_ptr()), (int)rows,
+                       (int)len, (int)kp, ld, part_stride, (int)pattern, mfptr_or_null(norm_out), cur());
+  kcheck();
+}
+void som_argmin(Tensor dots, Tensor wnorm, Tensor argmins, c10::optional<Tensor> winners) {
+  TORCH_CHECK(dots.scalar_type() == torch::kFloat32 && wnorm.scalar_type() == torch::kFloat32 && dots.dim() == 2);
+  int* wp = (winners.has_value() && winners->defined()) ? winners->data_ptr<int>() : nullptr;
+  zn::launch_som_argmin(dots.data_ptr<float>(), wnorm.data_ptr<float>(), argmins.data_ptr<int>(), wp,
+                        (int)dots.size(0), (int)dots.size(1), cur());
+  kcheck();
+}
+void som_gravity_split(Tensor coords, Tensor argmins, Tensor dst, Tensor rowsum, int64_t batch, int64_t bp,
+                       double sigma) {
+  TORCH_CHECK(is_bf16(dst) && rowsum.scalar_type() == torch::kFloat32);
+  const int neurons = (int)rowsum.numel();
+  TORCH_CHECK(dst.numel() >= (int64_t)neurons * 3 * bp);
+  zn::launch_som_gravity_split(coords.data_ptr<float>(), argmins.data_ptr<int>(),
+                               reinterpret_cast<__nv_bfloat16*>(dst.data_ptr()), rowsum.data_ptr<float>(),
+                               neurons, (int)batch, (int)bp, (float)sigma, cur());
+  kcheck();
+}
+void som_apply(Tensor w, Tensor m, Tensor rowsum, double gmult) {
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32 && m.scalar_type() == torch::kFloat32 && w.numel() == m.numel());
+  const int neurons = (int)rowsum.numel();
+  zn::launch_som_apply(w.data_ptr<float>(), m.data_ptr<float>(), rowsum.data_ptr<float>(), neurons,
+                       (int)(w.numel() / neurons), (float)gmult, cur());
+  kcheck();
+}
 void som_winners(Tensor x, Tensor w, Tensor argmins, c10::optional<Tensor> winners) {
   TORCH_CHECK(x.scalar_type() == torch::kFloat32 && w.scalar_type() == torch::kFloat32);
   int batch = (int)x.size(0), neurons = (int)w.size(0), len = (int)(w.numel() / w.size(0));
@@ -760,6 +800,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("softmax_rows", &softmax_rows); m.def("evaluate_softmax", &evaluate_softmax);
   m.def("evaluate_mse", &evaluate_mse); m.def("mse_find_closest", &mse_find_closest);
   m.def("fused_update", &fused_update); m.def("update_blocks", &update_blocks);
+  m.def("som_split", &som_split); m.def("som_argmin", &som_argmin);
+  m.def("som_gravity_split", &som_gravity_split); m.def("som_apply", &som_apply);
   m.def("multi_update_table", &multi_update_table);
   m.def("set_dp_gradient_scale", [](double s) { zn::set_dp_gradient_scale((float)s); });
   m.def("get_dp_gradient_scale", []() { return (double)zn::get_dp_gradient_scale(); });

@@ -105,9 +105,67 @@ class KohonenForward(KohonenBase, AcceleratedUnit):
             x = self.input.dev
             if x.dtype != self.weights.dev.dtype:
                 x = x.float()
-            self.ext_.som_winners(x.view(x.shape[0], -1), self.weights.dev,
-                                  self.output.dev_out, None)
+            som_winners_device(self, x.view(x.shape[0], -1), self.weights.dev,
+                               self.output.dev_out, None)
         self._store_total()
+
+
+def _som_tmp(unit, name, shape, dtype):
+    import torch
+    key = "som_%s_" % name
+    t = unit.__dict__.get(key)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        t = torch.zeros(shape, dtype=dtype, device=unit.weights.dev.device)
+        unit.__dict__[key] = t
+    return t
+
+
+def som_winners_device(unit, x, w, argmins, winners):
+    """Winners of a minibatch. Feature vectors of >= 16 elements on >= 32 neurons: distances as
+    ONE tcgen05 GEMM over bf16 hi/lo split operands (csrc/som.cu), otherwise the scalar kernel.
+    Returns the split x operand (reused by the update) or None when the scalar path ran."""
+    import torch
+    ext = unit.ext_
+    batch, length = int(x.shape[0]), int(x.shape[1])
+    neurons = int(w.shape[0])
+    if length < 16 or neurons < 32:
+        ext.som_winners(x, w, argmins, winners)
+        return None
+    kp = (length + 7) // 8 * 8
+    xa = _som_tmp(unit, "xa", (batch, 3 * kp), torch.bfloat16)        # [x_hi | x_hi | x_lo]
+    wb = _som_tmp(unit, "wb", (neurons, 3 * kp), torch.bfloat16)      # [w_hi | w_lo | w_hi]
+    wn = _som_tmp(unit, "wn", (neurons,), torch.float32)
+    dots = _som_tmp(unit, "dots", (batch, neurons), torch.float32)
+    ext.som_split(x, xa, batch, length, kp, 3 * kp, kp, 0, None)
+    ext.som_split(w.view(neurons, -1), wb, neurons, length, kp, 3 * kp, kp, 1, wn)
+    r = ext.gemm(xa, 3 * kp, False, wb, 3 * kp, True, dots, neurons, False, batch, neurons, 3 * kp,
+                 None, 0, 1.0, 0.0, 1, 0, 1)
+    if r != 0:
+        raise RuntimeError("%s: tcgen05 SOM distance GEMM refused (code %d)" % (unit, r))
+    ext.som_argmin(dots, wn, argmins, winners)
+    return xa
+
+
+def som_update_device(unit, x, w, sigma, gmult):
+    """w += gmult * (G . x - rowsum(G) o w) with the [neurons x len x batch] product on the
+    tcgen05 GEMM (split operands: G parts along K, x parts stacked along its rows)."""
+    import torch
+    ext = unit.ext_
+    batch, length = int(x.shape[0]), int(x.shape[1])
+    neurons = int(w.shape[0])
+    bp = (batch + 7) // 8 * 8
+    lp = (length + 7) // 8 * 8
+    ga = _som_tmp(unit, "ga", (neurons, 3 * bp), torch.bfloat16)      # [G_hi | G_hi | G_lo]
+    xs = _som_tmp(unit, "xs", (3 * bp, lp), torch.bfloat16)           # [x_hi ; x_lo ; x_hi]
+    rs = _som_tmp(unit, "rowsum", (neurons,), torch.float32)
+    m = _som_tmp(unit, "m", (neurons, length), torch.float32)
+    ext.som_gravity_split(unit._coords.dev, unit.argmins.dev, ga, rs, batch, bp, sigma)
+    ext.som_split(x, xs, batch, length, lp, lp, bp * lp, 1, None)
+    r = ext.gemm(ga, 3 * bp, False, xs, lp, False, m, length, False, neurons, length, 3 * bp,
+                 None, 0, 1.0, 0.0, 1, 0, 1)
+    if r != 0:
+        raise RuntimeError("%s: tcgen05 SOM update GEMM refused (code %d)" % (unit, r))
+    ext.som_apply(w, m, rs, gmult)
 
 
 class KohonenTrainer(KohonenBase, AcceleratedUnit):
@@ -219,10 +277,14 @@ class KohonenTrainer(KohonenBase, AcceleratedUnit):
             x = x.float()
         x = x.view(x.shape[0], -1)
         w = self.weights.dev
-        self.ext_.som_winners(x, w, self.argmins.dev_out, self.winners.dev)
+        split = som_winners_device(self, x, w, self.argmins.dev_out, self.winners.dev)
         self.winners.dev_written()
-        self.ext_.som_update(x, w, self._coords.dev, self.argmins.dev,
-                             float(self.gravity_radius), float(self.gradient_multiplier))
+        if split is None:
+            self.ext_.som_update(x, w, self._coords.dev, self.argmins.dev,
+                                 float(self.gravity_radius), float(self.gradient_multiplier))
+        else:
+            som_update_device(self, x, w, float(self.gravity_radius),
+                              float(self.gradient_multiplier))
         self.weights.dev_written()
 
 
