@@ -45,13 +45,13 @@ sys.path.insert(0, %r)
 import run_reference as rr
 tiny = [
  {"name": "conv1", "type": "conv", "->": {"n_kernels": 8, "kx": 5, "ky": 5, "padding": (2,2,2,2), "sliding": (1,1), "weights_filling": "gaussian", "weights_stddev": 0.01, "bias_filling": "constant", "bias_stddev": 0},
-  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.002, "weights_decay": 0.0005, "weights_decay_bias": 0.0005, "factor_ortho": 0.001, "gradient_moment": 0.9, "gradient_moment_bias": 0.9}},
+  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.002, "weights_decay": 0.0005, "weights_decay_bias": 0.0005, "factor_ortho": 0.001, "gradient_moment": 0, "gradient_moment_bias": 0}},
  {"name": "pool1", "type": "max_pooling", "->": {"kx": 3, "ky": 3, "sliding": (2, 2)}},
  {"name": "relu1", "type": "activation_str"},
  {"name": "norm1", "type": "norm", "alpha": 0.00005, "beta": 0.75, "n": 3, "k": 1},
  {"name": "pool2", "type": "avg_pooling", "->": {"kx": 8, "ky": 8, "sliding": (8, 8)}},
  {"name": "fc_softmax4", "type": "softmax", "->": {"output_sample_shape": 10, "weights_filling": "gaussian", "weights_stddev": 0.01, "bias_filling": "constant", "bias_stddev": 0},
-  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.002, "weights_decay": 1.0, "weights_decay_bias": 0, "gradient_moment": 0.9, "gradient_moment_bias": 0.9}}]
+  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.002, "weights_decay": 1.0, "weights_decay_bias": 0, "gradient_moment": 0, "gradient_moment_bias": 0}}]
 """
 
 
@@ -153,7 +153,7 @@ for i, f in enumerate(wf.forwards):
         out['w%d' % i] = f.weights.mem.ravel()[:64].tolist(); out['b%d' % i] = f.bias.mem.ravel()[:8].tolist()
 wf.forwards[-1].output.map_read(); out['y'] = wf.forwards[-1].output.mem.ravel()[:50].tolist()
 wf.gds[0].gradient_weights.map_read(); out['gw0'] = wf.gds[0].gradient_weights.mem.ravel()[:64].tolist()
-wf.evaluator.n_err.map_read(); out['n_err'] = [int(v) for v in wf.decision.epoch_n_err]; out['cls'] = wf.loader.minibatch_class
+wf.evaluator.n_err.map_read(); out['n_err'] = [None if v is None else int(v) for v in wf.decision.epoch_n_err]; out['cls'] = wf.loader.minibatch_class
 print(json.dumps(out))
 """
     tiny_pool = body.replace('"kx": 8, "ky": 8, "sliding": (8, 8)', '"kx": 4, "ky": 4, "sliding": (4, 4)')
@@ -173,4 +173,5 @@ print(json.dumps(out))
     for k, v in res["numpy"].items():
         if k[0] in "wbyg":
             a, b = numpy.array(v), numpy.array(res["cuda"][k])
-            assert numpy.abs(a - b).max() <= 1e-3 * max(numpy.abs(a).max(), 1e-4) + 1e-7, (k, a[:4], b[:4])
+            assert numpy.abs(a - b).max() <= 1e-3 * max(numpy.abs(a).max(), 1e-4) + 1e-7, \
+                (k, a[:4].tolist(), b[:4].tolist(), float(numpy.abs(a - b).max()))

@@ -47,6 +47,8 @@ void launch_lstm_cell_bwd(const void*, long long, const void*, long long, const 
 int fc_small_max_out();
 void launch_fc_small_forward(const void*, bool, const float*, const float*, void*, float*, int*, int, int, int, int, int, const int*, void*, int, const float*, int*, int*, float*, cudaStream_t);
 void launch_fc_small_backward(void*, const void*, const void*, bool, const float*, void*, float*, float*, int, int, int, int, float, float, int, cudaStream_t);
+int launch_gemm_pair(const void*, long long, const void*, long long, void*, int, long long, int, int, int,
+                     const float*, int, float, cudaStream_t);
 size_t multi_update_desc_size();
 void set_dp_gradient_scale(float);
 float get_dp_gradient_scale();
@@ -622,6 +624,18 @@ int64_t gemm(Tensor a, int64_t lda, bool transa, Tensor b, int64_t ldb, bool tra
   kcheck();
   return 0;
 }
+// 2-CTA persistent tcgen05 GEMM (gemm_pair.cu): out[M][N] = act(alpha * a[M][K] . b[N][K]^T + bias)
+int64_t gemm_pair(Tensor a, Tensor b, Tensor out, c10::optional<Tensor> bias, int64_t act, double alpha) {
+  chk(a, "a"); chk(b, "b"); chk(out, "out");
+  TORCH_CHECK(is_bf16(a) && is_bf16(b) && a.dim() == 2 && b.dim() == 2 && out.dim() == 2);
+  TORCH_CHECK(a.size(1) == b.size(1) && out.size(0) == a.size(0) && out.size(1) == b.size(0));
+  TORCH_CHECK(is_bf16(out) || out.scalar_type() == torch::kFloat32);
+  int r = zn::launch_gemm_pair(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                               is_bf16(out) ? 0 : 1, out.stride(0), (int)a.size(0), (int)b.size(0),
+                               (int)a.size(1), fptr_or_null(bias), (int)act, (float)alpha, cur());
+  if (r == 0) kcheck();
+  return r;
+}
 int64_t pick_splits(int64_t M, int64_t N, int64_t K, int64_t max_splits) {
   return zn::umma_pick_splits((int)M, (int)N, (int)K, (int)max_splits);
 }
@@ -810,6 +824,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lstm_cell_fwd", &lstm_cell_fwd); m.def("lstm_cell_bwd", &lstm_cell_bwd);
   m.def("fc_small_max_out", &fc_small_max_out); m.def("fc_small_forward", &fc_small_forward);
   m.def("fc_small_backward", &fc_small_backward);
-  m.def("gemm", &gemm); m.def("pick_splits", &pick_splits);
+  m.def("gemm", &gemm); m.def("pick_splits", &pick_splits); m.def("gemm_pair", &gemm_pair);
   m.def("conv_fprop", &conv_fprop); m.def("conv_dgrad", &conv_dgrad); m.def("conv_wgrad", &conv_wgrad);
 }
