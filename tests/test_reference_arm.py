@@ -169,7 +169,9 @@ print(json.dumps(out))
         res[be] = json.loads(r.stdout.strip().splitlines()[-1])
     import numpy
     assert res["numpy"]["cls"] == 2 and res["cuda"]["cls"] == 2
-    assert res["numpy"]["n_err"] == res["cuda"]["n_err"]
+    for x, y in zip(res["numpy"]["n_err"], res["cuda"]["n_err"]):
+        assert (x is None) == (y is None)
+        assert x is None or abs(x - y) <= 1          # (an argmax near-tie may flip in fp32)
     for k, v in res["numpy"].items():
         if k[0] in "wbyg":
             a, b = numpy.array(v), numpy.array(res["cuda"][k])
