@@ -42,58 +42,65 @@ class LSTM(FullyConnectedOutput, AcceleratedWorkflow):
     """
     MAPPING = {"LSTM"}
 
+    # The cell is a small dataflow graph; it is declared as data and wired by one loop.
+    #   c_t = i . g + f . c_{t-1};   h_t = o . tanh(c_t)
+    #   i, f, o = sigmoid(W [x, h_{t-1}] (+ peephole to c_t for o when not ``simple``))
+    # node -> (factory, constructor kwargs taken from the gate kwargs?)
+    _NODES = (
+        ("ij", InputJoiner, False), ("input_gate", All2AllSigmoid, True),
+        ("forget_gate", All2AllSigmoid, True), ("memory_maker", All2AllTanh, True),
+        ("output_gate", All2AllSigmoid, True), ("output_activation", ForwardTanh, False),
+        ("input_mul", Multiplier, False), ("forget_mul", Multiplier, False),
+        ("summator", Summator, False), ("output_mul", Multiplier, False),
+    )
+    # consumer -> ((attribute of the consumer, producer, attribute of the producer), ...);
+    # "self" is the cell itself, "@gate_src" the joiner feeding the output gate
+    _EDGES = {
+        "input_gate": (("input", "ij", "output"),),
+        "forget_gate": (("input", "ij", "output"),),
+        "memory_maker": (("input", "ij", "output"),),
+        "input_mul": (("x", "input_gate", "output"), ("y", "memory_maker", "output")),
+        "forget_mul": (("x", "forget_gate", "output"), ("y", "self", "prev_memory")),
+        "summator": (("x", "input_mul", "output"), ("y", "forget_mul", "output")),
+        "output_activation": (("input", "summator", "output"),),
+        "output_gate": (("input", "@gate_src", "output"),),
+        "output_mul": (("x", "output_gate", "output"), ("y", "output_activation", "output")),
+    }
+
     def __init__(self, workflow, **kwargs):
         super().__init__(workflow, **kwargs)
         self.simple = kwargs.pop("simple", True)
-        gkw = {k: kwargs[k] for k in _GATE_KW if k in kwargs}
-        self.ij = InputJoiner(self)
-        self.input_gate = All2AllSigmoid(self, name="input_gate", **gkw)
-        self.forget_gate = All2AllSigmoid(self, name="forget_gate", **gkw)
-        self.memory_maker = All2AllTanh(self, name="memory_maker", **gkw)
-        if not self.simple:
+        gate_kw = {k: kwargs[k] for k in _GATE_KW if k in kwargs}
+        names = {"summator": "memory_cell"}
+        for attr, factory, takes_gate_kw in self._NODES:
+            kw = dict(gate_kw) if takes_gate_kw else {}
+            if factory is not InputJoiner:
+                kw["name"] = names.get(attr, attr)
+            setattr(self, attr, factory(self, **kw))
+        gate_src = "ij"
+        if not self.simple:               # peephole: the output gate also sees the new cell state
             self.ij_output = InputJoiner(self)
-        self.output_gate = All2AllSigmoid(self, name="output_gate", **gkw)
-        self.output_activation = ForwardTanh(self, name="output_activation")
-        self.input_mul = Multiplier(self, name="input_mul")
-        self.forget_mul = Multiplier(self, name="forget_mul")
-        self.summator = Summator(self, name="memory_cell")
-        self.output_mul = Multiplier(self, name="output_mul")
+            gate_src = "ij_output"
 
+        def node(key):
+            return self if key == "self" else getattr(self, gate_src if key == "@gate_src" else key)
+
+        # data aliases, and the control edges they imply (a unit runs after its producers)
         self.ij.link_from(self.start_point)
-        self.input_gate.link_from(self.ij)
-        self.forget_gate.link_from(self.ij)
-        self.memory_maker.link_from(self.ij)
-        self.input_mul.link_from(self.input_gate, self.memory_maker)
-        self.forget_mul.link_from(self.forget_gate)
-        self.summator.link_from(self.input_mul, self.forget_mul)
-        if not self.simple:
-            self.ij_output.link_from(self.summator, self.ij)
-            self.output_gate.link_from(self.ij_output)
-        else:
-            self.output_gate.link_from(self.ij)
-        self.output_activation.link_from(self.summator)
-        self.output_mul.link_from(self.output_activation, self.output_gate)
-        self.end_point.link_from(self.output_mul)
-
         self.ij.link_inputs(self, "input", "prev_output")
-        self.input_gate.link_attrs(self.ij, ("input", "output"))
-        self.forget_gate.link_attrs(self.ij, ("input", "output"))
-        self.memory_maker.link_attrs(self.ij, ("input", "output"))
-        self.input_mul.link_attrs(self.input_gate, ("x", "output"))
-        self.input_mul.link_attrs(self.memory_maker, ("y", "output"))
-        self.forget_mul.link_attrs(self.forget_gate, ("x", "output"))
-        self.forget_mul.link_attrs(self, ("y", "prev_memory"))
-        self.summator.link_attrs(self.input_mul, ("x", "output"))
-        self.summator.link_attrs(self.forget_mul, ("y", "output"))
-        self.output_activation.link_attrs(self.summator, ("input", "output"))
         if not self.simple:
             self.ij_output.link_inputs(self.ij, "output")
             self.ij_output.link_inputs(self.summator, "output")
-            self.output_gate.link_attrs(self.ij_output, ("input", "output"))
-        else:
-            self.output_gate.link_attrs(self.ij, ("input", "output"))
-        self.output_mul.link_attrs(self.output_gate, ("x", "output"))
-        self.output_mul.link_attrs(self.output_activation, ("y", "output"))
+            self.ij_output.link_from(self.summator, self.ij)
+        for consumer, edges in self._EDGES.items():
+            unit = getattr(self, consumer)
+            producers = []
+            for mine, src, theirs in edges:
+                unit.link_attrs(node(src), (mine, theirs))
+                if src != "self":
+                    producers.append(node(src))
+            unit.link_from(*producers)
+        self.end_point.link_from(self.output_mul)
         self.link_attrs(self.output_mul, "output")
         self.link_attrs(self.summator, ("memory", "output"))
         self.demand("input", "prev_output", "prev_memory")
@@ -140,21 +147,16 @@ class GDLSTM(AcceleratedWorkflow):
         self.ij_to_input = Cutter1D(self, name="ij_to_input", alpha=1, beta=0)
         self.ij_to_prev_output = Cutter1D(self, name="ij_to_prev_output", alpha=1, beta=0)
 
-        prev = self.gd_output_mul.link_from(self.start_point)
-        prev = self.gd_output_activation.link_from(prev)
-        prev = self.add_err_memory.link_from(prev)
-        prev = self.gd_output_gate.link_from(prev)
+        # control order = reverse topological order of the forward cell (a linear chain)
+        order = ["gd_output_mul", "gd_output_activation", "add_err_memory", "gd_output_gate"]
         if not forward.simple:
-            prev = self.og_to_summator.link_from(prev)
-            prev = self.og_to_ij.link_from(prev)
-        prev = self.gd_forget_mul.link_from(prev)
-        prev = self.gd_input_mul.link_from(prev)
-        prev = self.gd_forget_gate.link_from(prev)
-        prev = self.gd_memory_maker.link_from(prev)
-        prev = self.gd_input_gate.link_from(prev)
-        prev = self.ij_to_input.link_from(prev)
-        prev = self.ij_to_prev_output.link_from(prev)
-        self.end_point.link_from(prev)
+            order += ["og_to_summator", "og_to_ij"]
+        order += ["gd_forget_mul", "gd_input_mul", "gd_forget_gate", "gd_memory_maker",
+                  "gd_input_gate", "ij_to_input", "ij_to_prev_output"]
+        tail = self.start_point
+        for unit_name in order:
+            tail = getattr(self, unit_name).link_from(tail)
+        self.end_point.link_from(tail)
 
         self.gd_output_mul.link_attrs(self, "err_output")
         self.gd_output_mul.link_attrs(forward.output_mul, "x", "y")

@@ -80,14 +80,11 @@ class DecisionBase(Unit, metaclass=DecisionsRegistry):
 
     @max_epochs.setter
     def max_epochs(self, value):
-        if value is None:
-            self._max_epochs = None
-            return
-        if not isinstance(value, int):
-            raise TypeError(
-                "max_epochs must be an integer or None (got %s)" % type(value))
-        if value < 1:
-            raise ValueError("max_epochs must be greater than 0 (got %d)" % value)
+        ok_type = value is None or (isinstance(value, int) and not isinstance(value, bool))
+        if not ok_type:
+            raise TypeError("max_epochs: int >= 1 or None expected, got %r" % (value,))
+        if value is not None and value < 1:
+            raise ValueError("max_epochs: int >= 1 or None expected, got %r" % (value,))
         self._max_epochs = value
 
     def initialize(self, **kwargs):
@@ -150,20 +147,27 @@ class DecisionBase(Unit, metaclass=DecisionsRegistry):
 
     # -- epoch logic --------------------------------------------------------------------
     def _on_last_minibatch(self):
+        """End of one sample class. At the end of an epoch the hooks decide, in this order:
+        did train improve, did the tracked (minimax) error improve, what is the snapshot called,
+        are we done."""
         self.on_last_minibatch()
-        if bool(self.epoch_ended):
-            self.train_improved <<= self.train_improve_condition()
-            improved = self.improve_condition()
-            if improved:
-                self.improved_epoch_number = self.epoch_number
-            self.improved <<= improved
-            suffixes = []
-            self.fill_snapshot_suffixes(suffixes)
-            self.snapshot_suffix = "_".join(suffixes)
-            self.complete <<= self._stop_condition()
+        if self.epoch_ended:
+            self._close_epoch()
         if self.minibatch_class == TRAIN:
             self.on_training_finished()
         self._print_statistics()
+
+    def _close_epoch(self):
+        train_better = bool(self.train_improve_condition())
+        better = bool(self.improve_condition())
+        self.train_improved <<= train_better
+        self.improved <<= better
+        if better:
+            self.improved_epoch_number = self.epoch_number
+        parts = []
+        self.fill_snapshot_suffixes(parts)
+        self.snapshot_suffix = "_".join(parts)
+        self.complete <<= self._stop_condition()
 
     def _stop_condition(self):
         if self.testing:
@@ -325,32 +329,32 @@ class DecisionGD(DecisionBase):
             if store:
                 self.best_n_err_pt_others[i][:] = self.epoch_n_err_pt
                 self._store_best_n_err_pt_others[i] = False
-        mc = self.minibatch_class
-        if (nmax(self.epoch_n_err_pt[mc], self.epoch_n_err_pt[TRAIN], self.BIGNUM) <
-                nmax(self.best_minimax_n_err_pt[mc], self.best_minimax_n_err_pt[TRAIN],
-                     self.BIGNUM)):
-            for i in (mc, TRAIN, TEST):
-                self.best_minimax_n_err_pt[i] = self.epoch_n_err_pt[i]
-            self.best_minimax_n_err_pt_epoch_number = self.epoch_number
-            return True
-        return False
+        # minimax: the worse of (this class, TRAIN) must beat the best such pair seen so far
+        cls = self.minibatch_class
+        now, best = self.epoch_n_err_pt, self.best_minimax_n_err_pt
+        if not nmax(now[cls], now[TRAIN], self.BIGNUM) < nmax(best[cls], best[TRAIN], self.BIGNUM):
+            return False
+        best[cls], best[TRAIN], best[TEST] = now[cls], now[TRAIN], now[TEST]
+        self.best_minimax_n_err_pt_epoch_number = self.epoch_number
+        return True
 
     def train_improve_condition(self):
-        if (nvl(self.epoch_n_err_pt[TRAIN], self.BIGNUM) <
-                nvl(self.best_n_err_pt[TRAIN], self.BIGNUM)):
-            self.best_n_err_pt[TRAIN] = self.epoch_n_err_pt[TRAIN]
-            self.best_n_err_pt_epoch_number[TRAIN] = self.epoch_number
-            self._store_best_n_err_pt_others[TRAIN] = True
-            return True
-        return False
+        now = nvl(self.epoch_n_err_pt[TRAIN], self.BIGNUM)
+        if not now < nvl(self.best_n_err_pt[TRAIN], self.BIGNUM):
+            return False
+        self.best_n_err_pt[TRAIN] = self.epoch_n_err_pt[TRAIN]
+        self.best_n_err_pt_epoch_number[TRAIN] = self.epoch_number
+        self._store_best_n_err_pt_others[TRAIN] = True
+        return True
+
+    _SLAVE_PAYLOAD = ("minibatch_n_err", "minibatch_max_err_y_sum", "minibatch_confusion_matrix")
 
     def on_generate_data_for_master(self, data):
-        for attr in ("minibatch_n_err", "minibatch_max_err_y_sum",
-                     "minibatch_confusion_matrix"):
-            attrval = getattr(self, attr)
-            if attrval is not None and attrval:
-                attrval.map_read()
-                data[attr] = attrval.mem.copy()
+        for name in self._SLAVE_PAYLOAD:
+            arr = getattr(self, name)
+            if arr:
+                arr.map_read()
+                data[name] = numpy.array(arr.mem, copy=True)
 
     def on_generate_data_for_slave(self, data):
         data["improved"] = bool(self.improved)
@@ -362,17 +366,14 @@ class DecisionGD(DecisionBase):
         self.best_minimax_n_err_pt[TRAIN] = 0
 
     def on_apply_data_from_slave(self, data, slave):
-        if self.minibatch_n_err and "minibatch_n_err" in data:
-            self.minibatch_n_err.map_write()
-            self.minibatch_n_err.mem += data["minibatch_n_err"]
-        me = self.minibatch_max_err_y_sum
-        if me is not None and me and "minibatch_max_err_y_sum" in data:
-            me.map_write()
-            numpy.maximum(me.mem, data["minibatch_max_err_y_sum"], me.mem)
-        cm = self.minibatch_confusion_matrix
-        if cm is not None and cm and "minibatch_confusion_matrix" in data:
-            cm.map_write()
-            cm.mem += data["minibatch_confusion_matrix"]
+        # counts and the confusion matrix add up, the gradient-norm watermark is a maximum
+        merge = {"minibatch_n_err": numpy.add, "minibatch_confusion_matrix": numpy.add,
+                 "minibatch_max_err_y_sum": numpy.maximum}
+        for name, op in merge.items():
+            arr = getattr(self, name)
+            if arr and name in data:
+                arr.map_write()
+                op(arr.mem, data[name], out=arr.mem)
 
     def stop_condition(self):
         if all(nvl(self.best_minimax_n_err_pt[i], 0) <= 0 for i in (VALID, TRAIN)):

@@ -303,32 +303,36 @@ class StandardWorkflowBase(nn_units.NNWorkflow):
         return self.loader
 
     def link_end_point(self, *parents):
-        self.repeater.link_from(*parents)
-        self.end_point.link_from(*parents)
+        for sink in (self.repeater, self.end_point):      # close the loop and offer the exit
+            sink.link_from(*parents)
         return self.end_point
 
     def create_workflow(self):
-        self.link_repeater(self.start_point)
-        self.link_loader(self.repeater)
-        self.link_forwards(("input", "minibatch_data"), self.loader)
-        self.end_point.gate_block = ~self.loader.complete
+        """Forward-only skeleton: start -> repeater -> loader -> forwards; the exit stays shut
+        until the loader reports completion."""
+        loader = self.link_loader(self.link_repeater(self.start_point))
+        self.link_forwards(("input", "minibatch_data"), loader)
+        self.end_point.gate_block = ~loader.complete
+
+    _LAYER_META_KEYS = frozenset(("type", "->", "<-", "name"))
 
     def _get_layer_type_kwargs(self, layer):
-        tpe = layer.get("type", "").strip()
-        if not tpe:
+        """One ``layers`` entry -> (registry type, forward kwargs, GD kwargs): "->" feeds the
+        forward unit, "<-" the GD unit, every other key both; ``name`` gets a per-direction
+        suffix (DSL semantics: /root/reference/standard_workflow_base.py:406-422)."""
+        kind = str(layer.get("type", "")).strip()
+        if kind == "":
             raise ValueError("layer type must not be an empty string")
-        if tpe not in self.layer_map:
-            raise ValueError("Unknown layer type %s" % tpe)
-        kwargs_forward = dict(layer.get("->", {}))
-        kwargs_backward = dict(layer.get("<-", {}))
-        others = {k: v for k, v in layer.items()
-                  if k not in ("type", "->", "<-", "name")}
-        kwargs_forward.update(others)
-        kwargs_backward.update(others)
-        if "name" in layer:
-            kwargs_forward["name"] = layer["name"] + "_forward"
-            kwargs_backward["name"] = layer["name"] + "_backward"
-        return tpe, kwargs_forward, kwargs_backward
+        if kind not in self.layer_map:
+            raise ValueError("Unknown layer type %s" % kind)
+        shared = {k: v for k, v in layer.items() if k not in self._LAYER_META_KEYS}
+        per_direction = []
+        for arrow, suffix in (("->", "_forward"), ("<-", "_backward")):
+            kw = dict(layer.get(arrow, {}), **shared)
+            if "name" in layer:
+                kw["name"] = layer["name"] + suffix
+            per_direction.append(kw)
+        return kind, per_direction[0], per_direction[1]
 
     def _add_forward_unit(self, new_unit, init_attrs=None, *parents):
         if self.forwards:
