@@ -246,3 +246,16 @@ def test_minibatches_saver_roundtrip(tmp_path):
     assert list(ml.class_lengths) == [5, 10, 30]
     ld.original_data.map_read()
     numpy.testing.assert_allclose(ml.original_data.mem, ld.original_data.mem, rtol=1e-6)
+
+
+def test_model_manifests_and_packaging(tmp_path):
+    """manifest.json packaging (/root/reference/samples/Wine/manifest.json)."""
+    from veles.znicz_b200.utils import forge
+    names = forge.list_models()
+    assert {"Wine", "MNIST", "CIFAR10", "Kanji", "Lines", "YaleFaces", "DemoKohonen"} <= set(names)
+    for n in names:
+        m = forge.load_manifest(n)
+        assert m["name"] == n and m["workflow"].endswith(".py")
+    pkg = forge.pack("Wine", str(tmp_path / "wine.tar.gz"))
+    m = forge.unpack(pkg, str(tmp_path / "out"))
+    assert m["name"] == "Wine" and (tmp_path / "out" / "wine.py").is_file()
