@@ -27,7 +27,10 @@ namespace zn {
 
 using namespace umma;
 
-enum { A_TMA_K = 0, A_TMA_MN = 1, A_GATHER_K = 2, A_GATHER_MN = 3 };
+// A_IM2COL_K / A_IM2COL_MN: the same implicit-GEMM operands as A_GATHER_K / A_GATHER_MN, but
+// fetched by TMA in im2col mode (one instruction per [pixels x 64 channels] block instead of a
+// 128-thread LDGSTS gather) - channel counts that are multiples of 64 only.
+enum { A_TMA_K = 0, A_TMA_MN = 1, A_GATHER_K = 2, A_GATHER_MN = 3, A_IM2COL_K = 4, A_IM2COL_MN = 5 };
 enum { B_TMA_K = 0, B_TMA_MN = 1 };
 enum { G_NONE = 0, G_IM2COL = 1, G_DGRAD = 2 };
 
@@ -291,7 +294,7 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int B_BYTES = b_bytes<BLOCK_N, B_MODE>();
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr bool A_GATHER = (A_MODE == A_GATHER_K || A_MODE == A_GATHER_MN);
-  constexpr bool A_MN = (A_MODE == A_TMA_MN || A_MODE == A_GATHER_MN);
+  constexpr bool A_MN = (A_MODE == A_TMA_MN || A_MODE == A_GATHER_MN || A_MODE == A_IM2COL_MN);
   constexpr bool B_MN = (B_MODE == B_TMA_MN);
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t IDESC = FP8 ? make_idesc_e4m3(BLOCK_M, BLOCK_N)
@@ -367,8 +370,44 @@ gemm_umma_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         uint8_t* sb = sa + A_BYTES;
         const int k0 = (kb_begin + i) * KBLK;
         if (p.dbg & 4) { mbar_arrive(&full_bar[s]); continue; }
-        mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
-        if (A_MODE == A_TMA_K) {
+        if (A_MODE == A_IM2COL_MN) {
+          // conv wgrad: tile = [64 pixels (reduction rows)][128 reduction-weight indices] = two
+          // [64 pixels x 64 channels] im2col boxes (one tap each); a block past Kw is skipped
+          const ConvGeomU& g = p.g;
+          const int pix0 = (kb_begin + i) * BLOCK_K;
+          const int q = pix0 % g.OW; const int t2 = pix0 / g.OW;
+          const int pr = t2 % g.OH; const int n = t2 / g.OH;
+          const int w0 = q * g.SX - g.PL, h0 = pr * g.SY - g.PT;
+          const int nblk = (m0 + 64 < p.gK) ? 2 : 1;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(B_BYTES + nblk * 8192));
+          for (int mb = 0; mb < nblk; ++mb) {
+            const int kidx0 = m0 + mb * 64;
+            const int tap = kidx0 / g.C, c0 = kidx0 - tap * g.C;
+            tma_load_im2col_4d(sa + mb * 8192, &tmap_a, &full_bar[s], c0, w0, h0, n,
+                               (uint16_t)(tap % g.KX), (uint16_t)(tap / g.KX));
+          }
+        } else {
+          mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
+        }
+        if (A_MODE == A_IM2COL_K) {
+          // conv fprop / stride-1 dgrad: tile rows = pixels m0 .. m0 + 127, k-block = 64
+          // channels of ONE filter tap
+          const ConvGeomU& g = p.g;
+          const int tap = k0 / g.inner, c0 = k0 - tap * g.inner;
+          const int ky = tap / g.KX, kx = tap - ky * g.KX;
+          int w0, h0, n, ow, oh;
+          if (GKIND == G_IM2COL) {
+            const int q = m0 % g.OW; const int t2 = m0 / g.OW;
+            const int pr = t2 % g.OH; n = t2 / g.OH;
+            w0 = q * g.SX - g.PL; h0 = pr * g.SY - g.PT; ow = kx; oh = ky;
+          } else {                                   // dgrad: correlation with the flipped filter
+            const int ix = m0 % g.W; const int t2 = m0 / g.W;
+            const int iy = t2 % g.H; n = t2 / g.H;
+            w0 = ix - (g.KX - 1 - g.PL); h0 = iy - (g.KY - 1 - g.PT);
+            ow = g.KX - 1 - kx; oh = g.KY - 1 - ky;
+          }
+          tma_load_im2col_4d(sa, &tmap_a, &full_bar[s], c0, w0, h0, n, (uint16_t)ow, (uint16_t)oh);
+        } else if (A_MODE == A_TMA_K) {
           tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
         } else if (A_MODE == A_TMA_MN) {
           tma_load_2d(sa, &tmap_a, &full_bar[s], m0, k0);
@@ -714,6 +753,49 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// ---- im2col-mode tensor map over an NHWC bf16 tensor [N][H][W][C] --------------------------------
+// Filter-window base positions along w run from lower_w to W + upper_w (exclusive) in steps of the
+// traversal stride; upper_* are chosen by the callers so that exactly OW x OH positions exist.
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return nullptr;
+    fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  return fn;
+}
+static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int lower_w,
+                           int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int pixels) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) return -1;
+  if (lower_w < -128 || lower_h < -128 || upper_w < -128 || upper_h < -128 || lower_w > 127 ||
+      lower_h > 127 || upper_w > 127 || upper_h > 127 || stride_w > 8 || stride_h > 8)
+    return -7;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower,
+                   upper, 64u, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+// ZNICZ_IM2COL_TMA=0 keeps the LDGSTS gather producers (A/B measurements, fallback)
+static bool im2col_tma_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ZNICZ_IM2COL_TMA"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on != 0;
+}
+
 // bf16 output tile map for the TMA-store epilogue: dims {N, M}, box {BN, 32}, no swizzle
 static int make_map_out(CUtensorMap* m, const void* ptr, long long N, long long M, long long ldo, int bn) {
   EncodeTiledFn enc = get_encode();
@@ -977,6 +1059,15 @@ int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
   p.mt = pick_mt(p.M, p.N, bn);
+  if (C % 64 == 0 && im2col_tma_enabled()) {
+    // A operand by TMA im2col: window bases -PL .. W + upper_w, OW x OH of them
+    CUtensorMap ti;
+    if (make_map_im2col(&ti, x, N, H, W, C, -PL, -PT, (OW - 1) * SX + 1 - PL - W,
+                        (OH - 1) * SY + 1 - PT - H, SX, SY, BLOCK_M) == 0) {
+      p.g.inner = C; p.mt = 1;
+      return launch_bn<A_IM2COL_K, B_TMA_K, G_IM2COL, 0>(bn, ti, tb, p, 1, st);
+    }
+  }
   if (set_tap_mode(p.g, C, false)) return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 2>(bn, ta, tb, p, 1, st);
   if (C % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 1>(bn, ta, tb, p, 1, st);
   return launch_bn<A_GATHER_K, B_TMA_K, G_IM2COL, 0>(bn, ta, tb, p, 1, st);
@@ -1009,6 +1100,17 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
   p.gather_kind = G_DGRAD; p.gK = Kd;
   p.dmul = (const __nv_bfloat16*)dmul; p.dact = dmul ? dact : 0;
   p.mt = pick_mt(p.M, p.N, bn);
+  if (F % 64 == 0 && SY == 1 && SX == 1 && im2col_tma_enabled()) {
+    // unit stride: dgrad is a correlation of err_out with the flipped filter; W x H window bases
+    // starting at -(K - 1 - pad) over the [N][OH][OW][F] tensor
+    CUtensorMap ti;
+    const int lw = -(KX - 1 - PL), lh = -(KY - 1 - PT);
+    if (make_map_im2col(&ti, err_out, N, OH, OW, F, lw, lh, W + lw - OW, H + lh - OH, 1, 1,
+                        BLOCK_M) == 0) {
+      p.g.inner = F; p.mt = 1;
+      return launch_bn<A_IM2COL_K, B_TMA_MN, G_DGRAD, 0>(bn, ti, tb, p, 1, st);
+    }
+  }
   if (set_tap_mode(p.g, F, true)) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 2>(bn, ta, tb, p, 1, st);
   if (F % 8 == 0) return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 1>(bn, ta, tb, p, 1, st);
   return launch_bn<A_GATHER_K, B_TMA_MN, G_DGRAD, 0>(bn, ta, tb, p, 1, st);
@@ -1041,6 +1143,16 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
   p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.beta = 0.f; p.split_stride = (long long)F * Kw;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
+  if (C % 64 == 0 && im2col_tma_enabled()) {
+    // im2col operand by TMA, 64 pixels x 64 channels per box (no "ones" row here: the caller
+    // computes the bias gradient with the column-sum kernel when this returns 0)
+    CUtensorMap ti;
+    if (make_map_im2col(&ti, x, N, H, W, C, -PL, -PT, (OW - 1) * SX + 1 - PL - W,
+                        (OH - 1) * SY + 1 - PT - H, SX, SY, 64) == 0) {
+      p.g.inner = C;
+      return launch_bn<A_IM2COL_MN, B_TMA_MN, G_IM2COL, 0>(bn, ti, tb, p, splits, st);
+    }
+  }
   if (set_tap_mode(p.g, C, false)) {
     bool row = bias_parts != nullptr && (Kw % BLOCK_M) != 0;
     if (row) {

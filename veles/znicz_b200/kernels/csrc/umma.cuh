@@ -94,6 +94,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// im2col-mode TMA (NHWC activation tensor, map built by cuTensorMapEncodeIm2col): loads
+// `pixelsPerColumn` consecutive filter-window positions starting at base coordinate (w, h, n) -
+// the window's top-left corner in input coordinates, i.e. q * stride - pad - walking W, then H,
+// then N inside the bounding box, `channelsPerPixel` channels from c of the pixel at
+// base + (off_w, off_h) each; out-of-image pixels arrive as zeros. One instruction replaces the
+// 128-thread LDGSTS gather of a [128 pixels x 64 channels] operand block.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                   int c, int w, int h, int n, uint16_t off_w,
+                                                   uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 // shared -> global tile store (async proxy); smem must stay valid until wait_group.read
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0,
                                              int c1) {
