@@ -125,7 +125,11 @@ def build_workflow(streaming, compute, graphs, n_train, model="cifar_caffe"):
     from veles.znicz_b200.models import alexnet
     return alexnet.build(
         loader_name="synthetic_imagenet", layers=alexnet.alexnet_layers(1000),
-        loader_config={"minibatch_size": batch, "n_train": min(n_train, 1024), "n_valid": 0,
+        # (per-rank dataset size constant under weak scaling: the sharded loader otherwise ends an
+        # epoch - NCCL metric reduction + a 1000 x 1000 confusion matrix - every step at 8 ranks)
+        loader_config={"minibatch_size": batch,
+                       "n_train": min(n_train, 1024) * max(1, int(os.environ.get("WORLD_SIZE", "1"))),
+                       "n_valid": 0,
                        "n_test": 0, "n_classes": 1000, "normalization_type": "internal_mean",
                        "on_device": not streaming, "shuffle_limit": 2000000000}, **common)
 

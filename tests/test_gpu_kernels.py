@@ -113,6 +113,7 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
     n, h, w_, c, f, ky, kx, pad, stride = case
     torch.manual_seed(3)
     dev = "cuda"
+    tma0 = ext.im2col_tma_launches()
     oh = 1 + (h - ky + pad[1] + pad[3]) // stride[1]
     ow = 1 + (w_ - kx + pad[0] + pad[2]) // stride[0]
     kw = ky * kx * c
@@ -173,6 +174,11 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
     if r == 1:      # bias gradient delivered as the extra "ones" row of the product
         ref_b = eo.float().reshape(-1, f).sum(0)
         assert _rel(bparts.sum(0), ref_b) < 5e-3
+    if engine == 1:
+        # the TMA im2col producer really ran where the geometry allows it (no silent fallback)
+        want = (2 if c % 64 == 0 else 0) + (1 if (f % 64 == 0 and stride == (1, 1)) else 0)
+        want += 1 if (c % 8 == 0 and f % 64 == 0 and stride == (1, 1)) else 0   # folded-derivative dgrad
+        assert ext.im2col_tma_launches() - tma0 == want, (ext.im2col_tma_launches() - tma0, want)
 
 
 def test_fused_update_matches_reference_formula(ext):

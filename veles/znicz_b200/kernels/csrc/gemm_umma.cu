@@ -789,6 +789,8 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
+static long long g_im2col_launches = 0;
+long long im2col_tma_launches() { return g_im2col_launches; }
 // ZNICZ_IM2COL_TMA=0 keeps the LDGSTS gather producers (A/B measurements, fallback)
 static bool im2col_tma_enabled() {
   static int on = -1;
@@ -1065,6 +1067,7 @@ int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const
     if (make_map_im2col(&ti, x, N, H, W, C, -PL, -PT, (OW - 1) * SX + 1 - PL - W,
                         (OH - 1) * SY + 1 - PT - H, SX, SY, BLOCK_M) == 0) {
       p.g.inner = C; p.mt = 1;
+      ++g_im2col_launches;
       return launch_bn<A_IM2COL_K, B_TMA_K, G_IM2COL, 0>(bn, ti, tb, p, 1, st);
     }
   }
@@ -1108,6 +1111,7 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
     if (make_map_im2col(&ti, err_out, N, OH, OW, F, lw, lh, W + lw - OW, H + lh - OH, 1, 1,
                         BLOCK_M) == 0) {
       p.g.inner = F; p.mt = 1;
+      ++g_im2col_launches;
       return launch_bn<A_IM2COL_K, B_TMA_MN, G_DGRAD, 0>(bn, ti, tb, p, 1, st);
     }
   }
@@ -1150,6 +1154,7 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
     if (make_map_im2col(&ti, x, N, H, W, C, -PL, -PT, (OW - 1) * SX + 1 - PL - W,
                         (OH - 1) * SY + 1 - PT - H, SX, SY, 64) == 0) {
       p.g.inner = C;
+      ++g_im2col_launches;
       return launch_bn<A_IM2COL_MN, B_TMA_MN, G_IM2COL, 0>(bn, ti, tb, p, splits, st);
     }
   }
