@@ -104,6 +104,11 @@ CONV_CASES = [
     (3, 14, 17, 64, 64, 3, 5, (2, 1, 1, 0), (1, 1)),    # asymmetric padding, tiles span images
     (2, 16, 16, 64, 64, 3, 3, (1, 1, 1, 1), (2, 2)),    # strided windows (dgrad stays on gather)
     (5, 13, 13, 192, 128, 3, 3, (1, 1, 1, 1), (1, 1)),  # AlexNet conv3-like, 3 channel slices / tap
+    # large layers: 2-CTA persistent kernel (gemm_pair.cu) with the TMA im2col operand
+    (8, 13, 13, 128, 256, 3, 3, (1, 1, 1, 1), (1, 1)),  # fprop BN 256; dgrad N = 128
+    (4, 20, 20, 64, 384, 5, 5, (2, 2, 2, 2), (1, 1)),   # fprop 3 N-tiles of 128
+    (3, 20, 21, 256, 128, 3, 3, (1, 1, 1, 1), (1, 1)),  # dgrad BN 256, ragged M
+    (5, 31, 31, 64, 128, 5, 5, (2, 2, 2, 2), (2, 2)),   # strided fprop on the pair kernel
 ]
 
 
@@ -113,7 +118,7 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
     n, h, w_, c, f, ky, kx, pad, stride = case
     torch.manual_seed(3)
     dev = "cuda"
-    tma0 = ext.im2col_tma_launches()
+    tma0, pair0 = ext.im2col_tma_launches(), ext.conv_pair_launches()
     oh = 1 + (h - ky + pad[1] + pad[3]) // stride[1]
     ow = 1 + (w_ - kx + pad[0] + pad[2]) // stride[0]
     kw = ky * kx * c
@@ -176,9 +181,14 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
         assert _rel(bparts.sum(0), ref_b) < 5e-3
     if engine == 1:
         # the TMA im2col producer really ran where the geometry allows it (no silent fallback)
-        want = (2 if c % 64 == 0 else 0) + (1 if (f % 64 == 0 and stride == (1, 1)) else 0)
-        want += 1 if (c % 8 == 0 and f % 64 == 0 and stride == (1, 1)) else 0   # folded-derivative dgrad
-        assert ext.im2col_tma_launches() - tma0 == want, (ext.im2col_tma_launches() - tma0, want)
+        f_pair = c % 64 == 0 and f >= 128 and n * oh * ow >= 1024
+        d_pair = f % 64 == 0 and stride == (1, 1) and c >= 128 and n * h * w_ >= 1024
+        d_tma = f % 64 == 0 and stride == (1, 1) and not d_pair
+        want_pair = int(f_pair) + 2 * int(d_pair)           # (dgrad runs twice: plain + folded f')
+        want_tma = (1 if (c % 64 == 0 and not f_pair) else 0) + (1 if c % 64 == 0 else 0) + \
+            (2 if (d_tma and c % 8 == 0) else int(d_tma))
+        got = (ext.conv_pair_launches() - pair0, ext.im2col_tma_launches() - tma0)
+        assert got == (want_pair, want_tma), (got, want_pair, want_tma)
 
 
 def test_fused_update_matches_reference_formula(ext):

@@ -50,6 +50,7 @@ void launch_fc_small_backward(void*, const void*, const void*, bool, const float
 int launch_gemm_pair(const void*, long long, const void*, long long, void*, int, long long, int, int, int,
                      const float*, int, float, cudaStream_t);
 long long im2col_tma_launches();
+long long conv_pair_launches();
 size_t multi_update_desc_size();
 void set_dp_gradient_scale(float);
 float get_dp_gradient_scale();
@@ -825,6 +826,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lstm_cell_fwd", &lstm_cell_fwd); m.def("lstm_cell_bwd", &lstm_cell_bwd);
   m.def("fc_small_max_out", &fc_small_max_out); m.def("fc_small_forward", &fc_small_forward);
   m.def("fc_small_backward", &fc_small_backward);
+  m.def("conv_pair_launches", []() { return (int64_t)zn::conv_pair_launches(); });
   m.def("im2col_tma_launches", []() { return (int64_t)zn::im2col_tma_launches(); });
   m.def("gemm", &gemm); m.def("pick_splits", &pick_splits); m.def("gemm_pair", &gemm_pair);
   m.def("conv_fprop", &conv_fprop); m.def("conv_dgrad", &conv_dgrad); m.def("conv_wgrad", &conv_wgrad);

@@ -34,10 +34,19 @@ constexpr int A_BYTES = BM * 128;
 constexpr int EPI_BUF = 128 * 128;      // 128 rows x 128 bytes per staging buffer
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit: "same variable in CTA 0"
 
+// A operand: dense [M][K] tile, or the implicit-GEMM operand of a convolution fetched by TMA in
+// im2col mode (one [128 pixels x 64 channels] box per k-block): fprop = im2col(x), dgrad
+// (unit stride) = windows of err_out for the flipped filter.
+enum { AM_DENSE = 0, AM_IM2COL_FPROP = 1, AM_IM2COL_DGRAD = 2 };
+
+struct ConvP { int H, W, OH, OW, KY, KX, SY, SX, PT, PL, inner; };
+
 struct Params {
   int M, N, K;
   const float* bias; int act; float alpha;
   int tiles_m, tiles_n;
+  ConvP g;
+  const __nv_bfloat16* dmul; int dact; long long ldo;   // dgrad: out *= f'(dmul[row][col])
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -88,6 +97,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// im2col-mode load (see umma.cuh::tma_load_im2col_4d), 2-CTA form: bytes complete on CTA 0's barrier
+__device__ __forceinline__ void tma_load_im2col_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                    int c, int w, int h, int n, uint16_t off_w,
+                                                    uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
@@ -115,7 +134,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   tm = m0 + (r - tn * gm);
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int AMODE = AM_DENSE, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const Params p) {
@@ -124,7 +143,7 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int NST = (BN == 256) ? 6 : 8;
   constexpr int EPI_COLS = OUT_F32 ? 32 : 64;          // 128-byte staging rows
   constexpr int NCHUNK = BN / EPI_COLS;
-  constexpr uint32_t IDESC = make_idesc_bf16(2 * BM, BN, 0, 0);
+  constexpr uint32_t IDESC = make_idesc_bf16(2 * BM, BN, 0, B_MN ? 1 : 0);
   constexpr uint32_t TMEM_COLS = 2 * BN;               // double-buffered accumulator (256 or 512)
 
   extern __shared__ uint8_t smem_raw[];
@@ -175,8 +194,35 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           // the leader's barrier expects the bytes of BOTH CTAs; the peer's copies may complete
           // before this expect_tx is posted (the tx-count just goes negative for a moment)
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * STAGE);
-          tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], kb * BK, m0);
-          tma_load_2d_2sm(sa + A_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
+          if (AMODE == AM_DENSE) {
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], kb * BK, m0);
+          } else {
+            // this CTA's 128 pixels start at m0; k-block = 64 channels of one filter tap
+            const ConvP& g = p.g;
+            const int k0 = kb * BK;
+            const int tap = k0 / g.inner, c0 = k0 - tap * g.inner;
+            const int ky = tap / g.KX, kx = tap - ky * g.KX;
+            int w0, h0, n, ow, oh;
+            if (AMODE == AM_IM2COL_FPROP) {
+              const int q = m0 % g.OW; const int t2 = m0 / g.OW;
+              const int pr = t2 % g.OH; n = t2 / g.OH;
+              w0 = q * g.SX - g.PL; h0 = pr * g.SY - g.PT; ow = kx; oh = ky;
+            } else {
+              const int ix = m0 % g.W; const int t2 = m0 / g.W;
+              const int iy = t2 % g.H; n = t2 / g.H;
+              w0 = ix - (g.KX - 1 - g.PL); h0 = iy - (g.KY - 1 - g.PT);
+              ow = g.KX - 1 - kx; oh = g.KY - 1 - ky;
+            }
+            tma_load_im2col_2sm(sa, &tmap_a, &full_bar[s], c0, w0, h0, n, (uint16_t)ow, (uint16_t)oh);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sa + A_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
+          } else {
+            // B stored [K][N] (N contiguous): 64 x 64 boxes, one per 64 columns of this CTA's half
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_2d_2sm(sa + A_BYTES + j * 8192, &tmap_b, &full_bar[s], n0 + j * 64, kb * BK);
+          }
         }
       }
     }
@@ -198,7 +244,8 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                     : make_smem_desc(sb + k * 32, 16, 1024);
             mma_f16_2sm(d_tmem, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
           }
           mma_commit_2sm(&empty_bar[s], 3);              // frees the stage in both CTAs
@@ -261,6 +308,22 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 if (p.bias != nullptr && n < p.N) x += __ldg(p.bias + n);
                 v[j] = act_fwd5_fast(p.act, x);
               }
+              if (p.dmul != nullptr) {
+                // err_input *= f'(x): x has the layout of the output (row pitch ldo)
+                const int row = m0 + et;
+                const int n8 = nb + q * 8;
+                if (row < p.M && n8 + 8 <= p.N) {
+                  float xv[8];
+                  ld8(p.dmul + (long long)row * p.ldo + n8, xv);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] *= act_deriv(p.dact, 0.f, xv[j]);
+                } else if (row < p.M) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (n8 + j < p.N)
+                      v[j] *= act_deriv(p.dact, 0.f, __bfloat162float(p.dmul[(long long)row * p.ldo + n8 + j]));
+                }
+              }
               st8(reinterpret_cast<__nv_bfloat16*>(rowp + (((h * 4 + q) ^ sw) << 4)), v);
             }
           }
@@ -319,14 +382,14 @@ static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int AMODE = AM_DENSE, bool B_MN = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Params& p,
                   cudaStream_t st) {
   constexpr int NST = (BN == 256) ? 6 : 8;
   constexpr int smem = NST * (A_BYTES + (BN / 2) * 128) + 2 * EPI_BUF + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_k<BN, OUT_F32>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_k<BN, OUT_F32, AMODE, B_MN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -344,11 +407,107 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   const int tiles = p.tiles_m * p.tiles_n;
   int clusters = sms / 2;
   if (clusters > tiles) clusters = tiles;
-  gemm_pair_k<BN, OUT_F32><<<dim3(2 * clusters), dim3(256), smem, st>>>(ta, tb, tc, p);
+  gemm_pair_k<BN, OUT_F32, AMODE, B_MN><<<dim3(2 * clusters), dim3(256), smem, st>>>(ta, tb, tc, p);
   return (int)cudaGetLastError();
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// im2col-mode map over NHWC bf16 [N][H][W][C]: 128 window positions x 64 channels per load
+static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int lower_w,
+                           int lower_h, int upper_w, int upper_h, int stride_w, int stride_h) {
+  static EncodeIm2colFn enc = nullptr;
+  if (!enc) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &q, cudaEnableDefault, &qr) != cudaSuccess || !q)
+      return -1;
+    enc = reinterpret_cast<EncodeIm2colFn>(q);
+  }
+  const int v[6] = {lower_w, lower_h, upper_w, upper_h, 0, 0};
+  for (int i = 0; i < 4; ++i) if (v[i] < -128 || v[i] > 127) return -7;
+  if (stride_w > 8 || stride_h > 8) return -7;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower,
+                   upper, 64u, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+static bool conv_pair_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("ZNICZ_CONV_PAIR"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on != 0;
+}
+
 }  // namespace pr
+
+// Convolution forward as an implicit GEMM on the 2-CTA persistent kernel: A = im2col(x) by TMA
+// (im2col mode), B = w_lp [F][ldw] (K = (tap, c) contiguous). out[pix][f] = act(. + bias[f]).
+// Returns 0 when launched, non-zero when the geometry is not served here (caller falls back).
+int launch_conv_fprop_pair(const void* x, const void* w_lp, long long ldw, const float* bias, void* out,
+                           int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX, int SY,
+                           int SX, int PT, int PL, int act, cudaStream_t st) {
+  using namespace pr;
+  if (!conv_pair_enabled()) return -8;
+  const int M = N * OH * OW, K = KY * KX * C;
+  if ((C % 64) || F < 128 || (F % 8) || M < 1024 || (ldw % 8)) return -6;
+  if (((uintptr_t)x & 15) || ((uintptr_t)w_lp & 15) || ((uintptr_t)out & 15)) return -3;
+  const int bn = (F % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb, tc;
+  int r = make_map_im2col(&ta, x, N, H, W, C, -PL, -PT, (OW - 1) * SX + 1 - PL - W,
+                          (OH - 1) * SY + 1 - PT - H, SX, SY);
+  if (r) return r;
+  r = make_map(&tb, w_lp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, F, ldw, 64, bn / 2);
+  if (r) return r;
+  r = make_map(&tc, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, F, M, F, 64, BM);
+  if (r) return r;
+  Params p{};
+  p.M = M; p.N = F; p.K = K; p.bias = bias; p.act = act; p.alpha = 1.f;
+  p.tiles_m = (M + 2 * BM - 1) / (2 * BM);
+  p.tiles_n = (F + bn - 1) / bn;
+  p.g = ConvP{H, W, OH, OW, KY, KX, SY, SX, PT, PL, C};
+  p.ldo = F;
+  return bn == 256 ? launch<256, false, AM_IM2COL_FPROP, false>(ta, tb, tc, p, st)
+                   : launch<128, false, AM_IM2COL_FPROP, false>(ta, tb, tc, p, st);
+}
+
+// Unit-stride conv dgrad on the same kernel: A = windows of err_out [N][OH][OW][F] for the flipped
+// filter (TMA im2col), B = wd_lp [(tap, f)][ldc] (N = input channels contiguous),
+// err_in[ipix][c] = alpha * (.) (* f'(dmul)).
+int launch_conv_dgrad_pair(const void* err_out, const void* wd_lp, long long ldc, void* err_in, int N,
+                           int H, int W, int C, int OH, int OW, int F, int KY, int KX, int PT, int PL,
+                           float alpha, const void* dmul, int dact, cudaStream_t st) {
+  using namespace pr;
+  if (!conv_pair_enabled()) return -8;
+  const int M = N * H * W, K = KY * KX * F;
+  if ((F % 64) || C < 128 || (C % 8) || M < 1024 || (ldc % 8)) return -6;
+  if (((uintptr_t)err_out & 15) || ((uintptr_t)wd_lp & 15) || ((uintptr_t)err_in & 15)) return -3;
+  const int bn = (C % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb, tc;
+  const int lw = -(KX - 1 - PL), lh = -(KY - 1 - PT);
+  int r = make_map_im2col(&ta, err_out, N, OH, OW, F, lw, lh, W + lw - OW, H + lh - OH, 1, 1);
+  if (r) return r;
+  // B stored [K][ldc]: inner dim = N (channels), boxes of 64 x 64
+  r = make_map(&tb, wd_lp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ldc, K, ldc, 64, 64);
+  if (r) return r;
+  r = make_map(&tc, err_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, M, C, 64, BM);
+  if (r) return r;
+  Params p{};
+  p.M = M; p.N = C; p.K = K; p.bias = nullptr; p.act = 0; p.alpha = alpha;
+  p.tiles_m = (M + 2 * BM - 1) / (2 * BM);
+  p.tiles_n = (C + bn - 1) / bn;
+  p.g = ConvP{H, W, OH, OW, KY, KX, 1, 1, PT, PL, F};
+  p.dmul = (const __nv_bfloat16*)dmul; p.dact = dmul ? dact : 0; p.ldo = C;
+  return bn == 256 ? launch<256, false, AM_IM2COL_DGRAD, true>(ta, tb, tc, p, st)
+                   : launch<128, false, AM_IM2COL_DGRAD, true>(ta, tb, tc, p, st);
+}
 
 // a [M][lda] bf16, b [N][ldb] bf16 (both K contiguous), out [M][ldo] bf16 or fp32.
 // Returns 0, or non-zero when the shape / alignment is not served by this kernel (nothing launched).

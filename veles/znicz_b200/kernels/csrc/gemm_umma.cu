@@ -1041,11 +1041,23 @@ static bool set_tap_mode(ConvGeomU& g, int inner, bool dgrad) {
   return true;
 }
 
+int launch_conv_fprop_pair(const void*, const void*, long long, const float*, void*, int, int, int, int, int,
+                           int, int, int, int, int, int, int, int, int, cudaStream_t);
+int launch_conv_dgrad_pair(const void*, const void*, long long, void*, int, int, int, int, int, int, int, int,
+                           int, int, int, float, const void*, int, cudaStream_t);
+static long long g_pair_conv_launches = 0;
+long long conv_pair_launches() { return g_pair_conv_launches; }
+
 // out[pix, f] = act(im2col(x)[pix, :] . w_lp[f, :] + bias[f]); w_lp stored [F][ldw] bf16 (ldw % 8 == 0)
 int launch_conv_fprop_umma(const void* x, const void* w_lp, long long ldw, const float* bias, void* out,
                            int out_bf16, int N, int H, int W, int C, int OH, int OW, int F, int KY, int KX,
                            int SY, int SX, int PT, int PL, int act, cudaStream_t st) {
   if ((ldw % 8) || ((uintptr_t)w_lp & 15) || ((uintptr_t)x & 15)) return -3;
+  if (out_bf16 && launch_conv_fprop_pair(x, w_lp, ldw, bias, out, N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT,
+                                         PL, act, st) == 0) {
+    ++g_pair_conv_launches;        // large layer: 2-CTA persistent kernel, A by TMA im2col
+    return 0;
+  }
   int Kw = KY * KX * C;
   if ((C % 8 == 0 ? (Kw + 7) / 8 : Kw) > KTAB || KY > 255 || KX > 255) return -4;
   CUtensorMap ta, tb;
@@ -1085,6 +1097,12 @@ int launch_conv_dgrad_umma(const void* err_out, const void* wd_lp, long long ldc
   // the folded derivative needs the inline bf16 epilogue mode (row-major bf16 output, no beta)
   if (dmul && (!ei_bf16 || beta != 0.f || ((uintptr_t)dmul & 15))) return -5;
   if ((ldc % 8) || ((uintptr_t)wd_lp & 15) || ((uintptr_t)err_out & 15)) return -3;
+  if (ei_bf16 && beta == 0.f && SY == 1 && SX == 1 &&
+      launch_conv_dgrad_pair(err_out, wd_lp, ldc, err_in, N, H, W, C, OH, OW, F, KY, KX, PT, PL, alpha, dmul,
+                             dact, st) == 0) {
+    ++g_pair_conv_launches;
+    return 0;
+  }
   int Kd = KY * KX * F;
   if ((F % 8 == 0 ? (Kd + 7) / 8 : Kd) > KTAB || KY > 255 || KX > 255) return -4;
   CUtensorMap ta, tb;
