@@ -235,6 +235,11 @@ def run_arm(args, streaming):
         for t_, c_, n_ in rows[:25]:
             sys.stderr.write("  %-28s calls %6d  host %9.3f ms  (%.1f us/call)\n" % (
                 n_, c_, t_ * 1e3, 1e6 * t_ / max(c_, 1)))
+        try:
+            sys.stderr.write("conv launches (python-side, incl. capture): pair %d, im2col-TMA %d\n" % (
+                dev.ext.conv_pair_launches(), dev.ext.im2col_tma_launches()))
+        except Exception:
+            pass
         for sg in getattr(wf, "segments_", []):
             sys.stderr.write("  segment %s: replays %d eager %d\n" % (
                 sg.name, sg.replays, sg.eager_runs))

@@ -109,6 +109,8 @@ CONV_CASES = [
     (4, 20, 20, 64, 384, 5, 5, (2, 2, 2, 2), (1, 1)),   # fprop 3 N-tiles of 128
     (3, 20, 21, 256, 128, 3, 3, (1, 1, 1, 1), (1, 1)),  # dgrad BN 256, ragged M
     (5, 31, 31, 64, 128, 5, 5, (2, 2, 2, 2), (2, 2)),   # strided fprop on the pair kernel
+    (16, 20, 20, 64, 128, 3, 3, (1, 1, 1, 1), (1, 1)),  # pair wgrad: F = 128 (idle peer CTA), ragged Kw
+    (12, 19, 19, 128, 256, 3, 3, (1, 1, 1, 1), (1, 1)), # pair wgrad with split-K, F = 256
 ]
 
 
@@ -175,6 +177,7 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
     r = ext.conv_wgrad(eo, x, parts, splits, g, False, engine, bparts)
     assert r in (0, 1)
     torch.cuda.synchronize()
+    assert torch.isfinite(parts).all()           # every split-K partial slot was written
     assert _rel(parts.sum(0), wr.grad) < 5e-3
     if r == 1:      # bias gradient delivered as the extra "ones" row of the product
         ref_b = eo.float().reshape(-1, f).sum(0)
@@ -184,8 +187,9 @@ def test_conv_fprop_dgrad_wgrad(ext, engine, case):
         f_pair = c % 64 == 0 and f >= 128 and n * oh * ow >= 1024
         d_pair = f % 64 == 0 and stride == (1, 1) and c >= 128 and n * h * w_ >= 1024
         d_tma = f % 64 == 0 and stride == (1, 1) and not d_pair
-        want_pair = int(f_pair) + 2 * int(d_pair)           # (dgrad runs twice: plain + folded f')
-        want_tma = (1 if (c % 64 == 0 and not f_pair) else 0) + (1 if c % 64 == 0 else 0) + \
+        w_pair = c % 64 == 0 and f % 128 == 0 and n * oh * ow >= 4096
+        want_pair = int(f_pair) + 2 * int(d_pair) + int(w_pair)   # (dgrad runs twice: plain + folded f')
+        want_tma = (1 if (c % 64 == 0 and not f_pair) else 0) + \
             (2 if (d_tma and c % 8 == 0) else int(d_tma))
         got = (ext.conv_pair_launches() - pair0, ext.im2col_tma_launches() - tma0)
         assert got == (want_pair, want_tma), (got, want_pair, want_tma)
@@ -534,3 +538,42 @@ def test_gemm_fp8_e4m3(ext, M, N, K, out_dt):
     assert _rel(out.float(), ref_q) < (1e-2 if out_dt == torch.bfloat16 else 1e-5)
     ref = torch.relu(a @ b.t() + bias)
     assert _rel(out.float(), ref) < 6e-2
+
+
+@pytest.mark.parametrize("M,N,K,f32,act", [(256, 256, 64, False, 0), (1024, 1024, 512, False, 3),
+                                           (768, 384, 200, False, 0), (512, 256, 128, True, 0),
+                                           (2048, 4096, 1024, False, 0)])
+def test_gemm_pair_2cta_persistent(ext, M, N, K, f32, act):
+    """csrc/gemm_pair.cu (cta_group::2, persistent, TMEM double buffering, TMA store) vs fp32
+    PyTorch, with the 2x-NaN out-of-bounds guard."""
+    torch.manual_seed(M + N)
+    dev = "cuda"
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.randn(N, device=dev)
+    big = torch.full((2 * M, N), float("nan"), device=dev,
+                     dtype=torch.float32 if f32 else torch.bfloat16)
+    assert ext.gemm_pair(a, b, big[:M], bias, act, 0.5) == 0
+    torch.cuda.synchronize()
+    ref = 0.5 * (a.float() @ b.float().t()) + bias
+    if act == 3:
+        ref = torch.relu(ref)
+    assert _rel(big[:M], ref) < (1e-5 if f32 else 1e-2)
+    l2 = ((big[:M].float() - ref).norm() / ref.norm()).item()
+    assert l2 < (1e-6 if f32 else 4e-3)
+    assert torch.isnan(big[M:]).all()
+
+
+@pytest.mark.parametrize("batch,n_out,n_in", [(128, 512, 1024), (64, 1000, 768), (200, 256, 4104)])
+def test_fc_wgrad_pair(ext, batch, n_out, n_in):
+    """gradW[out][in] = err^T . x on the 2-CTA kernel (both operands MN-major, K = batch)."""
+    torch.manual_seed(batch)
+    dev = "cuda"
+    err = torch.randn(batch, n_out, device=dev).bfloat16()
+    x = torch.randn(batch, n_in, device=dev).bfloat16()
+    big = torch.full((2 * n_out, n_in), float("nan"), device=dev)
+    assert ext.fc_wgrad_pair(err, x, big[:n_out]) == 0
+    torch.cuda.synchronize()
+    ref = err.float().t() @ x.float()
+    assert _rel(big[:n_out], ref) < 1e-5
+    assert torch.isnan(big[n_out:]).all()

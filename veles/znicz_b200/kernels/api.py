@@ -396,7 +396,16 @@ def fc_backward(unit):
     # 3. gradW[out][in] = err^T . x  (reduction over the batch)
     gbuf = _grad_buffer(unit, "wgrad", (1,) + tuple(unit.weights.shape))
     with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-        if lp_ok and n_out % 8 == 0 and n_in % 8 == 0:
+        r = -1
+        if lp_ok and n_out % 8 == 0 and n_in % 8 == 0 and n_out >= 256 and n_in >= 256 \
+                and batch >= 64:
+            # large layers: err^T . x on the 2-CTA persistent kernel (both operands MN-major,
+            # TMA-store epilogue straight into the [neurons][in] gradient layout)
+            r = int(ext.fc_wgrad_pair(err.view(batch, n_out), x.view(batch, n_in),
+                                       gbuf.view(n_out, n_in)))
+        if r == 0:
+            pass
+        elif lp_ok and n_out % 8 == 0 and n_in % 8 == 0:
             # computed as (x^T . err) with a transposed store: for a fixed output column the 32
             # lanes of a warp then write 32 consecutive floats of gradW[out][in] (one 128-byte
             # store); the direct form wrote 16-byte pieces 36 KB apart and ran FC6's 151 MB

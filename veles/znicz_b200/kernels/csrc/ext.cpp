@@ -51,6 +51,8 @@ int launch_gemm_pair(const void*, long long, const void*, long long, void*, int,
                      const float*, int, float, cudaStream_t);
 long long im2col_tma_launches();
 long long conv_pair_launches();
+int launch_fc_wgrad_pair(const void*, long long, const void*, long long, float*, long long, int, int, int,
+                         cudaStream_t);
 size_t multi_update_desc_size();
 void set_dp_gradient_scale(float);
 float get_dp_gradient_scale();
@@ -638,6 +640,18 @@ int64_t gemm_pair(Tensor a, Tensor b, Tensor out, c10::optional<Tensor> bias, in
   if (r == 0) kcheck();
   return r;
 }
+// FC weight gradient on the 2-CTA kernel: out[n_out][n_in] fp32 = err[batch][n_out]^T . x[batch][n_in]
+int64_t fc_wgrad_pair(Tensor err, Tensor x, Tensor out) {
+  chk(err, "err"); chk(x, "x"); chk(out, "out");
+  TORCH_CHECK(is_bf16(err) && is_bf16(x) && out.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(err.dim() == 2 && x.dim() == 2 && err.size(0) == x.size(0));
+  TORCH_CHECK(out.numel() == err.size(1) * x.size(1));
+  int r = zn::launch_fc_wgrad_pair(err.data_ptr(), err.size(1), x.data_ptr(), x.size(1),
+                                   out.data_ptr<float>(), x.size(1), (int)err.size(1), (int)x.size(1),
+                                   (int)err.size(0), cur());
+  if (r == 0) kcheck();
+  return r;
+}
 int64_t pick_splits(int64_t M, int64_t N, int64_t K, int64_t max_splits) {
   return zn::umma_pick_splits((int)M, (int)N, (int)K, (int)max_splits);
 }
@@ -826,6 +840,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lstm_cell_fwd", &lstm_cell_fwd); m.def("lstm_cell_bwd", &lstm_cell_bwd);
   m.def("fc_small_max_out", &fc_small_max_out); m.def("fc_small_forward", &fc_small_forward);
   m.def("fc_small_backward", &fc_small_backward);
+  m.def("fc_wgrad_pair", &fc_wgrad_pair);
   m.def("conv_pair_launches", []() { return (int64_t)zn::conv_pair_launches(); });
   m.def("im2col_tma_launches", []() { return (int64_t)zn::im2col_tma_launches(); });
   m.def("gemm", &gemm); m.def("pick_splits", &pick_splits); m.def("gemm_pair", &gemm_pair);

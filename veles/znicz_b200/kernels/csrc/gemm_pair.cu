@@ -37,7 +37,11 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit: "same 
 // A operand: dense [M][K] tile, or the implicit-GEMM operand of a convolution fetched by TMA in
 // im2col mode (one [128 pixels x 64 channels] box per k-block): fprop = im2col(x), dgrad
 // (unit stride) = windows of err_out for the flipped filter.
-enum { AM_DENSE = 0, AM_IM2COL_FPROP = 1, AM_IM2COL_DGRAD = 2 };
+enum { AM_DENSE = 0, AM_IM2COL_FPROP = 1, AM_IM2COL_DGRAD = 2,
+       AM_DENSE_MN = 3 };          // A stored [K][M] (M contiguous): err^T of the weight-gradient GEMMs
+// B operand: K-major tile, MN-major tile ([K][N], N contiguous), or - conv wgrad - the im2col
+// operand as MN-major blocks fetched by TMA im2col ([64 pixels][64 channels of one tap])
+enum { BM_K = 0, BM_MN = 1, BM_IM2COL_MN = 2 };
 
 struct ConvP { int H, W, OH, OW, KY, KX, SY, SX, PT, PL, inner; };
 
@@ -45,6 +49,7 @@ struct Params {
   int M, N, K;
   const float* bias; int act; float alpha;
   int tiles_m, tiles_n;
+  int splits, kb_per_split;       // split-K over the reduction (fp32 partials [splits][M][N])
   ConvP g;
   const __nv_bfloat16* dmul; int dact; long long ldo;   // dgrad: out *= f'(dmul[row][col])
 };
@@ -134,7 +139,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   tm = m0 + (r - tn * gm);
 }
 
-template <int BN, bool OUT_F32, int AMODE = AM_DENSE, bool B_MN = false>
+template <int BN, bool OUT_F32, int AMODE = AM_DENSE, int BMODE = BM_K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const Params p) {
@@ -143,7 +148,9 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr int NST = (BN == 256) ? 6 : 8;
   constexpr int EPI_COLS = OUT_F32 ? 32 : 64;          // 128-byte staging rows
   constexpr int NCHUNK = BN / EPI_COLS;
-  constexpr uint32_t IDESC = make_idesc_bf16(2 * BM, BN, 0, B_MN ? 1 : 0);
+  constexpr bool A_MN = (AMODE == AM_DENSE_MN);
+  constexpr bool B_MN = (BMODE != BM_K);
+  constexpr uint32_t IDESC = make_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
   constexpr uint32_t TMEM_COLS = 2 * BN;               // double-buffered accumulator (256 or 512)
 
   extern __shared__ uint8_t smem_raw[];
@@ -161,8 +168,9 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-  const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int splits = p.splits > 1 ? p.splits : 1;
+  const int num_tiles = p.tiles_m * p.tiles_n * splits;      // work items (tile, k-split)
+  const int total_kb = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], 1u); }
@@ -184,18 +192,39 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t it = 0;
       for (int t = cid; t < num_tiles; t += nclusters) {
         int tm, tn;
-        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        tile_coords(t / splits, p.tiles_m, p.tiles_n, tm, tn);
+        const int split = t % splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = splits > 1 ? min(total_kb, kb0 + p.kb_per_split) : total_kb;
         const int m0 = tm * 2 * BM + (int)rank * BM;
         const int n0 = tn * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % NST; const uint32_t ph = (it / NST) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = tiles + (size_t)s * STAGE;
           // the leader's barrier expects the bytes of BOTH CTAs; the peer's copies may complete
           // before this expect_tx is posted (the tx-count just goes negative for a moment)
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2u * STAGE);
+          uint32_t tx = 2u * STAGE;
+          int nblk = BN / 128;                 // 64-wide B blocks this CTA loads (im2col B only)
+          if (BMODE == BM_IM2COL_MN) {
+            // blocks past the last reduction-weight index are not fetched: both CTAs' counts
+            const int base = tn * BN;
+            int cnt[2];
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+              const int left = p.N - (base + r2 * (BN / 2));
+              cnt[r2] = left <= 0 ? 0 : min(BN / 128, (left + 63) / 64);
+            }
+            nblk = cnt[rank];
+            tx = 2u * A_BYTES + (uint32_t)(cnt[0] + cnt[1]) * 8192u;
+          }
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], tx);
           if (AMODE == AM_DENSE) {
             tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], kb * BK, m0);
+          } else if (AMODE == AM_DENSE_MN) {
+            // A stored [K][M]: two [64 k][64 m] boxes for this CTA's 128 rows
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], m0, kb * BK);
+            tma_load_2d_2sm(sa + 8192, &tmap_a, &full_bar[s], m0 + 64, kb * BK);
           } else {
             // this CTA's 128 pixels start at m0; k-block = 64 channels of one filter tap
             const ConvP& g = p.g;
@@ -215,13 +244,27 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             tma_load_im2col_2sm(sa, &tmap_a, &full_bar[s], c0, w0, h0, n, (uint16_t)ow, (uint16_t)oh);
           }
-          if (!B_MN) {
+          if (BMODE == BM_K) {
             tma_load_2d_2sm(sa + A_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
-          } else {
+          } else if (BMODE == BM_MN) {
             // B stored [K][N] (N contiguous): 64 x 64 boxes, one per 64 columns of this CTA's half
 #pragma unroll
             for (int j = 0; j < BN / 128; ++j)
               tma_load_2d_2sm(sa + A_BYTES + j * 8192, &tmap_b, &full_bar[s], n0 + j * 64, kb * BK);
+          } else {
+            // conv wgrad: reduction = pixels kb * 64 .., N = (tap, channel); one im2col box of
+            // [64 pixels][64 channels] per 64-wide N block
+            const ConvP& g = p.g;
+            const int pix0 = kb * BK;
+            const int q = pix0 % g.OW; const int t2 = pix0 / g.OW;
+            const int pr = t2 % g.OH; const int n = t2 / g.OH;
+            const int w0 = q * g.SX - g.PL, h0 = pr * g.SY - g.PT;
+            for (int j = 0; j < nblk; ++j) {
+              const int kidx0 = n0 + j * 64;
+              const int tap = kidx0 / g.inner, c0 = kidx0 - tap * g.inner;
+              tma_load_im2col_2sm(sa + A_BYTES + j * 8192, &tmap_b, &full_bar[s], c0, w0, h0, n,
+                                  (uint16_t)(tap % g.KX), (uint16_t)(tap / g.KX));
+            }
           }
         }
       }
@@ -232,10 +275,13 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t it = 0, tcount = 0;
       for (int t = cid; t < num_tiles; t += nclusters, ++tcount) {
         const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+        const int split = t % splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = splits > 1 ? min(total_kb, kb0 + p.kb_per_split) : total_kb;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);      // both CTAs' epilogues drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % NST; const uint32_t ph = (it / NST) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -243,10 +289,11 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024)
+                                     : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024)
                                      : make_smem_desc(sb + k * 32, 16, 1024);
-            mma_f16_2sm(d_tmem, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+            mma_f16_2sm(d_tmem, da, db, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           mma_commit_2sm(&empty_bar[s], 3);              // frees the stage in both CTAs
         }
@@ -260,9 +307,14 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t tcount = 0, chunk_no = 0;
     for (int t = cid; t < num_tiles; t += nclusters, ++tcount) {
       int tm, tn;
-      tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+      tile_coords(t / splits, p.tiles_m, p.tiles_n, tm, tn);
+      const int split = t % splits;
       const int m0 = tm * 2 * BM + (int)rank * BM;
       const int n0 = tn * BN;
+      // split-K partial s lives at rows [s * M, (s + 1) * M) of the output map: a CTA whose 128
+      // rows lie entirely past M must not store (it would land in the next partial)
+      const bool store_ok = m0 < p.M;
+      const int row0 = split * p.M + m0;
       const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
@@ -337,7 +389,7 @@ gemm_pair_k(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (et == 0) {
-          tma_store_2d(&tmap_c, buf, n0 + c * EPI_COLS, m0);
+          if (store_ok) tma_store_2d(&tmap_c, buf, n0 + c * EPI_COLS, row0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -382,14 +434,14 @@ static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BN, bool OUT_F32, int AMODE = AM_DENSE, bool B_MN = false>
+template <int BN, bool OUT_F32, int AMODE = AM_DENSE, int BMODE = BM_K>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Params& p,
                   cudaStream_t st) {
   constexpr int NST = (BN == 256) ? 6 : 8;
   constexpr int smem = NST * (A_BYTES + (BN / 2) * 128) + 2 * EPI_BUF + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_k<BN, OUT_F32, AMODE, B_MN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_k<BN, OUT_F32, AMODE, BMODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -404,10 +456,10 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     }
     sms = cached;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * (p.splits > 1 ? p.splits : 1);
   int clusters = sms / 2;
   if (clusters > tiles) clusters = tiles;
-  gemm_pair_k<BN, OUT_F32, AMODE, B_MN><<<dim3(2 * clusters), dim3(256), smem, st>>>(ta, tb, tc, p);
+  gemm_pair_k<BN, OUT_F32, AMODE, BMODE><<<dim3(2 * clusters), dim3(256), smem, st>>>(ta, tb, tc, p);
   return (int)cudaGetLastError();
 }
 
@@ -417,7 +469,8 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // im2col-mode map over NHWC bf16 [N][H][W][C]: 128 window positions x 64 channels per load
 static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int lower_w,
-                           int lower_h, int upper_w, int upper_h, int stride_w, int stride_h) {
+                           int lower_h, int upper_w, int upper_h, int stride_w, int stride_h,
+                           int pixels = BM) {
   static EncodeIm2colFn enc = nullptr;
   if (!enc) {
     void* q = nullptr;
@@ -435,7 +488,7 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, int N, int H, int W,
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1u, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1u};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower,
-                   upper, 64u, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   upper, 64u, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
@@ -474,8 +527,9 @@ int launch_conv_fprop_pair(const void* x, const void* w_lp, long long ldw, const
   p.tiles_n = (F + bn - 1) / bn;
   p.g = ConvP{H, W, OH, OW, KY, KX, SY, SX, PT, PL, C};
   p.ldo = F;
-  return bn == 256 ? launch<256, false, AM_IM2COL_FPROP, false>(ta, tb, tc, p, st)
-                   : launch<128, false, AM_IM2COL_FPROP, false>(ta, tb, tc, p, st);
+  p.splits = 1; p.kb_per_split = (K + BK - 1) / BK;
+  return bn == 256 ? launch<256, false, AM_IM2COL_FPROP, BM_K>(ta, tb, tc, p, st)
+                   : launch<128, false, AM_IM2COL_FPROP, BM_K>(ta, tb, tc, p, st);
 }
 
 // Unit-stride conv dgrad on the same kernel: A = windows of err_out [N][OH][OW][F] for the flipped
@@ -505,8 +559,84 @@ int launch_conv_dgrad_pair(const void* err_out, const void* wd_lp, long long ldc
   p.tiles_n = (C + bn - 1) / bn;
   p.g = ConvP{H, W, OH, OW, KY, KX, 1, 1, PT, PL, F};
   p.dmul = (const __nv_bfloat16*)dmul; p.dact = dmul ? dact : 0; p.ldo = C;
-  return bn == 256 ? launch<256, false, AM_IM2COL_DGRAD, true>(ta, tb, tc, p, st)
-                   : launch<128, false, AM_IM2COL_DGRAD, true>(ta, tb, tc, p, st);
+  p.splits = 1; p.kb_per_split = (K + BK - 1) / BK;
+  return bn == 256 ? launch<256, false, AM_IM2COL_DGRAD, BM_MN>(ta, tb, tc, p, st)
+                   : launch<128, false, AM_IM2COL_DGRAD, BM_MN>(ta, tb, tc, p, st);
+}
+
+bool conv_pair_on() { return pr::conv_pair_enabled(); }
+
+// Conv weight gradient on the 2-CTA kernel: partials[s][f][kidx] (fp32) = sum over the pixels of
+// split s of err_out[pix][f] * im2col(x)[pix][kidx]. A = err_out^T (stored [pix][F]: MN-major),
+// B = im2col(x) as MN-major [64 pixels][64 channels] boxes (TMA im2col); the output is already in
+// the weights' [F][Kw] layout - no transposed store. F % 128 == 0, C % 64 == 0.
+int launch_conv_wgrad_pair(const void* err_out, const void* x, float* partials, int splits, int N, int H,
+                           int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX, int PT,
+                           int PL, cudaStream_t st) {
+  using namespace pr;
+  if (!conv_pair_enabled()) return -8;
+  const int Kw = KY * KX * C, P = N * OH * OW;
+  if ((C % 64) || (F % 128) || F < 128 || Kw < 128 || P < 4096) return -6;
+  if (((uintptr_t)err_out & 15) || ((uintptr_t)x & 15) || ((uintptr_t)partials & 15)) return -3;
+  const int bn = Kw >= 256 ? 256 : 128;
+  const int total_kb = (P + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  const int kbs = (total_kb + splits - 1) / splits;
+  if ((long long)(splits - 1) * kbs >= total_kb) return -6;      // an empty split: not here
+  CUtensorMap ta, tb, tc;
+  int r = make_map(&ta, err_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, F, P, F, 64, 64);
+  if (r) return r;
+  r = make_map_im2col(&tb, x, N, H, W, C, -PL, -PT, (OW - 1) * SX + 1 - PL - W,
+                      (OH - 1) * SY + 1 - PT - H, SX, SY, 64);
+  if (r) return r;
+  r = make_map(&tc, partials, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Kw, (long long)splits * F, Kw, 32, BM);
+  if (r) return r;
+  Params p{};
+  p.M = F; p.N = Kw; p.K = P; p.bias = nullptr; p.act = 0; p.alpha = 1.f;
+  p.tiles_m = (F + 2 * BM - 1) / (2 * BM);
+  p.tiles_n = (Kw + bn - 1) / bn;
+  p.splits = splits; p.kb_per_split = kbs;
+  p.g = ConvP{H, W, OH, OW, KY, KX, SY, SX, PT, PL, C};
+  p.ldo = Kw;
+  return bn == 256 ? launch<256, true, AM_DENSE_MN, BM_IM2COL_MN>(ta, tb, tc, p, st)
+                   : launch<128, true, AM_DENSE_MN, BM_IM2COL_MN>(ta, tb, tc, p, st);
+}
+// splits that give the 74 clusters of the pair kernel ~1 work item each (0: shape not served)
+int pair_wgrad_splits(int Kw, int F, int P, int max_splits) {
+  using namespace pr;
+  if (!conv_pair_enabled() || (Kw % 64) || (F % 128) || F < 128 || Kw < 128 || P < 4096) return 0;
+  const int bn = Kw >= 256 ? 256 : 128;
+  const long long tiles = (long long)((F + 255) / 256) * ((Kw + bn - 1) / bn);
+  int s = (int)((74 + tiles - 1) / tiles);
+  const int total_kb = (P + BK - 1) / BK;
+  if (s > total_kb / 8) s = total_kb / 8;
+  if (s > max_splits) s = max_splits;
+  return s < 1 ? 1 : s;
+}
+
+// Fully-connected weight gradient: out[n_out][n_in] (fp32) = err^T . x with err stored
+// [batch][n_out] and x stored [batch][n_in] (both MN-major operands, K = batch).
+int launch_fc_wgrad_pair(const void* err, long long lde, const void* x, long long ldx, float* out,
+                         long long ldo, int n_out, int n_in, int batch, cudaStream_t st) {
+  using namespace pr;
+  if (!conv_pair_enabled()) return -8;
+  if (n_out < 256 || n_in < 256 || (lde % 8) || (ldx % 8) || (ldo % 4) || batch < 64) return -6;
+  if (((uintptr_t)err & 15) || ((uintptr_t)x & 15) || ((uintptr_t)out & 15)) return -3;
+  const int bn = 256;
+  CUtensorMap ta, tb, tc;
+  int r = make_map(&ta, err, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_out, batch, lde, 64, 64);
+  if (r) return r;
+  r = make_map(&tb, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_in, batch, ldx, 64, 64);
+  if (r) return r;
+  r = make_map(&tc, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, n_in, n_out, ldo, 32, BM);
+  if (r) return r;
+  Params p{};
+  p.M = n_out; p.N = n_in; p.K = batch; p.alpha = 1.f;
+  p.tiles_m = (n_out + 2 * BM - 1) / (2 * BM);
+  p.tiles_n = (n_in + bn - 1) / bn;
+  p.splits = 1; p.kb_per_split = (batch + BK - 1) / BK;
+  p.ldo = ldo;
+  return launch<256, true, AM_DENSE_MN, BM_MN>(ta, tb, tc, p, st);
 }
 
 // a [M][lda] bf16, b [N][ldb] bf16 (both K contiguous), out [M][ldo] bf16 or fp32.
@@ -532,6 +662,7 @@ int launch_gemm_pair(const void* a, long long lda, const void* b, long long ldb,
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.act = act; p.alpha = alpha;
   p.tiles_m = (M + 2 * BM - 1) / (2 * BM);
   p.tiles_n = (N + bn - 1) / bn;
+  p.splits = 1; p.kb_per_split = (K + BK - 1) / BK;
   if (bn == 256) return out_f32 ? launch<256, true>(ta, tb, tc, p, st) : launch<256, false>(ta, tb, tc, p, st);
   return out_f32 ? launch<128, true>(ta, tb, tc, p, st) : launch<128, false>(ta, tb, tc, p, st);
 }

@@ -909,7 +909,14 @@ static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const
 
 static int pick_bn(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : (N <= 64 ? 64 : 128)); }
 
+int pair_wgrad_splits(int, int, int, int);      // gemm_pair.cu
+
 int umma_pick_splits(int M, int N, int K, int max_splits) {
+  {
+    // conv wgrad shapes served by the 2-CTA kernel (gemm_pair.cu) want ~74 work items
+    const int sp = pair_wgrad_splits(M, N, K, max_splits);
+    if (sp > 0) return sp;
+  }
   int bn = pick_bn(N);
   if (bn < 64) bn = 64;
   long long tiles = (long long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
@@ -1045,6 +1052,9 @@ int launch_conv_fprop_pair(const void*, const void*, long long, const float*, vo
                            int, int, int, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_dgrad_pair(const void*, const void*, long long, void*, int, int, int, int, int, int, int, int,
                            int, int, int, float, const void*, int, cudaStream_t);
+int launch_conv_wgrad_pair(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, int,
+                           int, int, int, int, cudaStream_t);
+int pair_wgrad_splits(int, int, int, int);
 static long long g_pair_conv_launches = 0;
 long long conv_pair_launches() { return g_pair_conv_launches; }
 
@@ -1148,6 +1158,11 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
                            int W, int C, int OH, int OW, int F, int KY, int KX, int SY, int SX, int PT,
                            int PL, float* bias_parts, cudaStream_t st) {
   if ((F % 8) || ((uintptr_t)err_out & 15) || ((uintptr_t)x & 15)) return -3;
+  if (launch_conv_wgrad_pair(err_out, x, partials, splits, N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL,
+                             st) == 0) {
+    ++g_pair_conv_launches;        // (no bias row: the caller falls back to the column-sum kernel)
+    return 0;
+  }
   int Kw = KY * KX * C, P = N * OH * OW;
   if ((C % 8 == 0 ? (Kw + 7) / 8 : Kw) > KTAB || KY > 255 || KX > 255) return -4;
   CUtensorMap ta, tb;
@@ -1165,7 +1180,12 @@ int launch_conv_wgrad_umma(const void* err_out, const void* x, float* partials, 
   p.bias = nullptr; p.act = 0; p.alpha = 1.f; p.beta = 0.f; p.split_stride = (long long)F * Kw;
   p.gsrc = (const __nv_bfloat16*)x; p.g = geom(N, H, W, C, OH, OW, F, KY, KX, SY, SX, PT, PL, C % 8 == 0);
   p.gather_kind = G_IM2COL; p.gK = Kw;
-  if (C % 64 == 0 && im2col_tma_enabled()) {
+  static int wg_tma = -1;
+  if (wg_tma < 0) { const char* e = getenv("ZNICZ_IM2COL_TMA_WGRAD"); wg_tma = (e && atoi(e)) ? 1 : 0; }
+  // (measured on the AlexNet shapes: 224-231 vs 231-249 TFLOP/s for the LDGSTS gather, which
+  // also delivers the bias row - so the single-CTA TMA form is opt-in; large layers take the
+  // 2-CTA kernel above)
+  if (wg_tma && C % 64 == 0 && im2col_tma_enabled()) {
     // im2col operand by TMA, 64 pixels x 64 channels per box (no "ones" row here: the caller
     // computes the bias gradient with the column-sum kernel when this returns 0)
     CUtensorMap ti;
