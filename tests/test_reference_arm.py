@@ -39,19 +39,23 @@ def test_vendored_reference_is_unmodified():
     assert install_reference.verify("/root/reference") == []
 
 
+# Hyper-parameters are chosen so that the reference's OWN numpy and GPU update rules coincide:
+# no momentum (gd.py:315-327 vs cuda/gradient_descent.store_output.cu differ), and bias == weights
+# learning rate / decay (its numpy_update applies learning_rate and weights_decay to the bias as
+# well, gd.py:363-365, while the GPU kernel uses learning_rate_bias / weights_decay_bias).
 TINY = """
 import sys, json, numpy
 sys.path.insert(0, %r)
 import run_reference as rr
 tiny = [
  {"name": "conv1", "type": "conv", "->": {"n_kernels": 8, "kx": 5, "ky": 5, "padding": (2,2,2,2), "sliding": (1,1), "weights_filling": "gaussian", "weights_stddev": 0.01, "bias_filling": "constant", "bias_stddev": 0},
-  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.002, "weights_decay": 0.0005, "weights_decay_bias": 0.0005, "factor_ortho": 0.001, "gradient_moment": 0, "gradient_moment_bias": 0}},
+  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.001, "weights_decay": 0.0005, "weights_decay_bias": 0.0005, "factor_ortho": 0.001, "gradient_moment": 0, "gradient_moment_bias": 0}},
  {"name": "pool1", "type": "max_pooling", "->": {"kx": 3, "ky": 3, "sliding": (2, 2)}},
  {"name": "relu1", "type": "activation_str"},
  {"name": "norm1", "type": "norm", "alpha": 0.00005, "beta": 0.75, "n": 3, "k": 1},
  {"name": "pool2", "type": "avg_pooling", "->": {"kx": 8, "ky": 8, "sliding": (8, 8)}},
  {"name": "fc_softmax4", "type": "softmax", "->": {"output_sample_shape": 10, "weights_filling": "gaussian", "weights_stddev": 0.01, "bias_filling": "constant", "bias_stddev": 0},
-  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.002, "weights_decay": 1.0, "weights_decay_bias": 0, "gradient_moment": 0, "gradient_moment_bias": 0}}]
+  "<-": {"learning_rate": 0.001, "learning_rate_bias": 0.001, "weights_decay": 0.01, "weights_decay_bias": 0.01, "gradient_moment": 0, "gradient_moment_bias": 0}}]
 """
 
 
