@@ -161,7 +161,7 @@ class FusedStep(object):
         if name == "auto":
             # Small models are latency bound: ONE flag barrier per step, every rank reduces every
             # element itself (one multimem.ld_reduce per float4 with NVLS, N peer loads without).
-            # Measured at 2 GPUs on the CIFAR net (0.58 MB of parameters, driver's 20-step run):
+            # Measured at 2 GPUs on the CIFAR net (0.36 MB of parameters, driver's 20-step run):
             # nvls1 0.2172 / oneshot 0.2165 / twoshot 0.2336 ms per step (1 GPU: 0.2042).
             # Large models are bandwidth bound: two-shot moves ~2 P floats per rank instead of
             # (N - 1) P and pays one more barrier.
