@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 RS = numpy.random.RandomState(5)
 
 
-def _pair(fwd_cls, gd_cls, x, fkw, gkw, device, links=("weights", "bias"), extra=()):
+def _pair(fwd_cls, gd_cls, x, fkw, gkw, device, links=("weights", "bias"), extra=(), mask=None):
     wf = DummyWorkflow()
     f = fwd_cls(wf, **fkw)
     f.input = Array(x.copy())
@@ -29,7 +29,10 @@ def _pair(fwd_cls, gd_cls, x, fkw, gkw, device, links=("weights", "bias"), extra
     kw.update(gkw)
     g = gd_cls(wf, **kw)
     rs = numpy.random.RandomState(9)
-    g.err_output = Array(rs.uniform(-1, 1, f.output.shape).astype(numpy.float32))
+    err = rs.uniform(-1, 1, f.output.shape).astype(numpy.float32)
+    if mask is not None:
+        err[mask.reshape(err.shape)] = 0
+    g.err_output = Array(err)
     g.err_output.dev_dtype = f.output.dev_dtype
     g.input, g.output = f.input, f.output
     for a in links:
@@ -50,10 +53,17 @@ def _compare(fwd_cls, gd_cls, x, fkw=None, gkw=None, links=("weights", "bias"), 
     from veles.znicz_b200.core import prng
     prng.get(1).seed(77)
     fn, gn = _pair(fwd_cls, gd_cls, x, fkw, gkw, None, links, extra)
+    mask = None
+    if compute == "fp32" and "StrictRELU" in fwd_cls.__name__:
+        # a hard gate at |y| ~ 1e-6 may open on one side only (the split-bf16 tensor-core product
+        # differs from numpy in the 6th digit): no error is injected at such outputs
+        mask = numpy.abs(fn.output.mem) < 1e-4
+        prng.get(1).seed(77)
+        fn, gn = _pair(fwd_cls, gd_cls, x, fkw, gkw, None, links, extra, mask)
     root.common.engine.compute_type = compute
     prng.get(1).seed(77)
     dev = get_device("cuda")
-    fc, gc = _pair(fwd_cls, gd_cls, x, fkw, gkw, dev, links, extra)
+    fc, gc = _pair(fwd_cls, gd_cls, x, fkw, gkw, dev, links, extra, mask)
     tol = tol or (2e-4 if compute == "fp32" else 6e-2)
     res = {}
     for name, a, b in (("output", fn.output, fc.output), ("err_input", gn.err_input, gc.err_input),

@@ -233,3 +233,42 @@ def test_stochastic_pool_depool_gpu():
     assert numpy.allclose(after[after != 0], x[after != 0])
     win = (after != 0).reshape(5, 4, 2, 4, 2, 6).sum(axis=(2, 4))
     assert (win == 1).all()
+
+
+def test_fp32_layers_run_on_tensor_cores():
+    """compute_type fp32 (the reference's precision): FC and conv layers run as split-bf16
+    (hi/lo) tcgen05 GEMMs (kernels/fp32x.py) and still match the numpy oracle to fp32-like
+    accuracy - 600x tighter than the bf16 path's bound; the switch restores the SIMT kernels."""
+    from test_gpu_units import _compare
+    from veles.znicz_b200.kernels import fp32x
+    from veles.znicz_b200.ops import all2all, gd, conv, gd_conv
+    rs = numpy.random.RandomState(3)
+    xf = rs.uniform(-1, 1, (96, 200)).astype(numpy.float32)
+    geoms = [((6, 16, 16, 32), 32, 5, 5, (2, 2, 2, 2), (1, 1)),
+             ((5, 28, 28, 1), 64, 5, 5, (0, 0, 0, 0), (1, 1)),        # MNIST conv1
+             ((6, 12, 12, 64), 87, 5, 5, (0, 0, 0, 0), (1, 1)),       # MNIST conv2 (GA-tuned 87)
+             ((3, 11, 9, 8), 24, 3, 2, (1, 0, 2, 1), (2, 1))]
+
+    def run_all(tol):
+        out = [_compare(all2all.All2AllTanh, gd.GDTanh, xf,
+                        {"output_sample_shape": 136, "weights_stddev": 0.1}, tol=tol)]
+        for shape, f, ky, kx, pad, sl in geoms:
+            x = rs.uniform(-1, 1, shape).astype(numpy.float32)
+            kw = {"n_kernels": f, "kx": kx, "ky": ky, "padding": pad, "sliding": sl,
+                  "weights_stddev": 0.1}
+            gkw = dict(kw)
+            gkw.pop("weights_stddev")
+            out.append(_compare(conv.ConvTanh, gd_conv.GDTanhConv, x, kw, gkw, tol=tol))
+        return out
+
+    before = dict(fp32x.counters)
+    res = run_all(1e-4)
+    # 3 tensor-core launches per layer: fprop, dgrad, wgrad
+    assert fp32x.counters["gemms"] - before["gemms"] == 3 * (1 + len(geoms)), (fp32x.counters, res)
+    root.common.engine.fp32_tensor_cores = False
+    try:
+        mid = dict(fp32x.counters)
+        run_all(2e-4)
+        assert fp32x.counters == mid                                  # SIMT kernels only
+    finally:
+        root.common.engine.fp32_tensor_cores = True

@@ -117,6 +117,42 @@ def test_fused_step_equals_per_layer_updates():
         assert numpy.abs(ba - bb).max() <= 1e-4 * max(1.0, numpy.abs(ba).max())
 
 
+def test_fp32_tensor_core_training_matches_simt():
+    """10 fp32 training steps with the split-bf16 tensor-core layers (kernels/fp32x.py, stacked
+    operands handed from the forward to the backward units from step 2 on) end at the same
+    weights as the SIMT fp32 kernels."""
+    from veles.znicz_b200.core import prng
+    from veles.znicz_b200.kernels import fp32x
+    results = []
+    for tc in (False, True):
+        root.common.engine.fp32_tensor_cores = tc
+        prng.get(1).seed(1234)
+        prng.get(2).seed(5678)
+        before = fp32x.counters["gemms"]
+        try:
+            wf = cifar.build(
+                layers=_fast_layers(), use_graphs=False,
+                loader_config={"minibatch_size": 20, "n_train": 200, "n_valid": 40,
+                               "normalization_type": "internal_mean", "noise": 0.3},
+                decision_config={"max_epochs": 1, "fail_iterations": 10},
+                snapshotter_config={"prefix": "cifar_x3", "interval": 100,
+                                    "time_interval": 1e9})
+            wf.initialize(device="cuda")
+            wf.run()
+            assert (fp32x.counters["gemms"] > before) == tc
+            ws = []
+            for f in wf.forwards:
+                if getattr(f, "weights", None):
+                    f.weights.map_read()
+                    ws.append(f.weights.mem.copy())
+            results.append(ws)
+        finally:
+            root.common.engine.fp32_tensor_cores = True
+    for wa, wb in zip(*results):
+        assert numpy.isfinite(wb).all()
+        assert numpy.abs(wa - wb).max() <= 2e-3 * numpy.abs(wa).max()
+
+
 @pytest.mark.parametrize("compute,tol", [("fp32", 2e-4), ("bf16", 4e-2)])
 def test_activation_fusion_equals_separate_units(compute, tol):
     """conv→relu / maxpool→relu / conv→relu folded into the producers' kernels (forward), the

@@ -188,4 +188,6 @@ print(json.dumps(out))
     # weights / outputs tight; biases loose: a conv bias gradient is a sum of ~2.5 K error terms of
     # both signs that nearly cancel, so a max-pooling near-tie routed differently (fp32 vs the
     # numpy path) moves it by a visible fraction of its own (tiny) magnitude
-    assert all(e <= (0.3 if k[0] == "b" else 2e-3) for k, e in errs.items()), errs
+    lim = {"b": 0.3, "w": 2e-3, "y": 2e-2}
+    bad = {k: e for k, e in errs.items() if e > lim[k[0]]}
+    assert not bad, json.dumps(errs)

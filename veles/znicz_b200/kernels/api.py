@@ -25,6 +25,9 @@ _MAX_SPLITS = 64
 counters = {"launches": 0}
 
 
+from . import fp32x  # noqa: E402
+
+
 def _ext(unit):
     ext = unit.ext_
     if ext is None:
@@ -171,6 +174,9 @@ def fc_forward(unit, softmax=False):
                      batch, n_out, n_in, bias, act, 1.0, 0.0, 1, 0, 1)
         if r != 0:
             raise RuntimeError("%s: tcgen05 FC forward refused the shape (code %d)" % (unit, r))
+    elif fp32x.enabled(unit) and fp32x.fc_forward(unit, ext, x, out, bias, act, batch, n_in,
+                                                  n_out):
+        pass          # fp32 operands as bf16 hi/lo parts on the tensor cores (kernels/fp32x.py)
     else:
         w = unit.weights.dev
         if unit.weights_transposed:   # stored [in][out]
@@ -283,7 +289,9 @@ def _update(unit, is_bias, grad_buf, nparts, part_stride, rows, cols, g_cpad=0):
         lp_conv = fwd.weights_lp_t_ if is_conv else None
         cpad_lp = lp_cpad(fwd)
     elif g_cpad:
-        raise RuntimeError("channel-padded gradients need the forward unit's shadow spec")
+        if fwd is None or not hasattr(fwd, "kx"):
+            raise RuntimeError("channel-padded gradients need the forward conv unit")
+        taps, c = fwd.kx * fwd.ky, fwd._n_channels     # fp32x wgrad: no bf16 shadows to refresh
     dp = unit.dp_
     if dp is not None and dp.symm is not None and step is None:
         ptrs, flag_ptrs, epoch_ptr, blocks = dp.symm.peers(unit, grad_buf)
@@ -370,11 +378,20 @@ def fc_backward(unit):
              unit.forward_unit is not None and
              getattr(unit.forward_unit, "weights_lp_", None) is not None)
     # the weight-gradient GEMM runs beside the err_input GEMM (see _fork_side)
+    x3 = ((not lp_ok) and fp32x.enabled(unit) and fp32x._f32(err, x) and n_in >= 32 and
+          n_out >= 32)
+    ec = es = None
+    if x3:
+        ec, es = fp32x.fc_split_err(unit, ext, err, batch, n_out, unit.need_err_input,
+                                    bool(need_w))
     side = _fork_side(unit) if (need_w and unit.need_err_input) else None
     # 2. err_input = alpha * err . W + beta * err_input
     if unit.need_err_input:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
-        if lp_ok and n_out % 8 == 0:
+        if x3 and fp32x.fc_dgrad(unit, ext, ec, ei, batch, n_in, n_out, unit.err_input_alpha,
+                                 unit.err_input_beta):
+            pass
+        elif lp_ok and n_out % 8 == 0:
             w = unit.forward_unit.weights_lp_
             r = ext.gemm(err, n_out, False, w, w.shape[1], False, ei, n_in, False,
                          batch, n_in, n_out, None, 0, float(unit.err_input_alpha),
@@ -404,6 +421,8 @@ def fc_backward(unit):
             r = int(ext.fc_wgrad_pair(err.view(batch, n_out), x.view(batch, n_in),
                                        gbuf.view(n_out, n_in)))
         if r == 0:
+            pass
+        elif x3 and fp32x.fc_wgrad(unit, ext, x, es, gbuf, batch, n_in, n_out):
             pass
         elif lp_ok and n_out % 8 == 0 and n_in % 8 == 0:
             # computed as (x^T . err) with a transposed store: for a fixed output column the 32
@@ -466,6 +485,8 @@ def conv_forward(unit):
                            out, _conv_geom(unit), eff_act(unit), 0)
         elif r != 0:
             raise RuntimeError("%s: tcgen05 conv fprop refused (code %d)" % (unit, r))
+    elif fp32x.enabled(unit) and fp32x.conv_forward(unit, ext, x, out, bias, g, eff_act(unit)):
+        pass          # (kernels/fp32x.py counts its split launches itself)
     else:
         w = unit.weights.dev
         ld = w.shape[1]
@@ -511,11 +532,19 @@ def conv_backward(unit):
         _launch()
         g_mm = list(g)
         g_mm[6] = f_pad
+    x3 = (not lp_ok) and fp32x.enabled(unit) and fp32x._f32(err, x)
+    ec = es = None
+    if x3:
+        ec, es = fp32x.conv_split_err(unit, ext, err, g, pixels, unit.need_err_input,
+                                      bool(need_w))
     # fork here: everything wgrad needs exists; it runs beside the dgrad launched next
     side = _fork_side(unit) if (need_w and unit.need_err_input) else None
     if unit.need_err_input:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
         r = -1
+        if x3 and fp32x.conv_dgrad(unit, ext, ec, ei, g, unit.err_input_alpha,
+                                   unit.err_input_beta):
+            r = 0
         # derivative of the producer layer's activation, folded into this dgrad's epilogue
         # (workflow/fusion.py::fuse_backward_derivatives)
         in_act = int(unit.__dict__.get("in_deriv_act_", 0) or 0)
@@ -554,6 +583,21 @@ def conv_backward(unit):
     use_umma = lp_ok
     g_cp = 0
     f_rows = f                    # rows of one gradient partial
+    if x3:
+        # fp32 wgrad on the tensor cores: hi/lo parts stacked along the images
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            xs, g3, kw3, cp3, f8 = fp32x.conv_wgrad_prepare(unit, ext, x, g, pixels)
+            splits = int(ext.pick_splits(kw3, f8, 3 * pixels, _MAX_SPLITS))
+            gbuf = _grad_buffer(unit, "wgrad", (splits, f8, kw3))
+            r = ext.conv_wgrad(es, xs, gbuf, splits, g3, False, 1, None)
+        if r in (0, 1):
+            fp32x.counters["gemms"] += 1
+            _launch()
+            _update(unit, False, gbuf, splits, f8 * kw3, f, unit._kernel_size, g_cpad=cp3)
+            if need_b:
+                _update(unit, True, parts, slices, f, 1, f)
+            return
+        _warn_once(unit, "wgrad", r)
     if use_umma:
         g_cp = lp_cpad(fwd)
         g = list(g_mm)

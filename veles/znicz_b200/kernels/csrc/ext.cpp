@@ -742,6 +742,40 @@ void som_split(Tensor src, Tensor dst, int64_t rows, int64_t len, int64_t kp, in
                        (int)len, (int)kp, ld, part_stride, (int)pattern, mfptr_or_null(norm_out), cur());
   kcheck();
 }
+namespace zn {
+void launch_split_parts(const float*, long long, int, __nv_bfloat16*, long long, long long, int, int, int,
+                        __nv_bfloat16*, long long, long long, int, int, int, cudaStream_t);
+void launch_split_conv_wt(const float*, __nv_bfloat16*, int, int, int, int, int, int, int, cudaStream_t);
+}
+// fp32 [rows][len] -> bf16 hi/lo parts (split.cu). Each destination is described by
+// [ld, part_stride, kp, nparts, pattern]; the second one is optional.
+void split_parts(Tensor src, int64_t rows, int64_t len, Tensor a, std::vector<int64_t> da,
+                 c10::optional<Tensor> b, std::vector<int64_t> db) {
+  TORCH_CHECK(src.scalar_type() == torch::kFloat32 && src.is_cuda() && src.is_contiguous());
+  TORCH_CHECK(src.numel() >= rows * len && is_bf16(a) && a.is_cuda() && da.size() == 5);
+  TORCH_CHECK(da[3] >= 1 && da[3] <= 4 && da[2] >= len);
+  TORCH_CHECK(a.numel() >= (da[3] - 1) * da[1] + (rows - 1) * da[0] + da[2], "split_parts: dst a too small");
+  __nv_bfloat16* bp = nullptr;
+  if (b.has_value() && b->defined()) {
+    TORCH_CHECK(is_bf16(*b) && b->is_cuda() && db.size() == 5 && db[3] >= 1 && db[3] <= 4 && db[2] >= len);
+    TORCH_CHECK(b->numel() >= (db[3] - 1) * db[1] + (rows - 1) * db[0] + db[2], "split_parts: dst b too small");
+    bp = reinterpret_cast<__nv_bfloat16*>(b->data_ptr());
+  } else {
+    db = {0, 0, 0, 0, 0};
+  }
+  zn::launch_split_parts(src.data_ptr<float>(), rows, (int)len, reinterpret_cast<__nv_bfloat16*>(a.data_ptr()),
+                         da[0], da[1], (int)da[2], (int)da[3], (int)da[4], bp, db[0], db[1], (int)db[2],
+                         (int)db[3], (int)db[4], cur());
+  kcheck();
+}
+void split_conv_wt(Tensor w, Tensor dst, int64_t F, int64_t taps, int64_t C, int64_t Fp, int64_t Cp,
+                   int64_t nparts, int64_t pattern) {
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32 && w.is_cuda() && w.is_contiguous() && is_bf16(dst));
+  TORCH_CHECK(w.numel() >= F * taps * C && dst.numel() >= taps * nparts * Fp * Cp && Fp >= F && Cp >= C);
+  zn::launch_split_conv_wt(w.data_ptr<float>(), reinterpret_cast<__nv_bfloat16*>(dst.data_ptr()), (int)F,
+                           (int)taps, (int)C, (int)Fp, (int)Cp, (int)nparts, (int)pattern, cur());
+  kcheck();
+}
 void som_argmin(Tensor dots, Tensor wnorm, Tensor argmins, c10::optional<Tensor> winners) {
   TORCH_CHECK(dots.scalar_type() == torch::kFloat32 && wnorm.scalar_type() == torch::kFloat32 && dots.dim() == 2);
   int* wp = (winners.has_value() && winners->defined()) ? winners->data_ptr<int>() : nullptr;
@@ -830,7 +864,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("softmax_rows", &softmax_rows); m.def("evaluate_softmax", &evaluate_softmax);
   m.def("evaluate_mse", &evaluate_mse); m.def("mse_find_closest", &mse_find_closest);
   m.def("fused_update", &fused_update); m.def("update_blocks", &update_blocks);
-  m.def("som_split", &som_split); m.def("som_argmin", &som_argmin);
+  m.def("som_split", &som_split); m.def("split_parts", &split_parts); m.def("split_conv_wt", &split_conv_wt); m.def("som_argmin", &som_argmin);
   m.def("som_gravity_split", &som_gravity_split); m.def("som_apply", &som_apply);
   m.def("multi_update_table", &multi_update_table);
   m.def("set_dp_gradient_scale", [](double s) { zn::set_dp_gradient_scale((float)s); });
