@@ -227,3 +227,32 @@ def test_lstm_sequence(compute, seq):
              {"gradient_moment": 0.0, "gradient_moment_bias": 0.0},
              extra=("gates", "cells", "hidden", "xh"), compute=compute,
              tol=None if compute == "fp32" else 8e-2)
+
+
+@pytest.mark.parametrize("seq", [True, False])
+@pytest.mark.parametrize("shape,hidden", [((40, 7, 64), 64), ((150, 5, 128), 256)])
+def test_lstm_persistent_kernels(seq, shape, hidden):
+    """Whole-sequence cluster kernels (csrc/lstm_persist.cu: W resident in shared memory, gates GEMM
+    on tcgen05, cell math from TMEM, h exchanged through L2 under barrier.cluster) against the
+    numpy oracle; batch 150 = two clusters with a ragged second tile; ZNICZ_LSTM_PERSIST=0 is the
+    per-step path and must agree as well."""
+    import os
+    from veles.znicz_b200.ops import lstm_seq
+    from veles.znicz_b200.kernels import load_extension
+    ext = load_extension(required=True)
+    x = RS.uniform(-1, 1, shape).astype(numpy.float32)
+    kw = ({"output_sample_shape": hidden, "weights_stddev": 0.1, "return_sequences": seq},
+          {"gradient_moment": 0.0, "gradient_moment_bias": 0.0})
+    before = ext.lstm_persist_launches()
+    res = _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x, *kw,
+                   extra=("gates", "cells", "hidden", "xh"), compute="bf16", tol=8e-2)
+    assert ext.lstm_persist_launches() - before == 2, "persistent kernels did not run"
+    os.environ["ZNICZ_LSTM_PERSIST"] = "0"
+    try:
+        res0 = _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x, *kw,
+                        extra=("gates", "cells", "hidden", "xh"), compute="bf16", tol=8e-2)
+        assert ext.lstm_persist_launches() - before == 2
+    finally:
+        del os.environ["ZNICZ_LSTM_PERSIST"]
+    for k in res:
+        assert res[k] < max(2.5 * res0[k], 2e-2), (k, res, res0)

@@ -976,6 +976,11 @@ def _lstm_gemm_nt(ext, unit, a, w_lp, w_f32, out, m, n, k, bias, beta):
     _launch()
 
 
+def _lstm_persist_enabled():
+    import os
+    return os.environ.get("ZNICZ_LSTM_PERSIST", "1") != "0"
+
+
 def lstm_seq_forward(unit):
     ext = _ext(unit)
     x = unit.input.dev                       # [B, T, I]
@@ -999,15 +1004,36 @@ def lstm_seq_forward(unit):
     _launch()
     ext.axpby_2d(xh[0], i, xh[0], i, h, 0.0, 0.0)
     _launch()
-    z = _tmp(unit, "z", (b, 4 * h), torch.float32)
     seq = unit.return_sequences
-    for s in range(t):
+    persist = -1
+    state = None
+    if w_lp is not None and _lstm_persist_enabled():
+        # the whole time loop in ONE cluster launch: W resident in shared memory, gates GEMM on
+        # tcgen05, cell math in the epilogue, h exchanged through distributed shared memory
+        # (csrc/lstm_persist.cu)
+        nstate = int(ext.lstm_state_floats(t, b, i, h))
+        if nstate:
+            state = _tmp(unit, "lstm_state", (nstate,), torch.float32)
+            persist = int(ext.lstm_fwd_persist(xh, w_lp, bias, state, h, None))
+        if persist == 0:
+            _launch()
+    # gates / cells of this pass live in the kernels' private layout (None: in the public arrays)
+    unit.__dict__["lstm_state_"] = state if persist == 0 else None
+    z = _tmp(unit, "z", (b, 4 * h), torch.float32) if persist != 0 else None
+    for s in range(t if persist != 0 else 0):
         _lstm_gemm_nt(ext, unit, xh[s], w_lp, w, z, b, 4 * h, i + h, bias, 0.0)
         ext.lstm_cell_fwd(z, cells[s - 1] if s else None, cells[s], gates[s],
                           hidden, s * b * h, h, xh, (s + 1) * b * (i + h) + i, i + h, b, h)
         _launch()
     # the unit's output: the whole sequence [B, T, H] or the last step [B, H]
-    if seq:
+    if persist == 0:
+        # the kernel leaves h_t only in the [x | h] operand of step t + 1
+        if seq:
+            ext.swap01_2d(xh[1:], i + h, i, out, h, 0, t, b, h)
+        else:
+            ext.axpby_2d(xh[t], i, out, 0, h, 1.0, 0.0)
+        _launch()
+    elif seq:
         ext.swap01_2d(hidden, h, 0, out, h, 0, t, b, h)      # [T][B][H] -> [B][T][H]
         _launch()
     else:
@@ -1036,7 +1062,29 @@ def lstm_seq_backward(unit):
     ei = None
     if need_ei:
         ei = unit.err_input.dev if unit.err_input_beta else unit.err_input.dev_out
-    for s in range(t - 1, -1, -1):
+    persist = -1
+    state = fwd.__dict__.get("lstm_state_") if fwd is not None else None
+    if (state is not None and w_lp is not None and _is_bf16(err) and
+            (not need_ei or (unit.err_input_alpha == 1 and not unit.err_input_beta))):
+        whp = _tmp(unit, "whp", (h, h4), torch.bfloat16)
+        part = _tmp(unit, "lstm_part", (int(ext.lstm_part_floats(b, h)),), torch.float32)
+        persist = int(ext.lstm_bwd_persist(err, bool(seq), state, part, dz, w_lp, whp, i))
+    if persist != 0 and state is not None:
+        # per-step fallback after a persistent forward: gates / cells back into the public arrays
+        ext.lstm_unpack_state(state, gates, cells)
+        _launch()
+    if persist == 0:
+        _launch(2)
+        if need_ei:
+            # dx for every step in one GEMM: [T B][4H] . W_x, then [T][B][I] -> [B][T][I]
+            dx = _tmp(unit, "dx_all", (t, b, i), ei.dtype)
+            r = ext.gemm(dz.view(t * b, h4), h4, False, w_lp, w_lp.shape[1], False, dx, i, False,
+                         t * b, i, h4, None, 0, 1.0, 0.0, 1, 0, 1)
+            if r != 0:
+                raise RuntimeError("%s: tcgen05 LSTM dx refused (code %d)" % (unit, r))
+            ext.swap01_2d(dx, i, 0, ei, i, 0, t, b, i)
+            _launch(2)
+    for s in range(t - 1 if persist != 0 else -1, -1, -1):
         if seq:
             e_t, e_off, lde = err, s * h, t * h
         else:

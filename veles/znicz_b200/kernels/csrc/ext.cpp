@@ -743,6 +743,64 @@ void som_split(Tensor src, Tensor dst, int64_t rows, int64_t len, int64_t kp, in
   kcheck();
 }
 namespace zn {
+int launch_lstm_fwd_persist(void*, const void*, long long, const float*, void*, int, int, int, int, long long*,
+                            cudaStream_t);
+int launch_lstm_bwd_persist(const void*, long long, int, const void*, void*, void*, const void*, long long, void*,
+                            int, int, int, int, cudaStream_t);
+void launch_lstm_unpack_state(const void*, float*, float*, int, int, int, cudaStream_t);
+long long lstm_persist_state_elems(int, int, int, int);
+long long lstm_persist_part_elems(int, int);
+long long lstm_persist_launches();
+}
+// whole LSTM time loop in one cluster launch (lstm_persist.cu); != 0: shape outside its range.
+// `state` (lstm_state_floats() fp32 words) carries gates / cells to the backward kernel; h_t is written into
+// the [x | h] operand xh[t + 1][:, I:].
+int64_t lstm_fwd_persist(Tensor xh, Tensor w_lp, c10::optional<Tensor> bias, Tensor state, int64_t hidden,
+                         c10::optional<Tensor> dbg) {
+  chk(xh, "xh"); chk(w_lp, "w_lp"); chk(state, "state");
+  TORCH_CHECK(is_bf16(xh) && is_bf16(w_lp) && xh.dim() == 3 && state.scalar_type() == torch::kFloat32);
+  const int T = (int)xh.size(0) - 1, B = (int)xh.size(1), H = (int)hidden;
+  const int I = (int)xh.size(2) - H;
+  TORCH_CHECK(T >= 1 && I > 0 && w_lp.size(0) == 4 * H && w_lp.size(1) >= I + H);
+  const long long need = zn::lstm_persist_state_elems(T, B, I, H);
+  if (need == 0) return -3;
+  TORCH_CHECK(state.numel() >= need * 4, "lstm state buffer too small");
+  int r = zn::launch_lstm_fwd_persist(xh.data_ptr(), w_lp.data_ptr(), w_lp.size(1), fptr_or_null(bias),
+                                      state.data_ptr(), T, B, I, H,
+                                      (dbg.has_value() && dbg->defined()) ? (long long*)dbg->data_ptr<int64_t>() : nullptr,
+                                      cur());
+  if (r == 0) kcheck();
+  return r;
+}
+int64_t lstm_bwd_persist(Tensor err, bool seq, Tensor state, Tensor part, Tensor dz, Tensor w_lp, Tensor whp,
+                         int64_t n_in) {
+  chk(err, "err"); chk(state, "state"); chk(part, "part"); chk(dz, "dz"); chk(w_lp, "w_lp"); chk(whp, "whp");
+  TORCH_CHECK(is_bf16(err) && is_bf16(dz) && is_bf16(w_lp) && is_bf16(whp) && dz.dim() == 3);
+  TORCH_CHECK(state.scalar_type() == torch::kFloat32 && part.scalar_type() == torch::kFloat32);
+  const int T = (int)dz.size(0), B = (int)dz.size(1), H = (int)dz.size(2) / 4;
+  const long long need = zn::lstm_persist_state_elems(T, B, (int)n_in, H);
+  if (need == 0) return -3;
+  TORCH_CHECK(state.numel() >= need * 4 && whp.numel() >= (int64_t)4 * H * H);
+  TORCH_CHECK(part.numel() >= zn::lstm_persist_part_elems(B, H) * 4, "lstm partial-sum buffer too small");
+  TORCH_CHECK(err.numel() == (int64_t)B * H * (seq ? T : 1) && w_lp.size(0) == 4 * H && w_lp.size(1) >= n_in + H);
+  int r = zn::launch_lstm_bwd_persist(err.data_ptr(), seq ? (long long)T * H : (long long)H, seq ? 1 : 0,
+                                      state.data_ptr(), part.data_ptr(), dz.data_ptr(), w_lp.data_ptr(),
+                                      w_lp.size(1), whp.data_ptr(), T, B, (int)n_in, H, cur());
+  if (r == 0) kcheck();
+  return r;
+}
+int64_t lstm_state_floats(int64_t T, int64_t B, int64_t I, int64_t H) {
+  return 4 * zn::lstm_persist_state_elems((int)T, (int)B, (int)I, (int)H);
+}
+int64_t lstm_part_floats(int64_t B, int64_t H) { return 4 * zn::lstm_persist_part_elems((int)B, (int)H); }
+void lstm_unpack_state(Tensor state, Tensor gates, Tensor cells) {
+  chk(state, "state"); chk(gates, "gates"); chk(cells, "cells");
+  TORCH_CHECK(gates.scalar_type() == torch::kFloat32 && cells.scalar_type() == torch::kFloat32 && gates.dim() == 3);
+  const int T = (int)gates.size(0), B = (int)gates.size(1), H = (int)gates.size(2) / 4;
+  zn::launch_lstm_unpack_state(state.data_ptr(), gates.data_ptr<float>(), cells.data_ptr<float>(), T, B, H, cur());
+  kcheck();
+}
+namespace zn {
 void launch_split_parts(const float*, long long, int, __nv_bfloat16*, long long, long long, int, int, int,
                         __nv_bfloat16*, long long, long long, int, int, int, cudaStream_t);
 void launch_split_conv_wt(const float*, __nv_bfloat16*, int, int, int, int, int, int, int, cudaStream_t);
@@ -871,6 +929,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("get_dp_gradient_scale", []() { return (double)zn::get_dp_gradient_scale(); });
   m.def("multi_update_max_tensors", []() { return (int64_t)zn::multi_update_max_tensors(); }); m.def("multi_update", &multi_update);
   m.def("col_sums", &col_sums); m.def("refresh_shadows", &refresh_shadows);
+  m.def("lstm_fwd_persist", &lstm_fwd_persist); m.def("lstm_bwd_persist", &lstm_bwd_persist);
+  m.def("lstm_state_floats", &lstm_state_floats); m.def("lstm_part_floats", &lstm_part_floats); m.def("lstm_unpack_state", &lstm_unpack_state);
+  m.def("lstm_persist_launches", []() { return (int64_t)zn::lstm_persist_launches(); });
   m.def("lstm_cell_fwd", &lstm_cell_fwd); m.def("lstm_cell_bwd", &lstm_cell_bwd);
   m.def("fc_small_max_out", &fc_small_max_out); m.def("fc_small_forward", &fc_small_forward);
   m.def("fc_small_backward", &fc_small_backward);
