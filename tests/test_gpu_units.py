@@ -247,6 +247,18 @@ def test_lstm_persistent_kernels(seq, shape, hidden):
     res = _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x, *kw,
                    extra=("gates", "cells", "hidden", "xh"), compute="bf16", tol=8e-2)
     assert ext.lstm_persist_launches() - before == 2, "persistent kernels did not run"
+    # rows per cluster: the default spreads 32-row clusters over the SMs; 64 / 128 rows per
+    # cluster (fewer, fatter CTAs) must give the same numbers
+    for rows in ("64", "128"):
+        os.environ["ZNICZ_LSTM_ROWS"] = rows
+        try:
+            res_r = _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x, *kw,
+                             extra=("gates", "cells", "hidden", "xh"), compute="bf16", tol=8e-2)
+        finally:
+            del os.environ["ZNICZ_LSTM_ROWS"]
+        for k in res:
+            assert abs(res_r[k] - res[k]) < 1e-3, (rows, k, res, res_r)
+    before = ext.lstm_persist_launches() - 2
     os.environ["ZNICZ_LSTM_PERSIST"] = "0"
     try:
         res0 = _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x, *kw,
@@ -256,3 +268,19 @@ def test_lstm_persistent_kernels(seq, shape, hidden):
         del os.environ["ZNICZ_LSTM_PERSIST"]
     for k in res:
         assert res[k] < max(2.5 * res0[k], 2e-2), (k, res, res0)
+
+
+def test_lstm_persistent_forward_then_per_step_backward():
+    """err_input_alpha != 1 keeps the backward pass on the per-step kernels: the gates / cells the
+    persistent forward kernel left in its private lane-major layout are unpacked into the unit's
+    public arrays first (lstm_unpack_state)."""
+    from veles.znicz_b200.ops import lstm_seq
+    from veles.znicz_b200.kernels import load_extension
+    ext = load_extension(required=True)
+    x = RS.uniform(-1, 1, (40, 6, 64)).astype(numpy.float32)
+    before = ext.lstm_persist_launches()
+    _compare(lstm_seq.LSTMSequence, lstm_seq.GDLSTMSequence, x,
+             {"output_sample_shape": 64, "weights_stddev": 0.1, "return_sequences": True},
+             {"gradient_moment": 0.0, "gradient_moment_bias": 0.0, "err_input_alpha": 0.5},
+             extra=("gates", "cells", "hidden", "xh"), compute="bf16", tol=8e-2)
+    assert ext.lstm_persist_launches() - before == 1          # forward only
