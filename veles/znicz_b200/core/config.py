@@ -158,7 +158,7 @@ def _defaults():
             "veles": base,
         },
         "disable": {"plotting": True, "snapshotting": False, "publishing": True},
-        "trace": {"run": False},
+        "trace": {"run": False, "nvtx": os.environ.get("ZNICZ_NVTX", "0") == "1"},
     })
 
 

@@ -35,6 +35,24 @@ class NotInitializedError(RuntimeError):
     pass
 
 
+_NVTX = []
+
+
+def _nvtx():
+    """torch.cuda.nvtx when CUDA is usable, else None (``root.common.trace.nvtx`` or
+    ZNICZ_NVTX=1 switch the per-unit ranges on)."""
+    if not _NVTX:
+        mod = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                mod = torch.cuda.nvtx
+        except Exception:        # pragma: no cover
+            mod = None
+        _NVTX.append(mod)
+    return _NVTX[0]
+
+
 class Unit(Logger, metaclass=UnitRegistry):
     hide_from_registry = True
     # wall-clock accounting (parity with the core's per-unit timers)
@@ -303,20 +321,45 @@ class Unit(Logger, metaclass=UnitRegistry):
         if bool(self._gate_block):
             return
         if not bool(self._gate_skip):
-            self._run_timed()
+            seg = self.__dict__.get("segment_")
+            if seg is not None and seg.units[0] is not self and not Unit._trace_any:
+                # member of a CUDA-graph segment whose first unit replayed the whole segment this
+                # iteration: nothing to run, nothing to time (30 of these per training step)
+                self._run_calls += 1
+            else:
+                self._run_timed()
         self.run_dependent()
+
+    # per-run tracing switches, refreshed by Workflow.run() (a Config lookup per unit run cost
+    # ~10 us per training step)
+    _trace_run = False
+    _trace_nvtx = False
+    _trace_any = False
+
+    @staticmethod
+    def refresh_trace_flags():
+        Unit._trace_run = bool(root.common.trace.run)
+        Unit._trace_nvtx = bool(root.common.trace.get("nvtx", False))
+        Unit._trace_any = Unit._trace_run or Unit._trace_nvtx
 
     def _run_timed(self):
         if not self._is_initialized:
             raise NotInitializedError("%s is not initialized" % self)
-        if root.common.trace.run:
+        if Unit._trace_run:
             self.debug("run")
+        nvtx = _nvtx() if Unit._trace_nvtx else None
+        if nvtx is not None:
+            nvtx.range_push(self.name)      # one range per unit run: shows up in nsys / ncu --nvtx
         t0 = time.perf_counter()
-        seg = self.__dict__.get("segment_")
-        if seg is not None:
-            seg.run_unit(self)
-        else:
-            self.run()
+        try:
+            seg = self.__dict__.get("segment_")
+            if seg is not None:
+                seg.run_unit(self)
+            else:
+                self.run()
+        finally:
+            if nvtx is not None:
+                nvtx.range_pop()
         self._run_time += time.perf_counter() - t0
         self._run_calls += 1
 

@@ -203,6 +203,7 @@ class Workflow(Unit):
         self._finished <<= False
         self._stopped = False
         self._run_started = time.time()
+        Unit.refresh_trace_flags()
         q = collections.deque()
         self._queue_ = q
         hooks = self.step_hooks_

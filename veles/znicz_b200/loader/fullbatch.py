@@ -235,7 +235,12 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         pk["early"] = bool(pk["pull"] and hasattr(ext, "device_copy") and
                            getattr(self.device, "copy_stream", None) is not None and
                            root.common.engine.get("loader_early_pull", True))
+        pk["ring"] = None
         if pk["early"]:
+            import os
+            if hasattr(ext, "stream_ring_step") and os.environ.get("ZNICZ_STREAM_RING", "1") != "0":
+                # the whole per-step copy sequence in one native call (events owned by the ring)
+                pk["ring"] = int(ext.stream_ring_create(3, depth))
             pk["stage"] = [torch.zeros_like(devp) for _ in range(3)]
             pk["stage_evt"] = [torch.cuda.Event() for _ in range(3)]
             pk["stage_used"] = [False] * 3
@@ -258,7 +263,7 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         sl = pk["slots"][pk["i"]]
         if not hit:
             if sl["used"]:
-                sl["event"].synchronize()      # the copy out of this slot must be done
+                self._slot_sync(pk["i"])       # the copy out of this slot must be done
             ext.host_gather_rows(pk["src"], pk["idx"], sl["data"], n)
         pk["hits"] = pk.get("hits", 0) + int(hit)
         if pk["labels"]:
@@ -273,7 +278,10 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         hn[0] = self.minibatch_size
         hn[1] = self.minibatch_class
         hn[2] = self.epoch_number
-        if pk.get("early"):
+        if pk.get("ring") is not None:
+            self.device.ext.stream_ring_step(pk["ring"], sl["pin"], pk["i"], pk["stage"], pk["dev"],
+                                             self.device.copy_stream.cuda_stream)
+        elif pk.get("early"):
             import torch
             ext = self.device.ext
             k = pk["s"]
@@ -304,6 +312,19 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
         if pk["prefetch"]:
             self._prefetch_next()
 
+    def _slot_done(self, i):
+        pk = self._packed_
+        if pk.get("ring") is not None:
+            return bool(self.device.ext.stream_ring_slot_done(pk["ring"], i))
+        return pk["slots"][i]["event"].query()
+
+    def _slot_sync(self, i):
+        pk = self._packed_
+        if pk.get("ring") is not None:
+            self.device.ext.stream_ring_slot_sync(pk["ring"], i)
+        else:
+            pk["slots"][i]["event"].synchronize()
+
     def peek_next_indices(self):
         """(start, count) of the slice of ``shuffled_indices`` the *next* ``run()`` will serve, or
         None when that run starts a new epoch (the train part is reshuffled first, so its indices
@@ -324,11 +345,11 @@ class FullBatchLoader(Loader, LoaderWithValidationRatio):
             return                              # epoch wrap: the train part is reshuffled first
         start, n = peek
         sl = pk["slots"][pk["i"]]
-        if sl["used"] and not sl["event"].query():
+        if sl["used"] and not self._slot_done(pk["i"]):
             # the copy out of this slot (issued depth - 1 steps ago) has not finished: the device
             # is that far behind, so the host has time to spare - wait for it rather than give
             # up the prefetch (bounds the run-ahead to depth - 1 steps)
-            sl["event"].synchronize()
+            self._slot_sync(pk["i"])
         idx = numpy.ascontiguousarray(self.shuffled_indices.mem[start:start + n], numpy.int32)
         import torch
         ticket = self.device.ext.host_prefetch_submit(pk["src"], torch.from_numpy(idx),
