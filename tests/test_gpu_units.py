@@ -284,3 +284,28 @@ def test_lstm_persistent_forward_then_per_step_backward():
              {"gradient_moment": 0.0, "gradient_moment_bias": 0.0, "err_input_alpha": 0.5},
              extra=("gates", "cells", "hidden", "xh"), compute="bf16", tol=8e-2)
     assert ext.lstm_persist_launches() - before == 1          # forward only
+
+
+@pytest.mark.parametrize("geom", [
+    ((4, 35, 35, 3), 16, 11, 11, (0, 0, 0, 0), (4, 4)),            # AlexNet conv1 in small
+    ((3, 21, 25, 3), 24, 5, 5, (2, 2, 2, 2), (2, 2)),              # padding, 12 channels per pixel
+    ((2, 30, 30, 4), 8, 9, 7, (1, 0, 2, 1), (3, 3))])              # ImagenetAE-like 9 x 9 / 3
+def test_strided_first_layer_conv_runs_in_space_to_depth_form(geom):
+    """Strided convolution over an image-like input = stride-1 convolution over the space-to-depth
+    tensor (csrc/s2d.cu): forward, weight gradient (unpacked from the transformed tap order) and
+    bias against the numpy oracle."""
+    from veles.znicz_b200.kernels import api
+    shape, f, ky, kx, pad, sl = geom
+    x = RS.uniform(-1, 1, shape).astype(numpy.float32)
+    kw = {"n_kernels": f, "kx": kx, "ky": ky, "padding": pad, "sliding": sl, "weights_stddev": 0.1}
+    gkw = dict(kw)
+    gkw.pop("weights_stddev")
+    before = api.counters.get("s2d", 0)
+    _compare(conv.ConvTanh, gd_conv.GDTanhConv, x, kw, gkw, compute="bf16")
+    assert api.counters.get("s2d", 0) == before + 1
+    root.common.engine.conv_s2d = False
+    try:
+        _compare(conv.ConvTanh, gd_conv.GDTanhConv, x, kw, gkw, compute="bf16")
+        assert api.counters.get("s2d", 0) == before + 1
+    finally:
+        root.common.engine.conv_s2d = True

@@ -77,6 +77,19 @@ class GraphSegment(object):
         self.eager_runs = 0
         for u in self.units:
             u.__dict__["segment_"] = self
+        self.express = self._is_linear_chain()
+
+    def _is_linear_chain(self):
+        """True when the member units form a plain chain (each one's only successor is the next
+        member, whose only predecessor it is). The first member executes the whole segment, so
+        the scheduler may then continue at the LAST member's successors instead of walking ~12
+        no-op units through queue, gates and timers (3 us each; the end-to-end CIFAR step was
+        host-bound by exactly that)."""
+        us = self.units
+        for a, b in zip(us, us[1:]):
+            if list(a.links_to) != [b] or list(b.links_from) != [a]:
+                return False
+        return len(us) > 1
 
     def detach(self):
         for u in self.units:

@@ -18,6 +18,7 @@ Scheduling is a deterministic single-threaded FIFO walk owned by the Workflow
 """
 from __future__ import annotations
 
+import os
 import time
 import uuid
 
@@ -328,6 +329,10 @@ class Unit(Logger, metaclass=UnitRegistry):
                 self._run_calls += 1
             else:
                 self._run_timed()
+                if seg is not None and seg.express and not Unit._trace_any and \
+                        Unit._express_segments:
+                    seg.units[-1].run_dependent()      # the chain in between has been executed
+                    return
         self.run_dependent()
 
     # per-run tracing switches, refreshed by Workflow.run() (a Config lookup per unit run cost
@@ -335,12 +340,15 @@ class Unit(Logger, metaclass=UnitRegistry):
     _trace_run = False
     _trace_nvtx = False
     _trace_any = False
+    _express_segments = True
 
     @staticmethod
     def refresh_trace_flags():
         Unit._trace_run = bool(root.common.trace.run)
         Unit._trace_nvtx = bool(root.common.trace.get("nvtx", False))
         Unit._trace_any = Unit._trace_run or Unit._trace_nvtx
+        Unit._express_segments = bool(root.common.engine.get("express_segments", True)) and \
+            os.environ.get("ZNICZ_EXPRESS", "1") != "0"
 
     def _run_timed(self):
         if not self._is_initialized:

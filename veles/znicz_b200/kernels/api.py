@@ -452,12 +452,53 @@ def _conv_geom(u):
             u.ky, u.kx, u.sliding[1], u.sliding[0], u.padding[1], u.padding[0]]
 
 
+_S2D_C = 64          # channels per pixel of the space-to-depth tensor (one 128-byte TMA row)
+
+
+def _s2d_geom(unit, g):
+    """Space-to-depth form of a strided convolution over an image-like input (AlexNet conv1:
+    11 x 11, stride 4, C = 3), or None. csrc/s2d.cu explains the transform."""
+    import os
+    n, h, w, c, oh, ow, f, ky, kx, sy, sx, pt, pl = g
+    s = sy
+    if sy != sx or s < 2 or c * s * s > _S2D_C or ky < s or kx < s or \
+            not root.common.engine.get("conv_s2d", True) or os.environ.get("ZNICZ_CONV_S2D", "1") == "0":
+        return None
+    kyp, kxp = -(-ky // s), -(-kx // s)
+    gs = [n, oh + kyp - 1, ow + kxp - 1, _S2D_C, oh, ow, f, kyp, kxp, 1, 1, 0, 0]
+    return {"s": s, "kyp": kyp, "kxp": kxp, "g": gs, "kw": kyp * kxp * _S2D_C, "pt": pt, "pl": pl}
+
+
+def _conv_forward_s2d(unit, ext, x, out, bias, g):
+    sd = _s2d_geom(unit, g)
+    if sd is None:
+        return False
+    n, f, ky, kx, c = g[0], g[6], g[7], g[8], g[3]
+    gs = sd["g"]
+    ensure_shadows(unit)          # the dgrad operand / update kernel keep their usual shadows
+    xs = _tmp(unit, "s2d_x", (n, gs[1], gs[2], _S2D_C), torch.bfloat16)
+    ws = _tmp(unit, "s2d_w", (f, sd["kw"]), torch.bfloat16)
+    ext.space_to_depth(x, xs, sd["s"], sd["pt"], sd["pl"])
+    ext.s2d_pack_weights(unit.weights.dev, ws, f, ky, kx, c, sd["s"], sd["kyp"], sd["kxp"], _S2D_C)
+    r = ext.conv_fprop(xs, ws, sd["kw"], False, bias, out, gs, eff_act(unit), 1)
+    if r != 0:
+        unit.__dict__["s2d_"] = None
+        return False
+    sd["xs"] = xs
+    unit.__dict__["s2d_"] = sd
+    counters["s2d"] = counters.get("s2d", 0) + 1
+    _launch(3)
+    return True
+
+
 def conv_forward(unit):
     ext = _ext(unit)
     x = unit.input.dev
     out = unit.output.dev_out
     bias = unit.bias.dev if (unit.include_bias and unit.bias) else None
     g = _conv_geom(unit)
+    if lp_enabled(unit) and _is_bf16(x) and _conv_forward_s2d(unit, ext, x, out, bias, g):
+        return
     if lp_enabled(unit) and _is_bf16(x):
         ensure_shadows(unit)
         w = unit.weights_lp_
@@ -598,7 +639,17 @@ def conv_backward(unit):
                 _update(unit, True, parts, slices, f, 1, f)
             return
         _warn_once(unit, "wgrad", r)
-    if use_umma:
+    s2d = fwd.__dict__.get("s2d_") if use_umma else None
+    if s2d is not None:
+        # first-layer strided convolution in its space-to-depth form (csrc/s2d.cu): the forward
+        # pass left the transformed input; the gradient comes out in the transformed tap order
+        x = s2d["xs"]
+        g = list(s2d["g"])
+        g[6] = f_pad
+        kw = s2d["kw"]
+        f_rows = f_pad
+        splits = int(ext.pick_splits(kw, f_rows, pixels, _MAX_SPLITS))
+    elif use_umma:
         g_cp = lp_cpad(fwd)
         g = list(g_mm)
         if g_cp:
@@ -613,9 +664,10 @@ def conv_backward(unit):
     else:
         tiles = ((f + 63) // 64) * ((kw + 63) // 64)
         splits = max(1, min(_MAX_SPLITS, (2 * 148) // tiles, (pixels + 255) // 256))
-    gbuf = _grad_buffer(unit, "wgrad", (splits, f_rows, kw))
+    gbuf = _grad_buffer(unit, "wgrad", (splits, f_rows, kw)) if s2d is None else \
+        _tmp(unit, "wgrad_s2d", (splits, f_rows, kw), torch.float32)
     brow = None
-    if bias_row and use_umma:
+    if bias_row and use_umma and s2d is None:
         brow = _grad_buffer(unit, "bias_row", (splits, f_rows))
     with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
         if use_umma:
@@ -624,6 +676,12 @@ def conv_backward(unit):
                 raise RuntimeError("%s: tcgen05 conv wgrad refused (code %d)" % (unit, r))
             if r == 0:
                 brow = None
+            if s2d is not None:
+                g2 = _grad_buffer(unit, "wgrad", (splits, f, unit._kernel_size))
+                ext.s2d_unpack_grad(gbuf, g2, splits, f, f_rows, unit.ky, unit.kx, unit._n_channels,
+                                    s2d["s"], s2d["kyp"], s2d["kxp"], _S2D_C)
+                _launch()
+                gbuf, f_rows, kw = g2, f, unit._kernel_size
         else:
             ext.conv_wgrad(err, x, gbuf, splits, g, bool(unit.weights_transposed), 0, None)
         _launch()

@@ -877,6 +877,39 @@ void lstm_unpack_state(Tensor state, Tensor gates, Tensor cells) {
   kcheck();
 }
 namespace zn {
+void launch_space_to_depth(const void*, bool, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+void launch_s2d_pack_weights(const float*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
+void launch_s2d_unpack_grad(const float*, float*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+}
+// space-to-depth form of a strided first-layer convolution (s2d.cu)
+void space_to_depth(Tensor x, Tensor xs, int64_t s, int64_t pad_t, int64_t pad_l) {
+  chk(x, "x"); chk(xs, "xs");
+  TORCH_CHECK(x.dim() == 4 && xs.dim() == 4 && is_bf16(xs) && xs.size(0) == x.size(0));
+  TORCH_CHECK(xs.size(3) >= s * s * x.size(3));
+  zn::launch_space_to_depth(x.data_ptr(), is_bf16(x), xs.data_ptr(), (int)x.size(0), (int)x.size(1),
+                            (int)x.size(2), (int)x.size(3), (int)s, (int)pad_t, (int)pad_l, (int)xs.size(1),
+                            (int)xs.size(2), (int)xs.size(3), cur());
+  kcheck();
+}
+void s2d_pack_weights(Tensor w, Tensor ws, int64_t F, int64_t ky, int64_t kx, int64_t C, int64_t s, int64_t kyp,
+                      int64_t kxp, int64_t Cp) {
+  chk(w, "w"); chk(ws, "ws");
+  TORCH_CHECK(w.scalar_type() == torch::kFloat32 && is_bf16(ws) && w.numel() >= F * ky * kx * C &&
+              ws.numel() >= F * kyp * kxp * Cp && Cp >= s * s * C);
+  zn::launch_s2d_pack_weights(w.data_ptr<float>(), ws.data_ptr(), (int)F, (int)ky, (int)kx, (int)C, (int)s, (int)kyp,
+                              (int)kxp, (int)Cp, cur());
+  kcheck();
+}
+void s2d_unpack_grad(Tensor gs, Tensor g, int64_t parts, int64_t F, int64_t Fr, int64_t ky, int64_t kx, int64_t C,
+                     int64_t s, int64_t kyp, int64_t kxp, int64_t Cp) {
+  chk(gs, "gs"); chk(g, "g");
+  TORCH_CHECK(gs.scalar_type() == torch::kFloat32 && g.scalar_type() == torch::kFloat32);
+  TORCH_CHECK(gs.numel() >= parts * Fr * kyp * kxp * Cp && g.numel() >= parts * F * ky * kx * C && Fr >= F);
+  zn::launch_s2d_unpack_grad(gs.data_ptr<float>(), g.data_ptr<float>(), (int)parts, (int)F, (int)Fr, (int)ky, (int)kx,
+                             (int)C, (int)s, (int)kyp, (int)kxp, (int)Cp, cur());
+  kcheck();
+}
+namespace zn {
 void launch_split_parts(const float*, long long, int, __nv_bfloat16*, long long, long long, int, int, int,
                         __nv_bfloat16*, long long, long long, int, int, int, cudaStream_t);
 void launch_split_conv_wt(const float*, __nv_bfloat16*, int, int, int, int, int, int, int, cudaStream_t);
@@ -987,6 +1020,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
   m.def("gather_minibatch", &gather_minibatch);
   m.def("swap01_2d", &swap01_2d); m.def("device_copy", &device_copy);
+  m.def("space_to_depth", &space_to_depth); m.def("s2d_pack_weights", &s2d_pack_weights); m.def("s2d_unpack_grad", &s2d_unpack_grad);
   m.def("stream_ring_create", &stream_ring_create); m.def("stream_ring_destroy", &stream_ring_destroy);
   m.def("stream_ring_step", &stream_ring_step); m.def("stream_ring_slot_done", &stream_ring_slot_done);
   m.def("stream_ring_slot_sync", &stream_ring_slot_sync);
