@@ -141,3 +141,13 @@ def test_native_cuda_matches_cpu(tmp_path):
     eng = native.NativeEngine(pkg)
     x = numpy.random.RandomState(2).uniform(-1, 1, (6, 32, 32, 3)).astype(numpy.float32)
     assert numpy.abs(eng.run(x, "cuda") - eng.run(x, "cpu")).max() < 1e-4
+    # the conv layers (and every FC layer with >= 32 inputs) ran as split-bf16 tcgen05 launches
+    assert eng.tensor_core_launches >= 3
+    import os
+    os.environ["ZNICZ_NATIVE_TC"] = "0"
+    try:
+        simt = native.NativeEngine(pkg)
+        assert numpy.abs(simt.run(x, "cuda") - eng.run(x, "cpu")).max() < 1e-4
+        assert simt.tensor_core_launches == 0
+    finally:
+        del os.environ["ZNICZ_NATIVE_TC"]

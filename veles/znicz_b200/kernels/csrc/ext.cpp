@@ -910,6 +910,25 @@ void s2d_unpack_grad(Tensor gs, Tensor g, int64_t parts, int64_t F, int64_t Fr, 
   kcheck();
 }
 namespace zn {
+void launch_metric_reduce(const double* const*, int, int, uint32_t* const*, uint32_t*, double*, int, int, int, cudaStream_t);
+}
+// epoch-end metrics: sum the first n_sum and take the maximum of the next n_max doubles of every rank's
+// symmetric slot (src_ptrs / flag_ptrs: one address per rank, epoch_ptr: this rank's counter)
+void metric_reduce(std::vector<int64_t> src_ptrs, std::vector<int64_t> flag_ptrs, int64_t epoch_ptr, int64_t rank,
+                   Tensor out, int64_t n_sum, int64_t n_max, int64_t slot) {
+  const int n = (int)src_ptrs.size();
+  TORCH_CHECK(n >= 1 && n <= 8 && (int)flag_ptrs.size() == n && rank >= 0 && rank < n);
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kFloat64 && out.numel() >= n_sum + n_max);
+  const double* src[8]; uint32_t* flags[8];
+  for (int r = 0; r < n; ++r) {
+    src[r] = reinterpret_cast<const double*>(src_ptrs[r]);
+    flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+  }
+  zn::launch_metric_reduce(src, n, (int)rank, flags, reinterpret_cast<uint32_t*>(epoch_ptr), out.data_ptr<double>(),
+                           (int)n_sum, (int)n_max, (int)slot, cur());
+  kcheck();
+}
+namespace zn {
 void launch_split_parts(const float*, long long, int, __nv_bfloat16*, long long, long long, int, int, int,
                         __nv_bfloat16*, long long, long long, int, int, int, cudaStream_t);
 void launch_split_conv_wt(const float*, __nv_bfloat16*, int, int, int, int, int, int, int, cudaStream_t);
@@ -1019,7 +1038,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mul_backward", &mul_backward); m.def("axpby_2d", &axpby_2d); m.def("crop_nhwc", &crop_nhwc);
   m.def("gather_rows", &gather_rows); m.def("gather_labels", &gather_labels);
   m.def("gather_minibatch", &gather_minibatch);
-  m.def("swap01_2d", &swap01_2d); m.def("device_copy", &device_copy);
+  m.def("swap01_2d", &swap01_2d); m.def("device_copy", &device_copy); m.def("metric_reduce", &metric_reduce);
   m.def("space_to_depth", &space_to_depth); m.def("s2d_pack_weights", &s2d_pack_weights); m.def("s2d_unpack_grad", &s2d_unpack_grad);
   m.def("stream_ring_create", &stream_ring_create); m.def("stream_ring_destroy", &stream_ring_destroy);
   m.def("stream_ring_step", &stream_ring_step); m.def("stream_ring_slot_done", &stream_ring_slot_done);

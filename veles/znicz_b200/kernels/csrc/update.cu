@@ -856,4 +856,43 @@ void launch_refresh_shadows(const float* w, long long size, int rows, int cols, 
   launch_k(refresh_shadows_k, (int)b, 256, 0, st, w, size, rows, cols, sh);
 }
 
+// ---- epoch-end metric reduction over the same peer-memory mechanism -------------------------------------
+// Each rank's metrics (error counts, confusion matrix, maxima; packed as doubles, sums first) sit in a
+// symmetric buffer with two slots (epoch parity); one block per rank publishes, waits for every
+// peer with the flag barrier of the gradient kernels and reduces in fixed rank order - every rank
+// ends with bit-identical totals and no library collective is involved.
+struct MetricSrc { const double* p[8]; };
+
+__global__ void metric_reduce_k(PeerSync ps, MetricSrc src, double* __restrict__ out, int n_sum, int n_max,
+                                int slot) {
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = ++ps.epoch[blockIdx.x];
+  __syncthreads();
+  const int n = n_sum + n_max;
+  peer_barrier(ps, s_epoch);                  // every rank's slot is written and visible
+  const size_t off = (size_t)slot * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double acc = src.p[0][off + i];
+    for (int r = 1; r < ps.nranks; ++r) {
+      const double v = src.p[r][off + i];
+      acc = i < n_sum ? acc + v : (v > acc ? v : acc);
+    }
+    out[i] = acc;
+  }
+  // no trailing barrier: the host alternates the slot, and a rank only gets to overwrite a slot two
+  // calls later - after it passed the next call's barrier, which every peer enters (block 0 exists
+  // in every call) after its previous kernel, i.e. these reads, completed
+}
+
+void launch_metric_reduce(const double* const* src, int nranks, int rank, uint32_t* const* peer_flags,
+                          uint32_t* epoch, double* out, int n_sum, int n_max, int slot, cudaStream_t st) {
+  PeerSync ps{};
+  ps.rank = rank; ps.nranks = nranks; ps.epoch = epoch;
+  MetricSrc ms{};
+  for (int r = 0; r < nranks; ++r) { ps.flags[r] = peer_flags[r]; ms.p[r] = src[r]; }
+  int blocks = (n_sum + n_max + 1023) / 1024;
+  blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+  metric_reduce_k<<<blocks, 256, 0, st>>>(ps, ms, out, n_sum, n_max, slot);
+}
+
 }  // namespace zn

@@ -29,6 +29,8 @@ def load_library():
         ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
         ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float), ctypes.c_longlong,
         ctypes.c_char_p, ctypes.c_int]
+    lib.znicz_engine_tc_launches.restype = ctypes.c_longlong
+    lib.znicz_engine_tc_launches.argtypes = [ctypes.c_void_p]
     _lib = lib
     return lib
 
@@ -57,6 +59,11 @@ class NativeEngine(object):
     @property
     def num_units(self):
         return self._lib.znicz_engine_num_units(self._h)
+
+    @property
+    def tensor_core_launches(self):
+        """tcgen05 GEMM / conv launches issued by the CUDA executor so far."""
+        return int(self._lib.znicz_engine_tc_launches(self._h))
 
     @staticmethod
     def _shape4(x):

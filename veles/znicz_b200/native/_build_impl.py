@@ -10,7 +10,9 @@ KBUILD = os.path.join(os.path.dirname(HERE), "kernels", "build")
 LIB = os.path.join(HERE, "libznicz_native.so")
 TEST_BIN = os.path.join(HERE, "znicz_native_test")
 INFER_BIN = os.path.join(HERE, "znicz_infer")
-KERNEL_OBJS = ("gemm_simt.o", "pooling.o", "elementwise.o", "softmax_eval.o")
+KERNEL_OBJS = ("gemm_simt.o", "pooling.o", "elementwise.o", "softmax_eval.o",
+               # tensor-core path of the CUDA executor (split-bf16 operands)
+               "gemm_umma.o", "gemm_pair.o", "split.o")
 
 
 def _run(cmd):

@@ -279,4 +279,5 @@ int znicz_engine_run(void* e, int backend, const float* input, const int* s, flo
   } catch (const std::exception& ex) { set_err(err, errlen, ex.what()); return 1; }
 }
 int znicz_cuda_available() { return Engine::cuda_available() ? 1 : 0; }
+long long znicz_engine_tc_launches(void* e) { return static_cast<Engine*>(e)->cuda_tensor_core_launches(); }
 }

@@ -9,6 +9,7 @@
 namespace znicz {
 
 bool Engine::cuda_available() { return false; }
+long long Engine::cuda_tensor_core_launches() const { return 0; }
 
 std::vector<float> Engine::run_cuda(const float*, const Shape4&) {
   throw std::runtime_error("znicz_native was built without CUDA support");

@@ -77,6 +77,8 @@ class Engine {
   // sm_100a executor (throws std::runtime_error when no CUDA device is usable).
   std::vector<float> run_cuda(const float* input, const Shape4& in);
   static bool cuda_available();
+  // tcgen05 GEMM / conv launches issued by run_cuda() so far (0: every layer took the SIMT path)
+  long long cuda_tensor_core_launches() const;
 
  private:
   struct CudaState;
@@ -98,4 +100,5 @@ int znicz_engine_infer(void* e, const int* in_shape4, int* out_shape4);
 int znicz_engine_run(void* e, int backend, const float* input, const int* in_shape4, float* output,
                      long long out_capacity, char* err, int errlen);
 int znicz_cuda_available();
+long long znicz_engine_tc_launches(void* e);
 }

@@ -91,9 +91,74 @@ class DataParallel(object):
                 f.refresh_shadows()
 
     # -- reductions on the slow path (epoch ends) ----------------------------------------------
+    # -- epoch-end metrics through the symmetric-memory mechanism (no library collective) ---------
+    def _metric_state(self, n):
+        import torch
+        import torch.distributed as dist
+        st = self.__dict__.get("_mstate_")
+        if st is None or st["cap"] < n:
+            cap = max(int(n), 4096)
+            t, h = self.symm._alloc(2 * cap, torch.float64)
+            t.zero_()
+            flags, epoch_ptr = self.symm.sync_state(("metrics", cap))
+            st = {"cap": cap, "t": t, "h": h, "ptrs": [int(p) for p in h.buffer_ptrs],
+                  "flags": flags, "epoch_ptr": epoch_ptr, "calls": 0,
+                  "out": torch.zeros(cap, dtype=torch.float64, device=self.device.torch_device)}
+            torch.cuda.synchronize()
+            dist.barrier()
+            self.__dict__["_mstate_"] = st
+        return st
+
+    def _reduce_symm(self, sums, maxs):
+        """Element-wise SUM of the ``sums`` arrays and MAX of the ``maxs`` arrays over all ranks by
+        ``metric_reduce_k`` (csrc/update.cu): every rank publishes its packed doubles in a
+        symmetric slot and reduces all peers' slots in fixed rank order."""
+        import torch
+        flat = [numpy.asarray(a, dtype=numpy.float64).ravel() for a in sums + maxs]
+        n_sum = sum(a.size for a in flat[:len(sums)])
+        n = sum(a.size for a in flat)
+        st = self._metric_state(n)
+        st["calls"] += 1
+        slot = st["calls"] & 1
+        packed = torch.from_numpy(numpy.concatenate(flat) if flat else numpy.zeros(0))
+        st["t"][slot * n:slot * n + n].copy_(packed)
+        self.device.ext.metric_reduce(st["ptrs"], st["flags"], st["epoch_ptr"], self.rank, st["out"],
+                                      n_sum, n - n_sum, slot)
+        res = st["out"][:n].cpu().numpy()
+        out, off = [], 0
+        for a in flat:
+            out.append(res[off:off + a.size])
+            off += a.size
+        return out[:len(sums)], out[len(sums):]
+
     def reduce_metrics(self, n_err=None, confusion=None, max_err=None, mse_metrics=None):
         import torch
         import torch.distributed as dist
+        if self.symm is not None and os.environ.get("ZNICZ_METRICS_NCCL", "0") != "1":
+            def host(arr):
+                arr.map_read()
+                return arr.mem
+            sums = [a for a in (n_err, confusion) if a is not None and a]
+            maxs = [a for a in (max_err,) if a is not None and a]
+            s_in = [host(a) for a in sums]
+            m_in = [host(a) for a in maxs]
+            mse = mse_metrics is not None and bool(mse_metrics)
+            if mse:
+                m = host(mse_metrics)
+                s_in.append(numpy.array([float(m[0])]))
+                m_in.append(numpy.array([float(m[1]), -float(m[2])]))
+            s_out, m_out = self._reduce_symm(s_in, m_in)
+            for arr, res in zip(sums + maxs, s_out[:len(sums)] + m_out[:len(maxs)]):
+                arr.map_invalidate()
+                arr.mem[...] = res.reshape(arr.mem.shape).astype(arr.mem.dtype)
+                arr.unmap()
+            if mse:
+                mse_metrics.map_invalidate()
+                mse_metrics.mem[0] = s_out[-1][0]
+                mse_metrics.mem[1] = m_out[-1][0]
+                mse_metrics.mem[2] = -m_out[-1][1]
+                mse_metrics.unmap()
+            return
 
         def _reduce(arr, op):
             if arr is None or not arr:
@@ -129,6 +194,13 @@ class DataParallel(object):
     def all_reduce_scalar(self, value, op="sum"):
         import torch
         import torch.distributed as dist
+        if self.symm is not None and op in ("sum", "max", "min") and \
+                os.environ.get("ZNICZ_METRICS_NCCL", "0") != "1":
+            v = numpy.array([float(value)])
+            if op == "sum":
+                return float(self._reduce_symm([v], [])[0][0][0])
+            sign = -1.0 if op == "min" else 1.0
+            return sign * float(self._reduce_symm([], [sign * v])[1][0][0])
         t = torch.tensor([float(value)], dtype=torch.float64)
         if self.device is not None and self.device.is_cuda:
             t = t.to(self.device.torch_device)
