@@ -336,7 +336,8 @@ def run_reference_arm(args, rank, world):
         "value": round(images / (main_res["ms_dev"] / 1e3), 1), "unit": "images/s", "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(main_res["ms_dev"] / args.steps, 5),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if args.strong_global_batch else "weak",
+        "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
         "config": {"model": MODELS["cifar_caffe"][1], "global_batch": batch * n,
                    "per_gpu_batch": batch, "image": "32x32x3",
@@ -380,6 +381,9 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--n-train", type=int, default=50000)
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--strong-global-batch", type=int, default=0,
+                    help="strong scaling: fix the GLOBAL batch (per-GPU batch = this / N) instead "
+                         "of the per-GPU batch of the config")
     ap.add_argument("--model", default="cifar_caffe", choices=sorted(MODELS),
                     help="cifar_caffe is the north-star config; the others are extra data points")
     args = ap.parse_args()
@@ -400,6 +404,10 @@ def main():
         args.warmup = 3
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.strong_global_batch:
+        if args.strong_global_batch % max(world, 1):
+            raise SystemExit("--strong-global-batch must be divisible by the number of GPUs")
+        os.environ["ZNICZ_BENCH_BATCH"] = str(args.strong_global_batch // max(world, 1))
     main_res = run_arm(args, streaming=False)
     e2e_res = None if args.skip_e2e else run_arm(args, streaming=True)
     if rank != 0:

@@ -401,9 +401,15 @@ class GradientDescentBase(AcceleratedUnit, metaclass=MatchingObject):
         if self.hyper_dev_ is None:
             self.hyper_dev_ = torch.zeros(16, dtype=torch.float32,
                                           device=self.device.torch_device)
-            self.hyper_host_ = torch.zeros(16, dtype=torch.float32).pin_memory()
-        self.hyper_host_.copy_(torch.tensor(vals, dtype=torch.float32))
-        self.hyper_dev_.copy_(self.hyper_host_, non_blocking=True)
+            # ring of pinned staging slots (per-iteration LR policies change the values every
+            # step while the host runs ahead of the device: a single slot could be rewritten
+            # before its queued async copy has executed)
+            self.hyper_host_ = [torch.zeros(16, dtype=torch.float32).pin_memory() for _ in range(8)]
+            self.__dict__["hyper_slot_"] = 0
+        k = self.__dict__["hyper_slot_"] = (self.__dict__.get("hyper_slot_", 0) + 1) % 8
+        host = self.hyper_host_[k]
+        host.copy_(torch.tensor(vals, dtype=torch.float32))
+        self.hyper_dev_.copy_(host, non_blocking=True)
         self.hyper_cache_ = vals
 
     def cuda_prepare(self):

@@ -89,10 +89,15 @@ class EvaluatorBase(AcceleratedUnit, TriviallyDistributable,
         if self.batch_dev_ is None:
             self.batch_dev_ = torch.zeros(2, dtype=torch.float32,
                                           device=self.device.torch_device)
-            self.batch_host_ = torch.zeros(2, dtype=torch.float32).pin_memory()
-        self.batch_host_[0] = float(bs)
-        self.batch_host_[1] = 1.0 / bs if self.mean else 1.0
-        self.batch_dev_.copy_(self.batch_host_, non_blocking=True)
+            # a ring of pinned staging slots: the host may run a few steps ahead of the device,
+            # so the slot of an earlier (still queued) async copy must not be rewritten
+            self.batch_host_ = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(8)]
+            self.__dict__["batch_slot_"] = 0
+        k = self.__dict__["batch_slot_"] = (self.__dict__.get("batch_slot_", 0) + 1) % 8
+        host = self.batch_host_[k]
+        host[0] = float(bs)
+        host[1] = 1.0 / bs if self.mean else 1.0
+        self.batch_dev_.copy_(host, non_blocking=True)
         self._batch_cache_ = bs
 
     def run(self):
