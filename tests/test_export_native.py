@@ -151,3 +151,31 @@ def test_native_cuda_matches_cpu(tmp_path):
         assert simt.tensor_core_launches == 0
     finally:
         del os.environ["ZNICZ_NATIVE_TC"]
+
+
+def test_cpu_only_cmake_configuration_builds_and_runs(tmp_path):
+    """The portable configuration the Android script cross-compiles (-DZNICZ_WITH_CUDA=OFF, OpenMP
+    loops; native/android/build_android.sh, reference: libZnicz/android/Android.mk.in) built with
+    the host toolchain: library, CLI and the C++ tests, then inference on the reference's own
+    packaged MNIST workflow. (No NDK in this image: the cross build itself stays unexecuted.)"""
+    import shutil
+    import subprocess
+    if shutil.which("cmake") is None:
+        pytest.skip("cmake not installed")
+    src = os.path.join(os.path.dirname(native.__file__))
+    build = str(tmp_path / "cpu")
+    for cmd in (["cmake", "-S", src, "-B", build, "-DZNICZ_WITH_CUDA=OFF", "-DZNICZ_OPENMP=ON",
+                 "-DCMAKE_BUILD_TYPE=Release"],
+                ["cmake", "--build", build, "-j", "4"]):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run(["ctest", "--test-dir", build, "--output-on-failure"], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    ref_pkg = "/root/reference/libZnicz/tests/workflow_files/mnist.zip"
+    if os.path.exists(ref_pkg):
+        numpy.zeros((2, 784), numpy.float32).tofile(tmp_path / "x.f32")
+        r = subprocess.run([os.path.join(build, "znicz_infer"), ref_pkg, str(tmp_path / "x.f32"),
+                            "2", "1", "1", "784"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-1000:]
+        assert "output 2x1x1x10" in r.stdout, r.stdout
