@@ -57,6 +57,13 @@ def _launch(n=1):
     counters["launches"] += n
 
 
+paths = {}          # unit name -> kernel families its eager launches used (diagnostics)
+
+
+def _path(unit, tag):
+    paths.setdefault(unit.name, set()).add(tag)
+
+
 # ------------------------------------------------------------------------------------------
 # weights: fp32 master + bf16 shadows in the layouts the tensor-core kernels consume
 # ------------------------------------------------------------------------------------------
@@ -399,6 +406,9 @@ def fc_backward(unit):
             if r != 0:
                 raise RuntimeError("%s: tcgen05 FC dgrad refused (code %d)" % (unit, r))
         else:
+            _path(unit, "fc_dgrad:simt(lp_ok=%s,err=%s,x=%s,lp=%s)" % (
+                lp_ok, err.dtype, x.dtype,
+                getattr(unit.forward_unit, "weights_lp_", None) is not None))
             w = unit.weights.dev
             if unit.weights_transposed:  # stored [in][out] => B(k=out, n=in) = w[n][k]
                 ext.gemm(err, n_out, False, w, n_out, True, ei, n_in, False, batch, n_in, n_out,
@@ -434,6 +444,7 @@ def fc_backward(unit):
             if r != 0:
                 raise RuntimeError("%s: tcgen05 FC wgrad refused (code %d)" % (unit, r))
         else:
+            _path(unit, "fc_wgrad:simt")
             ext.gemm(err, n_out, True, x, n_in, False, gbuf,
                      n_out if unit.weights_transposed else n_in,
                      bool(unit.weights_transposed), n_out, n_in, batch, None, 0, 1.0, 0.0, 1, 0, 0)
