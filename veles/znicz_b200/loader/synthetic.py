@@ -14,12 +14,16 @@ from .fullbatch import FullBatchLoader, FullBatchLoaderMSE
 
 
 def make_classification(n, shape, n_classes, seed, noise=0.5, dtype=numpy.float32,
-                        prototypes=None):
+                        prototypes=None, cover_classes=False):
     rs = numpy.random.RandomState(seed)
     if prototypes is None:
         prs = numpy.random.RandomState(seed ^ 0x5EED)
         prototypes = prs.normal(0, 1, (n_classes,) + tuple(shape)).astype(dtype)
     labels = rs.randint(0, n_classes, n).astype(numpy.int32)
+    if cover_classes and n >= n_classes:
+        # every class occurs: with 1000 classes and ~1000 samples plain sampling leaves ~37 % of
+        # the labels unseen and the workflow sizes its softmax layer by the labels it saw
+        labels[rs.permutation(n)[:n_classes]] = numpy.arange(n_classes, dtype=numpy.int32)
     data = prototypes[labels] + rs.normal(0, noise, (n,) + tuple(shape)).astype(dtype)
     return data.astype(dtype), labels, prototypes
 
@@ -38,6 +42,7 @@ class SyntheticImageLoader(FullBatchLoader):
         self.n_test = kwargs.get("n_test", 0)
         self.seed = kwargs.get("seed", 17)
         self.noise = kwargs.get("noise", 0.5)
+        self.cover_classes = kwargs.get("cover_classes", False)
 
     def load_data(self):
         parts_d, parts_l = [], []
@@ -47,7 +52,8 @@ class SyntheticImageLoader(FullBatchLoader):
             if n:
                 d, l, protos = make_classification(
                     n, self.sample_shape, self.n_classes, self.seed + 101 * i,
-                    self.noise, prototypes=protos)
+                    self.noise, prototypes=protos,
+                    cover_classes=getattr(self, "cover_classes", False))
                 parts_d.append(d)
                 parts_l.append(l)
         self.original_data.reset(numpy.concatenate(parts_d).astype(self.dtype))
@@ -78,6 +84,7 @@ class SyntheticImagenetLoader(SyntheticImageLoader):
     def __init__(self, workflow, **kwargs):
         kwargs.setdefault("shape", (227, 227, 3))
         kwargs.setdefault("n_classes", 1000)
+        kwargs.setdefault("cover_classes", True)
         super().__init__(workflow, **kwargs)
 
 
