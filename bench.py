@@ -119,16 +119,21 @@ def build_workflow(streaming, compute, graphs, n_train, model="cifar_caffe"):
     if model == "lstm":
         from veles.znicz_b200.models import lstm_seq
         return lstm_seq.build(
-            loader_config={"minibatch_size": batch, "n_train": min(n_train, 16384), "n_valid": 0,
+            # (per-rank dataset size constant under weak scaling, no epoch end inside the window)
+            loader_config={"minibatch_size": batch,
+                           "n_train": min(n_train, 32768) * max(1, int(os.environ.get("WORLD_SIZE", "1"))),
+                           "n_valid": 0,
                            "n_test": 0, "on_device": not streaming,
                            "shuffle_limit": 2000000000}, **common)
     from veles.znicz_b200.models import alexnet
     return alexnet.build(
         loader_name="synthetic_imagenet", layers=alexnet.alexnet_layers(1000),
-        # (per-rank dataset size constant under weak scaling: the sharded loader otherwise ends an
-        # epoch - NCCL metric reduction + a 1000 x 1000 confusion matrix - every step at 8 ranks)
+        # (per-rank dataset size constant under weak scaling and larger than the measured window:
+        # an epoch end - metric reduction incl. a 1000 x 1000 confusion matrix, decision - costs
+        # ~13 ms and belongs to the epoch, not to the step)
         loader_config={"minibatch_size": batch,
-                       "n_train": min(n_train, 1024) * max(1, int(os.environ.get("WORLD_SIZE", "1"))),
+                       "n_train": min(n_train, int(os.environ.get("ZNICZ_BENCH_ALEXNET_SAMPLES", "5120"))) *
+                       max(1, int(os.environ.get("WORLD_SIZE", "1"))),
                        "n_valid": 0,
                        "n_test": 0, "n_classes": 1000, "normalization_type": "internal_mean",
                        "on_device": not streaming, "shuffle_limit": 2000000000}, **common)
@@ -336,8 +341,7 @@ def run_reference_arm(args, rank, world):
         "value": round(images / (main_res["ms_dev"] / 1e3), 1), "unit": "images/s", "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(main_res["ms_dev"] / args.steps, 5),
-        "higher_is_better": True, "scaling": "strong" if args.strong_global_batch else "weak",
-        "vs_baseline": None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
         "config": {"model": MODELS["cifar_caffe"][1], "global_batch": batch * n,
                    "per_gpu_batch": batch, "image": "32x32x3",
@@ -423,7 +427,8 @@ def main():
                   " training %s/sec (whole job, device-timed, max over ranks)" % unit_name,
         "value": round(value, 1), "unit": unit_name + "/s", "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(main_res["ms_dev"] / args.steps, 5),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if args.strong_global_batch else "weak",
+        "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "impl": "znicz_b200" if args.impl == "b200" else "baseline(in-repo, reference-equivalent)",
         "config": {"model": MODELS[args.model][1],

@@ -72,6 +72,11 @@ class DataParallel(object):
             from .symmetric import SymmetricGradients
             gds = [g for g in workflow.gds if g is not None and g.weights]
             self.symm = SymmetricGradients(self, gds)
+            # the epoch-end metric exchange buffers exist before the first epoch ends (a
+            # symmetric allocation + rendezvous costs tens of milliseconds)
+            ev = getattr(workflow, "evaluator", None)
+            cm = getattr(ev, "confusion_matrix", None)
+            self._metric_state(64 + (int(cm.size) if cm is not None and cm else 0))
 
     def broadcast_parameters(self, forwards):
         import torch
