@@ -94,7 +94,14 @@ def test_loader_shard_is_idempotent_and_reshardable():
     state = pickle.loads(pickle.dumps({k: getattr(ld, k) for k in
                                        ("unsharded_indices", "unsharded_class_lengths")}))
     assert list(state["unsharded_class_lengths"]) == full
+    # rank 0's snapshot restored on another rank of the SAME world: new shard, same position
+    # inside the epoch (the replicas must stay in lock step with rank 0, which keeps its own)
+    ld.global_offset = 10
+    ld.shard(2, 4)
+    assert ld.global_offset == 10 and list(ld.class_lengths) == [n // 4 for n in full]
+    assert not (ld.shuffled_indices.mem == first).all()
     ld.shard(0, 2)                                  # resumed on 2 ranks: half, not 1/8
+    assert ld.global_offset == 0                    # other world size: every rank restarts the epoch
     assert list(ld.class_lengths) == [n // 2 for n in full]
     ld.shard(0, 1)                                  # resumed single-process: everything
     assert list(ld.class_lengths) == full

@@ -43,7 +43,28 @@ class Launcher(DummyLauncher):
         self.run_time = 0.0
 
     # -- load / main passed to the workflow module --------------------------------------------
+    @staticmethod
+    def resolve_snapshot(spec):
+        """``latest`` / ``latest:<prefix>`` -> the newest snapshot of the snapshot directory
+        (the ``<prefix>_current.lnk`` symlink when it exists), None when there is none yet - what
+        a job restarted by ``torchrun --max-restarts`` after a rank failure resumes from."""
+        if not spec or not str(spec).startswith("latest"):
+            return spec
+        prefix = str(spec).partition(":")[2]
+        directory = str(root.common.dirs.snapshots)
+        if not os.path.isdir(directory):
+            return None
+        names = [n for n in os.listdir(directory) if ".pickle" in n and ".tmp." not in n and
+                 (not prefix or n.startswith(prefix + "_"))]
+        link = os.path.join(directory, "%s_current.lnk" % prefix) if prefix else None
+        if link and os.path.exists(link):
+            return link
+        if not names:
+            return None
+        return max((os.path.join(directory, n) for n in names), key=os.path.getmtime)
+
     def load(self, workflow_class, **kwargs):
+        self.snapshot = self.resolve_snapshot(self.snapshot)
         if self.snapshot:
             from .core.snapshotter import SnapshotterToFile
             wf = SnapshotterToFile.import_file(self.snapshot)
@@ -131,7 +152,10 @@ def build_parser():
                    help="config .py file (use - for none)")
     p.add_argument("overrides", nargs="*", help="root.path.to.key=value assignments")
     p.add_argument("-b", "--backend", default=None, choices=("auto", "cuda", "numpy"))
-    p.add_argument("-s", "--snapshot", default=None, help="resume from this snapshot file")
+    p.add_argument("-s", "--snapshot", default=None,
+                   help="resume from this snapshot file; 'latest[:prefix]' = the newest one in "
+                        "root.common.dirs.snapshots, a fresh start when there is none (restart "
+                        "after a rank failure: torchrun --max-restarts N ... --snapshot latest)")
     p.add_argument("--test", action="store_true", help="testing mode (forward only)")
     p.add_argument("--result-file", default=None, help="write gathered metrics as JSON")
     p.add_argument("--dry-run", default=None, choices=("load", "init"))

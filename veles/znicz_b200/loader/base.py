@@ -275,7 +275,12 @@ class Loader(AcceleratedUnit, metaclass=UserLoaderRegistry):
             self.class_lengths[i] = keep
         self.shuffled_indices.reset(numpy.concatenate(parts).astype(numpy.int32))
         self._update_total_samples()
-        self.global_offset = 0
+        # Same world size, other rank (rank 0's snapshot restored on rank r): the class layout of
+        # every shard is identical, so the position inside the epoch is kept - rank 0 keeps its
+        # own, and the replicas must stay in lock step. A different world size moves every class
+        # boundary: all ranks restart the epoch (all of them take this branch).
+        if cur[1] != world:
+            self.global_offset = 0
         self.dp_rank, self.dp_world = rank, world
         self.prng = prng.RandomGenerator(seed=977 + rank)
 

@@ -16,6 +16,12 @@ import os
 
 import numpy
 
+from ..core.config import root
+
+
+class RankFailure(RuntimeError):
+    """A peer rank died or stalled (raised by ``DataParallel.check_ranks``)."""
+
 
 class DataParallel(object):
     def __init__(self, device, rank, world_size, mode=None):
@@ -49,8 +55,34 @@ class DataParallel(object):
             kw = {}
             if backend == "nccl":
                 kw["device_id"] = device.torch_device
+            # failure detection: a collective (or the monitored barrier of check_ranks) that a
+            # dead rank never joins raises after this many seconds instead of hanging the job
+            import datetime
+            kw["timeout"] = datetime.timedelta(seconds=float(os.environ.get(
+                "ZNICZ_DP_TIMEOUT_S", root.common.engine.get("dp_timeout_s", 600))))
             dist.init_process_group(backend=backend, rank=rank, world_size=ws, **kw)
         return cls(device, rank, ws)
+
+    def check_ranks(self, timeout_s=None):
+        """Epoch-end health check: every rank must arrive within ``timeout_s``; a missing rank
+        raises ``RankFailure`` naming it (gloo) or the backend's timeout error (nccl). Together
+        with rank-0 snapshots, ``--snapshot latest`` and ``torchrun --max-restarts`` this is the
+        recovery path: the group is restarted and resumes from the last snapshot - on fewer
+        ranks if need be (the loader re-shards). The reference's master re-queued the jobs of a
+        dropped slave (``drop_slave``, /root/reference/nn_rollback.py:94-95); with synchronous
+        replicas there is nothing to re-queue, the epoch is simply repeated."""
+        import datetime
+        import torch.distributed as dist
+        t = datetime.timedelta(seconds=float(timeout_s if timeout_s is not None else os.environ.get(
+            "ZNICZ_DP_TIMEOUT_S", root.common.engine.get("dp_timeout_s", 600))))
+        try:
+            if dist.get_backend() == "gloo":
+                dist.monitored_barrier(timeout=t, wait_all_ranks=True)
+            else:
+                dist.barrier()
+        except RuntimeError as e:
+            raise RankFailure("rank %d: a peer did not reach the epoch-end barrier: %s" % (
+                self.rank, str(e).splitlines()[0] if str(e) else type(e).__name__)) from e
 
     # -- wiring ---------------------------------------------------------------------------
     def attach(self, workflow):

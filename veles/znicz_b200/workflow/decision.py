@@ -291,6 +291,11 @@ class DecisionGD(DecisionBase):
         dp = self.dp_
         if dp is None or dp.world_size == 1:
             return
+        if dp.symm is None:
+            # host-side collectives follow: find a dead rank here, with its number in the error,
+            # rather than as a hang inside the reduction (the on-device flag barriers of the
+            # fused path trap on their own after ZN_PEER_TIMEOUT_NS)
+            dp.check_ranks()
         dp.reduce_metrics(n_err=self.minibatch_n_err,
                           confusion=self.minibatch_confusion_matrix,
                           max_err=self.minibatch_max_err_y_sum,
