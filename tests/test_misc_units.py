@@ -278,3 +278,72 @@ def test_stochastic_pooling_statistics_and_pool_depool():
     after = q.input.mem
     assert (after != 0).sum() == 3 * 2 * 2 * 2      # one survivor per window per channel
     assert numpy.allclose(after[after != 0], before[after != 0])
+
+
+def test_nn_rollback_raises_and_lowers_learning_rates_and_restores_weights():
+    """/root/reference/nn_rollback.py:44-181: improved -> lr x lr_plus and the weights are stashed;
+    `minus_steps` epochs without improvement (or NaNs at once) -> lr x lr_minus and the stashed
+    weights come back."""
+    from veles.znicz_b200.core.memory import Array
+    from veles.znicz_b200.core.mutable import Bool
+    from veles.znicz_b200.workflow.nn_rollback import NNRollback
+
+    class _GD(object):
+        def __init__(self):
+            self.learning_rate, self.learning_rate_bias = 0.1, 0.2
+            self.weights = Array(numpy.ones((2, 3), numpy.float32))
+            self.bias = Array(numpy.zeros(2, numpy.float32))
+            self.gradient_weights = Array()
+            self.gradient_bias = Array()
+            self.forward_unit = None
+
+    wf = DummyWorkflow()
+    rb = NNRollback(wf, lr_plus=1.5, lr_minus=0.5, minus_steps=2)
+    rb.improved = Bool(True)
+    gd = _GD()
+    rb.add_gd(gd)
+    rb.initialize()
+    rb.run()                                         # improved: raise the rate, stash weights
+    assert abs(gd.learning_rate - 0.15) < 1e-9 and abs(gd.learning_rate_bias - 0.3) < 1e-9
+    gd.weights.map_write()
+    gd.weights.mem[...] = 7.0                        # the epoch moved the weights somewhere bad
+    rb.improved <<= False
+    rb.run()                                         # 1st bad epoch: nothing yet
+    assert abs(gd.learning_rate - 0.15) < 1e-9
+    rb.run()                                         # 2nd: lower the rate, restore
+    assert abs(gd.learning_rate - 0.075) < 1e-9
+    gd.weights.map_read()
+    assert (gd.weights.mem == 1.0).all()
+    gd.weights.map_write()
+    gd.weights.mem[0, 0] = numpy.nan
+    rb.run()                                         # NaNs: immediate rollback
+    gd.weights.map_read()
+    assert numpy.isfinite(gd.weights.mem).all() and abs(gd.learning_rate - 0.0375) < 1e-9
+    # per-unit factors and the elastic hooks of the reference's IDistributable surface
+    rb.add_gd(gd, lr_plus=2.0, lr_minus=0.25)
+    rb.improved <<= True
+    rb.run()
+    assert abs(gd.learning_rate - 0.075) < 1e-9
+    rb.generate_data_for_slave("s1")
+    rb.drop_slave("s1")
+    assert not rb.slaves_
+
+
+def test_reference_style_imports_resolve_to_this_package():
+    """`from veles.znicz.conv import Conv`, `from veles.config import root` keep working through
+    the alias finder (compat.py; the reference's import surface is SURVEY §1.3)."""
+    import subprocess
+    import sys
+    code = (
+        "import veles.znicz_b200.compat as c; c.install()\n"
+        "from veles.config import root\n"
+        "from veles.znicz.conv import Conv\n"
+        "from veles.znicz.all2all import All2AllSoftmax\n"
+        "from veles.znicz.gd_conv import GradientDescentConv\n"
+        "from veles.memory import Array\n"
+        "from veles.mutable import Bool\n"
+        "import veles.znicz_b200.ops.conv as m, veles.znicz_b200.core.config as k\n"
+        "assert Conv is m.Conv and root is k.root\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
