@@ -93,3 +93,58 @@ def test_mcdnnic_topology_parsing():
         StandardWorkflowBase(DummyLauncher(), loader_name="synthetic_image",
                              layers=[{"type": "conv"}],
                              mcdnnic_topology="12x16x16-8C4-4N")
+
+
+def test_avatar_mirrors_loader_exports():
+    """`link_avatar` (/root/reference/standard_workflow.py:386-404): downstream units read the
+    avatar's stable copy of the loader's exports while the loader may run ahead."""
+    import numpy
+    from veles.znicz_b200.core.avatar import Avatar
+    from veles.znicz_b200.core.memory import Array
+    from veles.znicz_b200.core.mutable import Bool
+    from veles.znicz_b200.core.units import TrivialUnit
+    from veles.znicz_b200.core.workflow import DummyWorkflow
+    wf = DummyWorkflow()
+    real = TrivialUnit(wf, name="loader")
+    real.minibatch_data = Array(numpy.arange(6, dtype=numpy.float32).reshape(2, 3))
+    real.last_minibatch = Bool(False)
+    real.minibatch_size = 2
+    av = Avatar(wf)
+    av.reals[real] = ("minibatch_data", "last_minibatch", "minibatch_size")
+    av.initialize()
+    assert numpy.array_equal(av.minibatch_data.mem, real.minibatch_data.mem)
+    assert av.minibatch_data is not real.minibatch_data
+    real.minibatch_data.map_write()
+    real.minibatch_data.mem[...] = -1.0              # the real loader already serves the next batch
+    real.last_minibatch <<= True
+    real.minibatch_size = 1
+    assert av.minibatch_data.mem[0, 1] == 1.0 and not bool(av.last_minibatch) and av.minibatch_size == 2
+    av.run()
+    assert (av.minibatch_data.mem == -1.0).all() and bool(av.last_minibatch) and av.minibatch_size == 1
+
+
+def test_extract_forward_workflow_carries_trained_weights():
+    """`extract_forward_workflow` (/root/reference/standard_workflow.py:210-286): a forward-only
+    workflow over another loader with the trained parameters."""
+    import numpy
+    from veles.znicz_b200.models import mnist
+    wf = mnist.build(
+        layers=mnist.fc_layers(), loader_name="synthetic_mnist",
+        loader_config={"minibatch_size": 10, "n_train": 40, "n_valid": 20, "noise": 0.3,
+                       "normalization_type": "linear"},
+        decision_config={"max_epochs": 2, "fail_iterations": 5})
+    wf.initialize(device="numpy")
+    wf.run()
+    fwd = wf.extract_forward_workflow(
+        loader_name="synthetic_mnist",
+        loader_config={"minibatch_size": 10, "n_train": 0, "n_valid": 0, "n_test": 20,
+                       "noise": 0.3, "normalization_type": "linear"}, cyclic=False)
+    assert len(fwd.forwards) == len(wf.forwards)
+    fwd.initialize(device="numpy")
+    for a, b in zip(wf.forwards, fwd.forwards):
+        assert numpy.array_equal(a.weights.mem, b.weights.mem) and a.weights is not b.weights
+        assert numpy.array_equal(a.bias.mem, b.bias.mem)
+        assert b.forward_mode
+    fwd.run()
+    out = fwd.forwards[-1].output.mem
+    assert out.shape == (10, 10) and numpy.allclose(out.sum(axis=1), 1.0, atol=1e-4)
