@@ -87,9 +87,10 @@ class All2All(nn_units.FullyConnectedOutput, nn_units.NNLayerBase):
         self.output.map_invalidate()
         self.input.map_read()
         self.weights.map_read()
-        mem = numpy.dot(self.input.matrix,
-                        self.weights.mem if self.weights_transposed
-                        else self.weights.mem.transpose())
+        from ..utils import mxfp8
+        w = self.weights.mem if self.weights_transposed else self.weights.mem.transpose()
+        # (block-scaled fp8 emulation: both operands quantised along the reduction dimension)
+        mem = numpy.dot(mxfp8.operand(self.input.matrix, 1), mxfp8.operand(w, 0))
         if self.include_bias:
             self.bias.map_read()
             mem += self.bias.mem

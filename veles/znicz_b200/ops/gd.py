@@ -169,6 +169,9 @@ class GradientDescent(GDCommon):
         err_output = self.err_output.matrix
         inp = self.input.matrix
         self.gradient_weights.map_invalidate()
+        from ..utils import mxfp8
+        if mxfp8.enabled():      # reduction over the batch: quantise both operands along it
+            inp, err_output = mxfp8.operand(inp, 0), mxfp8.operand(err_output, 0)
         if self.weights_transposed:
             numpy.dot(inp.transpose(), err_output, self.gradient_weights.mem)
         else:
@@ -191,10 +194,9 @@ class GradientDescent(GDCommon):
         self.weights.map_read()
         err_output = self.err_output.matrix
         err_input = self.err_input.matrix
-        if self.weights_transposed:
-            bp = numpy.dot(err_output, self.weights.mem.transpose())
-        else:
-            bp = numpy.dot(err_output, self.weights.mem)
+        from ..utils import mxfp8
+        w = self.weights.mem.transpose() if self.weights_transposed else self.weights.mem
+        bp = numpy.dot(mxfp8.operand(err_output, 1), mxfp8.operand(w, 0))
         bp *= self.err_input_alpha
         if self.err_input_beta:
             err_input *= self.err_input_beta
