@@ -305,3 +305,47 @@ def test_two_stage_pipeline_localises_objects(tmp_path):
     assert "pic_b.npy" not in final or final["pic_b.npy"]["bbxs"] == []
     assert raw["pic_b.npy"]["bbxs"] == []                           # a plain picture: nothing found
     assert json.load(open(tmp_path / "result.json")) == final
+
+
+def test_pipeline_from_a_trained_workflow_snapshot(tmp_path):
+    """The forward units (and nothing else) are taken over from a snapshot of a trained workflow
+    (/root/reference/.../imagenet_forward.py:237-262)."""
+    from veles.znicz_b200.core.config import root
+    from veles.znicz_b200.models import mnist
+    old = root.common.disable.snapshotting
+    root.common.disable.snapshotting = False
+    try:
+        train = mnist.build(
+            layers=[{"type": "all2all_tanh", "->": {"output_sample_shape": 6, "weights_stddev": 0.1},
+                     "<-": {"learning_rate": 0.05}},
+                    {"type": "softmax", "->": {"output_sample_shape": 3, "weights_stddev": 0.1},
+                     "<-": {"learning_rate": 0.05}}],
+            loader_name="synthetic_image",
+            loader_config={"minibatch_size": 10, "n_train": 60, "n_valid": 30, "shape": (8, 8, 1),
+                           "n_classes": 3, "normalization_type": "none"},
+            decision_config={"max_epochs": 1, "fail_iterations": 5},
+            snapshotter_config={"prefix": "trained", "interval": 1, "time_interval": 0,
+                                "compression": "gz", "directory": str(tmp_path)})
+        train.initialize(device="numpy")
+        train.run()
+    finally:
+        root.common.disable.snapshotting = old
+    snap = str(tmp_path / "trained_current.lnk")
+    assert os.path.exists(snap)
+    pics = _pictures()
+    wf = ImagenetForward(
+        DummyLauncher(testing=True), trained_workflow=snap, entry_shape=(4, 8, 8, 1),
+        mean=numpy.zeros((8, 8, 1), numpy.float32), image_reader=lambda p: pics[p],
+        bboxes=_candidates(), result_path=str(tmp_path / "out.json"),
+        labels_mapping={0: "a", 1: "b", 2: "c"},
+        loader_config={"minibatch_size": 4, "raw_bboxes_min_size": 8, "raw_bboxes_min_area": 64,
+                       "add_relative_bboxes": False},
+        merge_config={"ignore_negative": True, "use_compatibility": False, "mode": "final",
+                      "probability_threshold": 0.0, "last_chance_probability_threshold": 0.0})
+    assert [type(f).__name__ for f in wf.forwards] == ["All2AllTanh", "All2AllSoftmax"]
+    assert wf.forwards[0].weights.mem.shape == (6, 64)               # the trained parameters
+    wf.initialize(device="numpy")
+    res = wf.run_stage()
+    assert set(res) == {"pic_a.npy", "pic_b.npy"}
+    assert all(b["label"] in ("b", "c") for v in res.values() for b in v["bbxs"])
+    assert json.load(open(tmp_path / "out.json")) == res
