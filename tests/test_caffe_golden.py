@@ -141,3 +141,38 @@ def test_lrn_matches_caffe():
     b.initialize(device="numpy")
     b.run()
     assert _rel(b.err_input.mem, bot_err) < 0.02
+
+
+def test_conv3_golden_arrays_forward_and_err_input():
+    """The reference ships golden arrays of the CIFAR net's conv3 (5 x 5, pad 2, 32 -> 64 channels,
+    3 images) under tests/data/gd_conv_data: forward output and err_input of
+    the numpy oracle against them (relative max error; the arrays come from a Caffe fp32 run)."""
+    import os
+    import numpy
+    import pytest
+    from veles.znicz_b200.core.memory import Array
+    from veles.znicz_b200.core.workflow import DummyWorkflow
+    from veles.znicz_b200.ops import conv, gd_conv
+    base = "/root/reference/tests/data/gd_conv_data/gd_conv3."
+    if not os.path.exists(base + "input.npz"):
+        pytest.skip("reference golden arrays not mounted")
+    x, w, b, y, eo, ei = [numpy.load(base + n + ".npz")["arr_0"] for n in
+                          ("input", "weights", "bias", "output", "err_output", "err_input")]
+    wf = DummyWorkflow()
+    kw = dict(n_kernels=64, kx=5, ky=5, padding=(2, 2, 2, 2), sliding=(1, 1))
+    c = conv.Conv(wf, weights_stddev=0.1, **kw)
+    c.input = Array(x.copy())
+    c.initialize(device=None)
+    c.weights.map_write()
+    c.bias.map_write()
+    c.weights.mem[...] = w
+    c.bias.mem[...] = b
+    c.run()
+    assert c.output.mem.shape == y.shape
+    assert numpy.abs(c.output.mem - y).max() / numpy.abs(y).max() < 1e-2
+    g = gd_conv.GradientDescentConv(wf, learning_rate=0, learning_rate_bias=0, **kw)
+    g.err_output = Array(eo.copy())
+    g.input, g.output, g.weights, g.bias = c.input, c.output, c.weights, c.bias
+    g.initialize(device=None)
+    g.run()
+    assert numpy.abs(g.err_input.mem - ei).max() / numpy.abs(ei).max() < 1e-3
