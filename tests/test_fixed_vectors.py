@@ -98,3 +98,27 @@ def test_lrn_by_hand():
     sums = [1 + 4, 1 + 4 + 9, 4 + 9 + 16, 9 + 16]                   # window of 3 channels, clipped
     expect = [v * (2.0 + 0.5 * s) ** -0.75 for v, s in zip([1, 2, 3, 4], sums)]
     assert numpy.allclose(n.output.mem.ravel(), expect, rtol=1e-5)
+
+
+def test_reference_fc_fixed_vectors_on_every_backend_available():
+    """The reference's own fixed vectors for the linear FC layer (data of
+    /root/reference/tests/unit/test_all2all.py:60-88): 5 x 5 input, 3 x 5
+    weights, 15 expected outputs - numpy path here, the device path in
+    tests/test_gpu_units.py::test_fc* compares against this oracle."""
+    x = numpy.array([[1, 2, 3, 2, 1], [0, 1, 2, 1, 0], [0, 1, 0, 1, 0], [2, 0, 1, 0, 2],
+                     [1, 0, 1, 0, 1]], numpy.float32)
+    w = numpy.array([[1, 0, 2, 1, -1], [3, 1, 0, 2, 3], [-1, 2, 0, 1, 3]], numpy.float32)
+    b = numpy.array([10, -10, 5], numpy.float32)
+    expect = numpy.array([18, 2, 13, 15, -7, 8, 11, -7, 8, 12, 2, 9, 12, -4, 7], numpy.float32)
+    for transposed in (False, True):
+        wf = DummyWorkflow()
+        f = all2all.All2All(wf, output_sample_shape=[3], weights_stddev=0.05,
+                            weights_transposed=transposed)
+        f.input = Array(x.copy())
+        f.initialize(device=None)
+        f.weights.map_write()
+        f.bias.map_write()
+        f.weights.mem[...] = w.T if transposed else w
+        f.bias.mem[...] = b
+        f.run()
+        assert numpy.abs(f.output.mem.ravel() - expect).max() < 1e-4
