@@ -176,3 +176,107 @@ def test_conv3_golden_arrays_forward_and_err_input():
     g.initialize(device=None)
     g.run()
     assert numpy.abs(g.err_input.mem - ei).max() / numpy.abs(ei).max() < 1e-3
+
+
+def _read_any(lines, name, shape):
+    """Blob reader for the dumps whose header carries no dimensions; ``*_flat`` blobs hold the
+    whole NCHW tensor in one row."""
+    start = [i for i, l in enumerate(lines) if l.strip().split("\t")[0] == name][0] + 1
+    n, h, w, c = shape
+    if name.endswith("_flat"):
+        vals = [float(v) for v in lines[start + 2].split()]
+        return numpy.array(vals).reshape(n, c, h, w).transpose(0, 2, 3, 1)
+    out = numpy.zeros(shape)
+    cur = start
+    for pic in range(n):
+        assert lines[cur].strip() == "num:%d" % pic
+        cur += 1
+        for ch in range(c):
+            assert lines[cur].strip() == "channels:%d" % ch
+            cur += 1
+            for y in range(h):
+                out[pic, y, :, ch] = [float(v) for v in lines[cur].split()]
+                cur += 1
+    return out
+
+
+def _conv_relu(wf, bottom, weights):
+    u = conv.ConvStrictRELU(wf, kx=5, ky=5, padding=(2, 2, 2, 2), sliding=(1, 1), n_kernels=2)
+    u.input = Array(bottom.copy())
+    u.initialize(device="numpy")
+    u.weights.mem[:] = weights.reshape(2, -1)
+    u.bias.mem[:] = 0
+    u.run()
+    return u
+
+
+def test_conv_relu_forward_matches_caffe():
+    """/root/reference/tests/functional/test_caffe.py (conv + ReLU pair, `conv_relu.txt`)."""
+    lines = _lines("conv_relu.txt")
+    bottom = _read_any(lines, "conv_bottom", (2, 32, 32, 3))
+    weights = _read_any(lines, "conv_weights", (2, 5, 5, 3))
+    relu_top = _read_any(lines, "relu_top_flat", (2, 32, 32, 2))
+    u = _conv_relu(DummyWorkflow(), bottom, weights)
+    assert _rel(u.output.mem, relu_top) < 5e-3        # weights printed with 6 decimals
+
+
+def test_conv_relu_backward_matches_caffe():
+    """`conv_relu_grad.txt`: the fused conv + ReLU GD unit against Caffe's ReLU backward followed
+    by its conv backward - err_input and the raw weight gradient."""
+    lines = _lines("conv_relu_grad.txt")
+    g = {name: _read_any(lines, name, shape) for name, shape in (
+        ("relu_bottom", (2, 32, 32, 2)), ("relu_top_diff", (2, 32, 32, 2)),
+        ("relu_bottom_diff", (2, 32, 32, 2)), ("conv_weights", (2, 5, 5, 3)),
+        ("conv_top_diff", (2, 32, 32, 2)), ("conv_bottom", (2, 32, 32, 3)),
+        ("conv_bottom_diff", (2, 32, 32, 3)), ("conv_weight_delta", (2, 5, 5, 3)),
+        ("relu_top_flat", (2, 32, 32, 2)))}
+    assert _rel(g["relu_top_diff"] * (g["relu_bottom"] > 0), g["relu_bottom_diff"]) < 1e-9
+    wf = DummyWorkflow()
+    u = _conv_relu(wf, g["conv_bottom"], g["conv_weights"])
+    assert _rel(u.output.mem, g["relu_top_flat"]) < 1e-4
+    gd = gd_conv.GDStrictRELUConv(wf, kx=5, ky=5, padding=(2, 2, 2, 2), sliding=(1, 1), n_kernels=2,
+                                  learning_rate=0.0, weights_decay=0.0, apply_gradient=False,
+                                  gradient_moment=0.0)
+    gd.err_output = Array(g["relu_top_diff"].copy())
+    gd.link_attrs(u, "input", "output", "weights", "bias")
+    gd.initialize(device="numpy")
+    gd.run()
+    assert _rel(gd.err_input.mem, g["conv_bottom_diff"]) < 1e-5
+    assert _rel(gd.gradient_weights.mem.reshape(2, 5, 5, 3), g["conv_weight_delta"]) < 1e-3
+
+
+def test_softmax_and_loss_gradient_match_caffe():
+    """`softmax.txt`: softmax of the logits and the SoftmaxWithLoss gradient (p - onehot) / batch."""
+    from veles.znicz_b200.ops import all2all
+    from veles.znicz_b200.workflow import evaluator
+    lines = _lines("softmax.txt")
+
+    def vec(name, width):
+        start = [i for i, l in enumerate(lines) if l.strip() == name][0] + 1
+        out = numpy.zeros((2, width))
+        cur = start
+        for pic in range(2):
+            assert lines[cur].strip() == "num:%d" % pic
+            cur += 1
+            for ch in range(width):
+                assert lines[cur].strip() == "channels:%d" % ch
+                out[pic, ch] = float(lines[cur + 1].split()[0])
+                cur += 2
+        return out
+    labels = vec("labels", 1)[:, 0].astype(numpy.int32)
+    logits, top, bottom_diff = vec("sm_bottom", 10), vec("sm_top", 10), vec("sm_bottom_diff", 10)
+    wf = DummyWorkflow()
+    f = all2all.All2AllSoftmax(wf, output_sample_shape=10, weights_stddev=0.1)
+    f.input = Array(logits.copy())
+    f.initialize(device="numpy")
+    f.weights.mem[:] = numpy.eye(10)
+    f.bias.mem[:] = 0
+    f.run()
+    assert numpy.abs(f.output.mem - top).max() < 2e-6
+    ev = evaluator.EvaluatorSoftmax(wf)
+    ev.output, ev.max_idx = f.output, f.max_idx
+    ev.labels = Array(labels.copy())
+    ev.batch_size = 2
+    ev.initialize(device="numpy")
+    ev.run()
+    assert numpy.abs(ev.err_output.mem - bottom_diff).max() < 2e-6
