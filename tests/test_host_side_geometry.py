@@ -100,3 +100,25 @@ def test_collective_choice():
     assert pick(small, False, "twoshot").algo_name == "twoshot_peer"      # no multicast on the platform
     with pytest.raises(RuntimeError):
         pick(small, False, "nvls1")
+
+
+def test_fused_step_leaves_tied_weights_to_immediate_updates():
+    """Two GD units updating one tensor (tied auto-encoder weights) must not become two entries of
+    the single whole-network update launch."""
+    import numpy
+    from veles.znicz_b200.core.memory import Array
+    from veles.znicz_b200.ops.fused_step import FusedStep
+
+    class _GD(object):
+        def __init__(self, w, b=None):
+            self.weights, self.bias = w, b
+
+    w_tied, w1, w2 = (Array(numpy.ones((2, 2), numpy.float32)) for _ in range(3))
+    b1 = Array(numpy.ones(2, numpy.float32))
+    empty = Array()
+    a, b, c, d = _GD(w_tied, b1), _GD(w1, empty), _GD(w_tied, empty), _GD(w2, None)
+    shared = FusedStep.units_sharing_weights([a, b, c, d])
+    assert shared == {id(a), id(c)}
+    assert FusedStep.units_sharing_weights([b, d]) == set()
+    e = _GD(w2, b1)                                   # shares only the bias with `a`
+    assert FusedStep.units_sharing_weights([a, e]) == {id(a), id(e)}

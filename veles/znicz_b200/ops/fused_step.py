@@ -63,9 +63,14 @@ class FusedStep(object):
         if not chain or not all(getattr(u, "on_cuda", False) for u in chain):
             return None
         fs = cls(workflow.device, dp)
+        shared = cls.units_sharing_weights(chain)
         for u in chain:
             if isinstance(u, GradientDescentBase) and u.weights:
-                u.step_ = fs
+                # Tied weights (GDDeconv + the GD unit of its Conv in the auto-encoders) would be
+                # two entries of ONE launch updating the same tensor concurrently: those units
+                # keep the immediate, stream-ordered per-tensor update - the reference's order
+                # (/root/reference/gd_deconv.py:306-365 updates right away as well)
+                u.step_ = None if id(u) in shared else fs
         last = chain[-1]
         inner = last._backend_run_
 
@@ -75,6 +80,18 @@ class FusedStep(object):
         last.__dict__["_backend_run_"] = run_and_flush
         fs.last_unit = last
         return fs
+
+    @staticmethod
+    def units_sharing_weights(chain):
+        """ids of the GD units whose ``weights`` (or ``bias``) Array is also updated by another
+        unit of the chain."""
+        owners = {}
+        for u in chain:
+            for name in ("weights", "bias"):
+                arr = getattr(u, name, None)
+                if arr is not None and arr:
+                    owners.setdefault(id(arr), []).append(u)
+        return {id(u) for us in owners.values() if len(us) > 1 for u in us}
 
     # -- registration (called by api._update in deferred mode) -----------------------------------
     def submit(self, unit, is_bias, fields, keep, grad_ptr):
