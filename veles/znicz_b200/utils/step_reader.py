@@ -16,6 +16,7 @@ class StepResultReader(object):
         self.evaluator = evaluator
         self.depth = depth
         self.slots = [torch.zeros(2, dtype=torch.int32).pin_memory() for _ in range(depth)]
+        self.views = [t.numpy() for t in self.slots]      # host reads without a torch dispatch
         self.events = [torch.cuda.Event() for _ in range(depth)]
         self.pending = [False] * depth
         self.i = 0
@@ -29,7 +30,7 @@ class StepResultReader(object):
         s = self.i % self.depth
         if self.pending[s]:
             self.events[s].synchronize()
-            self.last = self.slots[s].clone()
+            self.last = self.views[s].copy()
         ext = getattr(getattr(ev, "device", None), "ext", None)
         if ext is not None and hasattr(ext, "push_to_host"):
             ext.push_to_host(ev.n_err.devmem, self.slots[s])   # a kernel stores into pinned memory
