@@ -349,3 +349,58 @@ def test_pipeline_from_a_trained_workflow_snapshot(tmp_path):
     assert set(res) == {"pic_a.npy", "pic_b.npy"}
     assert all(b["label"] in ("b", "c") for v in res.values() for b in v["bbxs"])
     assert json.load(open(tmp_path / "out.json")) == res
+
+
+def test_ranks_share_the_candidate_stream(tmp_path):
+    """`run_from_config` under torchrun: each rank takes its `shard_range` of the pickled candidate
+    stream (the reference printed one command line per slave, distribute_forward.py:40-85) and
+    writes `<result>.rank<k>.json`; `merge_json` combines them - every picture exactly once."""
+    import socket
+    import subprocess
+    import sys
+    from veles.znicz_b200.core.config import root
+    from veles.znicz_b200.models import mnist
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    old = root.common.disable.snapshotting
+    root.common.disable.snapshotting = False
+    try:
+        train = mnist.build(
+            layers=[{"type": "softmax", "->": {"output_sample_shape": 3, "weights_stddev": 0.1},
+                     "<-": {"learning_rate": 0.05}}],
+            loader_name="synthetic_image",
+            loader_config={"minibatch_size": 10, "n_train": 30, "n_valid": 10, "shape": (8, 8, 1),
+                           "n_classes": 3, "normalization_type": "none"},
+            decision_config={"max_epochs": 1, "fail_iterations": 5},
+            snapshotter_config={"prefix": "trained", "interval": 1, "time_interval": 0,
+                                "compression": "", "directory": str(tmp_path)})
+        train.initialize(device="numpy")
+        train.run()
+    finally:
+        root.common.disable.snapshotting = old
+    pics = _pictures()
+    names = []
+    with open(tmp_path / "raw.pickle", "wb") as fout:
+        for i in range(4):                                  # four pictures, two kinds
+            src = "pic_a.npy" if i % 2 == 0 else "pic_b.npy"
+            path = str(tmp_path / ("img%d.npy" % i))
+            numpy.save(path, pics[src])
+            meta = dict(_candidates()[src], path=path)
+            pickle.dump((i, meta), fout)
+            names.append(os.path.basename(path))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", str(port),
+         os.path.join(repo, "tests", "imagenet_forward_worker.py"), str(tmp_path)],
+        env=dict(os.environ, PYTHONPATH=repo, OMP_NUM_THREADS="1"), capture_output=True, text=True,
+        timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    parts = [str(tmp_path / ("result.rank%d.json" % k)) for k in range(2)]
+    assert all(os.path.exists(p) for p in parts)
+    per_rank = [set(json.load(open(p))) for p in parts]
+    assert per_rank[0] and per_rank[1] and not (per_rank[0] & per_rank[1])
+    merged = W.merge_json(parts, str(tmp_path / "all.json"))
+    assert sorted(merged) == sorted(names)

@@ -2,7 +2,7 @@
 
 Runs the two-stage localisation pipeline configured under ``root.imagenet_forward`` (trained
 workflow snapshot, candidate-box stream, result path, thresholds); under ``torchrun`` every rank
-processes its share of the candidate stream and writes ``<result>.rank<k>`` (combine them with
+processes its share of the candidate stream and writes ``<result>.rank<k>.json`` (combine them with
 ``writer.merge_json``). Reference entry point:
 /root/reference/tests/research/ImagenetAE/imagenet_forward/imagenet_forward.py:365-388."""
 import json

@@ -113,8 +113,8 @@ class ForwardLoaderBbox(AcceleratedUnit):
         self.total = 0
         self.processed = 0
         self.entry_shape = kwargs.get("entry_shape")
-        self.mean = kwargs.get("mean")
-        self.demand("entry_shape", "mean")
+        self.mean = kwargs.get("mean")        # None: pixels outside the box are 0
+        self.demand("entry_shape")
 
     def init_unpickled(self):
         super().init_unpickled()

@@ -202,7 +202,7 @@ def shard_range(stream_path, rank, world):
 
 def run_from_config(device="auto"):
     """Entry point driven by ``root.imagenet_forward`` (imagenet_forward.py:365-388); under
-    torchrun every rank takes its ``shard_range`` and writes ``<result>.rank<k>``."""
+    torchrun every rank takes its ``shard_range`` and writes ``<result>.rank<k>.json``."""
     cfg = root.imagenet_forward
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     lcfg = {}
@@ -210,7 +210,8 @@ def run_from_config(device="auto"):
     if world > 1 and cfg.loader.path_to_bboxes:
         lo, hi = shard_range(cfg.loader.path_to_bboxes, rank, world)
         lcfg.update(min_index=lo, max_index=hi)
-        result_path = "%s.rank%d" % (result_path, rank)
+        base, ext = os.path.splitext(result_path)
+        result_path = "%s.rank%d%s" % (base, rank, ext)        # keeps the .json the final stage reads
     from ...core.workflow import DummyLauncher
     wf = ImagenetForward(DummyLauncher(testing=True), loader_config=lcfg, result_path=result_path)
     wf.initialize(device=device)
